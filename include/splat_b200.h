@@ -1,0 +1,260 @@
+/*
+ * splat_b200.h — C ABI of the B200-native per-frame splat pipeline.
+ *
+ * Drop-in boundary for the hot path of LioQing/wgpu-3dgs-viewer v0.6.1:
+ *   Viewer::render = Preprocessor::preprocess -> RadixSorter::sort -> Renderer::render
+ *   (reference src/lib.rs:266-275).
+ * The reference exposes this path as a Rust generic API over wgpu handles, not an FFI, so
+ * every entry point below names the Rust item it replaces (file:line under the reference
+ * root); a Rust shim crate binds these 1:1 (INTEGRATION.md shows the `extern "C"` block).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no C++/torch types cross the boundary;
+ *   - every call returns an SbStatus; sb_last_error_string() describes the last failure;
+ *   - `stream` arguments are cudaStream_t handles passed as void* (NULL = default stream);
+ *     render/preprocess/sort/draw only ENQUEUE work (like recording into a
+ *     wgpu::CommandEncoder) and never synchronise; update_* calls are applied in program
+ *     order to the next enqueue (like queue.write_buffer before submit);
+ *   - device pointers are marked d_*; everything else is host memory;
+ *   - there is no CPU fallback: without a CUDA device sb_ctx_create fails.
+ */
+#ifndef SPLAT_B200_H
+#define SPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_API __attribute__((visibility("default")))
+
+typedef int32_t SbStatus;
+enum {
+    SB_OK = 0,
+    SB_ERR_INVALID_ARG = 1,
+    SB_ERR_CUDA = 2,
+    SB_ERR_MODEL_TOO_LARGE = 3,   /* PreprocessorCreateError::ModelSizeExceedsDeviceLimit, src/error.rs:7-42 */
+    SB_ERR_MODEL_NOT_FOUND = 4,   /* MultiModelViewerAccessError::ModelNotFound, src/error.rs:44-50 */
+    SB_ERR_BAD_BUFFER_SIZE = 5,   /* core::FixedSizeBufferWrapperError (TryFrom<wgpu::Buffer>) */
+    SB_ERR_IO = 6,
+    SB_ERR_OVERFLOW = 7           /* tile-duplicate capacity exceeded in a previous frame */
+};
+
+/* GaussianPod format = (SH storage, cov3d storage); core::GaussianPodWith{Sh*}{Cov3d*}Configs.
+ * Default pod (src/lib.rs:44) = SB_SH_SINGLE + SB_COV_SINGLE, 224 bytes. */
+enum { SB_SH_SINGLE = 0, SB_SH_HALF = 1, SB_SH_NORM8 = 2, SB_SH_NONE = 3 };
+enum { SB_COV_SINGLE = 0, SB_COV_HALF = 1, SB_COV_ROT_SCALE = 2 };
+/* core::GaussianDisplayMode */
+enum { SB_MODE_SPLAT = 0, SB_MODE_ELLIPSE = 1, SB_MODE_POINT = 2 };
+/* wgpu::TextureFormat subset accepted as render target (src/renderer.rs:120-155) */
+enum { SB_TARGET_RGBA8_UNORM = 0, SB_TARGET_BGRA8_UNORM = 1, SB_TARGET_RGBA16_FLOAT = 2, SB_TARGET_RGBA32_FLOAT = 3 };
+
+/* core::Gaussian (tests/e2e/viewer.rs:42-48) — the un-packed source splat. */
+typedef struct {
+    float pos[3];
+    uint8_t color[4];
+    float sh[45];
+    float scale[3];
+    float rot[4];     /* xyzw */
+} SbGaussian;         /* 224 bytes */
+
+/* CameraPod, src/buffer/camera.rs:63-80 — byte-identical (144 bytes). */
+typedef struct {
+    float view[16];
+    float proj[16];
+    float size[2];
+    uint32_t _padding[2];
+} SbCameraPod;
+
+/* core::ModelTransformPod (48 bytes) */
+typedef struct {
+    float pos[3];   float _pad0;
+    float rot[4];   /* xyzw */
+    float scale[3]; float _pad1;
+} SbModelTransformPod;
+
+/* core::GaussianTransformPod (8 bytes) */
+typedef struct {
+    float size;
+    uint8_t display_mode;
+    uint8_t sh_deg;
+    uint8_t no_sh0;
+    uint8_t max_std_dev;   /* round(v / 3 * 255) */
+} SbGaussianTransformPod;
+
+/* wgpu::util::DrawIndirectArgs — IndirectArgsBuffer, src/buffer/indirect_args.rs:8-55 */
+typedef struct { uint32_t vertex_count, instance_count, first_vertex, first_instance; } SbDrawIndirectArgs;
+/* wgpu::util::DispatchIndirectArgs — RadixSortIndirectArgsBuffer, src/buffer/indirect_args.rs:59-100 */
+typedef struct { uint32_t x, y, z; } SbDispatchIndirectArgs;
+
+/* The render target (replaces &wgpu::TextureView): caller-owned DEVICE memory. */
+typedef struct {
+    void* d_pixels;
+    uint32_t pitch_bytes;   /* row pitch */
+    uint32_t width, height; /* must equal CameraPod.size for a full frame */
+    int32_t format;         /* SB_TARGET_* */
+    uint32_t row0, rows;    /* screen strip rendered into d_pixels (row0 of the frame lands at
+                               d_pixels + 0); rows == 0 means the full frame */
+} SbTarget;
+
+typedef struct SbContext SbContext;
+typedef struct SbViewer SbViewer;
+typedef struct SbMultiModelViewer SbMultiModelViewer;
+
+/* ---------------------------------------------------------------- host-only helpers (no GPU needed) */
+
+SB_API const char* sb_version(void);
+SB_API const char* sb_status_string(SbStatus s);
+
+/* size_of::<G>() for a pod format — pinned by tests/e2e/multi_model.rs:43-53 */
+SB_API uint32_t sb_pod_stride(int32_t sh_fmt, int32_t cov_fmt);
+/* GaussiansBuffer::new's CPU packing (core): Gaussian -> pod bytes; out = n * stride bytes */
+SB_API SbStatus sb_pack_gaussians(const SbGaussian* src, uint64_t n, int32_t sh_fmt, int32_t cov_fmt, void* out);
+/* wgpu_sort::keys_buffer_size_bytes, src/radix_sorter.rs:937-939 (GaussiansDepthBuffer size) */
+SB_API uint64_t sb_keys_buffer_size_bytes(uint32_t n);
+/* number of depth keys actually touched by one frame: ceil(n/3840)*3840 */
+SB_API uint32_t sb_padded_key_count(uint32_t n);
+
+/* Camera{pos,z,vertical_fov,pitch,yaw} -> CameraPod::new(camera, size): src/camera.rs:71-93,
+ * src/buffer/camera.rs:72-80 */
+SB_API SbStatus sb_camera_pod(const float pos[3], float yaw, float pitch, float z_near, float z_far,
+                              float vertical_fov, uint32_t width, uint32_t height, SbCameraPod* out);
+/* ModelTransformPod::new(pos, rot, scale) (core) */
+SB_API SbStatus sb_model_transform_pod(const float pos[3], const float rot_xyzw[4], const float scale[3],
+                                       SbModelTransformPod* out);
+/* GaussianTransformPod::new(size, display_mode, sh_deg, no_sh0, max_std_dev) (core);
+ * INVALID_ARG mirrors GaussianShDegree::new / GaussianMaxStdDev::new returning None */
+SB_API SbStatus sb_gaussian_transform_pod(float size, int32_t display_mode, int32_t sh_deg, int32_t no_sh0,
+                                          float max_std_dev, SbGaussianTransformPod* out);
+
+/* Gaussians::read_from_file(path, GaussiansSource::Ply) (core; examples/simple.rs:157-160).
+ * *out is malloc'ed; release with sb_free. */
+SB_API SbStatus sb_read_ply(const char* path, SbGaussian** out, uint64_t* n);
+SB_API void sb_free(void* p);
+
+/* ---------------------------------------------------------------- context */
+
+/* replaces the &wgpu::Device every constructor takes */
+SB_API SbStatus sb_ctx_create(int32_t device_ordinal, SbContext** out);
+SB_API void sb_ctx_destroy(SbContext* ctx);
+SB_API const char* sb_last_error_string(const SbContext* ctx); /* ctx may be NULL: last global error */
+/* device "max_storage_buffer_binding_size" analogue used for SB_ERR_MODEL_TOO_LARGE
+ * (src/preprocessor.rs:239-246); default = free device memory at creation */
+SB_API SbStatus sb_ctx_set_model_size_limit(SbContext* ctx, uint64_t bytes);
+
+/* ---------------------------------------------------------------- Viewer (src/lib.rs:65-276) */
+
+/* Viewer::new(device, texture_format, gaussians) with already packed pods (host memory);
+ * uploads n*stride bytes (GaussiansBuffer::new). */
+SB_API SbStatus sb_viewer_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format,
+                                 const void* packed_pods, uint64_t n, SbViewer** out);
+/* Viewer::new from source Gaussians (packs on the host, then uploads) */
+SB_API SbStatus sb_viewer_create_from_gaussians(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt,
+                                                int32_t target_format, const SbGaussian* src, uint64_t n,
+                                                SbViewer** out);
+/* GaussiansBuffer: TryFrom<wgpu::Buffer> — adopt caller-owned device memory (never freed here);
+ * d_bytes must equal n*stride else SB_ERR_BAD_BUFFER_SIZE */
+SB_API SbStatus sb_viewer_create_from_device(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt,
+                                             int32_t target_format, const void* d_pods, uint64_t d_bytes,
+                                             uint64_t n, SbViewer** out);
+SB_API void sb_viewer_destroy(SbViewer* v);
+
+/* Viewer::update_camera_with_pod / update_camera: src/lib.rs:202-214 */
+SB_API SbStatus sb_viewer_update_camera_with_pod(SbViewer* v, const SbCameraPod* pod);
+SB_API SbStatus sb_viewer_update_camera(SbViewer* v, const float pos[3], float yaw, float pitch, float z_near,
+                                        float z_far, float vertical_fov, uint32_t width, uint32_t height);
+/* Viewer::update_model_transform[_with_pod]: src/lib.rs:217-234 */
+SB_API SbStatus sb_viewer_update_model_transform(SbViewer* v, const float pos[3], const float rot_xyzw[4],
+                                                 const float scale[3]);
+SB_API SbStatus sb_viewer_update_model_transform_with_pod(SbViewer* v, const SbModelTransformPod* pod);
+/* Viewer::update_gaussian_transform[_with_pod]: src/lib.rs:237-263 */
+SB_API SbStatus sb_viewer_update_gaussian_transform(SbViewer* v, float size, int32_t display_mode, int32_t sh_deg,
+                                                    int32_t no_sh0, float max_std_dev);
+SB_API SbStatus sb_viewer_update_gaussian_transform_with_pod(SbViewer* v, const SbGaussianTransformPod* pod);
+
+/* viewer.selection_buffer (editor SelectionBuffer: bit i%32 of word i/32; src/lib.rs:137) and
+ * viewer.invert_selection_buffer.update (src/selection/buffer.rs:167-171; default invert = 1).
+ * Selection is off until sb_viewer_enable_selection is called (feature `viewer-selection`). */
+SB_API SbStatus sb_viewer_enable_selection(SbViewer* v, int32_t enabled);
+SB_API SbStatus sb_viewer_selection_ptr(SbViewer* v, uint32_t** d_words, uint64_t* n_words);
+SB_API SbStatus sb_viewer_set_selection(SbViewer* v, void* stream, const uint32_t* words, uint64_t n_words);
+SB_API SbStatus sb_viewer_read_selection(SbViewer* v, void* stream, uint32_t* out, uint64_t n_words); /* synchronises */
+SB_API SbStatus sb_viewer_set_invert_selection(SbViewer* v, int32_t invert);
+/* selection::viewport evaluation with an analytic rectangle mask:
+ * src/shader/selection/viewport.wesl:37-69 + viewport_texture_rectangle.wesl; pixels [x0,x1)x[y0,y1) */
+SB_API SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float y0, float x1, float y1);
+
+/* Viewer::render(encoder, texture_view): src/lib.rs:266-275 — enqueue the whole frame */
+SB_API SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target);
+/* The three public stages, individually (viewer.preprocessor / radix_sorter / renderer):
+ *   Preprocessor::preprocess  src/preprocessor.rs:283-290
+ *   RadixSorter::sort         src/radix_sorter.rs:56-66
+ *   Renderer::render          src/renderer.rs:163-184 */
+SB_API SbStatus sb_viewer_preprocess(SbViewer* v, void* stream);
+SB_API SbStatus sb_viewer_sort(SbViewer* v, void* stream);
+SB_API SbStatus sb_viewer_draw(SbViewer* v, void* stream, const SbTarget* target);
+
+/* Convenience for host-resident callers: update camera, render into an internal device
+ * target, copy the frame to host_pixels (pinned recommended) — all enqueued on `stream`. */
+SB_API SbStatus sb_viewer_render_to_host(SbViewer* v, void* stream, const SbCameraPod* cam,
+                                         void* host_pixels, uint64_t host_bytes);
+
+/* Public buffers of the Viewer (src/lib.rs:65-82) as device pointers */
+SB_API SbStatus sb_viewer_gaussians_ptr(SbViewer* v, const void** d_pods, uint64_t* bytes);
+SB_API SbStatus sb_viewer_indirect_args_ptr(SbViewer* v, const SbDrawIndirectArgs** d_args);
+SB_API SbStatus sb_viewer_radix_sort_indirect_args_ptr(SbViewer* v, const SbDispatchIndirectArgs** d_args);
+SB_API SbStatus sb_viewer_indirect_indices_ptr(SbViewer* v, const uint32_t** d_indices, uint64_t* count);
+SB_API SbStatus sb_viewer_gaussians_depth_ptr(SbViewer* v, const float** d_keys, uint64_t* bytes);
+/* synchronising read-backs for tests/tools (cudaMemcpy D2H after syncing `stream`) */
+SB_API SbStatus sb_viewer_read_indirect_args(SbViewer* v, void* stream, SbDrawIndirectArgs* draw,
+                                             SbDispatchIndirectArgs* dispatch);
+SB_API SbStatus sb_viewer_read_indices(SbViewer* v, void* stream, uint32_t* out, uint64_t count);
+SB_API SbStatus sb_viewer_read_depth_keys(SbViewer* v, void* stream, float* out, uint64_t count);
+/* frame statistics of the last rendered frame (synchronises): visible splats, (splat,tile)
+ * duplicates, overflow flag */
+SB_API SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible, uint64_t* duplicates,
+                                           uint32_t* overflowed);
+/* testing knob: 1 = bit-reproducible polynomial exp in the fragment stage (matches the
+ * oracle's strict_exp); 0 (default) = MUFU ex2 fast path */
+SB_API SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict);
+/* capacity (in duplicates) of the tile-binning buffers; default 8*n + tiles */
+SB_API SbStatus sb_viewer_reserve_duplicates(SbViewer* v, uint64_t capacity);
+
+/* ---------------------------------------------------------------- standalone sort (RadixSorter<()>) */
+
+/* RadixSorter::new_without_bind_groups + sort(encoder, bind_groups, args): src/radix_sorter.rs:71-96.
+ * Sorts the first min(d_args->x*3840, capacity) ... see DESIGN.md: `d_count` holds the key count.
+ * Stable ascending sort of (u32 key, u32 payload); result in d_keys/d_payload. */
+typedef struct SbRadixSorter SbRadixSorter;
+SB_API SbStatus sb_sorter_create(SbContext* ctx, uint32_t capacity, SbRadixSorter** out);
+SB_API void sb_sorter_destroy(SbRadixSorter* s);
+SB_API SbStatus sb_sorter_sort(SbRadixSorter* s, void* stream, uint32_t* d_keys, uint32_t* d_payload,
+                               const uint32_t* d_count, uint32_t max_count, int32_t begin_bit, int32_t end_bit);
+
+/* ---------------------------------------------------------------- MultiModelViewer (src/multi_model.rs:291-531) */
+
+SB_API SbStatus sb_mm_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format,
+                             SbMultiModelViewer** out);
+SB_API void sb_mm_destroy(SbMultiModelViewer* mm);
+/* insert_model(device, key, gaussians) -> Option<old>: *replaced = 1 when a model was replaced */
+SB_API SbStatus sb_mm_insert_model(SbMultiModelViewer* mm, uint64_t key, const void* packed_pods, uint64_t n,
+                                   int32_t* replaced);
+SB_API SbStatus sb_mm_remove_model(SbMultiModelViewer* mm, uint64_t key, int32_t* removed);
+SB_API SbStatus sb_mm_update_camera_with_pod(SbMultiModelViewer* mm, const SbCameraPod* pod);
+SB_API SbStatus sb_mm_update_model_transform_with_pod(SbMultiModelViewer* mm, uint64_t key,
+                                                      const SbModelTransformPod* pod);
+SB_API SbStatus sb_mm_update_gaussian_transform_with_pod(SbMultiModelViewer* mm, const SbGaussianTransformPod* pod);
+SB_API SbStatus sb_mm_set_selection(SbMultiModelViewer* mm, uint64_t key, void* stream, const uint32_t* words,
+                                    uint64_t n_words, int32_t invert);
+/* render(encoder, view, keys): models drawn in key order, model k+1 over model k */
+SB_API SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const uint64_t* keys,
+                             uint32_t n_keys);
+SB_API SbStatus sb_mm_read_model_indices(SbMultiModelViewer* mm, uint64_t key, void* stream, uint32_t* out,
+                                         uint64_t count, SbDrawIndirectArgs* draw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

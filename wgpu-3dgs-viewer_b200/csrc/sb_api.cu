@@ -1,0 +1,794 @@
+// sb_api.cu — the extern "C" layer: handles, buffers, uniforms, stage sequencing.
+//
+// Mirrors the reference's object model (src/lib.rs:65-276, src/multi_model.rs:291-531): a Viewer
+// owns the 8 public buffers and chains preprocess -> sort -> render; nothing here synchronises
+// with the device except the explicit read_* helpers.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sb_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Ctx {
+    int device = 0;
+    int num_sms = 0;
+    uint64_t model_size_limit = 0;
+    std::string last_error;
+};
+
+SbStatus fail(Ctx* ctx, SbStatus s, const std::string& msg) {
+    g_last_error = msg;
+    if (ctx) ctx->last_error = msg;
+    return s;
+}
+SbStatus fail_cuda(Ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, SB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define SB_CUDA(ctx, call)                                            \
+    do {                                                              \
+        cudaError_t _e = (call);                                      \
+        if (_e != cudaSuccess) return fail_cuda(ctx, _e, #call);      \
+    } while (0)
+
+bool is_unorm(int fmt) { return fmt == SB_TARGET_RGBA8_UNORM || fmt == SB_TARGET_BGRA8_UNORM; }
+uint32_t bytes_per_pixel(int fmt) { return is_unorm(fmt) ? 4u : fmt == SB_TARGET_RGBA16_FLOAT ? 8u : 16u; }
+
+// ---- strict host maths for the per-frame uniforms (this file is compiled with
+// -Xcompiler -ffp-contract=off): the same individually rounded operations, in the same order,
+// that the oracle contract fixes for the uniform part of the reference shaders.
+void mat4_mul(const float* a, const float* b, float* r) {  // column-major
+    for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++)
+            r[j * 4 + i] = ((a[i] * b[j * 4] + a[4 + i] * b[j * 4 + 1]) + a[8 + i] * b[j * 4 + 2]) + a[12 + i] * b[j * 4 + 3];
+}
+
+sb::Uniforms make_uniforms(const SbCameraPod& cam, const SbModelTransformPod& mt, const SbGaussianTransformPod& gt, int target_format) {
+    sb::Uniforms u;
+    std::memset(&u, 0, sizeof u);
+    // Mat3::from_quat
+    const float x = mt.rot[0], y = mt.rot[1], z = mt.rot[2], w = mt.rot[3];
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx = x * x2, xy = x * y2, xz = x * z2, yy = y * y2, yz = y * z2, zz = z * z2;
+    const float wx = w * x2, wy = w * y2, wz = w * z2;
+    const float r[9] = {1.0f - (yy + zz), xy + wz, xz - wy, xy - wz, 1.0f - (xx + zz), yz + wx, xz + wy, yz - wx, 1.0f - (xx + yy)};
+    for (int c = 0; c < 3; c++)
+        for (int rr = 0; rr < 3; rr++) {
+            u.sr[c * 3 + rr] = r[c * 3 + rr] * mt.scale[c];      // R S
+            u.inv_sr[c * 3 + rr] = r[rr * 3 + c] / mt.scale[rr];  // S^-1 R^T
+        }
+    for (int c = 0; c < 3; c++)
+        for (int rr = 0; rr < 3; rr++) u.model[c * 4 + rr] = u.sr[c * 3 + rr];
+    u.model[12] = mt.pos[0];
+    u.model[13] = mt.pos[1];
+    u.model[14] = mt.pos[2];
+    u.model[15] = 1.0f;
+    mat4_mul(cam.proj, cam.view, u.pv);
+    mat4_mul(cam.view, u.model, u.vm);
+    for (int c = 0; c < 3; c++)
+        for (int rr = 0; rr < 3; rr++) u.w[c * 3 + rr] = cam.view[c * 4 + rr];
+    u.size[0] = cam.size[0];
+    u.size[1] = cam.size[1];
+    u.focal[0] = cam.proj[0] * cam.size[0] * 0.5f;
+    u.focal[1] = cam.proj[5] * cam.size[1] * 0.5f;
+    for (int i = 0; i < 3; i++) {
+        const float d = (u.w[i * 3] * cam.view[12] + u.w[i * 3 + 1] * cam.view[13]) + u.w[i * 3 + 2] * cam.view[14];
+        u.cam_pos[i] = -d;
+    }
+    u.std_dev = (float)gt.max_std_dev / 255.0f * 3.0f;
+    u.gsize = gt.size;
+    u.color_scale = is_unorm(target_format) ? 255.0f : 1.0f;
+    u.mode = gt.display_mode;
+    u.sh_deg = gt.sh_deg;
+    u.no_sh0 = gt.no_sh0;
+    u.width = (uint32_t)cam.size[0];
+    u.height = (uint32_t)cam.size[1];
+    u.tiles_x = (u.width + sb::kTile - 1) / sb::kTile;
+    u.tiles_y = (u.height + sb::kTile - 1) / sb::kTile;
+    return u;
+}
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct SbContext : Ctx {};
+
+// One model's buffers and stage scratch.  A Viewer is one of these plus camera/gaussian
+// transform pods; a MultiModelViewer shares the world pods across many.
+struct SbViewer {
+    SbContext* ctx = nullptr;
+    int sh_fmt = 0, cov_fmt = 0, target_format = 0;
+    uint32_t stride = 0;
+    uint32_t n = 0;
+    uint32_t padded = 0;
+
+    const void* d_gaussians = nullptr;  // owned (gaussians_owned) or adopted
+    DeviceBuf gaussians_owned;
+    DeviceBuf indices, keys, args, recs, pre_scratch;
+    DeviceBuf sort_keys_alt, sort_vals_alt, sort_internal;
+    DeviceBuf dup_offsets, dup_keys, dup_vals, tile_recs, tile_ranges, bin_state;
+    DeviceBuf selection;
+    DeviceBuf internal_target;
+    uint64_t dup_capacity = 0;
+    uint32_t tile_capacity = 0;
+
+    SbCameraPod camera;
+    SbModelTransformPod model_transform;
+    SbGaussianTransformPod gaussian_transform;
+    bool selection_enabled = false;
+    uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
+    int strict_exp = 0;
+
+    SbDrawIndirectArgs* d_draw() const { return args.as<SbDrawIndirectArgs>(); }
+    SbDispatchIndirectArgs* d_dispatch() const { return reinterpret_cast<SbDispatchIndirectArgs*>(args.as<uint8_t>() + 16); }
+    uint32_t* d_visible() const { return reinterpret_cast<uint32_t*>(args.as<uint8_t>() + 32); }
+    // bin_state: [dup_count 4][overflow 4][pad 8][scan_counter 16][scan_status ...]
+    uint32_t* d_dup_count() const { return bin_state.as<uint32_t>(); }
+    uint32_t* d_overflow() const { return bin_state.as<uint32_t>() + 1; }
+    uint32_t* d_scan_counter() const { return bin_state.as<uint32_t>() + 4; }
+    unsigned long long* d_scan_status() const { return reinterpret_cast<unsigned long long*>(bin_state.as<uint8_t>() + 32); }
+};
+
+namespace {
+
+SbStatus viewer_alloc(SbViewer* v) {
+    SbContext* ctx = v->ctx;
+    const uint32_t n = v->n;
+    v->padded = sb_padded_key_count(n);
+    SB_CUDA(ctx, v->indices.alloc((size_t)(v->padded ? v->padded : 1) * 4));
+    SB_CUDA(ctx, v->keys.alloc((size_t)(v->padded ? v->padded : 1) * 4));
+    SB_CUDA(ctx, v->args.alloc(64));
+    SB_CUDA(ctx, v->recs.alloc((size_t)(n ? n : 1) * sizeof(sb::SplatRec)));
+    SB_CUDA(ctx, v->pre_scratch.alloc(sb::preprocess_scratch_bytes(n, v->sh_fmt, v->cov_fmt)));
+    SB_CUDA(ctx, v->selection.alloc(((size_t)n + 31) / 32 * 4 + 4));
+    SB_CUDA(ctx, cudaMemset(v->selection.p, 0, v->selection.bytes));
+    const SbDrawIndirectArgs d = {6, 0, 0, 0};          // IndirectArgsBuffer::new
+    const SbDispatchIndirectArgs s = {1, 1, 1};         // RadixSortIndirectArgsBuffer::new
+    uint8_t init[64] = {0};
+    std::memcpy(init, &d, sizeof d);
+    std::memcpy(init + 16, &s, sizeof s);
+    SB_CUDA(ctx, cudaMemcpy(v->args.p, init, sizeof init, cudaMemcpyHostToDevice));
+    SB_CUDA(ctx, v->dup_offsets.alloc(((size_t)n + 1) * 4));
+    const size_t scan_tiles = ((size_t)n + 1023) / 1024 + 2;
+    SB_CUDA(ctx, v->bin_state.alloc(32 + scan_tiles * sizeof(unsigned long long)));
+    SB_CUDA(ctx, cudaMemset(v->bin_state.p, 0, v->bin_state.bytes));
+    return SB_OK;
+}
+
+SbStatus viewer_reserve(SbViewer* v, uint64_t cap) {
+    SbContext* ctx = v->ctx;
+    if (cap < 4096) cap = 4096;
+    if (cap > 0x3fffffffull) cap = 0x3fffffffull;
+    v->dup_capacity = cap;
+    SB_CUDA(ctx, v->dup_keys.alloc(cap * 4));
+    SB_CUDA(ctx, v->dup_vals.alloc(cap * 4));
+    SB_CUDA(ctx, v->tile_recs.alloc(cap * sizeof(sb::SplatRec)));
+    const uint64_t sort_cap = cap > v->padded ? cap : v->padded;
+    SB_CUDA(ctx, v->sort_keys_alt.alloc(sort_cap * 4));
+    SB_CUDA(ctx, v->sort_vals_alt.alloc(sort_cap * 4));
+    SB_CUDA(ctx, v->sort_internal.alloc(sb::sort_internal_bytes((uint32_t)sort_cap)));
+    return SB_OK;
+}
+
+SbStatus viewer_new(SbContext* ctx, int sh_fmt, int cov_fmt, int target_format, uint64_t n, SbViewer** out) {
+    if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null context/out");
+    if (sb_pod_stride(sh_fmt, cov_fmt) == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
+    if (target_format < 0 || target_format > SB_TARGET_RGBA32_FLOAT) return fail(ctx, SB_ERR_INVALID_ARG, "unknown target format");
+    if (n > 0x3fffffffull) return fail(ctx, SB_ERR_MODEL_TOO_LARGE, "more than 2^30 gaussians");
+    const uint64_t model_size = n * sb_pod_stride(sh_fmt, cov_fmt);
+    if (model_size > ctx->model_size_limit) {  // src/preprocessor.rs:239-246
+        char msg[160];
+        std::snprintf(msg, sizeof msg, "model size %llu exceeds the device limit %llu", (unsigned long long)model_size,
+                      (unsigned long long)ctx->model_size_limit);
+        return fail(ctx, SB_ERR_MODEL_TOO_LARGE, msg);
+    }
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    SbViewer* v = new SbViewer();
+    v->ctx = ctx;
+    v->sh_fmt = sh_fmt;
+    v->cov_fmt = cov_fmt;
+    v->target_format = target_format;
+    v->stride = sb_pod_stride(sh_fmt, cov_fmt);
+    v->n = (uint32_t)n;
+    std::memset(&v->camera, 0, sizeof v->camera);
+    const float zero[3] = {0, 0, 0}, one[3] = {1, 1, 1}, ident[4] = {0, 0, 0, 1};
+    sb_model_transform_pod(zero, ident, one, &v->model_transform);                // identity default
+    sb_gaussian_transform_pod(1.0f, SB_MODE_SPLAT, 3, 0, 3.0f, &v->gaussian_transform);  // core defaults
+    SbStatus s = viewer_alloc(v);
+    if (s == SB_OK) s = viewer_reserve(v, 8ull * n + 65536);
+    if (s != SB_OK) {
+        sb_viewer_destroy(v);
+        return s;
+    }
+    *out = v;
+    return SB_OK;
+}
+
+SbStatus check_target(SbViewer* v, const SbTarget* t, const sb::Uniforms& u) {
+    if (!t || !t->d_pixels) return fail(v->ctx, SB_ERR_INVALID_ARG, "null target");
+    if (t->format != v->target_format) return fail(v->ctx, SB_ERR_INVALID_ARG, "target format differs from the viewer's texture_format");
+    if (t->width != u.width || t->height != u.height) return fail(v->ctx, SB_ERR_INVALID_ARG, "target size differs from CameraPod.size");
+    if (t->pitch_bytes < t->width * bytes_per_pixel(t->format)) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "target pitch too small");
+    if (t->rows != 0 && (t->row0 >= t->height || t->rows > t->height - t->row0)) return fail(v->ctx, SB_ERR_INVALID_ARG, "bad strip");
+    return SB_OK;
+}
+
+SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, cudaStream_t stream) {
+    sb::PreParams p;
+    std::memset(&p, 0, sizeof p);
+    p.gaussians = static_cast<const uint8_t*>(v->d_gaussians);
+    p.n = v->n;
+    p.selection = v->selection_enabled ? v->selection.as<uint32_t>() : nullptr;
+    p.invert_selection = v->invert_selection;
+    p.indices = v->indices.as<uint32_t>();
+    p.keys = v->keys.as<float>();
+    p.keys_capacity = v->padded;
+    p.draw_args = v->d_draw();
+    p.sort_args = v->d_dispatch();
+    p.recs = v->recs.as<sb::SplatRec>();
+    p.visible_count = v->d_visible();
+    p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
+    SB_CUDA(v->ctx, sb::launch_preprocess(v->sh_fmt, v->cov_fmt, p, v->pre_scratch.p, v->pre_scratch.bytes, v->ctx->num_sms, stream));
+    return SB_OK;
+}
+
+sb::SortScratch sort_scratch(SbViewer* v) {
+    sb::SortScratch s;
+    s.keys_alt = v->sort_keys_alt.as<uint32_t>();
+    s.payload_alt = v->sort_vals_alt.as<uint32_t>();
+    s.internal = v->sort_internal.as<uint32_t>();
+    s.internal_bytes = v->sort_internal.bytes;
+    return s;
+}
+
+SbStatus do_sort(SbViewer* v, cudaStream_t stream) {
+    // keys = f32 depth bit patterns in [0, 0x3F800000]; pads (2.0) beyond V are left in place
+    SB_CUDA(v->ctx, sb::launch_sort(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), v->d_visible(), v->n, 0, 32, sort_scratch(v),
+                                    v->ctx->num_sms, stream));
+    return SB_OK;
+}
+
+SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, const SbTarget* target, int clear,
+                 cudaStream_t stream) {
+    sb::RasterParams p;
+    std::memset(&p, 0, sizeof p);
+    p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
+    SbStatus s = check_target(v, target, p.u);
+    if (s != SB_OK) return s;
+    const uint32_t tiles = p.u.tiles_x * p.u.tiles_y;
+    if (tiles > v->tile_capacity) {
+        SB_CUDA(v->ctx, cudaStreamSynchronize(stream));
+        SB_CUDA(v->ctx, v->tile_ranges.alloc((size_t)tiles * 8));
+        v->tile_capacity = tiles;
+    }
+    p.recs = v->recs.as<sb::SplatRec>();
+    p.sorted_indices = v->indices.as<uint32_t>();
+    p.visible_count = v->d_visible();
+    p.max_visible = v->n;
+    p.buf.dup_offsets = v->dup_offsets.as<uint32_t>();
+    p.buf.dup_keys = v->dup_keys.as<uint32_t>();
+    p.buf.dup_vals = v->dup_vals.as<uint32_t>();
+    p.buf.tile_ranges = v->tile_ranges.as<uint32_t>();
+    p.buf.dup_count = v->d_dup_count();
+    p.buf.overflow = v->d_overflow();
+    p.buf.scan_counter = v->d_scan_counter();
+    p.buf.scan_status = v->d_scan_status();
+    p.buf.tile_recs = v->tile_recs.as<sb::SplatRec>();
+    p.buf.dup_capacity = v->dup_capacity;
+    p.sort = sort_scratch(v);
+    p.target = *target;
+    p.strict_exp = v->strict_exp;
+    p.clear = clear;
+    SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sb_last_error_string(const SbContext* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+SbStatus sb_ctx_create(int32_t device_ordinal, SbContext** out) {
+    if (!out) return fail(nullptr, SB_ERR_INVALID_ARG, "null out");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(nullptr, SB_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device_ordinal < 0 || device_ordinal >= count) return fail(nullptr, SB_ERR_INVALID_ARG, "bad device ordinal");
+    cudaDeviceProp prop;
+    SB_CUDA(nullptr, cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major != 10) return fail(nullptr, SB_ERR_CUDA, "splat_b200 is built for sm_100a (Blackwell B200) only");
+    SB_CUDA(nullptr, cudaSetDevice(device_ordinal));
+    SbContext* ctx = new SbContext();
+    ctx->device = device_ordinal;
+    ctx->num_sms = prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    SB_CUDA(nullptr, cudaMemGetInfo(&free_b, &total_b));
+    ctx->model_size_limit = free_b;
+    *out = ctx;
+    return SB_OK;
+}
+
+void sb_ctx_destroy(SbContext* ctx) { delete ctx; }
+
+SbStatus sb_ctx_set_model_size_limit(SbContext* ctx, uint64_t bytes) {
+    if (!ctx) return fail(nullptr, SB_ERR_INVALID_ARG, "null context");
+    ctx->model_size_limit = bytes;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, const void* packed_pods, uint64_t n,
+                          SbViewer** out) {
+    if (n && !packed_pods) return fail(ctx, SB_ERR_INVALID_ARG, "null pods");
+    SbViewer* v = nullptr;
+    SbStatus s = viewer_new(ctx, sh_fmt, cov_fmt, target_format, n, &v);
+    if (s != SB_OK) return s;
+    cudaError_t e = v->gaussians_owned.alloc((size_t)n * v->stride);
+    if (e == cudaSuccess && n) e = cudaMemcpy(v->gaussians_owned.p, packed_pods, (size_t)n * v->stride, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sb_viewer_destroy(v);
+        return fail_cuda(ctx, e, "upload gaussians");
+    }
+    v->d_gaussians = v->gaussians_owned.p;
+    *out = v;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_create_from_gaussians(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, const SbGaussian* src,
+                                         uint64_t n, SbViewer** out) {
+    const uint32_t stride = sb_pod_stride(sh_fmt, cov_fmt);
+    if (stride == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
+    std::vector<uint8_t> pods((size_t)n * stride + 16);
+    SbStatus s = sb_pack_gaussians(src, n, sh_fmt, cov_fmt, pods.data());
+    if (s != SB_OK) return fail(ctx, s, "pack failed");
+    return sb_viewer_create(ctx, sh_fmt, cov_fmt, target_format, pods.data(), n, out);
+}
+
+SbStatus sb_viewer_create_from_device(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, const void* d_pods,
+                                      uint64_t d_bytes, uint64_t n, SbViewer** out) {
+    const uint32_t stride = sb_pod_stride(sh_fmt, cov_fmt);
+    if (stride == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
+    if (d_bytes != n * stride) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians buffer size != n * size_of::<G>()");
+    if (n && (!d_pods || (reinterpret_cast<uintptr_t>(d_pods) & 15u))) return fail(ctx, SB_ERR_INVALID_ARG, "device pods must be 16-byte aligned");
+    SbViewer* v = nullptr;
+    SbStatus s = viewer_new(ctx, sh_fmt, cov_fmt, target_format, n, &v);
+    if (s != SB_OK) return s;
+    v->d_gaussians = d_pods;
+    *out = v;
+    return SB_OK;
+}
+
+void sb_viewer_destroy(SbViewer* v) {
+    if (!v) return;
+    for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->pre_scratch, &v->sort_keys_alt,
+                         &v->sort_vals_alt, &v->sort_internal, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
+                         &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target})
+        b->release();
+    delete v;
+}
+
+SbStatus sb_viewer_update_camera_with_pod(SbViewer* v, const SbCameraPod* pod) {
+    if (!v || !pod) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    v->camera = *pod;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_update_camera(SbViewer* v, const float pos[3], float yaw, float pitch, float z_near, float z_far,
+                                 float vertical_fov, uint32_t width, uint32_t height) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    return sb_camera_pod(pos, yaw, pitch, z_near, z_far, vertical_fov, width, height, &v->camera);
+}
+
+SbStatus sb_viewer_update_model_transform(SbViewer* v, const float pos[3], const float rot[4], const float scale[3]) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    return sb_model_transform_pod(pos, rot, scale, &v->model_transform);
+}
+
+SbStatus sb_viewer_update_model_transform_with_pod(SbViewer* v, const SbModelTransformPod* pod) {
+    if (!v || !pod) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    v->model_transform = *pod;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_update_gaussian_transform(SbViewer* v, float size, int32_t display_mode, int32_t sh_deg, int32_t no_sh0,
+                                             float max_std_dev) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SbGaussianTransformPod pod;
+    SbStatus s = sb_gaussian_transform_pod(size, display_mode, sh_deg, no_sh0, max_std_dev, &pod);
+    if (s != SB_OK) return fail(v->ctx, s, "bad gaussian transform");
+    v->gaussian_transform = pod;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_update_gaussian_transform_with_pod(SbViewer* v, const SbGaussianTransformPod* pod) {
+    if (!v || !pod) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (pod->display_mode > 2 || pod->sh_deg > 3) return fail(v->ctx, SB_ERR_INVALID_ARG, "bad gaussian transform pod");
+    v->gaussian_transform = *pod;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_enable_selection(SbViewer* v, int32_t enabled) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    v->selection_enabled = enabled != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_selection_ptr(SbViewer* v, uint32_t** d_words, uint64_t* n_words) {
+    if (!v || !d_words || !n_words) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *d_words = v->selection.as<uint32_t>();
+    *n_words = ((uint64_t)v->n + 31) / 32;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_set_selection(SbViewer* v, void* stream, const uint32_t* words, uint64_t n_words) {
+    if (!v || (!words && n_words)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (n_words != ((uint64_t)v->n + 31) / 32) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "selection must hold ceil(n/32) words");
+    SB_CUDA(v->ctx, cudaMemcpyAsync(v->selection.p, words, n_words * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_read_selection(SbViewer* v, void* stream, uint32_t* out, uint64_t n_words) {
+    if (!v || (!out && n_words)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (n_words != ((uint64_t)v->n + 31) / 32) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "selection must hold ceil(n/32) words");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    SB_CUDA(v->ctx, cudaMemcpy(out, v->selection.p, n_words * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_set_invert_selection(SbViewer* v, int32_t invert) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    v->invert_selection = invert ? 1u : 0u;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float y0, float x1, float y1) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    SB_CUDA(v->ctx, sb::launch_select_rect(static_cast<const uint8_t*>(v->d_gaussians), v->n, v->stride, u, x0, y0, x1, y1,
+                                           v->selection.as<uint32_t>(), static_cast<cudaStream_t>(stream)));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_preprocess(SbViewer* v, void* stream) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    return do_preprocess(v, v->camera, v->gaussian_transform, static_cast<cudaStream_t>(stream));
+}
+
+SbStatus sb_viewer_sort(SbViewer* v, void* stream) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    return do_sort(v, static_cast<cudaStream_t>(stream));
+}
+
+SbStatus sb_viewer_draw(SbViewer* v, void* stream, const SbTarget* target) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    return do_draw(v, v->camera, v->gaussian_transform, target, 1, static_cast<cudaStream_t>(stream));
+}
+
+SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // validate before enqueuing anything
+    sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    SbStatus s = check_target(v, target, u);
+    if (s != SB_OK) return s;
+    s = do_preprocess(v, v->camera, v->gaussian_transform, st);
+    if (s != SB_OK) return s;
+    s = do_sort(v, st);
+    if (s != SB_OK) return s;
+    return do_draw(v, v->camera, v->gaussian_transform, target, 1, st);
+}
+
+SbStatus sb_viewer_render_to_host(SbViewer* v, void* stream, const SbCameraPod* cam, void* host_pixels, uint64_t host_bytes) {
+    if (!v || !cam || !host_pixels) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    const uint32_t w = (uint32_t)cam->size[0], h = (uint32_t)cam->size[1];
+    const uint64_t need = (uint64_t)w * h * bytes_per_pixel(v->target_format);
+    if (host_bytes != need) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "host frame buffer size mismatch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (v->internal_target.bytes < need) {
+        SB_CUDA(v->ctx, cudaStreamSynchronize(st));
+        SB_CUDA(v->ctx, v->internal_target.alloc(need));
+    }
+    v->camera = *cam;
+    SbTarget t;
+    t.d_pixels = v->internal_target.p;
+    t.pitch_bytes = w * bytes_per_pixel(v->target_format);
+    t.width = w;
+    t.height = h;
+    t.format = v->target_format;
+    t.row0 = 0;
+    t.rows = 0;
+    SbStatus s = sb_viewer_render(v, stream, &t);
+    if (s != SB_OK) return s;
+    SB_CUDA(v->ctx, cudaMemcpyAsync(host_pixels, v->internal_target.p, need, cudaMemcpyDeviceToHost, st));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_gaussians_ptr(SbViewer* v, const void** d_pods, uint64_t* bytes) {
+    if (!v || !d_pods || !bytes) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *d_pods = v->d_gaussians;
+    *bytes = (uint64_t)v->n * v->stride;
+    return SB_OK;
+}
+SbStatus sb_viewer_indirect_args_ptr(SbViewer* v, const SbDrawIndirectArgs** d_args) {
+    if (!v || !d_args) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *d_args = v->d_draw();
+    return SB_OK;
+}
+SbStatus sb_viewer_radix_sort_indirect_args_ptr(SbViewer* v, const SbDispatchIndirectArgs** d_args) {
+    if (!v || !d_args) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *d_args = v->d_dispatch();
+    return SB_OK;
+}
+SbStatus sb_viewer_indirect_indices_ptr(SbViewer* v, const uint32_t** d_indices, uint64_t* count) {
+    if (!v || !d_indices || !count) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *d_indices = v->indices.as<uint32_t>();
+    *count = v->n;
+    return SB_OK;
+}
+SbStatus sb_viewer_gaussians_depth_ptr(SbViewer* v, const float** d_keys, uint64_t* bytes) {
+    if (!v || !d_keys || !bytes) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *d_keys = v->keys.as<float>();
+    *bytes = (uint64_t)v->padded * 4;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_read_indirect_args(SbViewer* v, void* stream, SbDrawIndirectArgs* draw, SbDispatchIndirectArgs* dispatch) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (draw) SB_CUDA(v->ctx, cudaMemcpy(draw, v->d_draw(), sizeof *draw, cudaMemcpyDeviceToHost));
+    if (dispatch) SB_CUDA(v->ctx, cudaMemcpy(dispatch, v->d_dispatch(), sizeof *dispatch, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+SbStatus sb_viewer_read_indices(SbViewer* v, void* stream, uint32_t* out, uint64_t count) {
+    if (!v || (!out && count)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (count > v->padded) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "count exceeds buffer");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    SB_CUDA(v->ctx, cudaMemcpy(out, v->indices.p, count * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+SbStatus sb_viewer_read_depth_keys(SbViewer* v, void* stream, float* out, uint64_t count) {
+    if (!v || (!out && count)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (count > v->padded) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "count exceeds buffer");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    SB_CUDA(v->ctx, cudaMemcpy(out, v->keys.p, count * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible, uint64_t* duplicates, uint32_t* overflowed) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    uint32_t vis = 0, st[2] = {0, 0};
+    SB_CUDA(v->ctx, cudaMemcpy(&vis, v->d_visible(), 4, cudaMemcpyDeviceToHost));
+    SB_CUDA(v->ctx, cudaMemcpy(st, v->bin_state.p, 8, cudaMemcpyDeviceToHost));
+    if (visible) *visible = vis;
+    if (duplicates) *duplicates = st[0];
+    if (overflowed) *overflowed = st[1];
+    return st[1] ? fail(v->ctx, SB_ERR_OVERFLOW, "tile-duplicate capacity exceeded; call sb_viewer_reserve_duplicates") : SB_OK;
+}
+
+SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    v->strict_exp = strict != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_reserve_duplicates(SbViewer* v, uint64_t capacity) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SB_CUDA(v->ctx, cudaDeviceSynchronize());
+    SbStatus s = viewer_reserve(v, capacity);
+    if (s == SB_OK) SB_CUDA(v->ctx, cudaMemset(v->bin_state.p, 0, 8));
+    return s;
+}
+
+// ---------------------------------------------------------------- standalone sorter
+
+struct SbRadixSorter {
+    SbContext* ctx;
+    uint32_t capacity;
+    DeviceBuf keys_alt, vals_alt, internal;
+};
+
+SbStatus sb_sorter_create(SbContext* ctx, uint32_t capacity, SbRadixSorter** out) {
+    if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    SbRadixSorter* s = new SbRadixSorter();
+    s->ctx = ctx;
+    s->capacity = capacity;
+    cudaError_t e = s->keys_alt.alloc((size_t)capacity * 4);
+    if (e == cudaSuccess) e = s->vals_alt.alloc((size_t)capacity * 4);
+    if (e == cudaSuccess) e = s->internal.alloc(sb::sort_internal_bytes(capacity));
+    if (e != cudaSuccess) {
+        sb_sorter_destroy(s);
+        return fail_cuda(ctx, e, "sorter alloc");
+    }
+    *out = s;
+    return SB_OK;
+}
+
+void sb_sorter_destroy(SbRadixSorter* s) {
+    if (!s) return;
+    s->keys_alt.release();
+    s->vals_alt.release();
+    s->internal.release();
+    delete s;
+}
+
+SbStatus sb_sorter_sort(SbRadixSorter* s, void* stream, uint32_t* d_keys, uint32_t* d_payload, const uint32_t* d_count,
+                        uint32_t max_count, int32_t begin_bit, int32_t end_bit) {
+    if (!s || !d_keys || !d_payload || !d_count) return fail(s ? s->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (max_count > s->capacity) return fail(s->ctx, SB_ERR_BAD_BUFFER_SIZE, "max_count exceeds sorter capacity");
+    if (begin_bit < 0 || end_bit > 32 || begin_bit >= end_bit) return fail(s->ctx, SB_ERR_INVALID_ARG, "bad bit range");
+    sb::SortScratch sc;
+    sc.keys_alt = s->keys_alt.as<uint32_t>();
+    sc.payload_alt = s->vals_alt.as<uint32_t>();
+    sc.internal = s->internal.as<uint32_t>();
+    sc.internal_bytes = s->internal.bytes;
+    SB_CUDA(s->ctx, sb::launch_sort(d_keys, d_payload, d_count, max_count, begin_bit, end_bit, sc, s->ctx->num_sms,
+                                    static_cast<cudaStream_t>(stream)));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- MultiModelViewer
+
+}  // extern "C"
+
+struct SbMultiModelViewer {
+    SbContext* ctx = nullptr;
+    int sh_fmt = 0, cov_fmt = 0, target_format = 0;
+    SbCameraPod camera;
+    SbGaussianTransformPod gaussian_transform;
+    std::map<uint64_t, SbViewer*> models;  // HashMap<K, MultiModelViewerModel<G>>
+};
+
+extern "C" {
+
+SbStatus sb_mm_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, SbMultiModelViewer** out) {
+    if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    if (sb_pod_stride(sh_fmt, cov_fmt) == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
+    SbMultiModelViewer* mm = new SbMultiModelViewer();
+    mm->ctx = ctx;
+    mm->sh_fmt = sh_fmt;
+    mm->cov_fmt = cov_fmt;
+    mm->target_format = target_format;
+    std::memset(&mm->camera, 0, sizeof mm->camera);
+    sb_gaussian_transform_pod(1.0f, SB_MODE_SPLAT, 3, 0, 3.0f, &mm->gaussian_transform);
+    *out = mm;
+    return SB_OK;
+}
+
+void sb_mm_destroy(SbMultiModelViewer* mm) {
+    if (!mm) return;
+    for (auto& kv : mm->models) sb_viewer_destroy(kv.second);
+    delete mm;
+}
+
+SbStatus sb_mm_insert_model(SbMultiModelViewer* mm, uint64_t key, const void* packed_pods, uint64_t n, int32_t* replaced) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SbViewer* v = nullptr;
+    SbStatus s = sb_viewer_create(mm->ctx, mm->sh_fmt, mm->cov_fmt, mm->target_format, packed_pods, n, &v);
+    if (s != SB_OK) return s;
+    auto it = mm->models.find(key);
+    if (replaced) *replaced = it != mm->models.end();
+    if (it != mm->models.end()) {
+        cudaDeviceSynchronize();
+        sb_viewer_destroy(it->second);
+        it->second = v;
+    } else {
+        mm->models[key] = v;
+    }
+    return SB_OK;
+}
+
+SbStatus sb_mm_remove_model(SbMultiModelViewer* mm, uint64_t key, int32_t* removed) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (removed) *removed = it != mm->models.end();
+    if (it != mm->models.end()) {
+        cudaDeviceSynchronize();
+        sb_viewer_destroy(it->second);
+        mm->models.erase(it);
+    }
+    return SB_OK;
+}
+
+SbStatus sb_mm_update_camera_with_pod(SbMultiModelViewer* mm, const SbCameraPod* pod) {
+    if (!mm || !pod) return fail(mm ? mm->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    mm->camera = *pod;
+    return SB_OK;
+}
+
+SbStatus sb_mm_update_model_transform_with_pod(SbMultiModelViewer* mm, uint64_t key, const SbModelTransformPod* pod) {
+    if (!mm || !pod) return fail(mm ? mm->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    it->second->model_transform = *pod;
+    return SB_OK;
+}
+
+SbStatus sb_mm_update_gaussian_transform_with_pod(SbMultiModelViewer* mm, const SbGaussianTransformPod* pod) {
+    if (!mm || !pod) return fail(mm ? mm->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (pod->display_mode > 2 || pod->sh_deg > 3) return fail(mm->ctx, SB_ERR_INVALID_ARG, "bad gaussian transform pod");
+    mm->gaussian_transform = *pod;
+    return SB_OK;
+}
+
+SbStatus sb_mm_set_selection(SbMultiModelViewer* mm, uint64_t key, void* stream, const uint32_t* words, uint64_t n_words, int32_t invert) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    SbViewer* v = it->second;
+    if (!words) {
+        v->selection_enabled = false;
+        return SB_OK;
+    }
+    SbStatus s = sb_viewer_set_selection(v, stream, words, n_words);
+    if (s != SB_OK) return s;
+    v->selection_enabled = true;
+    v->invert_selection = invert ? 1u : 0u;
+    return SB_OK;
+}
+
+SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const uint64_t* keys, uint32_t n_keys) {
+    if (!mm || (!keys && n_keys)) return fail(mm ? mm->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<SbViewer*> models;
+    for (uint32_t i = 0; i < n_keys; i++) {  // multi_model.rs:482-489: resolve every key first
+        auto it = mm->models.find(keys[i]);
+        if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+        models.push_back(it->second);
+    }
+    for (SbViewer* v : models) {  // multi_model.rs:491-503
+        SbStatus s = do_preprocess(v, mm->camera, mm->gaussian_transform, st);
+        if (s != SB_OK) return s;
+        s = do_sort(v, st);
+        if (s != SB_OK) return s;
+    }
+    if (models.empty()) {  // a render pass that only clears
+        if (!target || !target->d_pixels) return fail(mm->ctx, SB_ERR_INVALID_ARG, "null target");
+        if (target->format != mm->target_format) return fail(mm->ctx, SB_ERR_INVALID_ARG, "target format mismatch");
+        SB_CUDA(mm->ctx, sb::launch_clear(*target, st));
+        return SB_OK;
+    }
+    int clear = 1;
+    for (SbViewer* v : models) {  // multi_model.rs:505-527: one pass, models in key order
+        SbStatus s = do_draw(v, mm->camera, mm->gaussian_transform, target, clear, st);
+        if (s != SB_OK) return s;
+        clear = 0;
+    }
+    return SB_OK;
+}
+
+SbStatus sb_mm_read_model_indices(SbMultiModelViewer* mm, uint64_t key, void* stream, uint32_t* out, uint64_t count,
+                                  SbDrawIndirectArgs* draw) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    SbStatus s = sb_viewer_read_indirect_args(it->second, stream, draw, nullptr);
+    if (s != SB_OK) return s;
+    return sb_viewer_read_indices(it->second, stream, out, count);
+}
+
+}  // extern "C"

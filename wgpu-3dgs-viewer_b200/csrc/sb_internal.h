@@ -1,0 +1,81 @@
+// sb_internal.h — launcher interfaces between the C-ABI layer (sb_api.cu) and the kernels.
+#pragma once
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+// ---------------------------------------------------------------- preprocess (sb_preprocess.cu)
+struct PreParams {
+    const uint8_t* gaussians;          // packed pods
+    uint32_t n;
+    uint32_t num_tiles;                // ceil(n / records-per-tile)
+    const uint32_t* selection;         // nullptr = selection feature off
+    uint32_t invert_selection;
+    uint32_t* indices;                 // IndirectIndicesBuffer
+    float* keys;                       // GaussiansDepthBuffer (first ceil(n/3840)*3840 floats used)
+    uint32_t keys_capacity;            // ceil(n/3840)*3840
+    SbDrawIndirectArgs* draw_args;     // IndirectArgsBuffer
+    SbDispatchIndirectArgs* sort_args; // RadixSortIndirectArgsBuffer
+    SplatRec* recs;                    // per-Gaussian projected record (indexed by Gaussian index)
+    uint32_t* tile_counter;            // dynamic tile ticket (zeroed before launch)
+    unsigned long long* tile_status;   // decoupled look-back state (zeroed before launch)
+    uint32_t* visible_count;           // V for downstream kernels
+    Uniforms u;
+};
+
+int preprocess_records_per_tile(int sh_fmt, int cov_fmt);
+// scratch bytes needed for tile_counter + tile_status
+size_t preprocess_scratch_bytes(uint32_t n, int sh_fmt, int cov_fmt);
+cudaError_t launch_preprocess(int sh_fmt, int cov_fmt, PreParams& p, void* scratch, size_t scratch_bytes,
+                              int num_sms, cudaStream_t stream);
+
+// ---------------------------------------------------------------- radix sort (sb_sort.cu)
+struct SortScratch {
+    uint32_t* keys_alt;
+    uint32_t* payload_alt;
+    uint32_t* internal;      // histograms + look-back tables + tickets
+    size_t internal_bytes;
+};
+size_t sort_internal_bytes(uint32_t capacity);
+// Stable ascending LSD sort of the first *d_count (clamped to max_count) (key,payload) pairs over
+// bits [begin_bit, end_bit).  Result lands in keys/payload when the pass count is even, and is
+// copied back otherwise.
+cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count,
+                        int begin_bit, int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream);
+
+// ---------------------------------------------------------------- binning + raster (sb_raster.cu)
+struct RasterBuffers {
+    uint32_t* dup_offsets;    // [n+1] exclusive scan of tiles-per-splat in sorted order
+    uint32_t* dup_keys;       // [dup_capacity] tile id
+    uint32_t* dup_vals;       // [dup_capacity] Gaussian index (in depth order within a tile)
+    uint32_t* tile_ranges;    // [tiles*2] begin,end into dup arrays
+    uint32_t* dup_count;      // D (device)
+    uint32_t* overflow;       // flag
+    unsigned long long* scan_status;
+    uint32_t* scan_counter;
+    SplatRec* tile_recs;      // [dup_capacity] records gathered in tile order (TMA staging source)
+    uint64_t dup_capacity;
+};
+
+struct RasterParams {
+    const SplatRec* recs;            // indexed by Gaussian index
+    const uint32_t* sorted_indices;  // depth order
+    const uint32_t* visible_count;
+    uint32_t max_visible;            // n
+    RasterBuffers buf;
+    SortScratch sort;                // for the tile sort
+    Uniforms u;
+    SbTarget target;
+    int strict_exp;
+    int clear;                       // 1: clear to BLACK first (first model of a frame)
+};
+cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_clear(const SbTarget& target, cudaStream_t stream);
+
+// ---------------------------------------------------------------- viewport selection (sb_select.cu)
+// selection::viewport::main with an analytic rectangle mask; writes ceil(n/32) words.
+cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, float x0, float y0, float x1,
+                               float y1, uint32_t* words, cudaStream_t stream);
+
+}  // namespace sb

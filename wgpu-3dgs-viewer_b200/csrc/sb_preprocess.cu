@@ -1,0 +1,514 @@
+// sb_preprocess.cu — K1: the fused Preprocessor.
+//
+// Replaces, in ONE launch, the reference's three compute dispatches
+//   pre / main / post                       (src/shader/preprocess.wesl:52-126)
+// and the per-vertex work that vert_main repeats 6x per splat
+//   color() + cov2d_axes() + clip position  (src/shader/render.wesl:58-130, utils.wesl:25-135).
+//
+// Shape: persistent CTAs (one per SM).  A producer warp streams tiles of T consecutive pods
+// from HBM into a shared-memory ring with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP)
+// signalled on mbarriers; T consumer threads each own one Gaussian of the tile.  Tiles are
+// handed out by a global ticket so the visible-splat compaction can be ORDER PRESERVING
+// (decoupled look-back over per-tile visible counts): slot order == ascending Gaussian index,
+// the canonical order of the reference's racy atomicAdd compaction.
+//
+// Bit-exact artefacts (visible mask, count, keys, indirect args) use strict f32 intrinsics
+// (__fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn) in the order fixed by the oracle contract.
+#include <cuda_fp16.h>
+
+#include "sb_internal.h"
+
+namespace sb {
+
+namespace {
+
+__host__ __device__ constexpr int sh_bytes(int sh) { return sh == SB_SH_SINGLE ? 180 : sh == SB_SH_HALF ? 92 : sh == SB_SH_NORM8 ? 52 : 0; }
+__host__ __device__ constexpr int cov_bytes(int cov) { return cov == SB_COV_SINGLE ? 24 : cov == SB_COV_HALF ? 12 : 28; }
+__host__ __device__ constexpr int pod_stride(int sh, int cov) { return (16 + sh_bytes(sh) + cov_bytes(cov) + 15) & ~15; }
+
+// Consumer threads per CTA (= pods per tile) and ring depth, chosen so the ring fits 227 KB.
+__host__ __device__ constexpr int tile_records(int stride) { return stride > 160 ? 384 : 512; }
+__host__ __device__ constexpr int ring_stages(int stride) {
+    int s = (200 * 1024) / (tile_records(stride) * stride);
+    return s < 2 ? 2 : (s > 4 ? 4 : s);
+}
+
+__device__ __forceinline__ float half_bits_to_float(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)h)); }
+
+// gaussian_unpack_cov3d (core WESL, external): [xx, xy, xz, yy, yz, zz]
+template <int SH, int COV>
+__device__ __forceinline__ void unpack_cov3d(const uint8_t* rec, float cov[6]) {
+    const uint8_t* c = rec + 16 + sh_bytes(SH);
+    if constexpr (COV == SB_COV_SINGLE) {
+        const float* f = reinterpret_cast<const float*>(c);  // 4-byte aligned
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov[k] = f[k];
+    } else if constexpr (COV == SB_COV_HALF) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(c);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t v = w[k];
+            cov[2 * k] = half_bits_to_float(v & 0xffffu);
+            cov[2 * k + 1] = half_bits_to_float(v >> 16);
+        }
+    } else {  // rot (xyzw) + scale: cov3d = (R S)(R S)^T, strict order of the oracle
+        const float* f = reinterpret_cast<const float*>(c);
+        float x = f[0], y = f[1], z = f[2], w = f[3];
+        float s0 = f[4], s1 = f[5], s2 = f[6];
+        float x2 = sadd(x, x), y2 = sadd(y, y), z2 = sadd(z, z);
+        float xx = smul(x, x2), xy = smul(x, y2), xz = smul(x, z2);
+        float yy = smul(y, y2), yz = smul(y, z2), zz = smul(z, z2);
+        float wx = smul(w, x2), wy = smul(w, y2), wz = smul(w, z2);
+        // R columns
+        float r00 = ssub(1.0f, sadd(yy, zz)), r01 = sadd(xy, wz), r02 = ssub(xz, wy);
+        float r10 = ssub(xy, wz), r11 = ssub(1.0f, sadd(xx, zz)), r12 = sadd(yz, wx);
+        float r20 = sadd(xz, wy), r21 = ssub(yz, wx), r22 = ssub(1.0f, sadd(xx, yy));
+        // m[row][col] = R[col][row] * s[col]
+        float m00 = smul(r00, s0), m01 = smul(r10, s1), m02 = smul(r20, s2);
+        float m10 = smul(r01, s0), m11 = smul(r11, s1), m12 = smul(r21, s2);
+        float m20 = smul(r02, s0), m21 = smul(r12, s1), m22 = smul(r22, s2);
+        cov[0] = sadd(sadd(smul(m00, m00), smul(m01, m01)), smul(m02, m02));
+        cov[1] = sadd(sadd(smul(m00, m10), smul(m01, m11)), smul(m02, m12));
+        cov[2] = sadd(sadd(smul(m00, m20), smul(m01, m21)), smul(m02, m22));
+        cov[3] = sadd(sadd(smul(m10, m10), smul(m11, m11)), smul(m12, m12));
+        cov[4] = sadd(sadd(smul(m10, m20), smul(m11, m21)), smul(m12, m22));
+        cov[5] = sadd(sadd(smul(m20, m20), smul(m21, m21)), smul(m22, m22));
+    }
+}
+
+// cov2d (utils.wesl:25-48) + cov2d_axes (utils.wesl:54-79), strict f32.
+__device__ __forceinline__ void cov2d_axes(const Uniforms& u, float px, float py, float pz, const float cov[6],
+                                           float std_dev, float axes[4]) {
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        t[i] = sadd(sadd(sadd(smul(u.vm[i], px), smul(u.vm[4 + i], py)), smul(u.vm[8 + i], pz)), u.vm[12 + i]);
+    float tz2 = smul(t[2], t[2]);
+    float j00 = sdiv(u.focal[0], t[2]);
+    float j02 = sdiv(-smul(u.focal[0], t[0]), tz2);
+    float j11 = sdiv(u.focal[1], t[2]);
+    float j12 = sdiv(-smul(u.focal[1], t[1]), tz2);
+    float jw0[3], jw1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        jw0[c] = sadd(smul(j00, u.w[c * 3 + 0]), smul(j02, u.w[c * 3 + 2]));
+        jw1[c] = sadd(smul(j11, u.w[c * 3 + 1]), smul(j12, u.w[c * 3 + 2]));
+    }
+    float t0[3], t1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        t0[c] = sadd(sadd(smul(jw0[0], u.sr[c * 3 + 0]), smul(jw0[1], u.sr[c * 3 + 1])), smul(jw0[2], u.sr[c * 3 + 2]));
+        t1[c] = sadd(sadd(smul(jw1[0], u.sr[c * 3 + 0]), smul(jw1[1], u.sr[c * 3 + 1])), smul(jw1[2], u.sr[c * 3 + 2]));
+    }
+    const float v[3][3] = {{cov[0], cov[1], cov[2]}, {cov[1], cov[3], cov[4]}, {cov[2], cov[4], cov[5]}};
+    float tv0[3], tv1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        tv0[c] = sadd(sadd(smul(t0[0], v[0][c]), smul(t0[1], v[1][c])), smul(t0[2], v[2][c]));
+        tv1[c] = sadd(sadd(smul(t1[0], v[0][c]), smul(t1[1], v[1][c])), smul(t1[2], v[2][c]));
+    }
+    float ca = sadd(sadd(smul(tv0[0], t0[0]), smul(tv0[1], t0[1])), smul(tv0[2], t0[2]));
+    float cb = sadd(sadd(smul(tv1[0], t0[0]), smul(tv1[1], t0[1])), smul(tv1[2], t0[2]));
+    float cc = sadd(sadd(smul(tv1[0], t1[0]), smul(tv1[1], t1[1])), smul(tv1[2], t1[2]));
+
+    float mid = smul(0.5f, sadd(ca, cc));
+    float hx = smul(0.5f, ssub(ca, cc));
+    float radius = ssqrt(sadd(smul(hx, hx), smul(cb, cb)));
+    float major_lambda = sadd(mid, radius);
+    float minor_lambda = ssub(mid, radius);
+    if (minor_lambda < 0.0f) {
+        axes[0] = axes[1] = axes[2] = axes[3] = 0.0f;
+        return;
+    }
+    float dx = cb, dy = ssub(major_lambda, ca);
+    float ddx, ddy;
+    if (dx == 0.0f && dy == 0.0f) {
+        ddx = 0.0f;
+        ddy = 1.0f;
+    } else {
+        float l = ssqrt(sadd(smul(dx, dx), smul(dy, dy)));
+        ddx = sdiv(dx, l);
+        ddy = sdiv(dy, l);
+    }
+    float major_len = fminf(smul(std_dev, ssqrt(major_lambda)), 1024.0f);
+    float minor_len = fminf(smul(std_dev, ssqrt(minor_lambda)), 1024.0f);
+    axes[0] = smul(major_len, ddx);
+    axes[1] = smul(major_len, ddy);
+    axes[2] = smul(minor_len, ddy);
+    axes[3] = smul(minor_len, -ddx);
+}
+
+// utils.wesl:18-20
+__device__ __forceinline__ bool cull(float x, float y, float z) {
+    return !((x >= -1.0f && y >= -1.0f && z >= 0.0f) && (x <= 1.0f && y <= 1.0f && z <= 1.0f));
+}
+
+// gaussian_unpack_sh(g, i) for i in 0..14 -> rgb
+template <int SH>
+__device__ __forceinline__ void unpack_sh(const uint8_t* rec, int i, float& r, float& g, float& b, float mn, float mx) {
+    const uint8_t* q = rec + 16;
+    if constexpr (SH == SB_SH_SINGLE) {
+        const float* f = reinterpret_cast<const float*>(q);
+        r = f[i * 3 + 0]; g = f[i * 3 + 1]; b = f[i * 3 + 2];
+    } else if constexpr (SH == SB_SH_HALF) {
+        const unsigned short* h = reinterpret_cast<const unsigned short*>(q);
+        r = half_bits_to_float(h[i * 3 + 0]); g = half_bits_to_float(h[i * 3 + 1]); b = half_bits_to_float(h[i * 3 + 2]);
+    } else if constexpr (SH == SB_SH_NORM8) {
+        const uint8_t* c = q + 4;
+        float tr = (float)c[i * 3 + 0] / 255.0f, tg = (float)c[i * 3 + 1] / 255.0f, tb = (float)c[i * 3 + 2] / 255.0f;
+        r = mn * (1.0f - tr) + mx * tr; g = mn * (1.0f - tg) + mx * tg; b = mn * (1.0f - tb) + mx * tb;
+    } else {
+        r = g = b = 0.0f;
+    }
+}
+
+// view_color (utils.wesl:82-135); evaluation order follows the WGSL text.
+template <int SH>
+__device__ __forceinline__ void view_color(const Uniforms& u, const uint8_t* rec, uint32_t packed_color, float x, float y,
+                                           float z, float rgb[3]) {
+    const float sh_c1 = 0.4886025f;
+    const float c2_0 = 1.0925484f, c2_1 = -1.0925484f, c2_2 = 0.3153916f, c2_3 = -1.0925484f, c2_4 = 0.5462742f;
+    const float c3_0 = -0.5900436f, c3_1 = 2.8906114f, c3_2 = -0.4570458f, c3_3 = 0.3731763f, c3_4 = -0.4570458f,
+                c3_5 = 1.4453057f, c3_6 = -0.5900436f;
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) res[c] = u.no_sh0 ? 0.5f : __fdiv_rn((float)((packed_color >> (8 * c)) & 255u), 255.0f);
+    if (SH != SB_SH_NONE && u.sh_deg >= 1) {
+        float mn = 0.0f, mx = 0.0f;
+        if constexpr (SH == SB_SH_NORM8) {
+            uint32_t mm = *reinterpret_cast<const uint32_t*>(rec + 16);
+            mn = half_bits_to_float(mm & 0xffffu);
+            mx = half_bits_to_float(mm >> 16);
+        }
+        float s[15][3];
+#pragma unroll
+        for (int i = 0; i < 15; i++) unpack_sh<SH>(rec, i, s[i][0], s[i][1], s[i][2], mn, mx);
+#pragma unroll
+        for (int c = 0; c < 3; c++) res[c] += sh_c1 * ((-s[0][c] * y + s[1][c] * z) - s[2][c] * x);
+        if (u.sh_deg >= 2) {
+            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                res[c] += (((c2_0 * xy * s[3][c] + c2_1 * yz * s[4][c]) + c2_2 * ((2.0f * zz - xx) - yy) * s[5][c]) +
+                           c2_3 * xz * s[6][c]) +
+                          c2_4 * (xx - yy) * s[7][c];
+            if (u.sh_deg >= 3) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    res[c] += (((((c3_0 * y * (3.0f * xx - yy) * s[8][c] + c3_1 * xy * z * s[9][c]) +
+                                  c3_2 * y * ((4.0f * zz - xx) - yy) * s[10][c]) +
+                                 c3_3 * z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy) * s[11][c]) +
+                                c3_4 * x * ((4.0f * zz - xx) - yy) * s[12][c]) +
+                               c3_5 * z * (xx - yy) * s[13][c]) +
+                              c3_6 * x * (xx - 3.0f * yy) * s[14][c];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) rgb[c] = fmaxf(res[c], 0.0f);
+}
+
+// Tile bbox of the alive region, with a 0.01 px safety margin against f32 rounding.
+__device__ __forceinline__ void tile_bbox(const Uniforms& u, float cx, float cy, float ex, float ey, uint32_t& tmin,
+                                          uint32_t& tmax) {
+    const float W = (float)u.width, H = (float)u.height;
+    float x0f = ceilf(cx - ex - 0.51f), x1f = floorf(cx + ex - 0.49f);
+    float y0f = ceilf(cy - ey - 0.51f), y1f = floorf(cy + ey - 0.49f);
+    bool ok = (x1f >= 0.0f) && (y1f >= 0.0f) && (x0f <= W - 1.0f) && (y0f <= H - 1.0f) && (x0f <= x1f) && (y0f <= y1f);
+    if (!ok) {  // also catches NaN
+        tmin = 1u | (1u << 16);
+        tmax = 0u;
+        return;
+    }
+    uint32_t x0 = (uint32_t)fmaxf(x0f, 0.0f), x1 = (uint32_t)fminf(x1f, W - 1.0f);
+    uint32_t y0 = (uint32_t)fmaxf(y0f, 0.0f), y1 = (uint32_t)fminf(y1f, H - 1.0f);
+    tmin = (x0 / kTile) | ((y0 / kTile) << 16);
+    tmax = (x1 / kTile) | ((y1 / kTile) << 16);
+}
+
+__device__ __forceinline__ bool finite4(float a, float b, float c, float d) {
+    return isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d);
+}
+
+template <int SH, int COV>
+__global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
+    preprocess_kernel(const __grid_constant__ PreParams p) {
+    constexpr int STRIDE = pod_stride(SH, COV);
+    constexpr int T = tile_records(STRIDE);
+    constexpr int S = ring_stages(STRIDE);
+    constexpr int NW = T / 32;
+    constexpr uint32_t STAGE_BYTES = T * STRIDE;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + S;
+    uint32_t* tile_id = reinterpret_cast<uint32_t*>(empty_bar + S);
+    uint32_t* warp_counts = tile_id + S;   // NW
+    uint32_t* bcast = warp_counts + NW;    // [0] tile base, [1] tile total
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const Uniforms& u = p.u;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ---------------- producer warp: ticket -> TMA bulk copy of one tile of pods
+        if (lane == 0) {
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t s = it % S, ph = (it / S) & 1u;
+                const uint32_t tile = atomicAdd(p.tile_counter, 1u);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                tile_id[s] = tile;
+                if (tile >= p.num_tiles) {
+                    mbar_arrive(&full_bar[s]);
+                    break;
+                }
+                const uint32_t first = tile * T;
+                const uint32_t cnt = min((uint32_t)T, p.n - first);
+                const uint32_t bytes = cnt * STRIDE;
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                bulk_g2s(smem + s * STAGE_BYTES, p.gaussians + (size_t)first * STRIDE, bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: one Gaussian per thread per tile
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        const uint32_t tile = tile_id[s];
+        if (tile >= p.num_tiles) break;
+
+        const uint32_t g = tile * T + tid;
+        const uint8_t* rec = smem + s * STAGE_BYTES + tid * STRIDE;
+        bool vis = g < p.n;
+        float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vis) head = *reinterpret_cast<const float4*>(rec);
+
+        // selection: preprocess.wesl:68-78
+        if (p.selection != nullptr && vis) {
+            const uint32_t word = __ldg(&p.selection[g >> 5]);
+            const bool bit = (word >> (g & 31u)) & 1u;
+            const bool inverted = p.invert_selection != 0u;
+            if (inverted == bit) vis = false;
+        }
+
+        // model_to_world + world_to_camera: preprocess.wesl:82-84 (strict)
+        float world[3], clip[4];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            world[i] = sadd(sadd(sadd(smul(u.model[i], head.x), smul(u.model[4 + i], head.y)), smul(u.model[8 + i], head.z)),
+                            u.model[12 + i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            clip[i] = sadd(sadd(sadd(smul(u.pv[i], world[0]), smul(u.pv[4 + i], world[1])), smul(u.pv[8 + i], world[2])),
+                           u.pv[12 + i]);
+        const float nx = sdiv(clip[0], clip[3]), ny = sdiv(clip[1], clip[3]), nz = sdiv(clip[2], clip[3]);
+
+        float cov[6];
+        float axes[4];
+        bool have_axes = false;
+        const float sd_size = smul(u.std_dev, u.gsize);
+        if (vis && cull(nx, ny, nz)) {  // preprocess.wesl:87-99
+            unpack_cov3d<SH, COV>(rec, cov);
+            cov2d_axes(u, head.x, head.y, head.z, cov, sd_size, axes);
+            have_axes = true;
+            const float mx = sdiv(smul(axes[0], u.std_dev), u.size[0]);
+            const float my = sdiv(smul(axes[1], u.std_dev), u.size[1]);
+            const float ndc_major_len = ssqrt(sadd(smul(mx, mx), smul(my, my)));
+            const float l = ssqrt(sadd(smul(nx, nx), smul(ny, ny)));
+            const float dirx = sdiv(-nx, l), diry = sdiv(-ny, l);
+            const float m = fminf(ndc_major_len, l);
+            const float bx = sadd(nx, smul(m, dirx)), by = sadd(ny, smul(m, diry));
+            if (cull(bx, by, nz)) vis = false;
+        }
+
+        // ---- order-preserving compaction: warp ballots -> CTA scan -> decoupled look-back
+        const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+        if (lane == 0) warp_counts[warp] = __popc(bal);
+        named_bar_sync(1, T);
+        uint32_t warp_excl = 0;
+        {
+            uint32_t c = lane < NW ? warp_counts[lane] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)lane >= o) inc += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            warp_excl = __shfl_sync(0xffffffffu, inc - c, warp);
+            if (warp == 0) {
+                const uint32_t excl = lookback(p.tile_status, tile, total, lane);
+                if (lane == 0) {
+                    bcast[0] = excl;
+                    bcast[1] = total;
+                }
+            }
+        }
+
+        // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
+        if (vis) {
+            SplatRec out;
+            out.cx = smul(smul(sadd(nx, 1.0f), 0.5f), u.size[0]);
+            out.cy = smul(smul(ssub(1.0f, ny), 0.5f), u.size[1]);
+            // color(): render.wesl:58-73
+            const float vdx = u.cam_pos[0] - world[0], vdy = u.cam_pos[1] - world[1], vdz = u.cam_pos[2] - world[2];
+            float md[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) md[i] = (u.inv_sr[i] * vdx + u.inv_sr[3 + i] * vdy) + u.inv_sr[6 + i] * vdz;
+            const float ml = sqrtf((md[0] * md[0] + md[1] * md[1]) + md[2] * md[2]);
+            float rgb[3];
+            const uint32_t packed = __float_as_uint(head.w);
+            view_color<SH>(u, rec, packed, -(md[0] / ml), -(md[1] / ml), -(md[2] / ml), rgb);
+            out.r = rgb[0] * u.color_scale;
+            out.g = rgb[1] * u.color_scale;
+            out.b = rgb[2] * u.color_scale;
+            out.a = __fdiv_rn((float)(packed >> 24), 255.0f);
+            float ex, ey;
+            bool valid;
+            if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
+                float vp[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    vp[i] = sadd(sadd(sadd(smul(u.vm[i], head.x), smul(u.vm[4 + i], head.y)), smul(u.vm[8 + i], head.z)),
+                                 u.vm[12 + i]);
+                const float len = ssqrt(sadd(sadd(smul(vp[0], vp[0]), smul(vp[1], vp[1])), smul(vp[2], vp[2])));
+                const float half = sdiv(smul(smul(smul(0.01f, u.gsize), 0.5f), u.size[1]), len);
+                const float inv = sdiv(1.0f, half);
+                out.ax = inv; out.ay = 0.0f; out.bx = 0.0f; out.by = inv;
+                ex = half; ey = half;
+                valid = (half > 0.0f) && isfinite(inv) && isfinite(out.cx) && isfinite(out.cy);
+            } else {
+                if (!have_axes) {
+                    unpack_cov3d<SH, COV>(rec, cov);
+                    cov2d_axes(u, head.x, head.y, head.z, cov, sd_size, axes);
+                }
+                const float mm = sadd(smul(axes[0], axes[0]), smul(axes[1], axes[1]));
+                const float nn = sadd(smul(axes[2], axes[2]), smul(axes[3], axes[3]));
+                out.ax = sdiv(smul(2.0f, axes[0]), mm);
+                out.ay = -sdiv(smul(2.0f, axes[1]), mm);
+                out.bx = sdiv(smul(2.0f, axes[2]), nn);
+                out.by = -sdiv(smul(2.0f, axes[3]), nn);
+                const float hs = smul(0.5f, u.std_dev);
+                ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
+                ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
+                valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, ex, ey);
+            }
+            if (valid) {
+                tile_bbox(u, out.cx, out.cy, ex, ey, out.tmin, out.tmax);
+            } else {
+                out.tmin = 1u | (1u << 16);
+                out.tmax = 0u;
+            }
+            float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
+            dst[0] = make_float4(out.cx, out.cy, out.ax, out.ay);
+            dst[1] = make_float4(out.bx, out.by, out.r, out.g);
+            dst[2] = make_float4(out.b, out.a, __uint_as_float(out.tmin), __uint_as_float(out.tmax));
+        }
+
+        // smem slot is no longer needed by this warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        named_bar_sync(1, T);
+        const uint32_t tile_base = bcast[0];
+        const uint32_t tile_total = bcast[1];
+        if (vis) {
+            const uint32_t slot = tile_base + warp_excl + __popc(bal & lanemask_lt());
+            p.indices[slot] = g;
+            p.keys[slot] = ssub(1.0f, nz);  // preprocess.wesl:105
+        }
+        if (tile == p.num_tiles - 1) {
+            // post: preprocess.wesl:108-126 — indirect args + pad keys with 2.0
+            const uint32_t v = tile_base + tile_total;
+            const uint32_t blocks = (v + kHistoBlockKvs - 1) / kHistoBlockKvs;
+            if (tid == 0) {
+                p.draw_args->vertex_count = 6;
+                p.draw_args->instance_count = v;
+                p.draw_args->first_vertex = 0;
+                p.draw_args->first_instance = 0;
+                p.sort_args->x = blocks;
+                p.sort_args->y = 1;
+                p.sort_args->z = 1;
+                *p.visible_count = v;
+            }
+            const uint32_t padded = min(blocks * kHistoBlockKvs, p.keys_capacity);
+            for (uint32_t i = v + tid; i < padded; i += T) p.keys[i] = 2.0f;
+        }
+        // bcast/warp_counts are rewritten only after the next tile's first barrier, which every
+        // consumer reaches after reading them here.
+    }
+}
+
+template <int SH, int COV>
+cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
+    constexpr int STRIDE = pod_stride(SH, COV);
+    constexpr int T = tile_records(STRIDE);
+    constexpr int S = ring_stages(STRIDE);
+    constexpr size_t smem = (size_t)S * T * STRIDE + S * 8 * 2 + S * 4 + (T / 32) * 4 + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<SH, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    p.num_tiles = (p.n + T - 1) / T;
+    const int grid = (int)min((uint32_t)num_sms, p.num_tiles);
+    preprocess_kernel<SH, COV><<<grid, T + 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int preprocess_records_per_tile(int sh_fmt, int cov_fmt) { return tile_records(pod_stride(sh_fmt, cov_fmt)); }
+
+size_t preprocess_scratch_bytes(uint32_t n, int sh_fmt, int cov_fmt) {
+    const int t = preprocess_records_per_tile(sh_fmt, cov_fmt);
+    const size_t tiles = (n + t - 1) / t;
+    return 16 + tiles * sizeof(unsigned long long);
+}
+
+cudaError_t launch_preprocess(int sh_fmt, int cov_fmt, PreParams& p, void* scratch, size_t scratch_bytes, int num_sms,
+                              cudaStream_t stream) {
+    if (p.n == 0) {  // nothing to do: args = {6,0,0,0} / {0,1,1}
+        const SbDrawIndirectArgs d = {6, 0, 0, 0};
+        const SbDispatchIndirectArgs s = {0, 1, 1};
+        cudaError_t e = cudaMemcpyAsync(p.draw_args, &d, sizeof d, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(p.sort_args, &s, sizeof s, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        return cudaMemsetAsync(p.visible_count, 0, 4, stream);
+    }
+    cudaError_t e = cudaMemsetAsync(scratch, 0, scratch_bytes, stream);
+    if (e != cudaSuccess) return e;
+    p.tile_counter = reinterpret_cast<uint32_t*>(scratch);
+    p.tile_status = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(scratch) + 16);
+#define SB_CASE(SHV, COVV) \
+    if (sh_fmt == SHV && cov_fmt == COVV) return launch_one<SHV, COVV>(p, num_sms, stream);
+    SB_CASE(SB_SH_SINGLE, SB_COV_SINGLE)
+    SB_CASE(SB_SH_SINGLE, SB_COV_HALF)
+    SB_CASE(SB_SH_SINGLE, SB_COV_ROT_SCALE)
+    SB_CASE(SB_SH_HALF, SB_COV_SINGLE)
+    SB_CASE(SB_SH_HALF, SB_COV_HALF)
+    SB_CASE(SB_SH_HALF, SB_COV_ROT_SCALE)
+    SB_CASE(SB_SH_NORM8, SB_COV_SINGLE)
+    SB_CASE(SB_SH_NORM8, SB_COV_HALF)
+    SB_CASE(SB_SH_NORM8, SB_COV_ROT_SCALE)
+    SB_CASE(SB_SH_NONE, SB_COV_SINGLE)
+    SB_CASE(SB_SH_NONE, SB_COV_HALF)
+    SB_CASE(SB_SH_NONE, SB_COV_ROT_SCALE)
+#undef SB_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sb

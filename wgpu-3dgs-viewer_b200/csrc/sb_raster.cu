@@ -1,0 +1,449 @@
+// sb_raster.cu — K4/K5/K6: tile binning and the tile rasterizer.
+//
+// Replaces Renderer::render's instanced-quad draw + fixed-function ALPHA_BLENDING
+// (src/renderer.rs:163-195, 284-308; fragment stage src/shader/render.wesl:143-181):
+//   K4 dup_scan    depth-ordered splats -> exclusive scan of tiles-per-splat (chained scan)
+//   K5 dup_emit    (tile id, Gaussian index) duplicates, emitted in depth order
+//      tile sort   stable onesweep over the tile-id bits only (sb_sort.cu): because the input is
+//                  already in the reference's draw order, stability alone preserves it per tile
+//   K5b gather     tile ranges + splat records gathered into tile order (contiguous batches)
+//   K6 raster      one CTA per 16x16 tile; batches staged into shared memory with TMA bulk
+//                  copies; one pixel per thread composites back-to-front in exactly the
+//                  reference's order, re-quantising after every blend on unorm8 targets.
+#include <cuda_fp16.h>
+
+#include "sb_internal.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct BinParams {
+    const SplatRec* recs;
+    const uint32_t* sorted_indices;
+    const uint32_t* visible_count;
+    uint32_t* dup_offsets;
+    uint32_t* dup_keys;
+    uint32_t* dup_vals;
+    uint32_t* dup_count;
+    uint32_t* overflow;
+    unsigned long long* scan_status;
+    uint32_t* scan_counter;
+    uint32_t dup_capacity;
+    uint32_t tiles_x;
+    uint32_t ty_lo, ty_hi;  // tile rows of the rendered strip (inclusive)
+};
+
+// tiles of one splat, clipped to the strip's tile rows
+__device__ __forceinline__ uint32_t splat_tiles(const SplatRec* recs, uint32_t g, uint32_t ty_lo, uint32_t ty_hi, uint32_t& x0,
+                                                uint32_t& y0, uint32_t& w) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(&recs[g]) + 2);
+    const uint32_t tmin = __float_as_uint(q.z), tmax = __float_as_uint(q.w);
+    x0 = tmin & 0xffffu;
+    y0 = tmin >> 16;
+    const uint32_t x1 = tmax & 0xffffu;
+    uint32_t y1 = tmax >> 16;
+    if (x0 > x1 || y0 > y1) return 0;
+    y0 = max(y0, ty_lo);
+    y1 = min(y1, ty_hi);
+    if (y0 > y1) return 0;
+    w = x1 - x0 + 1;
+    return w * (y1 - y0 + 1);
+}
+
+// K4: chained scan (decoupled look-back) of tiles-per-splat in depth order.
+__global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams p) {
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    __shared__ uint32_t s_tile, s_base;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t v = *p.visible_count;
+    if (blockIdx.x * kScanTile >= v && blockIdx.x > 0) return;
+    if (tid == 0) s_tile = atomicAdd(p.scan_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kScanTile + tid * kScanItems;
+    uint32_t cnt[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        const uint32_t r = base + i;
+        uint32_t x0, y0, w;
+        cnt[i] = r < v ? splat_tiles(p.recs, p.sorted_indices[r], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
+        sum += cnt[i];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    uint32_t wexcl = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) {
+        const uint32_t t = warp_sums[w];
+        if (w < (int)warp) wexcl += t;
+        total += t;
+    }
+    if (warp == 0) {
+        const uint32_t excl = lookback(p.scan_status, tile, total, lane);
+        if (lane == 0) s_base = excl;
+    }
+    __syncthreads();
+    uint32_t off = s_base + wexcl + inc - sum;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        const uint32_t r = base + i;
+        if (r < v) p.dup_offsets[r] = off;
+        off += cnt[i];
+    }
+    const uint32_t last_tile = v == 0 ? 0 : (v - 1) / kScanTile;
+    if (tile == last_tile && tid == 0) {
+        const uint32_t d = s_base + total;
+        if (d > p.dup_capacity) {
+            *p.overflow = 1u;
+            *p.dup_count = p.dup_capacity;
+        } else {
+            *p.dup_count = d;
+        }
+    }
+}
+
+// K5: emit (tile id, Gaussian index) in depth order.  One lane per splat; splats covering more
+// than 32 tiles are expanded by the whole warp.
+__global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
+    const uint32_t v = *p.visible_count;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = gridDim.x * (blockDim.x / 32);
+    for (uint32_t wbase = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * 32; wbase < v; wbase += warps_total * 32) {
+        const uint32_t r = wbase + lane;
+        uint32_t g = 0, n = 0, x0 = 0, y0 = 0, w = 1, off = 0;
+        if (r < v) {
+            g = p.sorted_indices[r];
+            n = splat_tiles(p.recs, g, p.ty_lo, p.ty_hi, x0, y0, w);
+            off = p.dup_offsets[r];
+        }
+        if (n > 0 && n <= 32) {
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t o = off + j;
+                if (o < p.dup_capacity) {
+                    p.dup_keys[o] = (y0 + j / w) * p.tiles_x + (x0 + j % w);
+                    p.dup_vals[o] = g;
+                }
+            }
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, n > 32);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bg = __shfl_sync(0xffffffffu, g, src);
+            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), boff = __shfl_sync(0xffffffffu, off, src);
+            for (uint32_t j = lane; j < bn; j += 32) {
+                const uint32_t o = boff + j;
+                if (o < p.dup_capacity) {
+                    p.dup_keys[o] = (by0 + j / bw) * p.tiles_x + (bx0 + j % bw);
+                    p.dup_vals[o] = bg;
+                }
+            }
+        }
+    }
+}
+
+// K5b: tile ranges from the tile-sorted keys + gather of the records into tile order.
+__global__ void __launch_bounds__(256)
+    gather_kernel(const uint32_t* __restrict__ dup_keys, const uint32_t* __restrict__ dup_vals, const uint32_t* __restrict__ dup_count,
+                  const SplatRec* __restrict__ recs, SplatRec* __restrict__ tile_recs, uint32_t* __restrict__ tile_ranges) {
+    const uint32_t d = *dup_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+        const uint32_t t = dup_keys[i];
+        if (i == 0 || dup_keys[i - 1] != t) tile_ranges[2 * t] = i;
+        if (i == d - 1 || dup_keys[i + 1] != t) tile_ranges[2 * t + 1] = i + 1;
+        const float4* src = reinterpret_cast<const float4*>(&recs[dup_vals[i]]);
+        float4* dst = reinterpret_cast<float4*>(&tile_recs[i]);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        dst[0] = a;
+        dst[1] = b;
+        dst[2] = c;
+    }
+}
+
+// ---------------------------------------------------------------- K6 rasterizer
+
+constexpr int kBatch = 256;  // splat records per shared-memory stage (12 KB)
+
+enum { FMT_UNORM8 = 0, FMT_F16 = 1, FMT_F32 = 2 };
+
+// exp(-x) from exactly rounded steps; mirrors so_exp_neg_poly in oracle/splat_oracle.c
+__device__ __forceinline__ float exp_neg_poly(float x) {
+    const float y = __fmul_rn(x, -1.44269504f);
+    const float n = rintf(y);
+    const float f = __fsub_rn(y, n);
+    float p = 1.54035304e-4f;
+    p = __fmaf_rn(p, f, 1.33335581e-3f);
+    p = __fmaf_rn(p, f, 9.61812911e-3f);
+    p = __fmaf_rn(p, f, 5.55041087e-2f);
+    p = __fmaf_rn(p, f, 2.40226507e-1f);
+    p = __fmaf_rn(p, f, 6.93147181e-1f);
+    p = __fmaf_rn(p, f, 1.0f);
+    if (n < -125.0f) return 0.0f;
+    return __uint_as_float(__float_as_uint(p) + ((uint32_t)(int)n << 23));
+}
+
+// round-to-nearest-even of x in [0, 2^22) without the (quarter-rate) FRND instruction
+__device__ __forceinline__ float rint_small(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
+
+struct RasterKernelParams {
+    const SplatRec* tile_recs;
+    const uint32_t* tile_ranges;
+    uint8_t* pixels;
+    uint32_t pitch;
+    uint32_t width, height;
+    uint32_t row0, rows;
+    uint32_t tiles_x;
+    uint32_t ty_lo;
+    float sd2;      // std_dev^2
+    float outline;  // (std_dev - 0.1)^2
+    int bgra;
+    int clear;
+};
+
+template <int MODE, int FMT, bool STRICT>
+__global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p) {
+    __shared__ __align__(128) float4 stage[2][kBatch * 3];
+    __shared__ __align__(8) uint64_t full_bar[2];
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
+    const uint32_t tile = tile_y * p.tiles_x + tile_x;
+    // each warp owns an 8x4 pixel patch
+    const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane & 7u);
+    const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+
+    const uint32_t begin = p.tile_ranges[2 * tile], end = p.tile_ranges[2 * tile + 1];
+    const uint32_t total = end - begin;
+    const uint32_t batches = (total + kBatch - 1) / kBatch;
+
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0 && batches > 0) {
+        const uint32_t bytes = min((uint32_t)kBatch, total) * (uint32_t)sizeof(SplatRec);
+        mbar_arrive_expect_tx(&full_bar[0], bytes);
+        bulk_g2s(stage[0], p.tile_recs + begin, bytes, &full_bar[0]);
+    }
+
+    // destination state: 0..255 units on unorm8 targets (re-quantised after every blend)
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 1.0f;
+    uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
+    if (!p.clear && inside) {
+        if constexpr (FMT == FMT_UNORM8) {
+            const uchar4 c = reinterpret_cast<const uchar4*>(dst)[x];
+            d0 = p.bgra ? c.z : c.x;
+            d1 = c.y;
+            d2 = p.bgra ? c.x : c.z;
+        } else if constexpr (FMT == FMT_F16) {
+            const __half* h = reinterpret_cast<const __half*>(dst) + 4 * x;
+            d0 = __half2float(h[0]); d1 = __half2float(h[1]); d2 = __half2float(h[2]); d3 = __half2float(h[3]);
+        } else {
+            const float4 c = reinterpret_cast<const float4*>(dst)[x];
+            d0 = c.x; d1 = c.y; d2 = c.z; d3 = c.w;
+        }
+    }
+
+    for (uint32_t k = 0; k < batches; k++) {
+        const uint32_t s = k & 1u;
+        if (tid == 0 && k + 1 < batches) {
+            const uint32_t nb = min((uint32_t)kBatch, total - (k + 1) * kBatch) * (uint32_t)sizeof(SplatRec);
+            mbar_arrive_expect_tx(&full_bar[s ^ 1u], nb);
+            bulk_g2s(stage[s ^ 1u], p.tile_recs + begin + (size_t)(k + 1) * kBatch, nb, &full_bar[s ^ 1u]);
+        }
+        mbar_wait(&full_bar[s], (k >> 1) & 1u);
+        const uint32_t cnt = min((uint32_t)kBatch, total - k * kBatch);
+        const float4* recs = stage[s];
+        for (uint32_t j = 0; j < cnt; j++) {
+            const float4 q0 = recs[j * 3 + 0];
+            const float4 q1 = recs[j * 3 + 1];
+            const float4 q2 = recs[j * 3 + 2];
+            const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
+            const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
+            const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
+            float alpha;
+            if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
+                if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
+                alpha = 1.0f;
+            } else {
+                const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
+                if (!(r2 <= p.sd2)) continue;  // discard: render.wesl:145,155
+                if constexpr (MODE == SB_MODE_SPLAT) {
+                    const float e = STRICT ? exp_neg_poly(r2) : __expf(-r2);
+                    alpha = __fmul_rn(q2.y, e);  // render.wesl:149
+                } else {
+                    const float ol = r2 > p.outline ? 1.0f : 0.0f;  // render.wesl:159-160
+                    alpha = __fadd_rn(q2.y, __fmul_rn(__fsub_rn(1.0f, q2.y), ol));
+                }
+            }
+            const float om = __fsub_rn(1.0f, alpha);
+            if constexpr (FMT == FMT_UNORM8) {
+                d0 = rint_small(fminf(__fmaf_rn(d0, om, __fmul_rn(q1.z, alpha)), 255.0f));
+                d1 = rint_small(fminf(__fmaf_rn(d1, om, __fmul_rn(q1.w, alpha)), 255.0f));
+                d2 = rint_small(fminf(__fmaf_rn(d2, om, __fmul_rn(q2.x, alpha)), 255.0f));
+            } else {
+                d0 = __fmaf_rn(d0, om, __fmul_rn(q1.z, alpha));
+                d1 = __fmaf_rn(d1, om, __fmul_rn(q1.w, alpha));
+                d2 = __fmaf_rn(d2, om, __fmul_rn(q2.x, alpha));
+                d3 = __fmaf_rn(d3, om, alpha);
+                if constexpr (FMT == FMT_F16) {
+                    d0 = __half2float(__float2half_rn(d0)); d1 = __half2float(__float2half_rn(d1));
+                    d2 = __half2float(__float2half_rn(d2)); d3 = __half2float(__float2half_rn(d3));
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with stage[s] before it is refilled
+    }
+
+    if (inside) {
+        if constexpr (FMT == FMT_UNORM8) {
+            uchar4 c;
+            c.x = (unsigned char)(p.bgra ? d2 : d0);
+            c.y = (unsigned char)d1;
+            c.z = (unsigned char)(p.bgra ? d0 : d2);
+            c.w = 255;
+            reinterpret_cast<uchar4*>(dst)[x] = c;
+        } else if constexpr (FMT == FMT_F16) {
+            __half2 lo = __floats2half2_rn(d0, d1), hi = __floats2half2_rn(d2, d3);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(dst)[x] = o;
+        } else {
+            reinterpret_cast<float4*>(dst)[x] = make_float4(d0, d1, d2, d3);
+        }
+    }
+}
+
+// A render pass that only clears (Color::BLACK = 0,0,0,1): src/renderer.rs:171-177
+__global__ void clear_kernel(uint8_t* pixels, uint32_t pitch, uint32_t width, uint32_t rows, int fmt) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width || y >= rows) return;
+    uint8_t* row = pixels + (size_t)y * pitch;
+    if (fmt == FMT_UNORM8) {
+        reinterpret_cast<uchar4*>(row)[x] = make_uchar4(0, 0, 0, 255);
+    } else if (fmt == FMT_F16) {
+        reinterpret_cast<uint2*>(row)[x] = make_uint2(0u, 0x3c000000u);
+    } else {
+        reinterpret_cast<float4*>(row)[x] = make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+}
+
+template <int MODE, int FMT, bool STRICT>
+void launch_raster(const RasterKernelParams& kp, dim3 grid, cudaStream_t stream) {
+    raster_kernel<MODE, FMT, STRICT><<<grid, 256, 0, stream>>>(kp);
+}
+
+}  // namespace
+
+cudaError_t launch_clear(const SbTarget& t, cudaStream_t stream) {
+    const uint32_t rows = t.rows == 0 ? t.height : t.rows;
+    if (rows == 0 || t.width == 0) return cudaSuccess;
+    const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
+                    : t.format == SB_TARGET_RGBA16_FLOAT                                       ? FMT_F16
+                                                                                               : FMT_F32;
+    clear_kernel<<<dim3((t.width + 255) / 256, rows), 256, 0, stream>>>(reinterpret_cast<uint8_t*>(t.d_pixels), t.pitch_bytes, t.width,
+                                                                      rows, fmt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream_t stream) {
+    const Uniforms& u = p.u;
+    const SbTarget& t = p.target;
+    const uint32_t rows = t.rows == 0 ? u.height : t.rows;
+    const uint32_t row0 = t.rows == 0 ? 0 : t.row0;
+    if (rows == 0 || u.width == 0) return cudaSuccess;
+    const uint32_t ty_lo = row0 / kTile, ty_hi = (row0 + rows - 1) / kTile;
+    const uint32_t num_tiles = u.tiles_x * u.tiles_y;
+
+    cudaError_t e;
+    // scan state: [counter(16B)] [status...] ; tile ranges zeroed (empty tiles -> begin=end=0)
+    const size_t scan_tiles = ((size_t)p.max_visible + kScanTile - 1) / kScanTile + 1;
+    e = cudaMemsetAsync(p.buf.scan_counter, 0, 16 + scan_tiles * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(p.buf.tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+
+    BinParams bp;
+    bp.recs = p.recs;
+    bp.sorted_indices = p.sorted_indices;
+    bp.visible_count = p.visible_count;
+    bp.dup_offsets = p.buf.dup_offsets;
+    bp.dup_keys = p.buf.dup_keys;
+    bp.dup_vals = p.buf.dup_vals;
+    bp.dup_count = p.buf.dup_count;
+    bp.overflow = p.buf.overflow;
+    bp.scan_status = p.buf.scan_status;
+    bp.scan_counter = p.buf.scan_counter;
+    bp.dup_capacity = (uint32_t)p.buf.dup_capacity;
+    bp.tiles_x = u.tiles_x;
+    bp.ty_lo = ty_lo;
+    bp.ty_hi = ty_hi;
+
+    const unsigned scan_grid = (unsigned)(((size_t)p.max_visible + kScanTile - 1) / kScanTile);
+    dup_scan_kernel<<<scan_grid > 0 ? scan_grid : 1, kScanThreads, 0, stream>>>(bp);
+    dup_emit_kernel<<<num_sms * 8, 256, 0, stream>>>(bp);
+
+    int bits = 1;
+    while ((1u << bits) < num_tiles) bits++;
+    e = launch_sort(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, (uint32_t)p.buf.dup_capacity, 0, bits, p.sort, num_sms, stream);
+    if (e != cudaSuccess) return e;
+
+    gather_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, p.recs, p.buf.tile_recs,
+                                                  p.buf.tile_ranges);
+
+    RasterKernelParams kp;
+    kp.tile_recs = p.buf.tile_recs;
+    kp.tile_ranges = p.buf.tile_ranges;
+    kp.pixels = reinterpret_cast<uint8_t*>(t.d_pixels);
+    kp.pitch = t.pitch_bytes;
+    kp.width = u.width;
+    kp.height = u.height;
+    kp.row0 = row0;
+    kp.rows = rows;
+    kp.tiles_x = u.tiles_x;
+    kp.ty_lo = ty_lo;
+    kp.sd2 = u.std_dev * u.std_dev;
+    kp.outline = (u.std_dev - 0.1f) * (u.std_dev - 0.1f);
+    kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
+    kp.clear = p.clear;
+    const dim3 grid(u.tiles_x, ty_hi - ty_lo + 1);
+    const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
+                    : t.format == SB_TARGET_RGBA16_FLOAT                                       ? FMT_F16
+                                                                                               : FMT_F32;
+#define SB_RASTER(M, F)                                                        \
+    if (u.mode == M && fmt == F) {                                             \
+        if (M == SB_MODE_SPLAT && p.strict_exp) launch_raster<M, F, true>(kp, grid, stream); \
+        else launch_raster<M, F, false>(kp, grid, stream);                     \
+    }
+    SB_RASTER(SB_MODE_SPLAT, FMT_UNORM8)
+    SB_RASTER(SB_MODE_SPLAT, FMT_F16)
+    SB_RASTER(SB_MODE_SPLAT, FMT_F32)
+    SB_RASTER(SB_MODE_ELLIPSE, FMT_UNORM8)
+    SB_RASTER(SB_MODE_ELLIPSE, FMT_F16)
+    SB_RASTER(SB_MODE_ELLIPSE, FMT_F32)
+    SB_RASTER(SB_MODE_POINT, FMT_UNORM8)
+    SB_RASTER(SB_MODE_POINT, FMT_F16)
+    SB_RASTER(SB_MODE_POINT, FMT_F32)
+#undef SB_RASTER
+    return cudaGetLastError();
+}
+
+}  // namespace sb

@@ -1,0 +1,56 @@
+// sb_select.cu — K7: viewport selection evaluation.
+//
+// Replaces selection::viewport::main (src/shader/selection/viewport.wesl:37-69) fed by the
+// rectangle mask texture (src/shader/selection/viewport_texture_rectangle.wesl): a Gaussian is
+// selected iff its centre passes cull() and the mask texel under it is set.  The rectangle is
+// evaluated analytically: texel (ix,iy) is set iff its centre lies in [x0,x1) x [y0,y1).
+// One warp owns one 32-bit selection word, so no atomics are needed.
+#include "sb_internal.h"
+
+namespace sb {
+
+namespace {
+
+__global__ void __launch_bounds__(256) select_rect_kernel(const uint8_t* __restrict__ gaussians, uint32_t n, uint32_t stride,
+                                                          const __grid_constant__ Uniforms u, float x0, float y0, float x1, float y1,
+                                                          uint32_t* __restrict__ words) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool sel = false;
+    if (g < n) {
+        const float4 head = __ldg(reinterpret_cast<const float4*>(gaussians + (size_t)g * stride));
+        float world[3], clip[4];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            world[i] = sadd(sadd(sadd(smul(u.model[i], head.x), smul(u.model[4 + i], head.y)), smul(u.model[8 + i], head.z)),
+                            u.model[12 + i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            clip[i] = sadd(sadd(sadd(smul(u.pv[i], world[0]), smul(u.pv[4 + i], world[1])), smul(u.pv[8 + i], world[2])),
+                           u.pv[12 + i]);
+        const float nx = sdiv(clip[0], clip[3]), ny = sdiv(clip[1], clip[3]), nz = sdiv(clip[2], clip[3]);
+        const bool culled = !((nx >= -1.0f && ny >= -1.0f && nz >= 0.0f) && (nx <= 1.0f && ny <= 1.0f && nz <= 1.0f));
+        if (!culled) {
+            // ndc_to_camera_texture (camera.wesl:18-20) then vec2<i32>() truncation (viewport.wesl:60)
+            const float tx = smul(smul(sadd(smul(nx, 1.0f), 1.0f), u.size[0]), 0.5f);
+            const float ty = smul(smul(sadd(smul(ny, -1.0f), 1.0f), u.size[1]), 0.5f);
+            const int ix = (int)tx, iy = (int)ty;
+            if (ix >= 0 && iy >= 0 && ix < (int)u.size[0] && iy < (int)u.size[1]) {
+                const float px = (float)ix + 0.5f, py = (float)iy + 0.5f;
+                sel = px >= x0 && px < x1 && py >= y0 && py < y1;
+            }
+        }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, sel);
+    if ((threadIdx.x & 31u) == 0 && g < n) words[g >> 5] = bits;
+}
+
+}  // namespace
+
+cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, float x0, float y0, float x1,
+                               float y1, uint32_t* words, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    select_rect_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, u, x0, y0, x1, y1, words);
+    return cudaGetLastError();
+}
+
+}  // namespace sb
