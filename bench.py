@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the per-frame splat pipeline (Viewer::render).
+
+Metric (BASELINE.json): 1080p frames/sec on a 6M-Gaussian SH3 scene, next to the radix-sort
+Gkeys/s and the achieved HBM GB/s of the preprocess and sort kernels.
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (CUDA, C ABI)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle port, all host cores)
+
+A "step" = one frame: camera update + preprocess + depth sort + tile binning + rasterisation of
+the whole scene into an RGBA8 1080p target.  N > 1 (torchrun, one rank per GPU) shards a batch
+of camera views across GPUs with the scene replicated (BASELINE.json config 5a): no data-path
+collective, weak scaling, value = frames of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "wgpu-3dgs-viewer_b200"))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+N_GAUSSIANS = 6_000_000
+SCENE_SEED = 0x3D65 + 2
+SH_FMT, COV_FMT = 0, 0           # pod single/single, 224 B
+N_VIEWS = 64                     # orbit cameras (config 5a)
+METRIC = "frames_per_sec_1080p_6M_gaussians"
+KERNELS_PER_FRAME = 13           # preprocess 1, depth sort 1+4, scan 1, emit 1, tile sort 1+2, gather 1, raster 1
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(n: int):
+    import splat_b200 as sb
+    g = sb.scenes.synthetic_gaussians(n, SCENE_SEED)
+    pods = sb.pack_gaussians(g, SH_FMT, COV_FMT)
+    return pods
+
+
+def view_camera(sb, k: int):
+    pos, yaw, pitch = sb.scenes.orbit_camera(k % N_VIEWS, N_VIEWS)
+    return sb.camera_pod(pos, yaw, pitch, WIDTH, HEIGHT)
+
+
+# ------------------------------------------------------------------------------------------ own arm
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import splat_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sb.load()  # fails loudly if the CUDA extension is missing: there is no fallback
+    ctx = sb.Context(local_rank)
+    n = args.n
+    pods = build_scene(n)
+    viewer = sb.Viewer(ctx, pods, n, sh_fmt=SH_FMT, cov_fmt=COV_FMT, target_format=sb.TARGET_RGBA8)
+    stride = sb.pod_stride(SH_FMT, COV_FMT)
+    scene_bytes = pods.nbytes
+    viewer.update_gaussian_transform(1.0, sb.MODE_SPLAT, 3, False, 3.0)
+    target = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.uint8, device="cuda")
+    host_frame = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.Stream()
+    cams = [view_camera(sb, k) for k in range(N_VIEWS)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step_device(i):
+        viewer.update_camera_with_pod(cams[(i * world + rank) % N_VIEWS])
+        viewer.render(target, WIDTH, HEIGHT, stream=stream)
+
+    def step_e2e(i):
+        viewer.render_to_host(cams[(i * world + rank) % N_VIEWS], host_frame.data_ptr(), host_frame.numel(), stream=stream)
+
+    def timed(step_fn, steps, warmup, sample_clocks=False):
+        for i in range(warmup):
+            step_fn(i)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(warmup + i)
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    ms, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    frames = args.steps * world
+
+    # per-stage device times of the same frames (cudaEvents inside the library, same stream)
+    viewer.set_stage_timing(True)
+    acc = {}
+    vis, dup = [], []
+    for i in range(min(args.steps, 16)):
+        step_device(args.warmup + i)
+        for k, v in viewer.read_stage_times(stream).items():
+            acc.setdefault(k, []).append(v)
+        st = viewer.read_frame_stats(stream)
+        vis.append(st["visible"])
+        dup.append(st["duplicates"])
+        assert not st["overflowed"], "tile-duplicate buffer overflowed"
+    viewer.set_stage_timing(False)
+    stage = {k: float(np.mean(v)) for k, v in acc.items()}
+    V, D = float(np.mean(vis)), float(np.mean(dup))
+
+    # sanity: the frame is not empty and alpha is opaque
+    stream.synchronize()
+    frame = target.cpu().numpy()
+    assert frame[..., 3].min() == 255 and frame[..., :3].max() > 0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    pre_bytes = n * 16 + V * (stride - 16) + 8 * V
+    sort_bytes = V * 68.0
+    pre_gbs = pre_bytes / stage["preprocess"] / 1e6
+    sort_gbs = sort_bytes / stage["depth_sort"] / 1e6
+    frame_stage_ms = sum(stage.values())
+    dominant = max(stage, key=stage.get)
+    pairs = D * 256.0                                       # (pixel, splat) evaluations: one per thread per tile duplicate
+    out = {
+        "metric": METRIC, "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{n}-Gaussian SH3 scene (pod single/single, 224 B), 1920x1080 RGBA8, splat mode, "
+                               f"{N_VIEWS}-view orbit, one view per step per GPU (BASELINE.json config 2b / 5a)",
+                   "gaussians": n, "resolution": [WIDTH, HEIGHT], "pod_stride": stride, "scene_bytes": int(scene_bytes),
+                   "l2_policy": "scene (1.34 GB) is larger than L2; no explicit flush",
+                   "parallelism": f"views sharded over {world} GPU(s), scene replicated"},
+        "clocks": clocks,
+        "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 144, "d2h_bytes_per_step": int(host_frame.numel())},
+        "gpu_launches": KERNELS_PER_FRAME * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "preprocess_kernel<single,single> (K1)", "achieved": pre_gbs, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": pre_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": pre_bytes, "ms": stage["preprocess"]},
+        "stages": {
+            "ms": stage, "sum_ms": frame_stage_ms, "dominant": dominant, "visible": V, "tile_duplicates": D,
+            "sort": {"gkeys_per_s": V / stage["depth_sort"] / 1e6, "achieved_gbs": sort_gbs, "frac_hbm": sort_gbs / hbm_peak,
+                     "algorithmic_bytes_per_key": 68},
+            "raster": {"pairs": pairs, "gpairs_per_s": pairs / stage["raster"] / 1e6},
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_sample(args.cpu_sample)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def cpu_frames_per_sec(sample_n: int, steps: int, warmup: int):
+    """Times the CPU oracle (faithful restatement of the reference's three stages; the unmodified
+    reference cannot be built here: no Rust toolchain, no Vulkan) on a `sample_n`-Gaussian scene
+    drawn from the bench scene's generator (same seed and distributions), all host threads."""
+    from oracle import binding as ob
+    import splat_b200 as sb
+    pods = build_scene(sample_n)
+    model = ob.OracleModel(pods, sample_n)
+    gt = ob.gaussian_transform_pod()
+    threads = ob.lib().so_max_threads()
+    times = []
+    for i in range(warmup + steps):
+        pos, yaw, pitch = sb.scenes.orbit_camera(i % N_VIEWS, N_VIEWS)
+        cam = ob.camera_pod(pos, yaw, pitch, WIDTH, HEIGHT)
+        t0 = time.perf_counter()
+        ob.render(model, cam, gt, ob.TARGET_RGBA8, n_threads=threads)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.sum(times)), threads
+
+
+def cpu_baseline_sample(sample_n: int):
+    secs, threads = cpu_frames_per_sec(sample_n, steps=2, warmup=1)
+    fps_sample = 2 / secs
+    return {"value": fps_sample * sample_n / N_GAUSSIANS, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"oracle render of a {sample_n}-Gaussian scene from the bench generator at 1920x1080, 2 frames, "
+                      f"{fps_sample:.3f} frames/s on the sample, scaled by {sample_n}/{N_GAUSSIANS} (cost is linear in splats)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_n = args.cpu_sample
+    secs, threads = cpu_frames_per_sec(sample_n, args.steps, args.warmup)
+    scale = sample_n / N_GAUSSIANS
+    value = args.steps / secs * scale
+    sample = (f"each step = oracle/splat_oracle.c render of a {sample_n}-Gaussian scene from the bench generator at 1920x1080 "
+              f"(all {threads} host threads); frames/s scaled by {sample_n}/{N_GAUSSIANS}")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3 / scale, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{N_GAUSSIANS}-Gaussian SH3 scene (pod single/single, 224 B), 1920x1080 RGBA8, splat mode "
+                               "(CPU restatement of the reference algorithm, not lavapipe: the crate cannot be built here)",
+                   "gaussians": N_GAUSSIANS, "resolution": [WIDTH, HEIGHT]},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--n", type=int, default=N_GAUSSIANS, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

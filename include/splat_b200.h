@@ -219,6 +219,11 @@ SB_API SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* 
 /* testing knob: 1 = bit-reproducible polynomial exp in the fragment stage (matches the
  * oracle's strict_exp); 0 (default) = MUFU ex2 fast path */
 SB_API SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict);
+/* Tracing (the reference has none: every pass has timestamp_writes: None, src/radix_sorter.rs:504-507).
+ * When enabled, cudaEvents are recorded on the launching stream between the stages of a frame;
+ * ms[0..5] = preprocess, depth sort, tile count+emit, tile sort, gather, raster. */
+SB_API SbStatus sb_viewer_set_stage_timing(SbViewer* v, int32_t enabled);
+SB_API SbStatus sb_viewer_read_stage_times(SbViewer* v, void* stream, float ms[6]);
 /* capacity (in duplicates) of the tile-binning buffers; default 8*n + tiles */
 SB_API SbStatus sb_viewer_reserve_duplicates(SbViewer* v, uint64_t capacity);
 

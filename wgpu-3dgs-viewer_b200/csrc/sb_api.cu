@@ -143,6 +143,8 @@ struct SbViewer {
     bool selection_enabled = false;
     uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
     int strict_exp = 0;
+    bool timing = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     SbDrawIndirectArgs* d_draw() const { return args.as<SbDrawIndirectArgs>(); }
     SbDispatchIndirectArgs* d_dispatch() const { return reinterpret_cast<SbDispatchIndirectArgs*>(args.as<uint8_t>() + 16); }
@@ -253,7 +255,9 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.recs = v->recs.as<sb::SplatRec>();
     p.visible_count = v->d_visible();
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
+    if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[0], stream));
     SB_CUDA(v->ctx, sb::launch_preprocess(v->sh_fmt, v->cov_fmt, p, v->pre_scratch.p, v->pre_scratch.bytes, v->ctx->num_sms, stream));
+    if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[1], stream));
     return SB_OK;
 }
 
@@ -270,6 +274,7 @@ SbStatus do_sort(SbViewer* v, cudaStream_t stream) {
     // keys = f32 depth bit patterns in [0, 0x3F800000]; pads (2.0) beyond V are left in place
     SB_CUDA(v->ctx, sb::launch_sort(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), v->d_visible(), v->n, 0, 32, sort_scratch(v),
                                     v->ctx->num_sms, stream));
+    if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[2], stream));
     return SB_OK;
 }
 
@@ -304,6 +309,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.target = *target;
     p.strict_exp = v->strict_exp;
     p.clear = clear;
+    p.events = v->timing ? &v->ev[3] : nullptr;
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
     return SB_OK;
 }
@@ -389,6 +395,8 @@ void sb_viewer_destroy(SbViewer* v) {
                          &v->sort_vals_alt, &v->sort_internal, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
                          &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target})
         b->release();
+    for (cudaEvent_t e : v->ev)
+        if (e) cudaEventDestroy(e);
     delete v;
 }
 
@@ -593,6 +601,22 @@ SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible
 SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     v->strict_exp = strict != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_set_stage_timing(SbViewer* v, int32_t enabled) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    if (enabled && !v->ev[0])
+        for (cudaEvent_t& e : v->ev) SB_CUDA(v->ctx, cudaEventCreate(&e));
+    v->timing = enabled != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_read_stage_times(SbViewer* v, void* stream, float ms[6]) {
+    if (!v || !ms) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (!v->timing) return fail(v->ctx, SB_ERR_INVALID_ARG, "stage timing is not enabled");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    for (int i = 0; i < 6; i++) SB_CUDA(v->ctx, cudaEventElapsedTime(&ms[i], v->ev[i], v->ev[i + 1]));
     return SB_OK;
 }
 

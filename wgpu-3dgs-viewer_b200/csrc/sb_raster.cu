@@ -400,14 +400,17 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     const unsigned scan_grid = (unsigned)(((size_t)p.max_visible + kScanTile - 1) / kScanTile);
     dup_scan_kernel<<<scan_grid > 0 ? scan_grid : 1, kScanThreads, 0, stream>>>(bp);
     dup_emit_kernel<<<num_sms * 8, 256, 0, stream>>>(bp);
+    if (p.events) cudaEventRecord(p.events[0], stream);
 
     int bits = 1;
     while ((1u << bits) < num_tiles) bits++;
     e = launch_sort(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, (uint32_t)p.buf.dup_capacity, 0, bits, p.sort, num_sms, stream);
     if (e != cudaSuccess) return e;
+    if (p.events) cudaEventRecord(p.events[1], stream);
 
     gather_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, p.recs, p.buf.tile_recs,
                                                   p.buf.tile_ranges);
+    if (p.events) cudaEventRecord(p.events[2], stream);
 
     RasterKernelParams kp;
     kp.tile_recs = p.buf.tile_recs;
@@ -443,6 +446,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     SB_RASTER(SB_MODE_POINT, FMT_F16)
     SB_RASTER(SB_MODE_POINT, FMT_F32)
 #undef SB_RASTER
+    if (p.events) cudaEventRecord(p.events[3], stream);
     return cudaGetLastError();
 }
 

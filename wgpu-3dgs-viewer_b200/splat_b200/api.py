@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
     "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_set_strict_exp",
+    "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times",
     "sb_viewer_reserve_duplicates", "sb_sorter_create", "sb_sorter_destroy", "sb_sorter_sort", "sb_mm_create",
     "sb_mm_destroy", "sb_mm_insert_model", "sb_mm_remove_model", "sb_mm_update_camera_with_pod",
     "sb_mm_update_model_transform_with_pod", "sb_mm_update_gaussian_transform_with_pod", "sb_mm_set_selection",
@@ -154,6 +155,8 @@ def load() -> C.CDLL:
     sig("sb_viewer_read_depth_keys", i32, vp, vp, vp, u64)
     sig("sb_viewer_read_frame_stats", i32, vp, vp, P(u64), P(u64), P(u32))
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
+    sig("sb_viewer_set_stage_timing", i32, vp, i32)
+    sig("sb_viewer_read_stage_times", i32, vp, vp, P(f32))
     sig("sb_viewer_reserve_duplicates", i32, vp, u64)
     sig("sb_sorter_create", i32, vp, u32, P(vp))
     sig("sb_sorter_destroy", None, vp)
@@ -400,6 +403,16 @@ class Viewer:
 
     def set_strict_exp(self, strict: bool):
         _check(load().sb_viewer_set_strict_exp(self._h, int(strict)), self.ctx._h)
+
+    STAGES = ("preprocess", "depth_sort", "tile_emit", "tile_sort", "gather", "raster")
+
+    def set_stage_timing(self, enabled: bool):
+        _check(load().sb_viewer_set_stage_timing(self._h, int(enabled)), self.ctx._h)
+
+    def read_stage_times(self, stream=None) -> dict:
+        ms = (C.c_float * 6)()
+        _check(load().sb_viewer_read_stage_times(self._h, _stream_handle(stream), ms), self.ctx._h)
+        return dict(zip(self.STAGES, [float(x) for x in ms]))
 
     def reserve_duplicates(self, capacity: int):
         _check(load().sb_viewer_reserve_duplicates(self._h, capacity), self.ctx._h)
