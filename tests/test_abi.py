@@ -1,0 +1,109 @@
+"""CPU: the C-ABI library loads, exports every symbol include/splat_b200.h declares, and its
+host-only helpers agree with the oracle.  No compute entry point is called (no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+
+def header_symbols():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "splat_b200.h")).read()
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(sb):
+    lib = sb.load()
+    declared = header_symbols()
+    assert len(declared) >= 60
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/splat_b200.h but not exported"
+    assert sorted(sb.EXPORTED_SYMBOLS) == declared, "api.py binding list out of sync with the header"
+    out = subprocess.run(["nm", "-D", "--defined-only", sb.lib_path()], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(declared) <= exported
+    leaked = [s for s in exported if not s.startswith("sb_")]
+    assert not leaked, f"non-ABI symbols exported: {leaked[:5]}"
+
+
+def test_library_is_sm100a_cuda_and_has_no_oracle_dependency(sb):
+    out = subprocess.run(["cuobjdump", "-lelf", sb.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    needed = subprocess.run(["readelf", "-d", sb.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in needed
+
+
+def test_pod_layout_sizes(sb, ob):
+    # reference: buffer sizes == size_of::<Pod>() (tests/buffer/camera.rs, indirect_args.rs)
+    assert ctypes.sizeof(sb.CameraPod) == 144
+    assert ctypes.sizeof(sb.ModelTransformPod) == 48
+    assert ctypes.sizeof(sb.GaussianTransformPod) == 8
+    expect = {(0, 0): 224, (0, 1): 208, (0, 2): 224, (1, 0): 144, (1, 1): 128, (1, 2): 144, (2, 0): 96, (2, 1): 80,
+              (2, 2): 96, (3, 0): 48, (3, 1): 32, (3, 2): 48}
+    for (sh, cov), stride in expect.items():
+        assert sb.pod_stride(sh, cov) == stride == ob.pod_stride(sh, cov)
+    assert sb.pod_stride(7, 0) == 0
+    # wgpu_sort::keys_buffer_size_bytes (radix_sorter.rs:922-939)
+    for n in (0, 1, 3839, 3840, 3841, 1_000_000, 6_000_000):
+        assert sb.padded_key_count(n) == (n + 3839) // 3840 * 3840
+        assert sb.keys_buffer_size_bytes(n) == sb.padded_key_count(n) * 16
+
+
+def test_host_packer_matches_oracle(sb, ob):
+    g = sb.scenes.synthetic_gaussians(2000, 4)
+    g["sh"][5] = 0.0  # degenerate norm8 range
+    g["sh"][6] = 0.25
+    for sh in range(4):
+        for cov in range(3):
+            a = sb.pack_gaussians(g, sh, cov)
+            b = ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE), sh, cov)
+            assert np.array_equal(a, b), (sh, cov)
+
+
+def test_camera_and_transform_pods_match_oracle(sb, ob):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        pos = rng.uniform(-20, 20, 3)
+        yaw, pitch = rng.uniform(0, 6.28), rng.uniform(-1.5, 1.5)
+        w, h = int(rng.integers(16, 4000)), int(rng.integers(16, 3000))
+        assert bytes(sb.camera_pod(pos, yaw, pitch, w, h)) == bytes(ob.camera_pod(pos, yaw, pitch, w, h))
+    # CameraPod::new semantics (tests/buffer/camera.rs:95-125): yaw = 0 looks down +Z, depth 0..1
+    pod = sb.camera_pod((0, 0, 0), 0.0, 0.0, 100, 100)
+    view = np.array(pod.view).reshape(4, 4).T
+    assert np.allclose(view @ np.array([0, 0, 1, 1.0]), [0, 0, -1, 1])
+    proj = np.array(pod.proj).reshape(4, 4).T
+    near = proj @ np.array([0, 0, -0.1, 1.0])
+    far = proj @ np.array([0, 0, -1e4, 1.0])
+    assert abs(near[2] / near[3]) < 1e-6 and abs(far[2] / far[3] - 1) < 1e-4
+    assert bytes(sb.model_transform_pod((1, 2, 3), (0, 0, 0, 1), (2, 2, 2))) == bytes(ob.model_transform_pod((1, 2, 3), (0, 0, 0, 1), (2, 2, 2)))
+    for sd in (0.0, 1.0, 2.5, 3.0):
+        assert bytes(sb.gaussian_transform_pod(1.5, 1, 2, True, sd)) == bytes(ob.gaussian_transform_pod(1.5, 1, 2, True, sd))
+
+
+def test_ply_reader_matches_oracle(sb, ob, tmp_path):
+    here = os.path.dirname(os.path.abspath(__file__))
+    props = np.load(os.path.join(here, "golden", "model_ply_props.npy"))
+    names = (["x", "y", "z", "nx", "ny", "nz"] + [f"f_dc_{i}" for i in range(3)] + [f"f_rest_{i}" for i in range(45)]
+             + ["opacity"] + [f"scale_{i}" for i in range(3)] + [f"rot_{i}" for i in range(4)])
+    hdr = "ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % len(props)
+    hdr += "".join(f"property float {n}\n" for n in names) + "end_header\n"
+    path = tmp_path / "model.ply"
+    path.write_bytes(hdr.encode() + props.astype("<f4").tobytes())
+    g = sb.read_ply(str(path))
+    og = ob.gaussians_from_ply_props(props)
+    assert g.tobytes() == og.tobytes()
+    assert len(g) == 9 and g["color"][0].tolist() == [255, 0, 0, 255]
+
+
+def test_no_context_without_gpu(sb):
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        sb.Context(0)
+    except sb.SplatError as e:
+        assert e.status == 2 and "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("sb_ctx_create must fail loudly without a CUDA device")

@@ -1,0 +1,74 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic of the N > 1 paths."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "wgpu-3dgs-viewer_b200"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, height, width, out):
+    sys.path.insert(0, os.path.join(ROOT, "wgpu-3dgs-viewer_b200"))
+    from splat_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the "frame": row index in every channel, so a mis-placed strip is detected
+    r0, rows = sharding.strip_rows(height, world, rank)
+    strip = torch.arange(r0, r0 + rows, dtype=torch.int32).view(-1, 1, 1).expand(rows, width, 4).contiguous()
+    full = sharding.gather_strips(strip, height, world, rank, dst=0)
+    # view sharding: every view rendered exactly once; "render" = view id; max-over-ranks timing
+    mine = sharding.views_for_rank(64, world, rank)
+    counts = torch.zeros(64, dtype=torch.int32)
+    counts[mine] += 1
+    dist.all_reduce(counts)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        expect = torch.arange(height, dtype=torch.int32).view(-1, 1, 1).expand(height, width, 4)
+        out.put((bool(torch.equal(full, expect)), counts.tolist(), float(t.item())))
+    else:
+        assert full is None
+    dist.destroy_process_group()
+
+
+def test_strip_partition_properties():
+    from splat_b200 import sharding
+    for height in (1, 15, 16, 17, 360, 1080, 2160, 4320):
+        for world in (1, 2, 3, 4, 8):
+            rows = [sharding.strip_rows(height, world, r) for r in range(world)]
+            assert rows[0][0] == 0 and sum(n for _, n in rows) == height
+            for (a0, an), (b0, _) in zip(rows, rows[1:]):
+                assert a0 + an == b0
+            for r0, n in rows:
+                assert r0 % 16 == 0 or n == 0
+
+
+def test_gather_strips_and_view_sharding_gloo_ws2():
+    world, height, width = 2, 200, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, height, width, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, counts, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok, "gathered strips do not reassemble the frame"
+    assert counts == [1] * 64, "every view must be rendered by exactly one rank"
+    assert tmax == 2.0

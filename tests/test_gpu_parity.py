@@ -95,3 +95,292 @@ def test_frame_small_fast_exp(sb, ob, ctx):
     check_artifacts(ob, r, n)
     diff = np.abs(r["img"].astype(np.int32) - r["oimg"].astype(np.int32))
     assert diff.max() <= 2, f"max-abs {diff.max()} > 2/255"
+
+
+def img_diff(r):
+    a, b = r["img"], r["oimg"]
+    if a.dtype == np.uint8:
+        return np.abs(a.astype(np.int32) - b.astype(np.int32)).max()
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+
+
+# every pod format the reference can instantiate (SH x cov3d): strides pinned in test_abi.py
+FORMATS = [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (3, 0), (3, 1), (3, 2)]
+
+
+@pytest.mark.parametrize("sh_fmt,cov_fmt", FORMATS)
+def test_pod_formats(sb, ob, ctx, sh_fmt, cov_fmt):
+    n = 6000 + 37 * sh_fmt + 11 * cov_fmt  # ragged: not a multiple of any tile size
+    g, pods = make_scene(sb, ob, n, 10 + sh_fmt * 3 + cov_fmt, sh_fmt, cov_fmt)
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_INSIDE, 480, 270, sh_fmt, cov_fmt)
+    check_artifacts(ob, r, n)
+    assert img_diff(r) <= 1, f"max-abs {img_diff(r)}"
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("target_format", [0, 1, 2, 3])
+def test_modes_and_targets(sb, ob, ctx, mode, target_format):
+    n = 8000
+    g, pods = make_scene(sb, ob, n, 40 + mode)
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, 512, 288, mode=mode, target_format=target_format)
+    check_artifacts(ob, r, n)
+    d = img_diff(r)
+    if target_format in (0, 1):
+        assert d <= 1, f"unorm8 max-abs {d}/255"       # tolerance 2/255 (north star); strict exp => expect 0-1
+        assert np.all(r["img"][..., 3] == 255)
+    else:
+        assert d <= 1e-3, f"float target max-abs {d}"  # north-star tolerance for float targets
+
+
+@pytest.mark.parametrize("sh_deg,no_sh0,std_dev,size", [(0, False, 3.0, 1.0), (1, False, 2.0, 1.0), (2, True, 3.0, 0.5),
+                                                        (3, True, 1.0, 2.0), (3, False, 0.0, 1.0)])
+def test_gaussian_transform_knobs(sb, ob, ctx, sh_deg, no_sh0, std_dev, size):
+    n = 5000
+    g, pods = make_scene(sb, ob, n, 60 + sh_deg)
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_INSIDE, 400, 300, sh_deg=sh_deg, no_sh0=no_sh0, std_dev=std_dev, size=size)
+    check_artifacts(ob, r, n)
+    assert img_diff(r) <= 1
+
+
+def test_model_transform(sb, ob, ctx):
+    n = 7000
+    g, pods = make_scene(sb, ob, n, 70)
+    q = np.array([0.1, 0.7, -0.2, 0.6], dtype=np.float32)
+    q /= np.linalg.norm(q)
+    mt = ((1.5, -2.0, 3.0), tuple(q), (1.3, 0.8, 1.1))
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, 640, 360, model_transform=mt)
+    check_artifacts(ob, r, n)
+    assert img_diff(r) <= 1
+
+
+@pytest.mark.parametrize("invert", [1, 0])
+def test_selection_mask(sb, ob, ctx, invert):
+    n = 9000
+    g, pods = make_scene(sb, ob, n, 80)
+    rng = np.random.default_rng(5)
+    words = rng.integers(0, 2**32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32)
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, 480, 270, selection=words, invert=invert)
+    check_artifacts(ob, r, n)
+    assert 0 < r["V"] < n
+    assert img_diff(r) <= 1
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 383, 384, 385, 3839, 3840, 3841])
+def test_ragged_sizes(sb, ob, ctx, n):
+    g = sb.scenes.synthetic_gaussians(max(n, 1), 90 + n, extent=3.0, log_scale=(-3.0, -1.5))[:n]
+    pods = sb.pack_gaussians(g) if n else np.zeros(0, dtype=np.uint8)
+    r = run_frame(sb, ob, ctx, pods, n, ((0.0, 0.0, -8.0), 0.05, 0.05), 320, 200)
+    check_artifacts(ob, r, n)
+    assert img_diff(r) <= 1
+
+
+def test_huge_near_splats(sb, ob, ctx):
+    """Axes clamp at 1024 px (utils.wesl:73-74): near-camera splats cover every tile."""
+    n = 300
+    g = sb.scenes.synthetic_gaussians(n, 99, extent=1.5, log_scale=(-2.0, 0.5))
+    pods = sb.pack_gaussians(g)
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_INSIDE, 640, 360)
+    check_artifacts(ob, r, n)
+    assert not r["stats"]["overflowed"]
+    assert img_diff(r) <= 1
+
+
+def test_deep_low_alpha_stack(sb, ob, ctx):
+    """Per-blend re-quantisation on unorm8: many faint layers over one pixel region."""
+    n = 4000
+    g = sb.scenes.synthetic_gaussians(n, 123, extent=0.2, log_scale=(-2.5, -2.0))
+    g["pos"][:, 2] = np.linspace(2.0, 6.0, n)
+    g["color"][:, 3] = 3  # alpha ~ 0.012
+    pods = sb.pack_gaussians(g)
+    r = run_frame(sb, ob, ctx, pods, n, ((0.0, 0.0, 0.0), 0.0, 0.0), 256, 256)
+    check_artifacts(ob, r, n)
+    assert img_diff(r) == 0
+    # a float-accumulating compositor would differ from the per-blend quantised result by many levels
+    fr = run_frame(sb, ob, ctx, pods, n, ((0.0, 0.0, 0.0), 0.0, 0.0), 256, 256, target_format=3)
+    f8 = np.clip(np.rint(fr["img"][..., :3] * 255.0), 0, 255).astype(np.int32)
+    assert np.abs(f8 - r["img"][..., :3].astype(np.int32)).max() > 3
+
+
+def test_equal_depth_ties_keep_index_order(sb, ob, ctx):
+    """equal keys are the norm; the canonical order inside a run is ascending index."""
+    n = 5000
+    g = sb.scenes.synthetic_gaussians(n, 77)
+    g["pos"][:, 2] = np.repeat(np.linspace(-5, 5, 10), n // 10).astype(np.float32)
+    pods = sb.pack_gaussians(g)
+    r = run_frame(sb, ob, ctx, pods, n, ((0.0, 0.0, -30.0), 0.0, 0.0), 480, 270)
+    check_artifacts(ob, r, n)
+    k = r["keys"][: r["V"]].view(np.uint32)
+    assert len(np.unique(k)) < r["V"] // 4
+    same = k[1:] == k[:-1]
+    assert np.all(r["idx"][1:][same] > r["idx"][:-1][same])
+    assert img_diff(r) == 0
+
+
+def test_screen_strips_match_full_frame(sb, ob, ctx):
+    """Config 5b: a frame rendered as horizontal strips equals the full frame bit for bit."""
+    torch = _torch()
+    n, w, h = 20000, 640, 360
+    g, pods = make_scene(sb, ob, n, 31)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    cam = sb.camera_pod(pos, yaw, pitch, w, h)
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera_with_pod(cam)
+    full = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    v.render(full, w, h)
+    for parts in (2, 3, 8):
+        out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        bounds = [h * i // parts for i in range(parts + 1)]
+        for i in range(parts):
+            r0, r1 = bounds[i], bounds[i + 1]
+            strip = torch.zeros((r1 - r0, w, 4), dtype=torch.uint8, device="cuda")
+            v.render(strip, w, h, row0=r0, rows=r1 - r0)
+            out[r0:r1] = strip
+        torch.cuda.synchronize()
+        assert torch.equal(out, full), f"{parts} strips differ from the full frame"
+    ocam = ob.camera_pod(pos, yaw, pitch, w, h)
+    om = ob.OracleModel(pods, n)
+    ostrip, _ = ob.render(om, ocam, ob.gaussian_transform_pod(), row0=100, rows=57)
+    assert np.abs(full[100:157].cpu().numpy().astype(np.int32) - ostrip.astype(np.int32)).max() <= 2
+    v.close()
+
+
+def test_multi_model_draw_order_and_selection(sb, ob, ctx):
+    """Config 4: models composited in caller key order (multi_model.rs:505-527), per-model
+    transforms, per-model selection masks."""
+    torch = _torch()
+    w, h, n = 640, 360, 6000
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    cam = sb.camera_pod(pos, yaw, pitch, w, h)
+    ocam = ob.camera_pod(pos, yaw, pitch, w, h)
+    mm = sb.MultiModelViewer(ctx)
+    mm.update_camera_with_pod(cam)
+    gt = sb.gaussian_transform_pod()
+    mm.update_gaussian_transform_with_pod(gt)
+    omodels = {}
+    rng = np.random.default_rng(3)
+    for k in range(4):
+        g = sb.scenes.synthetic_gaussians(n, 200 + k, extent=6.0, log_scale=(-3.5, -2.0))
+        pods = sb.pack_gaussians(g)
+        assert mm.insert_model(k, pods, n) is False
+        a = 0.3 * k
+        mt = ((6.0 * (k - 1.5), 0.0, 0.0), (0.0, float(np.sin(a / 2)), 0.0, float(np.cos(a / 2))), (1 + 0.05 * k,) * 3)
+        mm.update_model_transform_with_pod(k, sb.model_transform_pod(*mt))
+        sel = None
+        if k % 2 == 1:
+            sel = rng.integers(0, 2**32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32)
+            mm.set_selection(k, sel, invert=(k == 1))
+        omodels[k] = ob.OracleModel(pods, n, model_transform=ob.model_transform_pod(*mt), selection=sel, invert_selection=int(k == 1))
+    for order in ([0, 1, 2, 3], [3, 1, 0, 2], [2], [1, 1, 0]):
+        target = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        mm.render(target, w, h, order)
+        torch.cuda.synchronize()
+        oimg, _ = ob.render([omodels[k] for k in order], ocam, ob.gaussian_transform_pod())
+        d = np.abs(target.cpu().numpy().astype(np.int32) - oimg.astype(np.int32)).max()
+        assert d <= 2, f"order {order}: max-abs {d}"
+        for k in set(order):
+            pre = ob.preprocess(omodels[k], ocam, ob.gaussian_transform_pod())
+            idx, V = mm.read_model_indices(k, pre["count"])
+            assert V == pre["count"]
+            _, oi = ob.radix_sort(pre["keys"][:V].view(np.uint32), pre["indices"][:V])
+            assert np.array_equal(idx, oi)
+    with pytest.raises(sb.SplatError) as e:
+        mm.render(target, w, h, [0, 9])
+    assert e.value.status == 4  # ModelNotFound
+    assert mm.remove_model(2) is True and mm.remove_model(2) is False
+    with pytest.raises(sb.SplatError):
+        mm.render(target, w, h, [2])
+    mm.render(target, w, h, [])  # a pass that only clears
+    torch.cuda.synchronize()
+    t = target.cpu().numpy()
+    assert np.all(t[..., :3] == 0) and np.all(t[..., 3] == 255)
+    mm.close()
+
+
+def test_viewport_rect_selection(sb, ob, ctx):
+    """Next-row f1: selection::viewport evaluation with an analytic rectangle mask."""
+    n, w, h = 30000, 640, 360
+    g, pods = make_scene(sb, ob, n, 55)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.select_rect(160.0, 90.0, 480.0, 270.0)
+    words = v.read_selection()
+    om = ob.OracleModel(pods, n)
+    ow = ob.select_rect(om, ob.camera_pod(pos, yaw, pitch, w, h), 160.0, 90.0, 480.0, 270.0)
+    assert np.array_equal(words, ow)
+    assert 0 < np.unpackbits(words.view(np.uint8)).sum() < n
+    v.close()
+
+
+def test_standalone_radix_sorter(sb, ctx):
+    """RadixSorter<()>: stable ascending (key, payload) sort with a device-side count."""
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    for n, bits in ((1, 32), (4095, 32), (4096, 32), (100_001, 32), (250_000, 13), (70_000, 17)):
+        keys = rng.integers(0, 2**bits, size=n, dtype=np.uint64).astype(np.uint32)
+        if bits == 32:
+            keys[: n // 2] &= np.uint32(0xFF00FFFF)  # plenty of ties
+        vals = np.arange(n, dtype=np.uint32)
+        dk = torch.from_numpy(keys.view(np.int32)).cuda()
+        dv = torch.from_numpy(vals.view(np.int32)).cuda()
+        cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+        s = sb.RadixSorter(ctx, n + 100)
+        s.sort(dk.data_ptr(), dv.data_ptr(), cnt.data_ptr(), n, 0, bits)
+        torch.cuda.synchronize()
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(dk.cpu().numpy().view(np.uint32), keys[order])
+        assert np.array_equal(dv.cpu().numpy().view(np.uint32), vals[order])
+        s.close()
+
+
+def test_errors(sb, ctx):
+    pods = sb.pack_gaussians(sb.scenes.synthetic_gaussians(10, 1))
+    v = sb.Viewer(ctx, pods, 10)
+    import torch
+    t = torch.zeros((16, 16, 4), dtype=torch.uint8, device="cuda")
+    v.update_camera((0, 0, -5), 0.0, 0.0, 32, 32)
+    with pytest.raises(sb.SplatError):  # target size != CameraPod.size
+        v.render(t, 16, 16)
+    with pytest.raises(sb.SplatError):
+        v.update_gaussian_transform(1.0, 0, 4, False, 3.0)  # GaussianShDegree::new(4) is None
+    with pytest.raises(sb.SplatError):
+        v.update_gaussian_transform(1.0, 0, 3, False, 3.5)  # GaussianMaxStdDev::new(3.5) is None
+    v.close()
+    ctx.set_model_size_limit(100)
+    with pytest.raises(sb.SplatError) as e:  # ModelSizeExceedsDeviceLimit (preprocessor.rs:239-246)
+        sb.Viewer(ctx, pods, 10)
+    assert e.value.status == 3
+    ctx.set_model_size_limit(1 << 40)
+
+
+def test_full_size_properties(sb, ctx):
+    """BASELINE full size (6M, 1080p): size-independent properties instead of an oracle frame."""
+    torch = _torch()
+    n, w, h = 6_000_000, 1920, 1080
+    g = sb.scenes.synthetic_gaussians(n, sb.scenes.BASE_SEED + 2)
+    pods = sb.pack_gaussians(g)
+    v = sb.Viewer(ctx, pods, n)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v.update_camera(pos, yaw, pitch, w, h)
+    target = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    v.render(target, w, h)
+    draw, disp = v.read_indirect_args()
+    V = int(draw[1])
+    assert draw[0] == 6 and disp[0] == (V + 3839) // 3840 and 0 < V <= n
+    idx = v.read_indices(V)
+    keys = v.read_depth_keys(sb.padded_key_count(n))
+    ku = keys[:V].view(np.uint32)
+    assert np.all(ku[1:] >= ku[:-1]), "keys not ascending"
+    assert np.all(keys[V:int(disp[0]) * 3840] == 2.0)
+    assert len(np.unique(idx)) == V and idx.max() < n, "indices are not a set"
+    same = ku[1:] == ku[:-1]
+    assert np.all(idx[1:][same] > idx[:-1][same]), "ties not in ascending index order"
+    # idempotence: a second frame reproduces every artefact bit for bit
+    first = target.clone()
+    v.render(target, w, h)
+    torch.cuda.synchronize()
+    assert torch.equal(first, target)
+    assert np.array_equal(idx, v.read_indices(V))
+    assert not v.read_frame_stats()["overflowed"]
+    assert int(first[..., 3].min()) == 255 and int(first[..., :3].max()) > 0
+    v.close()

@@ -1,0 +1,192 @@
+"""CPU: the oracle against the committed golden vectors and against its numpy twin."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(HERE, "golden", "golden.json")))
+
+
+def hexes(a):
+    return [f"0x{int(x):08x}" for x in np.asarray(a).view(np.uint32)]
+
+
+def single_scene(ob):
+    g = np.zeros(1, dtype=ob.GAUSSIAN_DTYPE)
+    g["pos"][0] = (0, 0, 1); g["rot"][0] = (0, 0, 0, 1); g["scale"][0] = (1, 1, 1); g["color"][0] = (255, 0, 0, 255)
+    return ob.OracleModel(ob.pack_gaussians(g), 1), ob.camera_pod((0, 0, 0), 0.1, 0.1, 1024, 1024), ob.gaussian_transform_pod()
+
+
+def ply_scene(ob):
+    props = np.load(os.path.join(HERE, "golden", "model_ply_props.npy"))
+    gs = ob.gaussians_from_ply_props(props)
+    half = np.float32(np.pi) / 2  # examples/simple.rs:168-173: 180 degrees about Z
+    mt = ob.model_transform_pod((0, 0, 0), (0, 0, float(np.sin(half)), float(np.cos(half))), (1, 1, 1))
+    return gs, ob.OracleModel(ob.pack_gaussians(gs), 9, model_transform=mt), ob.camera_pod((0, 0, 0), 0.0, 0.0, 1280, 720), ob.gaussian_transform_pod()
+
+
+def ulp_distance(a_hex, b_hex):
+    return abs(int(a_hex, 16) - int(b_hex, 16))
+
+
+def test_survey_kat_single_gaussian(ob, gold):
+    m, cam, gt = single_scene(ob)
+    kat = gold["survey_kat"]["single"]
+    p = ob.preprocess(m, cam, gt)
+    assert p["count"] == 1
+    # key = 1 - ndc.z: SURVEY's value came from mixed f64/f32 numpy; allow 1 ulp of ndc.z (= 8 key ulps)
+    assert ulp_distance(hexes(p["keys"][:1])[0], kat["key"]) <= 8
+    s = ob.project(m, cam, gt, p["indices"][:1])[0]
+    assert abs(s["cx"] - kat["pixel_centre"][0]) < 0.01 and abs(s["cy"] - kat["pixel_centre"][1]) < 0.01
+    assert s["ext_x"] == kat["quad_half_extent"] and s["ext_y"] == kat["quad_half_extent"]  # both axes clamp at 1024
+    img, st = ob.render(m, cam, gt)
+    assert st["alive_pixels"] == 1024 * 1024  # covers the whole target
+    assert img[..., 0].min() > 0 and img[..., 1].max() == 0 and img[..., 2].max() == 0 and img[..., 3].min() == 255
+
+
+def test_survey_kat_model_ply(ob, gold):
+    gs, m, cam, gt = ply_scene(ob)
+    kat = gold["survey_kat"]["model_ply"]
+    p = ob.preprocess(m, cam, gt)
+    vis = p["indices"][: p["count"]].tolist()
+    assert vis == kat["visible"] and sorted(set(range(9)) - set(vis)) == kat["culled"]
+    keys = dict(zip(vis, hexes(p["keys"][: p["count"]])))
+    for k, v in kat["keys"].items():
+        assert ulp_distance(keys[int(k)], v) <= 128, (k, keys[int(k)], v)  # <= 2 ulp of ndc.z near 1.0
+    # tie structure: a 2-way and a 3-way tie
+    assert keys[1] == keys[5] and keys[3] == keys[6] == keys[8] and keys[2] not in (keys[1], keys[3])
+
+
+def test_oracle_regression_pins(ob, gold):
+    o = gold["oracle"]
+    m, cam, gt = single_scene(ob)
+    assert hexes(np.frombuffer(bytes(cam), dtype=np.uint32)) == o["single"]["camera_pod"]
+    p = ob.preprocess(m, cam, gt)
+    assert hexes(p["keys"][:1])[0] == o["single"]["key"]
+    assert p["draw_args"].tolist() == o["single"]["draw_args"] == [6, 1, 0, 0]
+    assert p["sort_args"].tolist() == o["single"]["sort_args"] == [1, 1, 1]
+    assert np.all(p["keys"][1:3840] == 2.0)  # post: pad to a whole 3840-key block
+    s = ob.project(m, cam, gt, p["indices"][:1])[0]
+    for k, v in o["single"]["splat"].items():
+        assert float(s[k]) == v, k
+    img, _ = ob.render(m, cam, gt)
+    assert [int(img[..., c].astype(np.int64).sum()) for c in range(4)] == o["single"]["image_sum_rgba"]
+    assert img[600, 600].tolist() == o["single"]["pixel_600_600"] and img[0, 0].tolist() == o["single"]["pixel_0_0"]
+
+    gs, m, cam, gt = ply_scene(ob)
+    assert gs["color"].tolist() == o["model_ply"]["colors"]
+    p = ob.preprocess(m, cam, gt)
+    V = p["count"]
+    assert V == o["model_ply"]["count"] and hexes(p["mask"]) == o["model_ply"]["mask"]
+    assert p["indices"][:V].tolist() == o["model_ply"]["indices_compacted"]
+    assert hexes(p["keys"][:V]) == o["model_ply"]["keys_compacted"]
+    sk, si = ob.radix_sort(p["keys"][:V].view(np.uint32), p["indices"][:V])
+    assert si.tolist() == o["model_ply"]["indices_sorted"] and hexes(sk) == o["model_ply"]["keys_sorted"]
+    img, st = ob.render(m, cam, gt)
+    assert [int(img[..., c].astype(np.int64).sum()) for c in range(4)] == o["model_ply"]["image_sum_rgba"]
+    assert st["alive_pixels"] == o["model_ply"]["alive_pixels"]
+    for k, v in o["strides"].items():
+        sh, cov = map(int, k.split(","))
+        assert ob.pod_stride(sh, cov) == v
+    for x, v in o["exp_neg_poly"].items():
+        assert hexes(np.array([ob.exp_neg_poly(float(x))], dtype=np.float32))[0] == v
+
+
+def test_exp_neg_poly_accuracy(ob):
+    xs = np.linspace(0, 12, 2001)
+    got = np.array([ob.exp_neg_poly(float(x)) for x in xs])
+    ref = np.exp(-xs.astype(np.float32).astype(np.float64))
+    assert np.max(np.abs(got - ref) / ref) < 2e-6
+
+
+def test_radix_sort_is_stable_lsd(ob):
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 2, 255, 256, 257, 3840, 50_000):
+        k = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        k[: n // 2] &= np.uint32(0xFFFF0000)
+        v = np.arange(n, dtype=np.uint32)
+        sk, sv = ob.radix_sort(k, v)
+        order = np.argsort(k, kind="stable")
+        assert np.array_equal(sk, k[order]) and np.array_equal(sv, v[order])
+
+
+@pytest.mark.parametrize("camera", ["outside", "inside"])
+def test_c_oracle_matches_numpy_twin(ob, sb, camera):
+    """Two independent statements of the arithmetic contract agree bit for bit (mask + keys)."""
+    from oracle import oracle_np
+    n = 40_000
+    g = sb.scenes.synthetic_gaussians(n, 17)
+    pods = ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE))
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE if camera == "outside" else sb.scenes.CAMERA_INSIDE
+    cam = ob.camera_pod(pos, yaw, pitch, 1280, 720)
+    q = np.array([0.2, -0.3, 0.1, 0.9], dtype=np.float32)
+    q /= np.linalg.norm(q)
+    mt = ob.model_transform_pod((0.5, -1.0, 2.0), tuple(q), (1.1, 0.9, 1.3))
+    gt = ob.gaussian_transform_pod(1.0, 0, 3, False, 3.0)
+    rng = np.random.default_rng(2)
+    sel = rng.integers(0, 2**32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32)
+    for selection, invert in ((None, 1), (sel, 1), (sel, 0)):
+        m = ob.OracleModel(pods, n, model_transform=mt, selection=selection, invert_selection=invert)
+        p = ob.preprocess(m, cam, gt)
+        cov3d = np.frombuffer(pods, dtype=np.float32).reshape(n, 56)[:, 49:55]
+        vis, keys, _ = oracle_np.preprocess(g["pos"], cov3d, cam, mt, gt, selection, invert)
+        idx = np.nonzero(vis)[0].astype(np.uint32)
+        assert p["count"] == len(idx)
+        assert np.array_equal(p["indices"][: p["count"]], idx)
+        assert np.array_equal(p["keys"][: p["count"]].view(np.uint32), keys[idx].view(np.uint32))
+        if camera == "inside":
+            assert 0 < len(idx) < n // 2
+
+
+def test_pad_and_args_semantics(ob, sb):
+    """post (preprocess.wesl:108-126): x = ceil(V/3840); keys [V, x*3840) = 2.0."""
+    n = 10_000
+    g = sb.scenes.synthetic_gaussians(n, 3)
+    m = ob.OracleModel(ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE)), n)
+    cam = ob.camera_pod(*sb.scenes.CAMERA_OUTSIDE, 640, 360)
+    p = ob.preprocess(m, cam, ob.gaussian_transform_pod())
+    V = p["count"]
+    assert p["draw_args"].tolist() == [6, V, 0, 0] and p["sort_args"].tolist() == [(V + 3839) // 3840, 1, 1]
+    assert np.all(p["keys"][V:(V + 3839) // 3840 * 3840] == 2.0)
+    assert np.all(p["keys"][:V] >= 0) and np.all(p["keys"][:V] <= 1)
+
+
+def test_selection_semantics(ob):
+    """invert = 1 (default): set bits are hidden; invert = 0: only set bits are shown."""
+    g = np.zeros(64, dtype=ob.GAUSSIAN_DTYPE)
+    g["pos"][:, 2] = 5.0
+    g["pos"][:, 0] = np.linspace(-1, 1, 64)
+    g["rot"][:, 3] = 1.0
+    g["scale"][:] = 0.01
+    g["color"][:] = 255
+    pods = ob.pack_gaussians(g)
+    cam = ob.camera_pod((0, 0, 0), 0.0, 0.0, 256, 256)
+    gt = ob.gaussian_transform_pod()
+    sel = np.array([0x0000FFFF, 0x80000001], dtype=np.uint32)
+    assert ob.preprocess(ob.OracleModel(pods, 64, selection=np.zeros(2, np.uint32), invert_selection=1), cam, gt)["count"] == 64
+    hid = ob.preprocess(ob.OracleModel(pods, 64, selection=sel, invert_selection=1), cam, gt)
+    assert hid["indices"][: hid["count"]].tolist() == [i for i in range(64) if not (sel[i // 32] >> (i % 32)) & 1]
+    only = ob.preprocess(ob.OracleModel(pods, 64, selection=sel, invert_selection=0), cam, gt)
+    assert only["indices"][: only["count"]].tolist() == [i for i in range(64) if (sel[i // 32] >> (i % 32)) & 1]
+
+
+def test_multi_model_order_matters(ob, sb):
+    """multi_model.rs:505-527: model k+1 is composited over model k (no depth merge)."""
+    def blob(color, z):
+        g = np.zeros(1, dtype=ob.GAUSSIAN_DTYPE)
+        g["pos"][0] = (0, 0, z); g["rot"][0] = (0, 0, 0, 1); g["scale"][0] = (0.3, 0.3, 0.3); g["color"][0] = color
+        return ob.OracleModel(ob.pack_gaussians(g), 1)
+    red, green = blob((255, 0, 0, 255), 3.0), blob((0, 255, 0, 255), 6.0)
+    cam = ob.camera_pod((0, 0, 0), 0.0, 0.0, 128, 128)
+    gt = ob.gaussian_transform_pod()
+    a, _ = ob.render([red, green], cam, gt)
+    b, _ = ob.render([green, red], cam, gt)
+    c = 64
+    assert a[c, c, 1] > a[c, c, 0]      # green drawn last wins although it is farther away
+    assert b[c, c, 0] > b[c, c, 1]

@@ -1,0 +1,113 @@
+"""The reference's own e2e tests (tests/e2e/viewer.rs, multi_model.rs, selection.rs) restated
+through the C ABI: presence/absence assertions on the rendered target."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+W = H = 1024  # tests/common/given.rs:22-37
+
+
+def given_camera(sb):
+    return sb.camera_pod((0, 0, 0), 0.1, 0.1, W, H)  # tests/common/given.rs:6-20
+
+
+def render(sb, ctx, g, *, transform=None, gt=None, pod_path=False):
+    import torch
+    v = sb.Viewer(ctx, gaussians=g)
+    cam = given_camera(sb)
+    if pod_path:
+        v.update_camera_with_pod(cam)
+    else:
+        v.update_camera((0, 0, 0), 0.1, 0.1, W, H)
+    if transform:
+        v.update_model_transform(*transform)
+    if gt:
+        v.update_gaussian_transform(*gt)
+    t = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    v.render(t, W, H)
+    torch.cuda.synchronize()
+    out = t.cpu().numpy()
+    v.close()
+    return out
+
+
+def sums(img):
+    return [(img[..., c] > 0).sum() for c in range(4)]
+
+
+def test_viewer_render_red_gaussian(sb, ctx):  # tests/e2e/viewer.rs:70-95
+    r, g, b, a = sums(render(sb, ctx, sb.scenes.single_red_gaussian()))
+    assert r > 1 and g < 1 and b < 1 and a > 1
+
+
+def test_viewer_pod_and_non_pod_paths_equal(sb, ctx):  # tests/e2e/viewer.rs:39-68
+    a = render(sb, ctx, sb.scenes.single_red_gaussian(), pod_path=True)
+    b = render(sb, ctx, sb.scenes.single_red_gaussian(), pod_path=False)
+    assert np.array_equal(a, b)
+
+
+def test_viewer_no_sh0_renders_grey(sb, ctx):  # tests/e2e/viewer.rs:97-124
+    r, g, b, a = sums(render(sb, ctx, sb.scenes.single_red_gaussian(), gt=(1.0, 0, 3, True, 3.0)))
+    assert r > 1 and g > 1 and b > 1 and a > 1
+
+
+def test_viewer_model_behind_camera_draws_nothing(sb, ctx):  # tests/e2e/viewer.rs:149-182
+    img = render(sb, ctx, sb.scenes.single_red_gaussian(), transform=((0, 0, -2), (0, 0, 0, 1), (1, 1, 1)))
+    r, g, b, a = sums(img)
+    assert r == 0 and g == 0 and b == 0
+
+
+def test_gaussians_buffer_size(sb, ctx):  # tests/e2e/multi_model.rs:43-53
+    g = sb.scenes.synthetic_gaussians(100, 1)
+    v = sb.Viewer(ctx, gaussians=g)
+    assert v.device_pointers()["gaussians"][1] == 100 * sb.pod_stride(0, 0) == 100 * 224
+    ptrs = v.device_pointers()
+    assert ptrs["indirect_args"][1] == 16 and ptrs["radix_sort_indirect_args"][1] == 12  # tests/buffer/indirect_args.rs
+    assert ptrs["indirect_indices"][1] == 100 * 4
+    v.close()
+
+
+def test_multi_model_red_and_green(sb, ctx):  # tests/e2e/multi_model.rs:100-154, 330-373
+    import torch
+    red = sb.scenes.single_red_gaussian()
+    green = red.copy()
+    green["color"][0] = (0, 255, 0, 255)
+    green["pos"][0] = (0.5, 0, 1)
+    green["scale"][0] = (0.05, 0.05, 0.05)
+    red["scale"][0] = (0.05, 0.05, 0.05)
+    mm = sb.MultiModelViewer(ctx)
+    mm.update_camera_with_pod(given_camera(sb))
+    mm.insert_model(1, sb.pack_gaussians(red), 1)
+    mm.insert_model(2, sb.pack_gaussians(green), 1)
+    t = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    mm.render(t, W, H, [1, 2])
+    torch.cuda.synchronize()
+    r, g, b, a = sums(t.cpu().numpy())
+    assert r > 1 and g > 1 and b < 1
+    mm.remove_model(2)
+    mm.render(t, W, H, [1])
+    torch.cuda.synchronize()
+    r, g, b, a = sums(t.cpu().numpy())
+    assert r > 1 and g < 1
+    mm.close()
+
+
+def test_selection_default_invert_hides_nothing(sb, ctx):  # src/selection/buffer.rs:157-165
+    import torch
+    v = sb.Viewer(ctx, gaussians=sb.scenes.single_red_gaussian())
+    v.update_camera_with_pod(given_camera(sb))
+    v.enable_selection(True)  # empty mask, invert = 1 (default)
+    t = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    v.render(t, W, H)
+    torch.cuda.synchronize()
+    assert sums(t.cpu().numpy())[0] > 1
+    v.set_selection(np.array([1], dtype=np.uint32))  # selected + inverted => hidden
+    v.render(t, W, H)
+    torch.cuda.synchronize()
+    assert sums(t.cpu().numpy())[0] == 0
+    v.set_invert_selection(False)  # show only selected
+    v.render(t, W, H)
+    torch.cuda.synchronize()
+    assert sums(t.cpu().numpy())[0] > 1
+    v.close()

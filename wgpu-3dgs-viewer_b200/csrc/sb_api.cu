@@ -3,6 +3,7 @@
 // Mirrors the reference's object model (src/lib.rs:65-276, src/multi_model.rs:291-531): a Viewer
 // owns the 8 public buffers and chains preprocess -> sort -> render; nothing here synchronises
 // with the device except the explicit read_* helpers.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -136,6 +137,8 @@ struct SbViewer {
     DeviceBuf internal_target;
     uint64_t dup_capacity = 0;
     uint32_t tile_capacity = 0;
+    volatile uint32_t* h_needed = nullptr;  // mapped pinned: duplicates the last binned frame needed
+    uint32_t* d_needed = nullptr;
 
     SbCameraPod camera;
     SbModelTransformPod model_transform;
@@ -179,6 +182,13 @@ SbStatus viewer_alloc(SbViewer* v) {
     const size_t scan_tiles = ((size_t)n + 1023) / 1024 + 2;
     SB_CUDA(ctx, v->bin_state.alloc(32 + scan_tiles * sizeof(unsigned long long)));
     SB_CUDA(ctx, cudaMemset(v->bin_state.p, 0, v->bin_state.bytes));
+    void* hp = nullptr;
+    SB_CUDA(ctx, cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+    std::memset(hp, 0, 64);
+    v->h_needed = static_cast<volatile uint32_t*>(hp);
+    void* dp = nullptr;
+    SB_CUDA(ctx, cudaHostGetDevicePointer(&dp, hp, 0));
+    v->d_needed = static_cast<uint32_t*>(dp);
     return SB_OK;
 }
 
@@ -286,6 +296,18 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     SbStatus s = check_target(v, target, p.u);
     if (s != SB_OK) return s;
     const uint32_t tiles = p.u.tiles_x * p.u.tiles_y;
+    // Capacity policy: a previous frame reported (through a mapped pinned word, no
+    // sync) how many (splat,tile) duplicates it needed; grow before enqueuing this frame.  The
+    // frame that overflowed dropped its nearest splats and is flagged by read_frame_stats.
+    const uint64_t want = std::max<uint64_t>(8ull * v->n + 128ull * tiles + (1ull << 20), (uint64_t)*v->h_needed * 3 / 2);
+    if (*v->h_needed > v->dup_capacity || (v->tile_capacity == 0 && want > v->dup_capacity) || tiles > v->tile_capacity) {
+        SB_CUDA(v->ctx, cudaStreamSynchronize(stream));
+        if (want > v->dup_capacity) {
+            SbStatus gs = viewer_reserve(v, want);
+            if (gs != SB_OK) return gs;
+        }
+        *v->h_needed = 0;
+    }
     if (tiles > v->tile_capacity) {
         SB_CUDA(v->ctx, cudaStreamSynchronize(stream));
         SB_CUDA(v->ctx, v->tile_ranges.alloc((size_t)tiles * 8));
@@ -301,6 +323,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.buf.tile_ranges = v->tile_ranges.as<uint32_t>();
     p.buf.dup_count = v->d_dup_count();
     p.buf.overflow = v->d_overflow();
+    p.buf.needed_host = v->d_needed;
     p.buf.scan_counter = v->d_scan_counter();
     p.buf.scan_status = v->d_scan_status();
     p.buf.tile_recs = v->tile_recs.as<sb::SplatRec>();
@@ -395,6 +418,7 @@ void sb_viewer_destroy(SbViewer* v) {
                          &v->sort_vals_alt, &v->sort_internal, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
                          &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target})
         b->release();
+    if (v->h_needed) cudaFreeHost(const_cast<uint32_t*>(v->h_needed));
     for (cudaEvent_t e : v->ev)
         if (e) cudaEventDestroy(e);
     delete v;

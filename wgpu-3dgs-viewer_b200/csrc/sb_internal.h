@@ -52,6 +52,7 @@ struct RasterBuffers {
     uint32_t* tile_ranges;    // [tiles*2] begin,end into dup arrays
     uint32_t* dup_count;      // D (device)
     uint32_t* overflow;       // flag
+    uint32_t* needed_host;    // device alias of a mapped pinned word (may be null)
     unsigned long long* scan_status;
     uint32_t* scan_counter;
     SplatRec* tile_recs;      // [dup_capacity] records gathered in tile order (TMA staging source)

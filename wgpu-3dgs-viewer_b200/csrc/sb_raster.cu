@@ -31,6 +31,7 @@ struct BinParams {
     uint32_t* dup_vals;
     uint32_t* dup_count;
     uint32_t* overflow;
+    uint32_t* needed_host;  // mapped pinned word: duplicates this frame needs (read by the next render call)
     unsigned long long* scan_status;
     uint32_t* scan_counter;
     uint32_t dup_capacity;
@@ -105,10 +106,12 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     const uint32_t last_tile = v == 0 ? 0 : (v - 1) / kScanTile;
     if (tile == last_tile && tid == 0) {
         const uint32_t d = s_base + total;
+        if (p.needed_host) *p.needed_host = d;
         if (d > p.dup_capacity) {
             *p.overflow = 1u;
             *p.dup_count = p.dup_capacity;
         } else {
+            *p.overflow = 0u;
             *p.dup_count = d;
         }
     }
@@ -390,6 +393,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     bp.dup_vals = p.buf.dup_vals;
     bp.dup_count = p.buf.dup_count;
     bp.overflow = p.buf.overflow;
+    bp.needed_host = p.buf.needed_host;
     bp.scan_status = p.buf.scan_status;
     bp.scan_counter = p.buf.scan_counter;
     bp.dup_capacity = (uint32_t)p.buf.dup_capacity;

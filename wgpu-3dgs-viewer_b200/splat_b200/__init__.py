@@ -13,4 +13,4 @@ from .api import (  # noqa: F401
     build, camera_pod, gaussian_transform_pod, lib_path, load, model_transform_pod, pack_gaussians,
     pod_stride, read_ply, padded_key_count, keys_buffer_size_bytes, EXPORTED_SYMBOLS,
 )
-from . import scenes  # noqa: F401
+from . import scenes, sharding  # noqa: F401
