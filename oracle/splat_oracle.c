@@ -500,7 +500,8 @@ void so_radix_sort(uint32_t* keys, uint32_t* payload, uint32_t count) {
 
 /* ------------------------------------------------------------------ vertex stage (render.wesl:58-130) */
 
-/* utils.wesl:82-135 */
+/* utils.wesl:82-135.  Contract: the polynomial is evaluated as one fma chain per degree (WGSL
+ * allows contraction); the basis factors are plain individually rounded products. */
 static void view_color(const Uniforms* u, const uint8_t* pod, int sh_fmt, const float dir[3], float rgba[4]) {
     const float sh_c1 = 0.4886025f;
     const float sh_c2[5] = { 1.0925484f, -1.0925484f, 0.3153916f, -1.0925484f, 0.5462742f };
@@ -510,25 +511,26 @@ static void view_color(const Uniforms* u, const uint8_t* pod, int sh_fmt, const 
     for (int c = 0; c < 4; c++) col[c] = (float)pod[12 + c] / 255.0f; /* unpack4x8unorm */
     float sh[45];
     unpack_sh(pod, sh_fmt, sh);
+    float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    float b2[5] = { sh_c2[0] * xy, sh_c2[1] * yz, sh_c2[2] * ((2.0f * zz - xx) - yy), sh_c2[3] * xz, sh_c2[4] * (xx - yy) };
+    float b3[7] = { sh_c3[0] * y * (3.0f * xx - yy), sh_c3[1] * xy * z, sh_c3[2] * y * ((4.0f * zz - xx) - yy),
+                    sh_c3[3] * z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy), sh_c3[4] * x * ((4.0f * zz - xx) - yy),
+                    sh_c3[5] * z * (xx - yy), sh_c3[6] * x * (xx - 3.0f * yy) };
     for (int c = 0; c < 3; c++) {
         float result = u->no_sh0 ? 0.5f : col[c];
         #define SH(i) sh[(i) * 3 + c]
         if (u->sh_deg >= 1 && sh_fmt != SO_SH_NONE) {
-            result += sh_c1 * ((-SH(0) * y + SH(1) * z) - SH(2) * x);
+            float t = fmaf(SH(1), z, -(SH(0) * y));          /* -sh0*y + sh1*z */
+            t = fmaf(-SH(2), x, t);                          /* ... - sh2*x */
+            result = fmaf(sh_c1, t, result);
             if (u->sh_deg >= 2) {
-                float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                result += (((sh_c2[0] * xy * SH(3) + sh_c2[1] * yz * SH(4)) +
-                            sh_c2[2] * ((2.0f * zz - xx) - yy) * SH(5)) +
-                           sh_c2[3] * xz * SH(6)) +
-                          sh_c2[4] * (xx - yy) * SH(7);
+                float acc = b2[0] * SH(3);
+                for (int k = 1; k < 5; k++) acc = fmaf(b2[k], SH(3 + k), acc);
+                result = result + acc;
                 if (u->sh_deg >= 3) {
-                    result += (((((sh_c3[0] * y * (3.0f * xx - yy) * SH(8) +
-                                   sh_c3[1] * xy * z * SH(9)) +
-                                  sh_c3[2] * y * ((4.0f * zz - xx) - yy) * SH(10)) +
-                                 sh_c3[3] * z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy) * SH(11)) +
-                                sh_c3[4] * x * ((4.0f * zz - xx) - yy) * SH(12)) +
-                               sh_c3[5] * z * (xx - yy) * SH(13)) +
-                              sh_c3[6] * x * (xx - 3.0f * yy) * SH(14);
+                    acc = b3[0] * SH(8);
+                    for (int k = 1; k < 7; k++) acc = fmaf(b3[k], SH(8 + k), acc);
+                    result = result + acc;
                 }
             }
         }
@@ -553,8 +555,9 @@ static void project_one(const Uniforms* u, const SoModel* model, uint32_t index,
     float md[3];
     for (int i = 0; i < 3; i++)
         md[i] = (u->inv_sr.c[0][i] * vd[0] + u->inv_sr.c[1][i] * vd[1]) + u->inv_sr.c[2][i] * vd[2];
-    float ml = sqrtf((md[0] * md[0] + md[1] * md[1]) + md[2] * md[2]);
-    float dir[3] = { -(md[0] / ml), -(md[1] / ml), -(md[2] / ml) };
+    /* -normalize(v): contract = v * (1 / length(v)) */
+    float inv_ml = 1.0f / sqrtf((md[0] * md[0] + md[1] * md[1]) + md[2] * md[2]);
+    float dir[3] = { -(md[0] * inv_ml), -(md[1] * inv_ml), -(md[2] * inv_ml) };
     float rgba[4];
     view_color(u, pod, model->sh_fmt, dir, rgba);
     s->r = rgba[0]; s->g = rgba[1]; s->b = rgba[2]; s->a = rgba[3];
@@ -740,6 +743,20 @@ void so_render(const SoModel* models, uint32_t n_models, const SoCameraPod* cam,
     }
     if (stats) *stats = st;
     free(acc);
+}
+
+/* Number of bytes x for which the product's division-free x/255 (one Newton step, fmaf) differs
+ * from the correctly rounded x / 255.0f.  Must be 0: lets the kernel avoid the IEEE div sequence. */
+int so_unorm8_newton_mismatches(void) {
+    int bad = 0;
+    for (int x = 0; x < 256; x++) {
+        float fx = (float)x;
+        float q = fx * 0.00392156886f;
+        float r = fmaf(-q, 255.0f, fx);
+        float y = fmaf(r, 0.00392156886f, q);
+        if (y != fx / 255.0f) bad++;
+    }
+    return bad;
 }
 
 /* ------------------------------------------------------------------ viewport selection (f1) */

@@ -147,6 +147,7 @@ void so_select_rect(const SoModel* model, const SoCameraPod* cam,
                     float x0, float y0, float x1, float y1, uint32_t* dest);
 
 int so_max_threads(void);
+int so_unorm8_newton_mismatches(void);
 
 #ifdef __cplusplus
 }

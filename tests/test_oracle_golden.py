@@ -190,3 +190,8 @@ def test_multi_model_order_matters(ob, sb):
     c = 64
     assert a[c, c, 1] > a[c, c, 0]      # green drawn last wins although it is farther away
     assert b[c, c, 0] > b[c, c, 1]
+
+
+def test_unorm8_newton_identity(ob):
+    """The kernel's division-free u8/255 is exact for every byte (see sb_preprocess.cu: unorm8)."""
+    assert ob.lib().so_unorm8_newton_mismatches() == 0

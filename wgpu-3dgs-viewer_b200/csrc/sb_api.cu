@@ -130,7 +130,7 @@ struct SbViewer {
 
     const void* d_gaussians = nullptr;  // owned (gaussians_owned) or adopted
     DeviceBuf gaussians_owned;
-    DeviceBuf indices, keys, args, recs, pre_scratch;
+    DeviceBuf indices, keys, args, recs, tboxes, pre_scratch;
     DeviceBuf sort_keys_alt, sort_vals_alt, sort_internal;
     DeviceBuf dup_offsets, dup_keys, dup_vals, tile_recs, tile_ranges, bin_state;
     DeviceBuf selection;
@@ -169,6 +169,7 @@ SbStatus viewer_alloc(SbViewer* v) {
     SB_CUDA(ctx, v->keys.alloc((size_t)(v->padded ? v->padded : 1) * 4));
     SB_CUDA(ctx, v->args.alloc(64));
     SB_CUDA(ctx, v->recs.alloc((size_t)(n ? n : 1) * sizeof(sb::SplatRec)));
+    SB_CUDA(ctx, v->tboxes.alloc((size_t)(n ? n : 1) * sizeof(sb::TileBox)));
     SB_CUDA(ctx, v->pre_scratch.alloc(sb::preprocess_scratch_bytes(n, v->sh_fmt, v->cov_fmt)));
     SB_CUDA(ctx, v->selection.alloc(((size_t)n + 31) / 32 * 4 + 4));
     SB_CUDA(ctx, cudaMemset(v->selection.p, 0, v->selection.bytes));
@@ -263,6 +264,7 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.draw_args = v->d_draw();
     p.sort_args = v->d_dispatch();
     p.recs = v->recs.as<sb::SplatRec>();
+    p.tboxes = v->tboxes.as<sb::TileBox>();
     p.visible_count = v->d_visible();
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
     if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[0], stream));
@@ -314,6 +316,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
         v->tile_capacity = tiles;
     }
     p.recs = v->recs.as<sb::SplatRec>();
+    p.tboxes = v->tboxes.as<sb::TileBox>();
     p.sorted_indices = v->indices.as<uint32_t>();
     p.visible_count = v->d_visible();
     p.max_visible = v->n;
@@ -414,7 +417,7 @@ SbStatus sb_viewer_create_from_device(SbContext* ctx, int32_t sh_fmt, int32_t co
 
 void sb_viewer_destroy(SbViewer* v) {
     if (!v) return;
-    for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->pre_scratch, &v->sort_keys_alt,
+    for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->tboxes, &v->pre_scratch, &v->sort_keys_alt,
                          &v->sort_vals_alt, &v->sort_internal, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
                          &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target})
         b->release();

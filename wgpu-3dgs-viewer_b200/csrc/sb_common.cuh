@@ -39,10 +39,14 @@ struct __align__(16) SplatRec {
     float cx, cy;   // pixel-space centre
     float ax, ay;   // quad_offset.x = dx*ax + dy*ay
     float bx, by;   // quad_offset.y = dx*bx + dy*by
+    float ex, ey;   // half extent (pixels) of the alive region: used for warp-level culling
     float r, g;     // colour * color_scale
     float b, a;
-    uint32_t tmin;  // tile bbox: x0 | y0 << 16   (tmin > tmax component-wise => no tiles)
-    uint32_t tmax;  // x1 | y1 << 16
+};
+// Tile bbox of a splat, kept in a separate 8-byte array so the binning gathers (random, in depth
+// order) stay L2-resident: x0 | y0 << 16, x1 | y1 << 16; min > max component-wise => no tiles.
+struct __align__(8) TileBox {
+    uint32_t tmin, tmax;
 };
 static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
 
@@ -72,6 +76,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

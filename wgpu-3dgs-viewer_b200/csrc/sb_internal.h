@@ -18,6 +18,7 @@ struct PreParams {
     SbDrawIndirectArgs* draw_args;     // IndirectArgsBuffer
     SbDispatchIndirectArgs* sort_args; // RadixSortIndirectArgsBuffer
     SplatRec* recs;                    // per-Gaussian projected record (indexed by Gaussian index)
+    TileBox* tboxes;                   // per-Gaussian tile bbox
     uint32_t* tile_counter;            // dynamic tile ticket (zeroed before launch)
     unsigned long long* tile_status;   // decoupled look-back state (zeroed before launch)
     uint32_t* visible_count;           // V for downstream kernels
@@ -61,6 +62,7 @@ struct RasterBuffers {
 
 struct RasterParams {
     const SplatRec* recs;            // indexed by Gaussian index
+    const TileBox* tboxes;
     const uint32_t* sorted_indices;  // depth order
     const uint32_t* visible_count;
     uint32_t max_visible;            // n

@@ -11,6 +11,9 @@
 // handed out by a global ticket so the visible-splat compaction can be ORDER PRESERVING
 // (decoupled look-back over per-tile visible counts): slot order == ascending Gaussian index,
 // the canonical order of the reference's racy atomicAdd compaction.
+// The CTA-wide scan uses SPLIT-PHASE mbarriers (arrive right after the cull decision, wait
+// only after the per-splat vertex work), so no warp ever blocks on bar.sync: round-1 ncu showed
+// 53% of issue stalls on the two blocking barriers this replaces.
 //
 // Bit-exact artefacts (visible mask, count, keys, indirect args) use strict f32 intrinsics
 // (__fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn) in the order fixed by the oracle contract.
@@ -27,9 +30,9 @@ __host__ __device__ constexpr int cov_bytes(int cov) { return cov == SB_COV_SING
 __host__ __device__ constexpr int pod_stride(int sh, int cov) { return (16 + sh_bytes(sh) + cov_bytes(cov) + 15) & ~15; }
 
 // Consumer threads per CTA (= pods per tile) and ring depth, chosen so the ring fits 227 KB.
-__host__ __device__ constexpr int tile_records(int stride) { return stride > 160 ? 384 : 512; }
+__host__ __device__ constexpr int tile_records(int) { return 512; }
 __host__ __device__ constexpr int ring_stages(int stride) {
-    int s = (200 * 1024) / (tile_records(stride) * stride);
+    int s = (226 * 1024) / (tile_records(stride) * stride);
     return s < 2 ? 2 : (s > 4 ? 4 : s);
 }
 
@@ -143,6 +146,15 @@ __device__ __forceinline__ bool cull(float x, float y, float z) {
     return !((x >= -1.0f && y >= -1.0f && z >= 0.0f) && (x <= 1.0f && y <= 1.0f && z <= 1.0f));
 }
 
+// u8 / 255 correctly rounded without the IEEE-division sequence: one Newton step on x * (1/255)
+// (the identity is verified exhaustively for x = 0..255 by so_unorm8_newton_mismatches(), tests/test_oracle_golden.py).
+__device__ __forceinline__ float unorm8(uint32_t x) {
+    const float fx = (float)x;
+    const float q = __fmul_rn(fx, 0.00392156886f);
+    const float r = __fmaf_rn(-q, 255.0f, fx);
+    return __fmaf_rn(r, 0.00392156886f, q);
+}
+
 // gaussian_unpack_sh(g, i) for i in 0..14 -> rgb
 template <int SH>
 __device__ __forceinline__ void unpack_sh(const uint8_t* rec, int i, float& r, float& g, float& b, float mn, float mx) {
@@ -155,14 +167,17 @@ __device__ __forceinline__ void unpack_sh(const uint8_t* rec, int i, float& r, f
         r = half_bits_to_float(h[i * 3 + 0]); g = half_bits_to_float(h[i * 3 + 1]); b = half_bits_to_float(h[i * 3 + 2]);
     } else if constexpr (SH == SB_SH_NORM8) {
         const uint8_t* c = q + 4;
-        float tr = (float)c[i * 3 + 0] / 255.0f, tg = (float)c[i * 3 + 1] / 255.0f, tb = (float)c[i * 3 + 2] / 255.0f;
-        r = mn * (1.0f - tr) + mx * tr; g = mn * (1.0f - tg) + mx * tg; b = mn * (1.0f - tb) + mx * tb;
+        const float tr = unorm8(c[i * 3 + 0]), tg = unorm8(c[i * 3 + 1]), tb = unorm8(c[i * 3 + 2]);
+        r = sadd(smul(mn, ssub(1.0f, tr)), smul(mx, tr));
+        g = sadd(smul(mn, ssub(1.0f, tg)), smul(mx, tg));
+        b = sadd(smul(mn, ssub(1.0f, tb)), smul(mx, tb));
     } else {
         r = g = b = 0.0f;
     }
 }
 
-// view_color (utils.wesl:82-135); evaluation order follows the WGSL text.
+// view_color (utils.wesl:82-135).  Contract (matches the oracle bit for bit): basis factors are
+// individually rounded products, each degree's sum is one fma chain.
 template <int SH>
 __device__ __forceinline__ void view_color(const Uniforms& u, const uint8_t* rec, uint32_t packed_color, float x, float y,
                                            float z, float rgb[3]) {
@@ -172,7 +187,7 @@ __device__ __forceinline__ void view_color(const Uniforms& u, const uint8_t* rec
                 c3_5 = 1.4453057f, c3_6 = -0.5900436f;
     float res[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) res[c] = u.no_sh0 ? 0.5f : __fdiv_rn((float)((packed_color >> (8 * c)) & 255u), 255.0f);
+    for (int c = 0; c < 3; c++) res[c] = u.no_sh0 ? 0.5f : unorm8((packed_color >> (8 * c)) & 255u);
     if (SH != SB_SH_NONE && u.sh_deg >= 1) {
         float mn = 0.0f, mx = 0.0f;
         if constexpr (SH == SB_SH_NORM8) {
@@ -184,23 +199,44 @@ __device__ __forceinline__ void view_color(const Uniforms& u, const uint8_t* rec
 #pragma unroll
         for (int i = 0; i < 15; i++) unpack_sh<SH>(rec, i, s[i][0], s[i][1], s[i][2], mn, mx);
 #pragma unroll
-        for (int c = 0; c < 3; c++) res[c] += sh_c1 * ((-s[0][c] * y + s[1][c] * z) - s[2][c] * x);
+        for (int c = 0; c < 3; c++) {
+            float t = __fmaf_rn(s[1][c], z, -smul(s[0][c], y));
+            t = __fmaf_rn(-s[2][c], x, t);
+            res[c] = __fmaf_rn(sh_c1, t, res[c]);
+        }
         if (u.sh_deg >= 2) {
-            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const float xx = smul(x, x), yy = smul(y, y), zz = smul(z, z), xy = smul(x, y), yz = smul(y, z), xz = smul(x, z);
+            const float b0 = smul(c2_0, xy), b1 = smul(c2_1, yz), b2 = smul(c2_2, ssub(ssub(smul(2.0f, zz), xx), yy)),
+                        b3 = smul(c2_3, xz), b4 = smul(c2_4, ssub(xx, yy));
 #pragma unroll
-            for (int c = 0; c < 3; c++)
-                res[c] += (((c2_0 * xy * s[3][c] + c2_1 * yz * s[4][c]) + c2_2 * ((2.0f * zz - xx) - yy) * s[5][c]) +
-                           c2_3 * xz * s[6][c]) +
-                          c2_4 * (xx - yy) * s[7][c];
+            for (int c = 0; c < 3; c++) {
+                float acc = smul(b0, s[3][c]);
+                acc = __fmaf_rn(b1, s[4][c], acc);
+                acc = __fmaf_rn(b2, s[5][c], acc);
+                acc = __fmaf_rn(b3, s[6][c], acc);
+                acc = __fmaf_rn(b4, s[7][c], acc);
+                res[c] = sadd(res[c], acc);
+            }
             if (u.sh_deg >= 3) {
+                const float zz4 = ssub(ssub(smul(4.0f, zz), xx), yy);
+                const float d0 = smul(smul(c3_0, y), ssub(smul(3.0f, xx), yy));
+                const float d1 = smul(smul(c3_1, xy), z);
+                const float d2 = smul(smul(c3_2, y), zz4);
+                const float d3 = smul(smul(c3_3, z), ssub(ssub(smul(2.0f, zz), smul(3.0f, xx)), smul(3.0f, yy)));
+                const float d4 = smul(smul(c3_4, x), zz4);
+                const float d5 = smul(smul(c3_5, z), ssub(xx, yy));
+                const float d6 = smul(smul(c3_6, x), ssub(xx, smul(3.0f, yy)));
 #pragma unroll
-                for (int c = 0; c < 3; c++)
-                    res[c] += (((((c3_0 * y * (3.0f * xx - yy) * s[8][c] + c3_1 * xy * z * s[9][c]) +
-                                  c3_2 * y * ((4.0f * zz - xx) - yy) * s[10][c]) +
-                                 c3_3 * z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy) * s[11][c]) +
-                                c3_4 * x * ((4.0f * zz - xx) - yy) * s[12][c]) +
-                               c3_5 * z * (xx - yy) * s[13][c]) +
-                              c3_6 * x * (xx - 3.0f * yy) * s[14][c];
+                for (int c = 0; c < 3; c++) {
+                    float acc = smul(d0, s[8][c]);
+                    acc = __fmaf_rn(d1, s[9][c], acc);
+                    acc = __fmaf_rn(d2, s[10][c], acc);
+                    acc = __fmaf_rn(d3, s[11][c], acc);
+                    acc = __fmaf_rn(d4, s[12][c], acc);
+                    acc = __fmaf_rn(d5, s[13][c], acc);
+                    acc = __fmaf_rn(d6, s[14][c], acc);
+                    res[c] = sadd(res[c], acc);
+                }
             }
         }
     }
@@ -231,7 +267,7 @@ __device__ __forceinline__ bool finite4(float a, float b, float c, float d) {
 }
 
 template <int SH, int COV>
-__global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
+__global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
     preprocess_kernel(const __grid_constant__ PreParams p) {
     constexpr int STRIDE = pod_stride(SH, COV);
     constexpr int T = tile_records(STRIDE);
@@ -239,54 +275,182 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
     constexpr int NW = T / 32;
     constexpr uint32_t STAGE_BYTES = T * STRIDE;
 
+    constexpr int R = 8;  // ring depth of the scan state (counts / base), > maximum warp drift
+
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + S;
-    uint32_t* tile_id = reinterpret_cast<uint32_t*>(empty_bar + S);
-    uint32_t* warp_counts = tile_id + S;   // NW
-    uint32_t* bcast = warp_counts + NW;    // [0] tile base, [1] tile total
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);  // [S][NW] chunk landed (TMA)
+    uint64_t* empty_bar = full_bar + S * NW;                                     // [S][NW] chunk consumed
+    uint64_t* counted_bar = empty_bar + S * NW;                                  // [R] all warp counts written
+    uint64_t* based_bar = counted_bar + R;                                       // [R] tile base known
+    uint32_t* tile_id = reinterpret_cast<uint32_t*>(based_bar + R);              // [S]
+    uint32_t* tile_base = tile_id + S;                                           // [R]
+    uint32_t* warp_counts = tile_base + R;                                       // [R][NW]
+    uint32_t* ring_tile = warp_counts + R * NW;                                  // [R] tile of a ring slot (0xffffffff = end)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5, lane = tid & 31u;
     const Uniforms& u = p.u;
 
     if (tid == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], NW);
+        for (int i = 0; i < S * NW; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < R; i++) {
+            mbar_init(&counted_bar[i], NW);
+            mbar_init(&based_bar[i], 1);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
     if (warp == NW) {
-        // ---------------- producer warp: ticket -> TMA bulk copy of one tile of pods
+        // ---------------- producer warp: ticket -> one TMA bulk copy per warp chunk (32 pods).
+        // The ticket is taken only once the first chunk slot of the stage is free, so a ticketed
+        // tile starts loading at once (successor tiles look back on its aggregate).  Chunks are
+        // refilled as soon as their own warp has released them: ~NW copies in flight per SM.
         if (lane == 0) {
             for (uint32_t it = 0;; ++it) {
                 const uint32_t s = it % S, ph = (it / S) & 1u;
+                mbar_wait(&empty_bar[s * NW], ph ^ 1u);
                 const uint32_t tile = atomicAdd(p.tile_counter, 1u);
-                mbar_wait(&empty_bar[s], ph ^ 1u);
                 tile_id[s] = tile;
                 if (tile >= p.num_tiles) {
-                    mbar_arrive(&full_bar[s]);
+                    for (int w = 0; w < NW; w++) mbar_arrive(&full_bar[s * NW + w]);
                     break;
                 }
                 const uint32_t first = tile * T;
                 const uint32_t cnt = min((uint32_t)T, p.n - first);
-                const uint32_t bytes = cnt * STRIDE;
-                mbar_arrive_expect_tx(&full_bar[s], bytes);
-                bulk_g2s(smem + s * STAGE_BYTES, p.gaussians + (size_t)first * STRIDE, bytes, &full_bar[s]);
+                const uint8_t* src = p.gaussians + (size_t)first * STRIDE;
+                uint8_t* dst = smem + s * STAGE_BYTES;
+                for (int w = 0; w < NW; w++) {
+                    if (w > 0) mbar_wait(&empty_bar[s * NW + w], ph ^ 1u);
+                    const uint32_t lo = min(cnt, (uint32_t)w * 32u), hi = min(cnt, (uint32_t)w * 32u + 32u);
+                    const uint32_t bytes = (hi - lo) * STRIDE;
+                    if (bytes == 0) {
+                        mbar_arrive(&full_bar[s * NW + w]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[s * NW + w], bytes);
+                        bulk_g2s(dst + (size_t)lo * STRIDE, src + (size_t)lo * STRIDE, bytes, &full_bar[s * NW + w]);
+                    }
+                }
             }
         }
         return;
     }
 
-    // ---------------- consumers: one Gaussian per thread per tile
+    if (warp == NW + 1) {
+        // ---------------- scan warp: publishes tile aggregates the moment a tile is counted and
+        // resolves the decoupled look-backs opportunistically.  Neither ever blocks the other (or the
+        // consumers): a blocking look-back in a consumer warp convoys every SM, because a tile's
+        // aggregate would be published only after its predecessor's look-back had finished.
+        uint32_t pub_it = 0, res_it = 0, acc = 0, my_agg = 0;
+        int win = -2;  // -2: look-back of tile res_it not started
+        bool pub_done = false;
+        for (;;) {
+            if (!pub_done && mbar_try_wait(&counted_bar[pub_it % R], (pub_it / R) & 1u)) {
+                const uint32_t ring = pub_it % R;
+                const uint32_t tile = ring_tile[ring];
+                if (tile == 0xffffffffu) {
+                    pub_done = true;
+                } else {
+                    uint32_t c = lane < NW ? warp_counts[ring * NW + lane] : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    if (lane == 0) st_relaxed_u64(&p.tile_status[tile], (tile == 0 ? kFlagPrefix : kFlagAggregate) | c);
+                    ++pub_it;
+                }
+            }
+            if (res_it < pub_it) {
+                const uint32_t ring = res_it % R;
+                const uint32_t tile = ring_tile[ring];
+                bool resolved = false;
+                if (win == -2) {
+                    acc = 0;
+                    win = (int)tile - 1;
+                    uint32_t c = lane < NW ? warp_counts[ring * NW + lane] : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    my_agg = c;
+                    resolved = tile == 0;
+                }
+                if (!resolved) {
+                    const int idx = win - (int)lane;
+                    const unsigned long long v = idx >= 0 ? ld_relaxed_u64(&p.tile_status[idx]) : kFlagPrefix;
+                    if (!__any_sync(0xffffffffu, (v >> 32) == 0)) {
+                        const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 32) == 2);
+                        const int first = pm ? (__ffs(pm) - 1) : 31;
+                        uint32_t contrib = ((int)lane <= first) ? (uint32_t)v : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                        acc += contrib;
+                        if (pm) resolved = true;
+                        else win -= 32;
+                    }
+                }
+                if (resolved) {
+                    if (lane == 0) {
+                        if (tile != 0) st_relaxed_u64(&p.tile_status[tile], kFlagPrefix | (unsigned long long)(acc + my_agg));
+                        tile_base[ring] = acc;
+                        mbar_arrive(&based_bar[ring]);
+                    }
+                    ++res_it;
+                    win = -2;
+                }
+            }
+            if (pub_done && res_it == pub_it) break;
+        }
+        return;
+    }
+
+    // ---------------- consumers: one Gaussian per thread per tile; warps never block on each other.
+    // The (index, key) writes of a tile need its base from the decoupled look-back; they are
+    // deferred by one iteration so that latency hides behind the next tile's work.
+    const float sd_size = smul(u.std_dev, u.gsize);
+    bool d_vis = false;          // deferred outputs of the previous tile
+    uint32_t d_g = 0, d_rank = 0, d_tile = 0xffffffffu, d_ring = 0, d_par = 0, d_total = 0;
+    float d_key = 0.0f;
+
+    auto flush = [&]() {
+        if (d_tile == 0xffffffffu) return;
+        mbar_wait(&based_bar[d_ring], d_par);
+        const uint32_t base = tile_base[d_ring];
+        if (d_vis) {
+            p.indices[base + d_rank] = d_g;
+            p.keys[base + d_rank] = d_key;
+        }
+        if (d_tile == p.num_tiles - 1) {
+            // post: preprocess.wesl:108-126 — indirect args + pad keys with 2.0
+            const uint32_t v = base + d_total;
+            const uint32_t blocks = (v + kHistoBlockKvs - 1) / kHistoBlockKvs;
+            if (tid == 0) {
+                p.draw_args->vertex_count = 6;
+                p.draw_args->instance_count = v;
+                p.draw_args->first_vertex = 0;
+                p.draw_args->first_instance = 0;
+                p.sort_args->x = blocks;
+                p.sort_args->y = 1;
+                p.sort_args->z = 1;
+                *p.visible_count = v;
+            }
+            const uint32_t padded = min(blocks * kHistoBlockKvs, p.keys_capacity);
+            for (uint32_t i = v + tid; i < padded; i += T) p.keys[i] = 2.0f;
+        }
+    };
+
     for (uint32_t it = 0;; ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
-        mbar_wait(&full_bar[s], ph);
+        const uint32_t ring = it % R, rpar = (it / R) & 1u;
+        mbar_wait(&full_bar[s * NW + warp], ph);
         const uint32_t tile = tile_id[s];
-        if (tile >= p.num_tiles) break;
+        if (tile >= p.num_tiles) {
+            if (tid == 0) {  // tell the scan warp that this CTA has no more tiles
+                ring_tile[ring] = 0xffffffffu;
+                mbar_arrive_n(&counted_bar[ring], NW);
+            }
+            break;
+        }
+        if (tid == 0) ring_tile[ring] = tile;
 
         const uint32_t g = tile * T + tid;
         const uint8_t* rec = smem + s * STAGE_BYTES + tid * STRIDE;
@@ -314,14 +478,16 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
                            u.pv[12 + i]);
         const float nx = sdiv(clip[0], clip[3]), ny = sdiv(clip[1], clip[3]), nz = sdiv(clip[2], clip[3]);
 
-        float cov[6];
-        float axes[4];
-        bool have_axes = false;
-        const float sd_size = smul(u.std_dev, u.gsize);
-        if (vis && cull(nx, ny, nz)) {  // preprocess.wesl:87-99
+        // cov2d_axes is needed by the border cull (centre outside) and by every survivor in
+        // splat/ellipse mode: evaluate it once, here, for whoever needs it.
+        const bool centre_out = cull(nx, ny, nz);
+        float axes[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vis && (centre_out || u.mode != SB_MODE_POINT)) {
+            float cov[6];
             unpack_cov3d<SH, COV>(rec, cov);
             cov2d_axes(u, head.x, head.y, head.z, cov, sd_size, axes);
-            have_axes = true;
+        }
+        if (vis && centre_out) {  // preprocess.wesl:87-99
             const float mx = sdiv(smul(axes[0], u.std_dev), u.size[0]);
             const float my = sdiv(smul(axes[1], u.std_dev), u.size[1]);
             const float ndc_major_len = ssqrt(sadd(smul(mx, mx), smul(my, my)));
@@ -332,49 +498,34 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
             if (cull(bx, by, nz)) vis = false;
         }
 
-        // ---- order-preserving compaction: warp ballots -> CTA scan -> decoupled look-back
+        // ---- order-preserving compaction, phase 1: publish this warp's count (non-blocking)
         const uint32_t bal = __ballot_sync(0xffffffffu, vis);
-        if (lane == 0) warp_counts[warp] = __popc(bal);
-        named_bar_sync(1, T);
-        uint32_t warp_excl = 0;
-        {
-            uint32_t c = lane < NW ? warp_counts[lane] : 0u;
-            uint32_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)lane >= o) inc += t;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-            warp_excl = __shfl_sync(0xffffffffu, inc - c, warp);
-            if (warp == 0) {
-                const uint32_t excl = lookback(p.tile_status, tile, total, lane);
-                if (lane == 0) {
-                    bcast[0] = excl;
-                    bcast[1] = total;
-                }
-            }
+        if (lane == 0) {
+            warp_counts[ring * NW + warp] = __popc(bal);
+            mbar_arrive(&counted_bar[ring]);
         }
+        // ---- the previous tile's (index, key) pairs: its base has had a whole tile time to arrive
+        flush();
 
         // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
         if (vis) {
             SplatRec out;
             out.cx = smul(smul(sadd(nx, 1.0f), 0.5f), u.size[0]);
             out.cy = smul(smul(ssub(1.0f, ny), 0.5f), u.size[1]);
-            // color(): render.wesl:58-73
-            const float vdx = u.cam_pos[0] - world[0], vdy = u.cam_pos[1] - world[1], vdz = u.cam_pos[2] - world[2];
+            // color(): render.wesl:58-73; -normalize(v) = -(v * (1/|v|))
+            const float vdx = ssub(u.cam_pos[0], world[0]), vdy = ssub(u.cam_pos[1], world[1]), vdz = ssub(u.cam_pos[2], world[2]);
             float md[3];
 #pragma unroll
-            for (int i = 0; i < 3; i++) md[i] = (u.inv_sr[i] * vdx + u.inv_sr[3 + i] * vdy) + u.inv_sr[6 + i] * vdz;
-            const float ml = sqrtf((md[0] * md[0] + md[1] * md[1]) + md[2] * md[2]);
+            for (int i = 0; i < 3; i++)
+                md[i] = sadd(sadd(smul(u.inv_sr[i], vdx), smul(u.inv_sr[3 + i], vdy)), smul(u.inv_sr[6 + i], vdz));
+            const float inv_ml = sdiv(1.0f, ssqrt(sadd(sadd(smul(md[0], md[0]), smul(md[1], md[1])), smul(md[2], md[2]))));
             float rgb[3];
             const uint32_t packed = __float_as_uint(head.w);
-            view_color<SH>(u, rec, packed, -(md[0] / ml), -(md[1] / ml), -(md[2] / ml), rgb);
-            out.r = rgb[0] * u.color_scale;
-            out.g = rgb[1] * u.color_scale;
-            out.b = rgb[2] * u.color_scale;
-            out.a = __fdiv_rn((float)(packed >> 24), 255.0f);
-            float ex, ey;
+            view_color<SH>(u, rec, packed, -smul(md[0], inv_ml), -smul(md[1], inv_ml), -smul(md[2], inv_ml), rgb);
+            out.r = smul(rgb[0], u.color_scale);
+            out.g = smul(rgb[1], u.color_scale);
+            out.b = smul(rgb[2], u.color_scale);
+            out.a = unorm8(packed >> 24);
             bool valid;
             if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
                 float vp[3];
@@ -386,13 +537,9 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
                 const float half = sdiv(smul(smul(smul(0.01f, u.gsize), 0.5f), u.size[1]), len);
                 const float inv = sdiv(1.0f, half);
                 out.ax = inv; out.ay = 0.0f; out.bx = 0.0f; out.by = inv;
-                ex = half; ey = half;
+                out.ex = half; out.ey = half;
                 valid = (half > 0.0f) && isfinite(inv) && isfinite(out.cx) && isfinite(out.cy);
             } else {
-                if (!have_axes) {
-                    unpack_cov3d<SH, COV>(rec, cov);
-                    cov2d_axes(u, head.x, head.y, head.z, cov, sd_size, axes);
-                }
                 const float mm = sadd(smul(axes[0], axes[0]), smul(axes[1], axes[1]));
                 const float nn = sadd(smul(axes[2], axes[2]), smul(axes[3], axes[3]));
                 out.ax = sdiv(smul(2.0f, axes[0]), mm);
@@ -400,54 +547,50 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 32, 1)
                 out.bx = sdiv(smul(2.0f, axes[2]), nn);
                 out.by = -sdiv(smul(2.0f, axes[3]), nn);
                 const float hs = smul(0.5f, u.std_dev);
-                ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
-                ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
-                valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, ex, ey);
+                out.ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
+                out.ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
+                valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, out.ex, out.ey);
             }
+            TileBox tb;
             if (valid) {
-                tile_bbox(u, out.cx, out.cy, ex, ey, out.tmin, out.tmax);
+                tile_bbox(u, out.cx, out.cy, out.ex, out.ey, tb.tmin, tb.tmax);
             } else {
-                out.tmin = 1u | (1u << 16);
-                out.tmax = 0u;
+                tb.tmin = 1u | (1u << 16);
+                tb.tmax = 0u;
+                out.ex = out.ey = 0.0f;
             }
             float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
             dst[0] = make_float4(out.cx, out.cy, out.ax, out.ay);
-            dst[1] = make_float4(out.bx, out.by, out.r, out.g);
-            dst[2] = make_float4(out.b, out.a, __uint_as_float(out.tmin), __uint_as_float(out.tmax));
+            dst[1] = make_float4(out.bx, out.by, out.ex, out.ey);
+            dst[2] = make_float4(out.r, out.g, out.b, out.a);
+            *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(tb.tmin, tb.tmax);
         }
 
-        // smem slot is no longer needed by this warp
+        // the pods of this chunk are no longer needed: let the producer refill the slot
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive(&empty_bar[s * NW + warp]);
 
-        named_bar_sync(1, T);
-        const uint32_t tile_base = bcast[0];
-        const uint32_t tile_total = bcast[1];
-        if (vis) {
-            const uint32_t slot = tile_base + warp_excl + __popc(bal & lanemask_lt());
-            p.indices[slot] = g;
-            p.keys[slot] = ssub(1.0f, nz);  // preprocess.wesl:105
-        }
-        if (tile == p.num_tiles - 1) {
-            // post: preprocess.wesl:108-126 — indirect args + pad keys with 2.0
-            const uint32_t v = tile_base + tile_total;
-            const uint32_t blocks = (v + kHistoBlockKvs - 1) / kHistoBlockKvs;
-            if (tid == 0) {
-                p.draw_args->vertex_count = 6;
-                p.draw_args->instance_count = v;
-                p.draw_args->first_vertex = 0;
-                p.draw_args->first_instance = 0;
-                p.sort_args->x = blocks;
-                p.sort_args->y = 1;
-                p.sort_args->z = 1;
-                *p.visible_count = v;
+        // ---- compaction, phase 2: ranks inside the tile (the other warps' counts are there by now)
+        mbar_wait(&counted_bar[ring], rpar);
+        {
+            const uint32_t c = lane < NW ? warp_counts[ring * NW + lane] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)lane >= o) inc += t;
             }
-            const uint32_t padded = min(blocks * kHistoBlockKvs, p.keys_capacity);
-            for (uint32_t i = v + tid; i < padded; i += T) p.keys[i] = 2.0f;
+            d_total = __shfl_sync(0xffffffffu, inc, 31);
+            d_rank = __shfl_sync(0xffffffffu, inc - c, warp) + __popc(bal & lanemask_lt());
         }
-        // bcast/warp_counts are rewritten only after the next tile's first barrier, which every
-        // consumer reaches after reading them here.
+        d_vis = vis;
+        d_g = g;
+        d_key = ssub(1.0f, nz);  // preprocess.wesl:105
+        d_tile = tile;
+        d_ring = ring;
+        d_par = rpar;
     }
+    flush();
 }
 
 template <int SH, int COV>
@@ -455,7 +598,7 @@ cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
     constexpr int STRIDE = pod_stride(SH, COV);
     constexpr int T = tile_records(STRIDE);
     constexpr int S = ring_stages(STRIDE);
-    constexpr size_t smem = (size_t)S * T * STRIDE + S * 8 * 2 + S * 4 + (T / 32) * 4 + 16;
+    constexpr size_t smem = (size_t)S * T * STRIDE + 8 * (2 * S * (T / 32) + 16) + 4 * (S + 8 + 8 * (T / 32) + 8);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<SH, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -464,7 +607,7 @@ cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
     }
     p.num_tiles = (p.n + T - 1) / T;
     const int grid = (int)min((uint32_t)num_sms, p.num_tiles);
-    preprocess_kernel<SH, COV><<<grid, T + 32, smem, stream>>>(p);
+    preprocess_kernel<SH, COV><<<grid, T + 64, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 struct BinParams {
-    const SplatRec* recs;
+    const TileBox* tboxes;
     const uint32_t* sorted_indices;
     const uint32_t* visible_count;
     uint32_t* dup_offsets;
@@ -40,10 +40,10 @@ struct BinParams {
 };
 
 // tiles of one splat, clipped to the strip's tile rows
-__device__ __forceinline__ uint32_t splat_tiles(const SplatRec* recs, uint32_t g, uint32_t ty_lo, uint32_t ty_hi, uint32_t& x0,
+__device__ __forceinline__ uint32_t splat_tiles(const TileBox* tboxes, uint32_t g, uint32_t ty_lo, uint32_t ty_hi, uint32_t& x0,
                                                 uint32_t& y0, uint32_t& w) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(&recs[g]) + 2);
-    const uint32_t tmin = __float_as_uint(q.z), tmax = __float_as_uint(q.w);
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(&tboxes[g]));
+    const uint32_t tmin = q.x, tmax = q.y;
     x0 = tmin & 0xffffu;
     y0 = tmin >> 16;
     const uint32_t x1 = tmax & 0xffffu;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     for (int i = 0; i < kScanItems; i++) {
         const uint32_t r = base + i;
         uint32_t x0, y0, w;
-        cnt[i] = r < v ? splat_tiles(p.recs, p.sorted_indices[r], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
+        cnt[i] = r < v ? splat_tiles(p.tboxes, p.sorted_indices[r], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
         sum += cnt[i];
     }
     uint32_t inc = sum;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
         uint32_t g = 0, n = 0, x0 = 0, y0 = 0, w = 1, off = 0;
         if (r < v) {
             g = p.sorted_indices[r];
-            n = splat_tiles(p.recs, g, p.ty_lo, p.ty_hi, x0, y0, w);
+            n = splat_tiles(p.tboxes, g, p.ty_lo, p.ty_hi, x0, y0, w);
             off = p.dup_offsets[r];
         }
         if (n > 0 && n <= 32) {
@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
     const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+    // centre of this warp's 8x4 patch of pixel centres (half extents 3.5 x 1.5)
+    const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 4.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
 
     const uint32_t begin = p.tile_ranges[2 * tile], end = p.tile_ranges[2 * tile + 1];
     const uint32_t total = end - begin;
@@ -274,41 +276,56 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
         mbar_wait(&full_bar[s], (k >> 1) & 1u);
         const uint32_t cnt = min((uint32_t)kBatch, total - k * kBatch);
         const float4* recs = stage[s];
-        for (uint32_t j = 0; j < cnt; j++) {
-            const float4 q0 = recs[j * 3 + 0];
-            const float4 q1 = recs[j * 3 + 1];
-            const float4 q2 = recs[j * 3 + 2];
-            const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
-            const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
-            const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
-            float alpha;
-            if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
-                if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
-                alpha = 1.0f;
-            } else {
-                const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
-                if (!(r2 <= p.sd2)) continue;  // discard: render.wesl:145,155
-                if constexpr (MODE == SB_MODE_SPLAT) {
-                    const float e = STRICT ? exp_neg_poly(r2) : __expf(-r2);
-                    alpha = __fmul_rn(q2.y, e);  // render.wesl:149
-                } else {
-                    const float ol = r2 > p.outline ? 1.0f : 0.0f;  // render.wesl:159-160
-                    alpha = __fadd_rn(q2.y, __fmul_rn(__fsub_rn(1.0f, q2.y), ol));
-                }
+        // Warp-level culling: each lane tests one splat's alive-region bbox against this warp's
+        // 8x4 pixel patch; only splats that can touch the patch are evaluated, in list order.
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t jl = base + lane;
+            bool hit = false;
+            if (jl < cnt) {
+                const float4 c0 = recs[jl * 3 + 0];
+                const float4 c1 = recs[jl * 3 + 1];
+                hit = fabsf(c0.x - pcx) <= c1.z + 3.51f && fabsf(c0.y - pcy) <= c1.w + 1.51f;
             }
-            const float om = __fsub_rn(1.0f, alpha);
-            if constexpr (FMT == FMT_UNORM8) {
-                d0 = rint_small(fminf(__fmaf_rn(d0, om, __fmul_rn(q1.z, alpha)), 255.0f));
-                d1 = rint_small(fminf(__fmaf_rn(d1, om, __fmul_rn(q1.w, alpha)), 255.0f));
-                d2 = rint_small(fminf(__fmaf_rn(d2, om, __fmul_rn(q2.x, alpha)), 255.0f));
-            } else {
-                d0 = __fmaf_rn(d0, om, __fmul_rn(q1.z, alpha));
-                d1 = __fmaf_rn(d1, om, __fmul_rn(q1.w, alpha));
-                d2 = __fmaf_rn(d2, om, __fmul_rn(q2.x, alpha));
-                d3 = __fmaf_rn(d3, om, alpha);
-                if constexpr (FMT == FMT_F16) {
-                    d0 = __half2float(__float2half_rn(d0)); d1 = __half2float(__float2half_rn(d1));
-                    d2 = __half2float(__float2half_rn(d2)); d3 = __half2float(__float2half_rn(d3));
+            uint32_t todo = __ballot_sync(0xffffffffu, hit);
+            while (todo) {
+                const uint32_t j = base + (uint32_t)(__ffs(todo) - 1);
+                todo &= todo - 1;
+                const float4 q0 = recs[j * 3 + 0];
+                const float4 q1 = recs[j * 3 + 1];
+                const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
+                const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
+                const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
+                float alpha;
+                if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
+                    if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
+                    alpha = 1.0f;
+                } else {
+                    const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
+                    if (!(r2 <= p.sd2)) continue;  // discard: render.wesl:145,155
+                    const float a = recs[j * 3 + 2].w;
+                    if constexpr (MODE == SB_MODE_SPLAT) {
+                        const float e = STRICT ? exp_neg_poly(r2) : __expf(-r2);
+                        alpha = __fmul_rn(a, e);  // render.wesl:149
+                    } else {
+                        const float ol = r2 > p.outline ? 1.0f : 0.0f;  // render.wesl:159-160
+                        alpha = __fadd_rn(a, __fmul_rn(__fsub_rn(1.0f, a), ol));
+                    }
+                }
+                const float4 q2 = recs[j * 3 + 2];
+                const float om = __fsub_rn(1.0f, alpha);
+                if constexpr (FMT == FMT_UNORM8) {
+                    d0 = rint_small(fminf(__fmaf_rn(d0, om, __fmul_rn(q2.x, alpha)), 255.0f));
+                    d1 = rint_small(fminf(__fmaf_rn(d1, om, __fmul_rn(q2.y, alpha)), 255.0f));
+                    d2 = rint_small(fminf(__fmaf_rn(d2, om, __fmul_rn(q2.z, alpha)), 255.0f));
+                } else {
+                    d0 = __fmaf_rn(d0, om, __fmul_rn(q2.x, alpha));
+                    d1 = __fmaf_rn(d1, om, __fmul_rn(q2.y, alpha));
+                    d2 = __fmaf_rn(d2, om, __fmul_rn(q2.z, alpha));
+                    d3 = __fmaf_rn(d3, om, alpha);
+                    if constexpr (FMT == FMT_F16) {
+                        d0 = __half2float(__float2half_rn(d0)); d1 = __half2float(__float2half_rn(d1));
+                        d2 = __half2float(__float2half_rn(d2)); d3 = __half2float(__float2half_rn(d3));
+                    }
                 }
             }
         }
@@ -385,7 +402,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     if (e != cudaSuccess) return e;
 
     BinParams bp;
-    bp.recs = p.recs;
+    bp.tboxes = p.tboxes;
     bp.sorted_indices = p.sorted_indices;
     bp.visible_count = p.visible_count;
     bp.dup_offsets = p.buf.dup_offsets;
