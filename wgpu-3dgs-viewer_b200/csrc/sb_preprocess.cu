@@ -405,23 +405,26 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
 
     // ---------------- consumers: one Gaussian per thread per tile; warps never block on each other.
     // The (index, key) writes of a tile need its base from the decoupled look-back; they are
-    // deferred by one iteration so that latency hides behind the next tile's work.
+    // deferred by two iterations so that latency hides behind the next tiles' work.
     const float sd_size = smul(u.std_dev, u.gsize);
-    bool d_vis = false;          // deferred outputs of the previous tile
-    uint32_t d_g = 0, d_rank = 0, d_tile = 0xffffffffu, d_ring = 0, d_par = 0, d_total = 0;
-    float d_key = 0.0f;
+    struct Deferred {
+        bool vis = false;
+        uint32_t g = 0, rank = 0, tile = 0xffffffffu, ring = 0, par = 0, total = 0;
+        float key = 0.0f;
+    };
+    Deferred d1, d2;  // outputs of the previous tile (d1) and of the one before (d2)
 
-    auto flush = [&]() {
-        if (d_tile == 0xffffffffu) return;
-        mbar_wait(&based_bar[d_ring], d_par);
-        const uint32_t base = tile_base[d_ring];
-        if (d_vis) {
-            p.indices[base + d_rank] = d_g;
-            p.keys[base + d_rank] = d_key;
+    auto flush = [&](const Deferred& d) {
+        if (d.tile == 0xffffffffu) return;
+        mbar_wait(&based_bar[d.ring], d.par);
+        const uint32_t base = tile_base[d.ring];
+        if (d.vis) {
+            p.indices[base + d.rank] = d.g;
+            p.keys[base + d.rank] = d.key;
         }
-        if (d_tile == p.num_tiles - 1) {
+        if (d.tile == p.num_tiles - 1) {
             // post: preprocess.wesl:108-126 — indirect args + pad keys with 2.0
-            const uint32_t v = base + d_total;
+            const uint32_t v = base + d.total;
             const uint32_t blocks = (v + kHistoBlockKvs - 1) / kHistoBlockKvs;
             if (tid == 0) {
                 p.draw_args->vertex_count = 6;
@@ -504,8 +507,9 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
             warp_counts[ring * NW + warp] = __popc(bal);
             mbar_arrive(&counted_bar[ring]);
         }
-        // ---- the previous tile's (index, key) pairs: its base has had a whole tile time to arrive
-        flush();
+        // ---- (index, key) pairs of the tile two iterations back: its base has had time to arrive
+        flush(d2);
+        d2 = d1;
 
         // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
         if (vis) {
@@ -580,17 +584,18 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
                 const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
                 if ((int)lane >= o) inc += t;
             }
-            d_total = __shfl_sync(0xffffffffu, inc, 31);
-            d_rank = __shfl_sync(0xffffffffu, inc - c, warp) + __popc(bal & lanemask_lt());
+            d1.total = __shfl_sync(0xffffffffu, inc, 31);
+            d1.rank = __shfl_sync(0xffffffffu, inc - c, warp) + __popc(bal & lanemask_lt());
         }
-        d_vis = vis;
-        d_g = g;
-        d_key = ssub(1.0f, nz);  // preprocess.wesl:105
-        d_tile = tile;
-        d_ring = ring;
-        d_par = rpar;
+        d1.vis = vis;
+        d1.g = g;
+        d1.key = ssub(1.0f, nz);  // preprocess.wesl:105
+        d1.tile = tile;
+        d1.ring = ring;
+        d1.par = rpar;
     }
-    flush();
+    flush(d2);
+    flush(d1);
 }
 
 template <int SH, int COV>
