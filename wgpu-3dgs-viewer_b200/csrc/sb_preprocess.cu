@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
     uint64_t* empty_bar = full_bar + S * NW;                                     // [S][NW] chunk consumed
     uint64_t* counted_bar = empty_bar + S * NW;                                  // [R] all warp counts written
     uint64_t* based_bar = counted_bar + R;                                       // [R] tile base known
-    uint32_t* tile_id = reinterpret_cast<uint32_t*>(based_bar + R);              // [S]
-    uint32_t* tile_base = tile_id + S;                                           // [R]
+    uint32_t* tile_id = reinterpret_cast<uint32_t*>(based_bar + R);              // [S][NW] (per warp: warps drift)
+    uint32_t* tile_base = tile_id + S * NW;                                         // [R]
     uint32_t* warp_counts = tile_base + R;                                       // [R][NW]
     uint32_t* ring_tile = warp_counts + R * NW;                                  // [R] tile of a ring slot (0xffffffff = end)
 
@@ -314,9 +314,12 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
                 const uint32_t s = it % S, ph = (it / S) & 1u;
                 mbar_wait(&empty_bar[s * NW], ph ^ 1u);
                 const uint32_t tile = atomicAdd(p.tile_counter, 1u);
-                tile_id[s] = tile;
                 if (tile >= p.num_tiles) {
-                    for (int w = 0; w < NW; w++) mbar_arrive(&full_bar[s * NW + w]);
+                    for (int w = 0; w < NW; w++) {
+                        if (w > 0) mbar_wait(&empty_bar[s * NW + w], ph ^ 1u);
+                        tile_id[s * NW + w] = tile;
+                        mbar_arrive(&full_bar[s * NW + w]);
+                    }
                     break;
                 }
                 const uint32_t first = tile * T;
@@ -324,7 +327,9 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
                 const uint8_t* src = p.gaussians + (size_t)first * STRIDE;
                 uint8_t* dst = smem + s * STAGE_BYTES;
                 for (int w = 0; w < NW; w++) {
+                    // a warp's slot (pods AND tile id) may be rewritten only after that warp released it
                     if (w > 0) mbar_wait(&empty_bar[s * NW + w], ph ^ 1u);
+                    tile_id[s * NW + w] = tile;
                     const uint32_t lo = min(cnt, (uint32_t)w * 32u), hi = min(cnt, (uint32_t)w * 32u + 32u);
                     const uint32_t bytes = (hi - lo) * STRIDE;
                     if (bytes == 0) {
@@ -348,7 +353,9 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         int win = -2;  // -2: look-back of tile res_it not started
         bool pub_done = false;
         for (;;) {
-            if (!pub_done && mbar_try_wait(&counted_bar[pub_it % R], (pub_it / R) & 1u)) {
+            // warp-uniform probe: lanes may observe the phase flip at different instants
+            const bool counted = !pub_done && __all_sync(0xffffffffu, mbar_test_wait(&counted_bar[pub_it % R], (pub_it / R) & 1u));
+            if (counted) {
                 const uint32_t ring = pub_it % R;
                 const uint32_t tile = ring_tile[ring];
                 if (tile == 0xffffffffu) {
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         const uint32_t s = it % S, ph = (it / S) & 1u;
         const uint32_t ring = it % R, rpar = (it / R) & 1u;
         mbar_wait(&full_bar[s * NW + warp], ph);
-        const uint32_t tile = tile_id[s];
+        const uint32_t tile = tile_id[s * NW + warp];
         if (tile >= p.num_tiles) {
             if (tid == 0) {  // tell the scan warp that this CTA has no more tiles
                 ring_tile[ring] = 0xffffffffu;
@@ -603,7 +610,7 @@ cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
     constexpr int STRIDE = pod_stride(SH, COV);
     constexpr int T = tile_records(STRIDE);
     constexpr int S = ring_stages(STRIDE);
-    constexpr size_t smem = (size_t)S * T * STRIDE + 8 * (2 * S * (T / 32) + 16) + 4 * (S + 8 + 8 * (T / 32) + 8);
+    constexpr size_t smem = (size_t)S * T * STRIDE + 8 * (2 * S * (T / 32) + 16) + 4 * (S * (T / 32) + 8 + 8 * (T / 32) + 8);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<SH, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
