@@ -18,10 +18,10 @@ namespace {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 16;
-constexpr int kSortTile = kSortThreads * kItems;  // 4096 pairs per tile
+constexpr int kSortTile = kSortThreads * kItems;  // 8192 pairs per tile: 32-key runs per digit on random digits
 constexpr int kMaxPasses = 4;
 
 constexpr uint32_t kLbAggregate = 1u << 30;
@@ -36,8 +36,25 @@ constexpr size_t kHistWords = kMaxPasses * kRadix;
 constexpr size_t kTicketOffset = kHistWords;
 constexpr size_t kLookbackOffset = kHistWords + 16;
 
-__global__ void __launch_bounds__(256) histogram_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count,
-                                                        uint32_t max_count, int begin_bit, int num_passes,
+// Lanes of the warp holding the same digit as this lane (and the same validity), built from one
+// ballot per digit bit: VOTE is a cheap uniform-datapath op, MATCH.ANY measured MIO-bound on B200.
+template <int NBITS>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool ok) {
+    uint32_t peers = __ballot_sync(0xffffffffu, ok);
+    if (!ok) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < NBITS; b++) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+// K2: one read of the keys, all digit histograms at once.  Warp-aggregated shared atomics
+// (match.any) so the clustered high digits of depth keys do not serialise on one address.
+__global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count,
+                                                        uint32_t max_count, int begin_bit, int end_bit, int num_passes,
                                                         uint32_t* __restrict__ ghist) {
     __shared__ uint32_t hist[kMaxPasses][kRadix];
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&hist[0][0])[i] = 0;
@@ -45,19 +62,33 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint32_t* __restri
     const uint32_t count = min(*d_count, max_count);
     const uint32_t nvec = count / 4;
     const uint4* kv = reinterpret_cast<const uint4*>(keys);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
-        const uint4 k = __ldg(&kv[i]);
+    const uint32_t lt = lanemask_lt();
+    // warp-uniform trip count so match.any sees every lane
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nvec; base += stride) {
+        const uint32_t i = base + threadIdx.x;
+        const bool ok = i < nvec;
+        uint4 k = make_uint4(0, 0, 0, 0);
+        if (ok) k = __ldg(&kv[i]);
         const uint32_t ks[4] = {k.x, k.y, k.z, k.w};
+        for (int p = 0; p < num_passes; p++) {
+            const int sh = begin_bit + p * kRadixBits;
+            const uint32_t mask = (1u << min(kRadixBits, end_bit - sh)) - 1u;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t key = ks[j];
-            for (int p = 0; p < num_passes; p++) atomicAdd(&hist[p][(key >> (begin_bit + p * kRadixBits)) & (kRadix - 1)], 1u);
+            for (int j = 0; j < 4; j++) {
+                const uint32_t d = (ks[j] >> sh) & mask;
+                const uint32_t peers = digit_peers<kRadixBits>(d, ok);
+                if (ok && (peers & lt) == 0) atomicAdd(&hist[p][d], (uint32_t)__popc(peers));
+            }
         }
     }
     if (blockIdx.x == 0) {
         for (uint32_t i = nvec * 4 + threadIdx.x; i < count; i += blockDim.x) {
             const uint32_t key = keys[i];
-            for (int p = 0; p < num_passes; p++) atomicAdd(&hist[p][(key >> (begin_bit + p * kRadixBits)) & (kRadix - 1)], 1u);
+            for (int p = 0; p < num_passes; p++) {
+                const int sh = begin_bit + p * kRadixBits;
+                atomicAdd(&hist[p][(key >> sh) & ((1u << min(kRadixBits, end_bit - sh)) - 1u)], 1u);
+            }
         }
     }
     __syncthreads();
@@ -76,11 +107,14 @@ struct SortSmem {
         } stage;
     };
     uint32_t digit_base[kRadix];   // global destination of the first key of each digit, minus its tile-local start
-    uint32_t scan_tmp[kSortWarps];
+    uint32_t scan_a[kSortWarps];
+    uint32_t scan_b[kSortWarps];
     uint32_t tile;
 };
 
-__global__ void __launch_bounds__(kSortThreads)
+// K3: one onesweep digit pass over NBITS significant digit bits.
+template <int NBITS>
+__global__ void __launch_bounds__(kSortThreads, 2)
     onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ d_count, uint32_t max_count, int shift,
                     const uint32_t* __restrict__ ghist /* this pass, 256 */, uint32_t* __restrict__ ticket,
@@ -89,13 +123,13 @@ __global__ void __launch_bounds__(kSortThreads)
     SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t count = min(*d_count, max_count);
+    if (blockIdx.x * kSortTile >= count) return;  // surplus CTA: exactly ceil(count/tile) CTAs take a ticket
 
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < kSortWarps * (kRadix + 32); i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = sm.tile;
     const uint32_t tile_base = tile * kSortTile;
-    if (tile_base >= count) return;
     const uint32_t tile_count = min((uint32_t)kSortTile, count - tile_base);
 
     // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l)
@@ -104,31 +138,35 @@ __global__ void __launch_bounds__(kSortThreads)
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
         const uint32_t idx = warp_base + i * 32 + lane;
-        const bool ok = idx < count;
-        key[i] = ok ? __ldg(&keys_in[idx]) : 0xffffffffu;
-        val[i] = ok ? __ldg(&vals_in[idx]) : 0u;
+        key[i] = idx < count ? __ldg(&keys_in[idx]) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; i++) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        val[i] = idx < count ? __ldg(&vals_in[idx]) : 0u;
     }
 
-    // ---- warp-level multi-split: rank of each key among equal digits of its warp, stable
+    // ---- warp-level multi-split: rank of each key among equal digits of its warp (stable):
+    // match.any finds the peers, the lowest peer claims the run with one shared atomic.
     uint32_t rank[kItems];
     uint32_t* wh = sm.warp_hist[warp];
+    const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
         const bool ok = (warp_base + i * 32 + lane) < count;
-        const uint32_t d = ok ? ((key[i] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t below = __popc(peers & lanemask_lt());
-        const uint32_t pre = wh[d];
-        __syncwarp();
-        if (below == 0) wh[d] = pre + __popc(peers);
-        __syncwarp();
+        const uint32_t d = (key[i] >> shift) & ((1u << NBITS) - 1);
+        const uint32_t peers = digit_peers<NBITS>(d, ok);
+        const uint32_t below = __popc(peers & lt);
+        uint32_t pre = 0;
+        if (below == 0 && ok) pre = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+        pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
         rank[i] = pre + below;
     }
     __syncthreads();
 
-    // ---- thread d owns digit d: scan over warps, publish the tile aggregate, look back
-    uint32_t digit_count;
-    {
+    // ---- thread d < 256 owns digit d: scan over warps, publish the tile aggregate, look back
+    uint32_t digit_count = 0, gcount = 0;
+    if (tid < kRadix) {
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; w++) {
@@ -137,12 +175,11 @@ __global__ void __launch_bounds__(kSortThreads)
             run += t;
         }
         digit_count = run;
+        st_relaxed_u32(&lookback[(size_t)tile * kRadix + tid], (tile == 0 ? kLbPrefix : kLbAggregate) | digit_count);
+        gcount = ghist[tid];
     }
-    uint32_t* lb = lookback + (size_t)tile * kRadix;
-    st_relaxed_u32(&lb[tid], (tile == 0 ? kLbPrefix : kLbAggregate) | digit_count);
 
-    // exclusive scan over digits: tile-local start of each digit, and global digit start
-    uint32_t gcount = ghist[tid];
+    // exclusive scans over digits: tile-local start of each digit, and global digit start
     uint32_t local_excl, global_excl;
     {
         uint32_t a = digit_count, b = gcount;
@@ -156,58 +193,61 @@ __global__ void __launch_bounds__(kSortThreads)
             }
         }
         if (lane == 31) {
-            sm.scan_tmp[warp] = a;
-            sm.digit_base[warp] = b;  // temporary use
+            sm.scan_a[warp] = a;
+            sm.scan_b[warp] = b;
         }
         __syncthreads();
         uint32_t wa = 0, wb = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; w++) {
+        for (int w = 0; w < kRadix / 32; w++) {
             if (w < (int)warp) {
-                wa += sm.scan_tmp[w];
-                wb += sm.digit_base[w];
+                wa += sm.scan_a[w];
+                wb += sm.scan_b[w];
             }
         }
         local_excl = a - digit_count + wa;
         global_excl = b - gcount + wb;
-        __syncthreads();
     }
 
-    uint32_t tile_excl = 0;
-    if (tile > 0) {
+    if (tid < kRadix) {
+        // decoupled look-back, 4 predecessors per round trip
+        uint32_t tile_excl = 0;
         int t = (int)tile - 1;
-        while (true) {
-            uint32_t v;
-            do {
-                v = ld_relaxed_u32(&lookback[(size_t)t * kRadix + tid]);
-            } while ((v >> 30) == 0);
-            tile_excl += v & kLbValueMask;
-            if ((v >> 30) == 2 || t == 0) break;
-            --t;
-        }
-        st_relaxed_u32(&lb[tid], kLbPrefix | (tile_excl + digit_count));
-    }
-    sm.digit_base[tid] = global_excl + tile_excl - local_excl;
-    // warp_hist[w][d] now holds the exclusive count of digit d in warps < w; fold in the
-    // tile-local digit start so a key's tile-sorted position is warp_hist[w][d] + rank.
+        while (t >= 0) {
+            uint32_t v[4];
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) sm.warp_hist[w][tid] += local_excl;
+            for (int j = 0; j < 4; j++) v[j] = (t - j) >= 0 ? ld_relaxed_u32(&lookback[(size_t)(t - j) * kRadix + tid]) : kLbPrefix;
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (done) break;
+                if ((v[j] >> 30) == 0) break;  // not published yet: retry from here
+                tile_excl += v[j] & kLbValueMask;
+                --t;
+                if ((v[j] >> 30) == 2) {
+                    done = true;
+                    t = -1;
+                }
+            }
+        }
+        if (tile > 0) st_relaxed_u32(&lookback[(size_t)tile * kRadix + tid], kLbPrefix | (tile_excl + digit_count));
+        sm.digit_base[tid] = global_excl + tile_excl - local_excl;
+        // warp_hist[w][d] holds the exclusive count of digit d in warps < w; fold in the tile-local
+        // digit start so a key's tile-sorted position is warp_hist[w][d] + rank.
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) sm.warp_hist[w][tid] += local_excl;
+    }
     __syncthreads();
 
     // ---- tile-sorted positions, then reorder through shared memory
-    uint32_t pos[kItems];
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        const uint32_t d = (key[i] >> shift) & (kRadix - 1);
-        pos[i] = wh[d] + rank[i];
-    }
+    for (int i = 0; i < kItems; i++) rank[i] += wh[(key[i] >> shift) & ((1u << NBITS) - 1)];
     __syncthreads();  // warp_hist is dead; its storage becomes the staging buffer
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
-        const bool ok = (warp_base + i * 32 + lane) < count;
-        if (ok) {
-            sm.stage.keys[pos[i]] = key[i];
-            sm.stage.vals[pos[i]] = val[i];
+        if ((warp_base + i * 32 + lane) < count) {
+            sm.stage.keys[rank[i]] = key[i];
+            sm.stage.vals[rank[i]] = val[i];
         }
     }
     __syncthreads();
@@ -216,10 +256,23 @@ __global__ void __launch_bounds__(kSortThreads)
         const uint32_t j = i * kSortThreads + tid;
         if (j < tile_count) {
             const uint32_t k = sm.stage.keys[j];
-            const uint32_t dst = sm.digit_base[(k >> shift) & (kRadix - 1)] + j;
+            const uint32_t dst = sm.digit_base[(k >> shift) & ((1u << NBITS) - 1)] + j;
             keys_out[dst] = k;
             vals_out[dst] = sm.stage.vals[j];
         }
+    }
+}
+
+// zeroes the histograms, tickets and the part of the look-back tables this sort will use
+__global__ void sort_init_kernel(uint32_t* __restrict__ internal, const uint32_t* __restrict__ d_count, uint32_t max_count,
+                                 int num_passes, uint32_t tiles_alloc) {
+    const uint32_t count = min(*d_count, max_count);
+    const uint32_t tiles = (count + kSortTile - 1) / kSortTile;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < kLookbackOffset; i += gridDim.x * blockDim.x) internal[i] = 0;
+    for (int p = 0; p < num_passes; p++) {
+        uint32_t* lb = internal + kLookbackOffset + (size_t)p * tiles_alloc * kRadix;
+        const uint32_t words = tiles * kRadix;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) lb[i] = 0;
     }
 }
 
@@ -230,6 +283,32 @@ __global__ void copy_pairs_kernel(const uint32_t* __restrict__ k_in, const uint3
         k_out[i] = k_in[i];
         v_out[i] = v_in[i];
     }
+}
+
+template <int NBITS>
+void launch_pass_n(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
+                   const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket, uint32_t* lb) {
+    onesweep_kernel<NBITS><<<tiles, kSortThreads, sizeof(SortSmem), stream>>>(kin, vin, kout, vout, d_count, max_count, shift, ghist,
+                                                                            ticket, lb);
+}
+
+void launch_pass(int nbits, unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin, uint32_t* kout,
+                 uint32_t* vout, const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket,
+                 uint32_t* lb) {
+    switch (nbits) {
+#define SB_PASS(N) case N: launch_pass_n<N>(tiles, stream, kin, vin, kout, vout, d_count, max_count, shift, ghist, ticket, lb); break;
+        SB_PASS(1) SB_PASS(2) SB_PASS(3) SB_PASS(4) SB_PASS(5) SB_PASS(6) SB_PASS(7)
+        default: launch_pass_n<8>(tiles, stream, kin, vin, kout, vout, d_count, max_count, shift, ghist, ticket, lb); break;
+#undef SB_PASS
+    }
+}
+
+cudaError_t set_smem_all() {
+    cudaError_t e = cudaSuccess;
+#define SB_ATTR(N) if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+    SB_ATTR(1) SB_ATTR(2) SB_ATTR(3) SB_ATTR(4) SB_ATTR(5) SB_ATTR(6) SB_ATTR(7) SB_ATTR(8)
+#undef SB_ATTR
+    return e;
 }
 
 }  // namespace
@@ -247,30 +326,29 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
     const size_t tiles = ((size_t)max_count + kSortTile - 1) / kSortTile;
     const size_t need = (kLookbackOffset + (size_t)num_passes * tiles * kRadix) * sizeof(uint32_t);
     if (need > scratch.internal_bytes) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(scratch.internal, 0, need, stream);
-    if (e != cudaSuccess) return e;
-
+    cudaError_t e;
     static bool configured = false;
     if (!configured) {
-        e = cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        e = set_smem_all();
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    sort_init_kernel<<<num_sms * 2, 256, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, (uint32_t)tiles);
     uint32_t* ghist = scratch.internal;
     uint32_t* tickets = scratch.internal + kTicketOffset;
     uint32_t* lookback = scratch.internal + kLookbackOffset;
 
-    const int hist_grid = (int)min((size_t)num_sms * 4, (tiles * kSortTile / 4 + 255) / 256);
-    histogram_kernel<<<hist_grid > 0 ? hist_grid : 1, 256, 0, stream>>>(keys, d_count, max_count, begin_bit, num_passes, ghist);
+    const int hist_grid = (int)min((size_t)num_sms * 2, (tiles * kSortTile / 4 + 511) / 512);
+    histogram_kernel<<<hist_grid > 0 ? hist_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, begin_bit, end_bit, num_passes, ghist);
 
     uint32_t* kin = keys;
     uint32_t* vin = payload;
     uint32_t* kout = scratch.keys_alt;
     uint32_t* vout = scratch.payload_alt;
     for (int p = 0; p < num_passes; p++) {
-        onesweep_kernel<<<(unsigned)tiles, kSortThreads, sizeof(SortSmem), stream>>>(
-            kin, vin, kout, vout, d_count, max_count, begin_bit + p * kRadixBits, ghist + p * kRadix, tickets + p,
-            lookback + (size_t)p * tiles * kRadix);
+        const int nbits = min(kRadixBits, end_bit - (begin_bit + p * kRadixBits));
+        launch_pass(nbits, (unsigned)tiles, stream, kin, vin, kout, vout, d_count, max_count, begin_bit + p * kRadixBits,
+                    ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix);
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
