@@ -23,6 +23,10 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 16;
 constexpr int kSortTile = kSortThreads * kItems;  // 8192 pairs per tile: 32-key runs per digit on random digits
 constexpr int kMaxPasses = 4;
+#ifndef SB_MATCH_EVERY
+#define SB_MATCH_EVERY 3
+#endif
+constexpr int kMatchEvery = SB_MATCH_EVERY;  // every k-th item is ranked with MATCH.ANY (0 = never)
 
 constexpr uint32_t kLbAggregate = 1u << 30;
 constexpr uint32_t kLbPrefix = 2u << 30;
@@ -112,56 +116,68 @@ struct SortSmem {
     uint32_t tile;
 };
 
-// K3: one onesweep digit pass over NBITS significant digit bits.
-template <int NBITS>
-__global__ void __launch_bounds__(kSortThreads, 2)
-    onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-                    uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ d_count, uint32_t max_count, int shift,
-                    const uint32_t* __restrict__ ghist /* this pass, 256 */, uint32_t* __restrict__ ticket,
-                    uint32_t* __restrict__ lookback /* this pass: tiles x 256 */) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+// Device-side sort state (after the histograms/tickets): lets a pass whose digit is the same for
+// every key be SKIPPED (depth keys of one frame share their top byte most of the time) while the
+// ping-pong direction stays consistent: [0] parity (0: data in keys/payload, 1: in the alt
+// buffers), [1 + pass] CTAs finished in that pass.
+constexpr size_t kStateOffset = kHistWords + 8;
+
+template <int NBITS, bool FULL>
+__device__ __forceinline__ void onesweep_tile(SortSmem& sm, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                              uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t count,
+                                              int shift, const uint32_t* __restrict__ ghist, uint32_t* __restrict__ lookback,
+                                              uint32_t tile) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t count = min(*d_count, max_count);
-    if (blockIdx.x * kSortTile >= count) return;  // surplus CTA: exactly ceil(count/tile) CTAs take a ticket
-
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < kSortWarps * (kRadix + 32); i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = sm.tile;
     const uint32_t tile_base = tile * kSortTile;
-    const uint32_t tile_count = min((uint32_t)kSortTile, count - tile_base);
+    const uint32_t tile_count = FULL ? (uint32_t)kSortTile : (count - tile_base);
+    constexpr uint32_t kMask = (1u << NBITS) - 1u;
 
-    // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l)
-    uint32_t key[kItems], val[kItems];
+    // ---- load keys (warp-striped: item i of lane l sits at warp_base + i*32 + l)
+    uint32_t key[kItems];
     const uint32_t warp_base = tile_base + warp * (32 * kItems);
+    const uint32_t* kp = keys_in + warp_base + lane;
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        const uint32_t idx = warp_base + i * 32 + lane;
-        key[i] = idx < count ? __ldg(&keys_in[idx]) : 0xffffffffu;
-    }
-#pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        const uint32_t idx = warp_base + i * 32 + lane;
-        val[i] = idx < count ? __ldg(&vals_in[idx]) : 0u;
-    }
+    for (int i = 0; i < kItems; i++) key[i] = (FULL || warp_base + i * 32 + lane < count) ? __ldg(kp + i * 32) : 0xffffffffu;
 
-    // ---- warp-level multi-split: rank of each key among equal digits of its warp (stable):
-    // match.any finds the peers, the lowest peer claims the run with one shared atomic.
-    uint32_t rank[kItems];
+    // ---- warp-level multi-split: rank of each key among equal digits of its warp (stable): one
+    // ballot per digit bit finds the peers, the lowest peer claims the run with one shared atomic.
+    uint32_t rank2[kItems / 2];  // two 16-bit ranks per register (a rank is < 8192)
     uint32_t* wh = sm.warp_hist[warp];
     const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
-        const bool ok = (warp_base + i * 32 + lane) < count;
-        const uint32_t d = (key[i] >> shift) & ((1u << NBITS) - 1);
-        const uint32_t peers = digit_peers<NBITS>(d, ok);
+        const bool ok = FULL || (warp_base + i * 32 + lane) < count;
+        const uint32_t d = (key[i] >> shift) & kMask;
+        uint32_t peers = 0xffffffffu;
+        if (kMatchEvery > 0 && (i % kMatchEvery) == kMatchEvery - 1) {
+            // MATCH.ANY runs on the MIO pipe, the ballot chain on the ALU pipe: mixing the two
+            // forms balances the pipes (ncu: all-MATCH is MIO-bound, all-ballot is issue-bound)
+            peers = __match_any_sync(0xffffffffu, ok ? d : 0xffffffffu);
+        } else {
+            if (!FULL) {
+                peers = __ballot_sync(0xffffffffu, ok);
+                if (!ok) peers = ~peers;
+            }
+#pragma unroll
+            for (int b = 0; b < NBITS; b++) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
+        }
         const uint32_t below = __popc(peers & lt);
         uint32_t pre = 0;
         if (below == 0 && ok) pre = atomicAdd(&wh[d], (uint32_t)__popc(peers));
         pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
-        rank[i] = pre + below;
+        if (i & 1) rank2[i >> 1] |= (pre + below) << 16;
+        else rank2[i >> 1] = pre + below;
     }
+    // payload: loaded late so it is not live across the ranking loop; its latency hides behind the
+    // digit scan and the look-back
+    uint32_t val[kItems];
+    const uint32_t* vp = vals_in + warp_base + lane;
+#pragma unroll
+    for (int i = 0; i < kItems; i++) val[i] = (FULL || warp_base + i * 32 + lane < count) ? __ldg(vp + i * 32) : 0u;
     __syncthreads();
 
     // ---- thread d < 256 owns digit d: scan over warps, publish the tile aggregate, look back
@@ -240,27 +256,92 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     __syncthreads();
 
     // ---- tile-sorted positions, then reorder through shared memory
+    uint32_t base2[kItems / 2];
 #pragma unroll
-    for (int i = 0; i < kItems; i++) rank[i] += wh[(key[i] >> shift) & ((1u << NBITS) - 1)];
+    for (int i = 0; i < kItems; i += 2)
+        base2[i >> 1] = wh[(key[i] >> shift) & kMask] | (wh[(key[i + 1] >> shift) & kMask] << 16);
     __syncthreads();  // warp_hist is dead; its storage becomes the staging buffer
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
-        if ((warp_base + i * 32 + lane) < count) {
-            sm.stage.keys[rank[i]] = key[i];
-            sm.stage.vals[rank[i]] = val[i];
+        if (FULL || (warp_base + i * 32 + lane) < count) {
+            const uint32_t pos = ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu) + ((base2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+            sm.stage.keys[pos] = key[i];
+            sm.stage.vals[pos] = val[i];
         }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
         const uint32_t j = i * kSortThreads + tid;
-        if (j < tile_count) {
+        if (FULL || j < tile_count) {
             const uint32_t k = sm.stage.keys[j];
-            const uint32_t dst = sm.digit_base[(k >> shift) & ((1u << NBITS) - 1)] + j;
+            const uint32_t dst = sm.digit_base[(k >> shift) & kMask] + j;
             keys_out[dst] = k;
             vals_out[dst] = sm.stage.vals[j];
         }
     }
+}
+
+// K3: one onesweep digit pass over NBITS significant digit bits.
+template <int NBITS>
+__global__ void __launch_bounds__(kSortThreads, 2)
+    onesweep_kernel(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
+                    uint32_t* __restrict__ vals_b, const uint32_t* __restrict__ d_count, uint32_t max_count, int shift,
+                    const uint32_t* __restrict__ ghist /* this pass, 256 */, uint32_t* __restrict__ ticket,
+                    uint32_t* __restrict__ lookback /* this pass: tiles x 256 */, uint32_t* __restrict__ state, int pass) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t count = min(*d_count, max_count);
+    if (blockIdx.x * kSortTile >= count) return;  // surplus CTA: exactly ceil(count/tile) CTAs take a ticket
+
+    // A pass whose digit is identical for all keys is the identity permutation: skip it.
+    const int degenerate = __syncthreads_or(tid < kRadix && ghist[tid] == count);
+    if (degenerate) return;
+
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < kSortWarps * (kRadix + 32); i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint32_t parity = ld_relaxed_u32(&state[0]);  // stable during the pass: flipped by the last CTA only
+    const uint32_t* kin = parity ? keys_b : keys_a;
+    const uint32_t* vin = parity ? vals_b : vals_a;
+    uint32_t* kout = parity ? keys_a : keys_b;
+    uint32_t* vout = parity ? vals_a : vals_b;
+    if ((tile + 1) * kSortTile <= count)
+        onesweep_tile<NBITS, true>(sm, kin, vin, kout, vout, count, shift, ghist, lookback, tile);
+    else
+        onesweep_tile<NBITS, false>(sm, kin, vin, kout, vout, count, shift, ghist, lookback, tile);
+
+    // the last CTA of the pass flips the ping-pong parity for the next kernel
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const uint32_t tiles = (count + kSortTile - 1) / kSortTile;
+        if (atomicAdd(&state[1 + pass], 1u) == tiles - 1) st_relaxed_u32(&state[0], parity ^ 1u);
+    }
+}
+
+// brings the result home when an odd number of passes ran (parity == 1)
+__global__ void sort_finish_kernel(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ keys_b,
+                                   const uint32_t* __restrict__ vals_b, const uint32_t* __restrict__ d_count, uint32_t max_count,
+                                   const uint32_t* __restrict__ state) {
+    if (state[0] == 0) return;
+    const uint32_t count = min(*d_count, max_count);
+    const uint32_t nvec = count / 4;
+    const uint4* kb = reinterpret_cast<const uint4*>(keys_b);
+    const uint4* vb = reinterpret_cast<const uint4*>(vals_b);
+    uint4* ka = reinterpret_cast<uint4*>(keys_a);
+    uint4* va = reinterpret_cast<uint4*>(vals_a);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        ka[i] = kb[i];
+        va[i] = vb[i];
+    }
+    if (blockIdx.x == 0)
+        for (uint32_t i = nvec * 4 + threadIdx.x; i < count; i += blockDim.x) {
+            keys_a[i] = keys_b[i];
+            vals_a[i] = vals_b[i];
+        }
 }
 
 // zeroes the histograms, tickets and the part of the look-back tables this sort will use
@@ -276,29 +357,21 @@ __global__ void sort_init_kernel(uint32_t* __restrict__ internal, const uint32_t
     }
 }
 
-__global__ void copy_pairs_kernel(const uint32_t* __restrict__ k_in, const uint32_t* __restrict__ v_in, uint32_t* __restrict__ k_out,
-                                  uint32_t* __restrict__ v_out, const uint32_t* __restrict__ d_count, uint32_t max_count) {
-    const uint32_t count = min(*d_count, max_count);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        k_out[i] = k_in[i];
-        v_out[i] = v_in[i];
-    }
-}
-
 template <int NBITS>
-void launch_pass_n(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
-                   const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket, uint32_t* lb) {
-    onesweep_kernel<NBITS><<<tiles, kSortThreads, sizeof(SortSmem), stream>>>(kin, vin, kout, vout, d_count, max_count, shift, ghist,
-                                                                            ticket, lb);
+void launch_pass_n(unsigned tiles, cudaStream_t stream, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb,
+                   const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket, uint32_t* lb,
+                   uint32_t* state, int pass) {
+    onesweep_kernel<NBITS><<<tiles, kSortThreads, sizeof(SortSmem), stream>>>(ka, va, kb, vb, d_count, max_count, shift, ghist, ticket,
+                                                                            lb, state, pass);
 }
 
-void launch_pass(int nbits, unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin, uint32_t* kout,
-                 uint32_t* vout, const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket,
-                 uint32_t* lb) {
+void launch_pass(int nbits, unsigned tiles, cudaStream_t stream, uint32_t* kin, uint32_t* vin, uint32_t* kout, uint32_t* vout,
+                 const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket, uint32_t* lb,
+                 uint32_t* state, int pass) {
     switch (nbits) {
-#define SB_PASS(N) case N: launch_pass_n<N>(tiles, stream, kin, vin, kout, vout, d_count, max_count, shift, ghist, ticket, lb); break;
+#define SB_PASS(N) case N: launch_pass_n<N>(tiles, stream, kin, vin, kout, vout, d_count, max_count, shift, ghist, ticket, lb, state, pass); break;
         SB_PASS(1) SB_PASS(2) SB_PASS(3) SB_PASS(4) SB_PASS(5) SB_PASS(6) SB_PASS(7)
-        default: launch_pass_n<8>(tiles, stream, kin, vin, kout, vout, d_count, max_count, shift, ghist, ticket, lb); break;
+        default: launch_pass_n<8>(tiles, stream, kin, vin, kout, vout, d_count, max_count, shift, ghist, ticket, lb, state, pass); break;
 #undef SB_PASS
     }
 }
@@ -341,20 +414,14 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
     const int hist_grid = (int)min((size_t)num_sms * 2, (tiles * kSortTile / 4 + 511) / 512);
     histogram_kernel<<<hist_grid > 0 ? hist_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, begin_bit, end_bit, num_passes, ghist);
 
-    uint32_t* kin = keys;
-    uint32_t* vin = payload;
-    uint32_t* kout = scratch.keys_alt;
-    uint32_t* vout = scratch.payload_alt;
+    uint32_t* state = scratch.internal + kStateOffset;
     for (int p = 0; p < num_passes; p++) {
         const int nbits = min(kRadixBits, end_bit - (begin_bit + p * kRadixBits));
-        launch_pass(nbits, (unsigned)tiles, stream, kin, vin, kout, vout, d_count, max_count, begin_bit + p * kRadixBits,
-                    ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix);
-        uint32_t* t = kin; kin = kout; kout = t;
-        t = vin; vin = vout; vout = t;
+        launch_pass(nbits, (unsigned)tiles, stream, keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count,
+                    begin_bit + p * kRadixBits, ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix, state, p);
     }
-    if (num_passes & 1) {  // result sits in the alt buffers: bring it home
-        copy_pairs_kernel<<<num_sms * 4, 256, 0, stream>>>(kin, vin, keys, payload, d_count, max_count);
-    }
+    // result sits in the alt buffers when an odd number of passes actually ran: bring it home
+    sort_finish_kernel<<<num_sms * 4, 256, 0, stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count, state);
     return cudaGetLastError();
 }
 
