@@ -34,7 +34,8 @@ SCENE_SEED = 0x3D65 + 2
 SH_FMT, COV_FMT = 0, 0           # pod single/single, 224 B
 N_VIEWS = 64                     # orbit cameras (config 5a)
 METRIC = "frames_per_sec_1080p_6M_gaussians"
-KERNELS_PER_FRAME = 13           # preprocess 1, depth sort 1+4, scan 1, emit 1, tile sort 1+2, gather 1, raster 1
+KERNELS_PER_FRAME = 17           # preprocess 1, depth sort 1+1+4+1 (init, hist, passes, finish), scan 1, emit 1,
+                                 # tile sort 1+1+2+1, gather 1, raster 1
 
 
 def peaks():
@@ -46,46 +47,47 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~2 ms; the same
+    fields as the profiling recipe's nvidia-smi line)."""
 
     def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self._stop = threading.Event()
+        self._ok = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._ok = True
+        except Exception:  # noqa: BLE001 - NVML missing: report no samples rather than fail the bench
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.p is not None:
-            self.p.terminate()
-            try:
-                self.p.wait(timeout=5)
-            except subprocess.TimeoutExpired:
-                self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        self.f.close()
-        os.unlink(self.f.name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._ok:
+            self._stop.set()
+            self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def build_scene(n: int):
@@ -183,6 +185,16 @@ def run_cuda(args):
     viewer.set_stage_timing(False)
     stage = {k: float(np.mean(v)) for k, v in acc.items()}
     V, D = float(np.mean(vis)), float(np.mean(dup))
+    # instrumented rasterizer build (outside every timed region): fragments blended / lane pairs evaluated
+    viewer.set_raster_counting(True)
+    alive, evaluated = [], []
+    for i in range(min(args.steps, 4)):
+        step_device(args.warmup + i)
+        c = viewer.read_raster_counters(stream)
+        alive.append(c["alive"])
+        evaluated.append(c["evaluated"])
+    viewer.set_raster_counting(False)
+    alive, evaluated = float(np.mean(alive)), float(np.mean(evaluated))
 
     # sanity: the frame is not empty and alpha is opaque
     stream.synchronize()
@@ -201,7 +213,25 @@ def run_cuda(args):
     sort_gbs = sort_bytes / stage["depth_sort"] / 1e6
     frame_stage_ms = sum(stage.values())
     dominant = max(stage, key=stage.get)
-    pairs = D * 256.0                                       # (pixel, splat) evaluations: one per thread per tile duplicate
+    # rasterizer: irreducible FP32 work = every blended fragment is tested (9 lane-ops) and blended
+    # (18 lane-ops on unorm8: exp scale, alpha, 1-alpha, 3 x (mul, fma, min, 2 add)); FMA counts once
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * sm_clock * 1e6 / 1e9           # G lane-ops/s at the clock sampled under load
+    raster_ops = alive * 27.0
+    raster_gops = raster_ops / stage["raster"] / 1e6
+    roofs = {
+        "raster": {"bound": "fp32", "kernel": "raster_kernel<splat,unorm8> (K6)", "achieved": raster_gops, "peak": fp32_peak,
+                   "unit": "Gop/s (FP32 lane-ops, FMA = 1)", "frac": raster_gops / fp32_peak, "traffic": None,
+                   "peak_source": f"nominal 148 SMs x 128 lanes x {sm_clock:.0f} MHz sampled under load (no measured FP32 peak in MEASURED_PEAKS.json)",
+                   "algorithmic_ops": raster_ops, "alive_fragments": alive, "evaluated_lane_pairs": evaluated,
+                   "lane_efficiency": alive / evaluated if evaluated else None, "ms": stage["raster"]},
+        "preprocess": {"bound": "hbm", "kernel": "preprocess_kernel<single,single> (K1)", "achieved": pre_gbs, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": pre_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                       "algorithmic_bytes": pre_bytes, "ms": stage["preprocess"]},
+        "depth_sort": {"bound": "hbm", "kernel": "histogram_kernel + onesweep_kernel x4 (K2/K3)", "achieved": sort_gbs, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                       "algorithmic_bytes": sort_bytes, "gkeys_per_s": V / stage["depth_sort"] / 1e6, "ms": stage["depth_sort"]},
+    }
     out = {
         "metric": METRIC, "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -215,15 +245,11 @@ def run_cuda(args):
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 144, "d2h_bytes_per_step": int(host_frame.numel())},
         "gpu_launches": KERNELS_PER_FRAME * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "preprocess_kernel<single,single> (K1)", "achieved": pre_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": pre_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes": pre_bytes, "ms": stage["preprocess"]},
-        "stages": {
-            "ms": stage, "sum_ms": frame_stage_ms, "dominant": dominant, "visible": V, "tile_duplicates": D,
-            "sort": {"gkeys_per_s": V / stage["depth_sort"] / 1e6, "achieved_gbs": sort_gbs, "frac_hbm": sort_gbs / hbm_peak,
-                     "algorithmic_bytes_per_key": 68},
-            "raster": {"pairs": pairs, "gpairs_per_s": pairs / stage["raster"] / 1e6},
-        },
+        # dominant kernel of the frame (largest share of device time) first; the two HBM-bound
+        # stages the north star grades follow in roofline_stages
+        "roofline": roofs[dominant] if dominant in roofs else roofs["raster"],
+        "roofline_stages": roofs,
+        "stages": {"ms": stage, "sum_ms": frame_stage_ms, "dominant": dominant, "visible": V, "tile_duplicates": D},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(args.cpu_sample)
@@ -290,7 +316,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--n", type=int, default=N_GAUSSIANS, help=argparse.SUPPRESS)

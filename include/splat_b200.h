@@ -224,6 +224,11 @@ SB_API SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict);
  * ms[0..5] = preprocess, depth sort, tile count+emit, tile sort, gather, raster. */
 SB_API SbStatus sb_viewer_set_stage_timing(SbViewer* v, int32_t enabled);
 SB_API SbStatus sb_viewer_read_stage_times(SbViewer* v, void* stream, float ms[6]);
+/* Instrumented rasterizer build (separate kernel instantiation, off by default): counts the
+ * fragments that were blended and the (pixel, splat) lane pairs that were evaluated in the last
+ * frame — the pair counts the FP32 roofline of the rasterizer is computed from. */
+SB_API SbStatus sb_viewer_set_raster_counting(SbViewer* v, int32_t enabled);
+SB_API SbStatus sb_viewer_read_raster_counters(SbViewer* v, void* stream, uint64_t* alive, uint64_t* evaluated);
 /* capacity (in duplicates) of the tile-binning buffers; default 8*n + tiles */
 SB_API SbStatus sb_viewer_reserve_duplicates(SbViewer* v, uint64_t capacity);
 

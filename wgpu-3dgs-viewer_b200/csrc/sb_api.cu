@@ -147,6 +147,8 @@ struct SbViewer {
     uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
     int strict_exp = 0;
     bool timing = false;
+    bool counting = false;
+    DeviceBuf counters;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     SbDrawIndirectArgs* d_draw() const { return args.as<SbDrawIndirectArgs>(); }
@@ -336,6 +338,8 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.strict_exp = v->strict_exp;
     p.clear = clear;
     p.events = v->timing ? &v->ev[3] : nullptr;
+    p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
+    if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 16, stream));
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
     return SB_OK;
 }
@@ -419,7 +423,7 @@ void sb_viewer_destroy(SbViewer* v) {
     if (!v) return;
     for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->tboxes, &v->pre_scratch, &v->sort_keys_alt,
                          &v->sort_vals_alt, &v->sort_internal, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
-                         &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target})
+                         &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target, &v->counters})
         b->release();
     if (v->h_needed) cudaFreeHost(const_cast<uint32_t*>(v->h_needed));
     for (cudaEvent_t e : v->ev)
@@ -628,6 +632,24 @@ SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible
 SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     v->strict_exp = strict != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_set_raster_counting(SbViewer* v, int32_t enabled) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    if (enabled && !v->counters.p) SB_CUDA(v->ctx, v->counters.alloc(16));
+    v->counting = enabled != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_read_raster_counters(SbViewer* v, void* stream, uint64_t* alive, uint64_t* evaluated) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    if (!v->counters.p) return fail(v->ctx, SB_ERR_INVALID_ARG, "raster counting was never enabled");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    unsigned long long c[2] = {0, 0};
+    SB_CUDA(v->ctx, cudaMemcpy(c, v->counters.p, 16, cudaMemcpyDeviceToHost));
+    if (alive) *alive = c[0];
+    if (evaluated) *evaluated = c[1];
     return SB_OK;
 }
 

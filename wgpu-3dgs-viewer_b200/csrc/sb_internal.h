@@ -72,6 +72,7 @@ struct RasterParams {
     SbTarget target;
     int strict_exp;
     int clear;                       // 1: clear to BLACK first (first model of a frame)
+    unsigned long long* counters;    // optional instrumentation: [0] alive fragments, [1] evaluated lane pairs
     cudaEvent_t* events;             // optional: [0]=after scan+emit, [1]=after tile sort, [2]=after gather, [3]=after raster
 };
 cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream_t stream);

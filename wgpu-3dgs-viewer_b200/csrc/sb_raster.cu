@@ -198,6 +198,14 @@ __device__ __forceinline__ float exp_neg_poly(float x) {
     return __uint_as_float(__float_as_uint(p) + ((uint32_t)(int)n << 23));
 }
 
+// exp(-x) for 0 <= x <= ~80 on the MUFU: ex2.approx.ftz of -x*log2(e).  __expf adds a range
+// fix-up for tiny results that cannot occur here (x <= std_dev^2 <= 9).
+__device__ __forceinline__ float exp_neg_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * -1.44269504f));
+    return y;
+}
+
 // round-to-nearest-even of x in [0, 2^22) without the (quarter-rate) FRND instruction
 __device__ __forceinline__ float rint_small(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
 
@@ -214,9 +222,10 @@ struct RasterKernelParams {
     float outline;  // (std_dev - 0.1)^2
     int bgra;
     int clear;
+    unsigned long long* counters;  // COUNT builds: [0] alive fragments, [1] evaluated (pixel,splat) lane pairs
 };
 
-template <int MODE, int FMT, bool STRICT>
+template <int MODE, int FMT, bool STRICT, bool COUNT>
 __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p) {
     __shared__ __align__(128) float4 stage[2][kBatch * 3];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
 
     // destination state: 0..255 units on unorm8 targets (re-quantised after every blend)
     float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 1.0f;
+    uint32_t n_alive = 0, n_eval = 0;
     uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
     if (!p.clear && inside) {
         if constexpr (FMT == FMT_UNORM8) {
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
                 const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
                 const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
                 const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
+                if constexpr (COUNT) n_eval += inside ? 1u : 0u;
                 float alpha;
                 if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
                     if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
                     if (!(r2 <= p.sd2)) continue;  // discard: render.wesl:145,155
                     const float a = recs[j * 3 + 2].w;
                     if constexpr (MODE == SB_MODE_SPLAT) {
-                        const float e = STRICT ? exp_neg_poly(r2) : __expf(-r2);
+                        const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
                         alpha = __fmul_rn(a, e);  // render.wesl:149
                     } else {
                         const float ol = r2 > p.outline ? 1.0f : 0.0f;  // render.wesl:159-160
@@ -312,6 +323,7 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
                     }
                 }
                 const float4 q2 = recs[j * 3 + 2];
+                if constexpr (COUNT) n_alive += inside ? 1u : 0u;
                 const float om = __fsub_rn(1.0f, alpha);
                 if constexpr (FMT == FMT_UNORM8) {
                     d0 = rint_small(fminf(__fmaf_rn(d0, om, __fmul_rn(q2.x, alpha)), 255.0f));
@@ -330,6 +342,18 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
             }
         }
         __syncthreads();  // everyone is done with stage[s] before it is refilled
+    }
+
+    if constexpr (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_alive += __shfl_xor_sync(0xffffffffu, n_alive, o);
+            n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+        }
+        if (lane == 0 && p.counters) {
+            atomicAdd(&p.counters[0], (unsigned long long)n_alive);
+            atomicAdd(&p.counters[1], (unsigned long long)n_eval);
+        }
     }
 
     if (inside) {
@@ -368,7 +392,8 @@ __global__ void clear_kernel(uint8_t* pixels, uint32_t pitch, uint32_t width, ui
 
 template <int MODE, int FMT, bool STRICT>
 void launch_raster(const RasterKernelParams& kp, dim3 grid, cudaStream_t stream) {
-    raster_kernel<MODE, FMT, STRICT><<<grid, 256, 0, stream>>>(kp);
+    if (kp.counters) raster_kernel<MODE, FMT, STRICT, true><<<grid, 256, 0, stream>>>(kp);
+    else raster_kernel<MODE, FMT, STRICT, false><<<grid, 256, 0, stream>>>(kp);
 }
 
 }  // namespace
@@ -448,6 +473,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     kp.outline = (u.std_dev - 0.1f) * (u.std_dev - 0.1f);
     kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
     kp.clear = p.clear;
+    kp.counters = p.counters;
     const dim3 grid(u.tiles_x, ty_hi - ty_lo + 1);
     const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
                     : t.format == SB_TARGET_RGBA16_FLOAT                                       ? FMT_F16

@@ -33,7 +33,8 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
     "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_set_strict_exp",
-    "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times",
+    "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times", "sb_viewer_set_raster_counting",
+    "sb_viewer_read_raster_counters",
     "sb_viewer_reserve_duplicates", "sb_sorter_create", "sb_sorter_destroy", "sb_sorter_sort", "sb_mm_create",
     "sb_mm_destroy", "sb_mm_insert_model", "sb_mm_remove_model", "sb_mm_update_camera_with_pod",
     "sb_mm_update_model_transform_with_pod", "sb_mm_update_gaussian_transform_with_pod", "sb_mm_set_selection",
@@ -155,6 +156,8 @@ def load() -> C.CDLL:
     sig("sb_viewer_read_depth_keys", i32, vp, vp, vp, u64)
     sig("sb_viewer_read_frame_stats", i32, vp, vp, P(u64), P(u64), P(u32))
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
+    sig("sb_viewer_set_raster_counting", i32, vp, i32)
+    sig("sb_viewer_read_raster_counters", i32, vp, vp, P(u64), P(u64))
     sig("sb_viewer_set_stage_timing", i32, vp, i32)
     sig("sb_viewer_read_stage_times", i32, vp, vp, P(f32))
     sig("sb_viewer_reserve_duplicates", i32, vp, u64)
@@ -405,6 +408,14 @@ class Viewer:
         _check(load().sb_viewer_set_strict_exp(self._h, int(strict)), self.ctx._h)
 
     STAGES = ("preprocess", "depth_sort", "tile_emit", "tile_sort", "gather", "raster")
+
+    def set_raster_counting(self, enabled: bool):
+        _check(load().sb_viewer_set_raster_counting(self._h, int(enabled)), self.ctx._h)
+
+    def read_raster_counters(self, stream=None) -> dict:
+        a, e = C.c_uint64(), C.c_uint64()
+        _check(load().sb_viewer_read_raster_counters(self._h, _stream_handle(stream), C.byref(a), C.byref(e)), self.ctx._h)
+        return dict(alive=a.value, evaluated=e.value)
 
     def set_stage_timing(self, enabled: bool):
         _check(load().sb_viewer_set_stage_timing(self._h, int(enabled)), self.ctx._h)
