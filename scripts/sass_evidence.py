@@ -1,0 +1,28 @@
+"""Mnemonic counts per kernel from cuobjdump -sass (committed as profiles/<tag>_sass_evidence.txt)."""
+import collections, re, subprocess, sys
+lib = "wgpu-3dgs-viewer_b200/lib/libsplat_b200.so"
+out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+keys = ["UBLKCP", "SYNCS", "VOTE", "MATCH", "ATOMS", "MUFU.EX2", "LDG", "STG", "LDS", "STS", "FFMA", "HMMA", "UTC", "LDTM", "UTMALDG"]
+fn, counts, total = None, collections.defaultdict(collections.Counter), collections.Counter()
+for line in out.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        fn = re.sub(r"\(anonymous namespace\)::", "", fn).split("(")[0].replace("void ", "")
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    if m and fn:
+        op = m.group(1)
+        total[fn] += 1
+        for k in keys:
+            if op.startswith(k):
+                counts[fn][k] += 1
+print("# cuobjdump -sass", lib)
+print("# UBLKCP = cp.async.bulk (TMA 1-D bulk copy); SYNCS = mbarrier; VOTE/MATCH = warp ballots; ATOMS = shared atomics;")
+print("# HMMA / UTC*MMA / LDTM / UTMALDG (tensor cores, TMEM, tensor-map TMA) are absent by design: no stage is a dense contraction.")
+want = sys.argv[1:] or ["preprocess_kernel<0, 0>", "preprocess_kernel<1, 1>", "preprocess_kernel<2, 1>", "onesweep_kernel<8>", "onesweep_kernel<5>",
+                        "histogram_kernel", "raster_kernel<0, 0, false, false>", "raster_kernel<1, 0, false, false>", "raster_kernel<0, 3, true, false>",
+                        "dup_scan_kernel", "dup_emit_kernel", "gather_kernel", "select_rect_kernel", "sort_init_kernel", "sort_finish_kernel"]
+for f in sorted(total):
+    if any(w in f for w in want):
+        print(f"{f:70s} total={total[f]:5d} " + " ".join(f"{k}={v}" for k, v in counts[f].items()))

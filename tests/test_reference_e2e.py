@@ -111,3 +111,13 @@ def test_selection_default_invert_hides_nothing(sb, ctx):  # src/selection/buffe
     torch.cuda.synchronize()
     assert sums(t.cpu().numpy())[0] > 1
     v.close()
+
+
+def test_cpp_host_mirror_e2e(sb):
+    """The typed C++ host mirror (host/splat_b200.hpp) runs the reference's viewer e2e test."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(sb.lib_path()), "..", "build", "e2e_viewer")
+    assert os.path.exists(exe), "build/e2e_viewer missing: run __graft_entry__.build()"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout + out.stderr
