@@ -18,13 +18,13 @@ namespace {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kSortThreads = 512;
+constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 16;
-constexpr int kSortTile = kSortThreads * kItems;  // 8192 pairs per tile: 32-key runs per digit on random digits
+constexpr int kSortTile = kSortThreads * kItems;  // pairs per tile
 constexpr int kMaxPasses = 4;
 #ifndef SB_MATCH_EVERY
-#define SB_MATCH_EVERY 3
+#define SB_MATCH_EVERY 0
 #endif
 constexpr int kMatchEvery = SB_MATCH_EVERY;  // every k-th item is ranked with MATCH.ANY (0 = never)
 
@@ -104,7 +104,10 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
 
 struct SortSmem {
     union {
-        uint32_t warp_hist[kSortWarps][kRadix + 32];  // +32: bin 256 collects out-of-range lanes
+        struct {
+            uint32_t warp_hist[kSortWarps][kRadix];
+            uint32_t warp_mask[kSortWarps][2][kRadix];  // peer bitmasks per digit, two planes (even/odd item)
+        };
         struct {
             uint32_t keys[kSortTile];
             uint32_t vals[kSortTile];
@@ -143,31 +146,27 @@ __device__ __forceinline__ void onesweep_tile(SortSmem& sm, const uint32_t* __re
     // ballot per digit bit finds the peers, the lowest peer claims the run with one shared atomic.
     uint32_t rank2[kItems / 2];  // two 16-bit ranks per register (a rank is < 8192)
     uint32_t* wh = sm.warp_hist[warp];
+    uint32_t* wm = sm.warp_mask[warp][0];
     const uint32_t lt = lanemask_lt();
+    const uint32_t my_bit = 1u << lane;
+    // Peer mask through shared memory: every lane ORs its lane bit into mask[digit] (commutative,
+    // hence deterministic), then reads the word back = the lanes holding the same digit.  ~18
+    // instructions per key instead of ~54 for a ballot per digit bit; MATCH.ANY is MIO-bound on B200.
+    // Two planes alternate so the leader's clear never races the next item's ORs.
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
         const bool ok = FULL || (warp_base + i * 32 + lane) < count;
         const uint32_t d = (key[i] >> shift) & kMask;
-        uint32_t peers = 0xffffffffu;
-        if (kMatchEvery > 0 && (i % kMatchEvery) == kMatchEvery - 1) {
-            // MATCH.ANY runs on the MIO pipe, the ballot chain on the ALU pipe: mixing the two
-            // forms balances the pipes (ncu: all-MATCH is MIO-bound, all-ballot is issue-bound)
-            peers = __match_any_sync(0xffffffffu, ok ? d : 0xffffffffu);
-        } else {
-            if (!FULL) {
-                peers = __ballot_sync(0xffffffffu, ok);
-                if (!ok) peers = ~peers;
-            }
-#pragma unroll
-            for (int b = 0; b < NBITS; b++) {
-                const bool bit = (d >> b) & 1u;
-                const uint32_t m = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? m : ~m;
-            }
-        }
+        uint32_t* plane = wm + (i & 1) * kRadix;
+        if (ok) atomicOr(&plane[d], my_bit);
+        __syncwarp();
+        const uint32_t peers = ok ? plane[d] : my_bit;
         const uint32_t below = __popc(peers & lt);
         uint32_t pre = 0;
-        if (below == 0 && ok) pre = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+        if (below == 0 && ok) {
+            pre = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+            plane[d] = 0;
+        }
         pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
         if (i & 1) rank2[i >> 1] |= (pre + below) << 16;
         else rank2[i >> 1] = pre + below;
@@ -225,17 +224,41 @@ __device__ __forceinline__ void onesweep_tile(SortSmem& sm, const uint32_t* __re
         global_excl = b - gcount + wb;
     }
 
+    // fold the tile-local digit start into warp_hist: a key's tile-sorted position is
+    // warp_hist[w][d] + rank (warp_hist[w][d] = exclusive count of digit d in warps < w)
     if (tid < kRadix) {
-        // decoupled look-back, 4 predecessors per round trip
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) sm.warp_hist[w][tid] += local_excl;
+    }
+    __syncthreads();
+
+    // ---- tile-sorted positions, then reorder through shared memory.  None of this needs the
+    // global offsets, so it runs BEFORE the look-back: predecessors get time to publish.
+    uint32_t base2[kItems / 2];
+#pragma unroll
+    for (int i = 0; i < kItems; i += 2)
+        base2[i >> 1] = wh[(key[i] >> shift) & kMask] | (wh[(key[i + 1] >> shift) & kMask] << 16);
+    __syncthreads();  // warp_hist/warp_mask are dead; their storage becomes the staging buffer
+#pragma unroll
+    for (int i = 0; i < kItems; i++) {
+        if (FULL || (warp_base + i * 32 + lane) < count) {
+            const uint32_t pos = ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu) + ((base2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+            sm.stage.keys[pos] = key[i];
+            sm.stage.vals[pos] = val[i];
+        }
+    }
+
+    if (tid < kRadix) {
+        // decoupled look-back, 8 predecessors per round trip
         uint32_t tile_excl = 0;
         int t = (int)tile - 1;
         while (t >= 0) {
-            uint32_t v[4];
+            uint32_t v[8];
 #pragma unroll
-            for (int j = 0; j < 4; j++) v[j] = (t - j) >= 0 ? ld_relaxed_u32(&lookback[(size_t)(t - j) * kRadix + tid]) : kLbPrefix;
+            for (int j = 0; j < 8; j++) v[j] = (t - j) >= 0 ? ld_relaxed_u32(&lookback[(size_t)(t - j) * kRadix + tid]) : kLbPrefix;
             bool done = false;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 8; j++) {
                 if (done) break;
                 if ((v[j] >> 30) == 0) break;  // not published yet: retry from here
                 tile_excl += v[j] & kLbValueMask;
@@ -248,26 +271,6 @@ __device__ __forceinline__ void onesweep_tile(SortSmem& sm, const uint32_t* __re
         }
         if (tile > 0) st_relaxed_u32(&lookback[(size_t)tile * kRadix + tid], kLbPrefix | (tile_excl + digit_count));
         sm.digit_base[tid] = global_excl + tile_excl - local_excl;
-        // warp_hist[w][d] holds the exclusive count of digit d in warps < w; fold in the tile-local
-        // digit start so a key's tile-sorted position is warp_hist[w][d] + rank.
-#pragma unroll
-        for (int w = 0; w < kSortWarps; w++) sm.warp_hist[w][tid] += local_excl;
-    }
-    __syncthreads();
-
-    // ---- tile-sorted positions, then reorder through shared memory
-    uint32_t base2[kItems / 2];
-#pragma unroll
-    for (int i = 0; i < kItems; i += 2)
-        base2[i >> 1] = wh[(key[i] >> shift) & kMask] | (wh[(key[i + 1] >> shift) & kMask] << 16);
-    __syncthreads();  // warp_hist is dead; its storage becomes the staging buffer
-#pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        if (FULL || (warp_base + i * 32 + lane) < count) {
-            const uint32_t pos = ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu) + ((base2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-            sm.stage.keys[pos] = key[i];
-            sm.stage.vals[pos] = val[i];
-        }
     }
     __syncthreads();
 #pragma unroll
@@ -284,7 +287,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem& sm, const uint32_t* __re
 
 // K3: one onesweep digit pass over NBITS significant digit bits.
 template <int NBITS>
-__global__ void __launch_bounds__(kSortThreads, 2)
+__global__ void __launch_bounds__(kSortThreads, 4)
     onesweep_kernel(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
                     uint32_t* __restrict__ vals_b, const uint32_t* __restrict__ d_count, uint32_t max_count, int shift,
                     const uint32_t* __restrict__ ghist /* this pass, 256 */, uint32_t* __restrict__ ticket,
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     if (degenerate) return;
 
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < kSortWarps * (kRadix + 32); i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < kSortWarps * kRadix * 3; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = sm.tile;
     const uint32_t parity = ld_relaxed_u32(&state[0]);  // stable during the pass: flipped by the last CTA only
