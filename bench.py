@@ -90,6 +90,30 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the hot kernels from the
+    committed `ncu --set full` capture of this same command (profiles/<tag>_ncu_full_summary.json)."""
+    import glob
+    out = {}
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_summary.json")))
+    if not files:
+        return out
+    with open(files[-1]) as f:
+        summ = json.load(f)
+
+    def to_bytes(txt):
+        val, unit = txt.split()[:2]
+        return float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+    for key, stage in (("preprocess_kernel", "preprocess"), ("raster_kernel", "raster")):
+        rows = summ.get(key) or []
+        vals = [to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"]) for r in rows
+                if "dram__bytes_read.sum" in r and "dram__bytes_write.sum" in r]
+        if vals:
+            out[stage] = {"bytes": float(np.mean(vals)), "source": os.path.basename(files[-1])}
+    return out
+
+
 def build_scene(n: int):
     import splat_b200 as sb
     g = sb.scenes.synthetic_gaussians(n, SCENE_SEED)
@@ -232,6 +256,9 @@ def run_cuda(args):
                        "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                        "algorithmic_bytes": sort_bytes, "gkeys_per_s": V / stage["depth_sort"] / 1e6, "ms": stage["depth_sort"]},
     }
+    for stage_name, t in ncu_traffic().items():
+        roofs[stage_name]["traffic"] = t["bytes"]
+        roofs[stage_name]["traffic_source"] = t["source"]
     out = {
         "metric": METRIC, "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
