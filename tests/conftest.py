@@ -27,6 +27,8 @@ def ob():
 def sb():
     """The product's Python harness over the C ABI; fails loudly if the .so is missing."""
     import splat_b200
+    if not os.path.exists(splat_b200.lib_path()):
+        splat_b200.build()  # fresh checkout: the .so is git-ignored (nvcc cross-compiles without a GPU)
     splat_b200.load()
     return splat_b200
 
