@@ -55,8 +55,7 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool ok) {
     return peers;
 }
 
-// K2: one read of the keys, all digit histograms at once.  Warp-aggregated shared atomics
-// (match.any) so the clustered high digits of depth keys do not serialise on one address.
+// K2: one read of the keys, all digit histograms at once (shared atomics, global merge).
 __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count,
                                                         uint32_t max_count, int begin_bit, int end_bit, int num_passes,
                                                         uint32_t* __restrict__ ghist) {
@@ -66,8 +65,7 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
     const uint32_t count = min(*d_count, max_count);
     const uint32_t nvec = count / 4;
     const uint4* kv = reinterpret_cast<const uint4*>(keys);
-    const uint32_t lt = lanemask_lt();
-    // warp-uniform trip count so match.any sees every lane
+    // warp-uniform trip count so the warp votes see every lane
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < nvec; base += stride) {
         const uint32_t i = base + threadIdx.x;
@@ -80,9 +78,16 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
             const uint32_t mask = (1u << min(kRadixBits, end_bit - sh)) - 1u;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                // one shared atomic per key and digit; when the whole warp holds the same digit
+                // (the top byte of one frame's depth keys) a single lane adds 32 instead of 32
+                // lanes serialising on one address
                 const uint32_t d = (ks[j] >> sh) & mask;
-                const uint32_t peers = digit_peers<kRadixBits>(d, ok);
-                if (ok && (peers & lt) == 0) atomicAdd(&hist[p][d], (uint32_t)__popc(peers));
+                const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+                if (__all_sync(0xffffffffu, ok && d == d0)) {
+                    if ((threadIdx.x & 31u) == 0) atomicAdd(&hist[p][d0], 32u);
+                } else if (ok) {
+                    atomicAdd(&hist[p][d], 1u);
+                }
             }
         }
     }
