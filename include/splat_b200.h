@@ -216,6 +216,9 @@ SB_API SbStatus sb_viewer_read_depth_keys(SbViewer* v, void* stream, float* out,
  * duplicates, overflow flag */
 SB_API SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible, uint64_t* duplicates,
                                            uint32_t* overflowed);
+/* how the rasterizer fetches splat records: 1 = TMA tile::gather4 straight from the per-Gaussian array
+ * (default), 0 = gathered copy + 1-D TMA bulk copies (environment SB_RASTER_PATH=bulk at viewer creation) */
+SB_API SbStatus sb_viewer_raster_path(SbViewer* v, int32_t* tma_gather4);
 /* testing knob: 1 = bit-reproducible polynomial exp in the fragment stage (matches the
  * oracle's strict_exp); 0 (default) = MUFU ex2 fast path */
 SB_API SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict);

@@ -59,7 +59,7 @@ for n in args.n:
         med = {k: float(np.median(x)) for k, x in acc.items()}
         frame = float(np.median(tot))
         pre_bytes = n * 16 + V * (stride - 16) + 8 * V
-        out = dict(n=n, cam=cam_name, size=[w, h], visible=V, duplicates=D, overflow=st["overflowed"], frame_ms=frame,
+        out = dict(path=v.raster_path(), n=n, cam=cam_name, size=[w, h], visible=V, duplicates=D, overflow=st["overflowed"], frame_ms=frame,
                    fps=1000.0 / frame, stages_ms=med,
                    preprocess_GBs=pre_bytes / med["preprocess"] / 1e6, sort_Gkeys=V / med["depth_sort"] / 1e6,
                    sort_GBs=V * 68 / med["depth_sort"] / 1e6, pairs_G=D * 256 / 1e9,

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -96,6 +97,27 @@ sb::Uniforms make_uniforms(const SbCameraPod& cam, const SbModelTransformPod& mt
     return u;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool encode_recs_map(void* d_recs, uint64_t n, CUtensorMap* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t gdim[2] = {12, n ? n : 1};
+    const cuuint64_t gstride[1] = {sizeof(sb::SplatRec)};
+    const cuuint32_t box[2] = {12, 1};  // gather4 fetches four 1-row boxes (probed: scripts/probes/probe_gather4.cu)
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_recs, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct DeviceBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -146,6 +168,8 @@ struct SbViewer {
     bool selection_enabled = false;
     uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
     int strict_exp = 0;
+    CUtensorMap recs_map;        // 2-D view of recs[] (12 x n floats, 48-byte rows) for TMA gather4
+    bool use_gather4 = false;
     bool timing = false;
     bool counting = false;
     DeviceBuf counters;
@@ -172,6 +196,12 @@ SbStatus viewer_alloc(SbViewer* v) {
     SB_CUDA(ctx, v->args.alloc(64));
     SB_CUDA(ctx, v->recs.alloc((size_t)(n ? n : 1) * sizeof(sb::SplatRec)));
     SB_CUDA(ctx, v->tboxes.alloc((size_t)(n ? n : 1) * sizeof(sb::TileBox)));
+    {
+        // rasterizer record fetch: TMA gather4 from recs[] (default) or a gathered copy + 1-D bulk copies
+        const char* path = std::getenv("SB_RASTER_PATH");
+        const bool want_bulk = path && std::string(path) == "bulk";
+        v->use_gather4 = !want_bulk && encode_recs_map(v->recs.p, n, &v->recs_map);
+    }
     SB_CUDA(ctx, v->pre_scratch.alloc(sb::preprocess_scratch_bytes(n, v->sh_fmt, v->cov_fmt)));
     SB_CUDA(ctx, v->selection.alloc(((size_t)n + 31) / 32 * 4 + 4));
     SB_CUDA(ctx, cudaMemset(v->selection.p, 0, v->selection.bytes));
@@ -202,7 +232,7 @@ SbStatus viewer_reserve(SbViewer* v, uint64_t cap) {
     v->dup_capacity = cap;
     SB_CUDA(ctx, v->dup_keys.alloc(cap * 4));
     SB_CUDA(ctx, v->dup_vals.alloc(cap * 4));
-    SB_CUDA(ctx, v->tile_recs.alloc(cap * sizeof(sb::SplatRec)));
+    if (!v->use_gather4) SB_CUDA(ctx, v->tile_recs.alloc(cap * sizeof(sb::SplatRec)));
     const uint64_t sort_cap = cap > v->padded ? cap : v->padded;
     SB_CUDA(ctx, v->sort_keys_alt.alloc(sort_cap * 4));
     SB_CUDA(ctx, v->sort_vals_alt.alloc(sort_cap * 4));
@@ -338,6 +368,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.strict_exp = v->strict_exp;
     p.clear = clear;
     p.events = v->timing ? &v->ev[3] : nullptr;
+    p.recs_map = v->use_gather4 ? &v->recs_map : nullptr;
     p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
     if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 16, stream));
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
@@ -627,6 +658,12 @@ SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible
     if (duplicates) *duplicates = st[0];
     if (overflowed) *overflowed = st[1];
     return st[1] ? fail(v->ctx, SB_ERR_OVERFLOW, "tile-duplicate capacity exceeded; call sb_viewer_reserve_duplicates") : SB_OK;
+}
+
+SbStatus sb_viewer_raster_path(SbViewer* v, int32_t* tma_gather4) {
+    if (!v || !tma_gather4) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    *tma_gather4 = v->use_gather4 ? 1 : 0;
+    return SB_OK;
 }
 
 SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {

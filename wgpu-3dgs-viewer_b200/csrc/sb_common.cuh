@@ -119,6 +119,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// TMA tile::gather4: four rows of a 2-D tensor (row indices r0..r3, column 0) -> four consecutive
+// rows in shared memory; completion (4 * row bytes) is signalled on the mbarrier.  SASS: UTMALDG.
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tensor_map, uint64_t* bar, uint32_t r0, uint32_t r1,
+                                            uint32_t r2, uint32_t r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+            "r"(smem_dst),
+        "l"(tensor_map), "r"(smem_u32(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

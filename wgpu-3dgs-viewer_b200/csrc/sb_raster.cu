@@ -10,6 +10,7 @@
 //   K6 raster      one CTA per 16x16 tile; batches staged into shared memory with TMA bulk
 //                  copies; one pixel per thread composites back-to-front in exactly the
 //                  reference's order, re-quantising after every blend on unorm8 targets.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "sb_internal.h"
@@ -179,6 +180,15 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------- K6 rasterizer
 
 constexpr int kBatch = 256;  // splat records per shared-memory stage (12 KB)
+// gather4 path: 256 records per batch = 32 producer lanes x 8 records (two gather4s per lane).  Each
+// gather4 (4 rows x 48 B) is written at a 256-byte pitch (the TMA destination must be 128-byte aligned).
+// float4 index of record q (0..7) of lane l: l * 32 + g4_q_off(q)
+constexpr int kG4Lanes = 32;
+constexpr int kBatchG4 = kG4Lanes * 8;
+constexpr int kG4Stages = 2;
+constexpr int kG4StageF4 = kG4Lanes * 2 * 16;
+__device__ __forceinline__ uint32_t g4_q_off(uint32_t q) { return (q >> 2) * 16 + (q & 3u) * 3; }
+__device__ __forceinline__ uint32_t g4_row_f4(uint32_t owner_lane, uint32_t q) { return owner_lane * 32 + g4_q_off(q); }
 
 enum { FMT_UNORM8 = 0, FMT_F16 = 1, FMT_F32 = 2 };
 
@@ -210,7 +220,8 @@ __device__ __forceinline__ float exp_neg_fast(float x) {
 __device__ __forceinline__ float rint_small(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
 
 struct RasterKernelParams {
-    const SplatRec* tile_recs;
+    const SplatRec* tile_recs;      // bulk path: records gathered into tile order
+    const uint32_t* dup_vals;       // gather4 path: Gaussian index per tile-sorted duplicate
     const uint32_t* tile_ranges;
     uint8_t* pixels;
     uint32_t pitch;
@@ -225,20 +236,143 @@ struct RasterKernelParams {
     unsigned long long* counters;  // COUNT builds: [0] alive fragments, [1] evaluated (pixel,splat) lane pairs
 };
 
+struct PixelState {
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 1.0f;  // destination; 0..255 units on unorm8 targets
+    uint32_t n_alive = 0, n_eval = 0;
+};
+
+template <int FMT>
+__device__ __forceinline__ void load_dst(PixelState& st, const uint8_t* row, uint32_t x, int bgra) {
+    if constexpr (FMT == FMT_UNORM8) {
+        const uchar4 c = reinterpret_cast<const uchar4*>(row)[x];
+        st.d0 = bgra ? c.z : c.x;
+        st.d1 = c.y;
+        st.d2 = bgra ? c.x : c.z;
+    } else if constexpr (FMT == FMT_F16) {
+        const __half* h = reinterpret_cast<const __half*>(row) + 4 * x;
+        st.d0 = __half2float(h[0]); st.d1 = __half2float(h[1]); st.d2 = __half2float(h[2]); st.d3 = __half2float(h[3]);
+    } else {
+        const float4 c = reinterpret_cast<const float4*>(row)[x];
+        st.d0 = c.x; st.d1 = c.y; st.d2 = c.z; st.d3 = c.w;
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_dst(const PixelState& st, uint8_t* row, uint32_t x, int bgra) {
+    if constexpr (FMT == FMT_UNORM8) {
+        uchar4 c;
+        c.x = (unsigned char)(bgra ? st.d2 : st.d0);
+        c.y = (unsigned char)st.d1;
+        c.z = (unsigned char)(bgra ? st.d0 : st.d2);
+        c.w = 255;
+        reinterpret_cast<uchar4*>(row)[x] = c;
+    } else if constexpr (FMT == FMT_F16) {
+        __half2 lo = __floats2half2_rn(st.d0, st.d1), hi = __floats2half2_rn(st.d2, st.d3);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(row)[x] = o;
+    } else {
+        reinterpret_cast<float4*>(row)[x] = make_float4(st.d0, st.d1, st.d2, st.d3);
+    }
+}
+
+// Composites one staged batch onto this thread's pixel, in list order.  PERM: record j of the batch
+// was fetched by producer lane j % 31 as its q = j / 31 -th record (layout: g4_row_f4).
+// Warp-level culling: each lane tests one splat's alive-region bbox against the warp's 8x4 pixel
+// patch; only splats that can touch the patch are evaluated.
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
+__device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, float px, float py, float pcx, float pcy,
+                                                uint32_t lane, bool inside, float sd2, float outline, PixelState& st) {
+    constexpr uint32_t kRound = PERM ? kG4Lanes : 32;  // records tested per warp round
+    for (uint32_t base = 0, q = 0; base < cnt; base += kRound, ++q) {
+        const uint32_t jl = base + lane;
+        const uint32_t qoff = PERM ? g4_q_off(q) : base * 3;  // per round, so the survivor loop adds one shift/mad
+        bool hit = false;
+        if (lane < kRound && jl < cnt) {
+            const uint32_t r4 = PERM ? (lane * 32 + qoff) : jl * 3;
+            const float4 c0 = recs[r4 + 0];
+            const float4 c1 = recs[r4 + 1];
+            hit = fabsf(c0.x - pcx) <= c1.z + 3.51f && fabsf(c0.y - pcy) <= c1.w + 1.51f;
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, hit);
+        while (todo) {
+            const uint32_t b = (uint32_t)(__ffs(todo) - 1);
+            todo &= todo - 1;
+            const uint32_t r4 = PERM ? (b * 32 + qoff) : (b * 3 + qoff);
+            const float4 q0 = recs[r4 + 0];
+            const float4 q1 = recs[r4 + 1];
+            const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
+            const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
+            const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
+            if constexpr (COUNT) st.n_eval += inside ? 1u : 0u;
+            float alpha;
+            if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
+                if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
+                alpha = 1.0f;
+            } else {
+                const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
+                if (!(r2 <= sd2)) continue;  // discard: render.wesl:145,155
+                const float a = recs[r4 + 2].w;
+                if constexpr (MODE == SB_MODE_SPLAT) {
+                    const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
+                    alpha = __fmul_rn(a, e);  // render.wesl:149
+                } else {
+                    const float ol = r2 > outline ? 1.0f : 0.0f;  // render.wesl:159-160
+                    alpha = __fadd_rn(a, __fmul_rn(__fsub_rn(1.0f, a), ol));
+                }
+            }
+            const float4 q2 = recs[r4 + 2];
+            if constexpr (COUNT) st.n_alive += inside ? 1u : 0u;
+            const float om = __fsub_rn(1.0f, alpha);
+            if constexpr (FMT == FMT_UNORM8) {
+                st.d0 = rint_small(fminf(__fmaf_rn(st.d0, om, __fmul_rn(q2.x, alpha)), 255.0f));
+                st.d1 = rint_small(fminf(__fmaf_rn(st.d1, om, __fmul_rn(q2.y, alpha)), 255.0f));
+                st.d2 = rint_small(fminf(__fmaf_rn(st.d2, om, __fmul_rn(q2.z, alpha)), 255.0f));
+            } else {
+                st.d0 = __fmaf_rn(st.d0, om, __fmul_rn(q2.x, alpha));
+                st.d1 = __fmaf_rn(st.d1, om, __fmul_rn(q2.y, alpha));
+                st.d2 = __fmaf_rn(st.d2, om, __fmul_rn(q2.z, alpha));
+                st.d3 = __fmaf_rn(st.d3, om, alpha);
+                if constexpr (FMT == FMT_F16) {
+                    st.d0 = __half2float(__float2half_rn(st.d0)); st.d1 = __half2float(__float2half_rn(st.d1));
+                    st.d2 = __half2float(__float2half_rn(st.d2)); st.d3 = __half2float(__float2half_rn(st.d3));
+                }
+            }
+        }
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void flush_counters(PixelState& st, uint32_t lane, unsigned long long* counters) {
+    if constexpr (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st.n_alive += __shfl_xor_sync(0xffffffffu, st.n_alive, o);
+            st.n_eval += __shfl_xor_sync(0xffffffffu, st.n_eval, o);
+        }
+        if (lane == 0 && counters) {
+            atomicAdd(&counters[0], (unsigned long long)st.n_alive);
+            atomicAdd(&counters[1], (unsigned long long)st.n_eval);
+        }
+    }
+}
+
+// K6 (a): batches are contiguous in tile_recs (written by gather_kernel); one elected thread
+// streams them in with 1-D TMA bulk copies, double buffered.
 template <int MODE, int FMT, bool STRICT, bool COUNT>
-__global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p) {
+__global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelParams p) {
     __shared__ __align__(128) float4 stage[2][kBatch * 3];
     __shared__ __align__(8) uint64_t full_bar[2];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
     const uint32_t tile = tile_y * p.tiles_x + tile_x;
-    // each warp owns an 8x4 pixel patch
+    // each warp owns an 8x4 pixel patch (pixel centres: half extents 3.5 x 1.5 around pcx, pcy)
     const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane & 7u);
     const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-    // centre of this warp's 8x4 patch of pixel centres (half extents 3.5 x 1.5)
     const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 4.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
 
     const uint32_t begin = p.tile_ranges[2 * tile], end = p.tile_ranges[2 * tile + 1];
@@ -257,24 +391,9 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
         bulk_g2s(stage[0], p.tile_recs + begin, bytes, &full_bar[0]);
     }
 
-    // destination state: 0..255 units on unorm8 targets (re-quantised after every blend)
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 1.0f;
-    uint32_t n_alive = 0, n_eval = 0;
+    PixelState st;
     uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
-    if (!p.clear && inside) {
-        if constexpr (FMT == FMT_UNORM8) {
-            const uchar4 c = reinterpret_cast<const uchar4*>(dst)[x];
-            d0 = p.bgra ? c.z : c.x;
-            d1 = c.y;
-            d2 = p.bgra ? c.x : c.z;
-        } else if constexpr (FMT == FMT_F16) {
-            const __half* h = reinterpret_cast<const __half*>(dst) + 4 * x;
-            d0 = __half2float(h[0]); d1 = __half2float(h[1]); d2 = __half2float(h[2]); d3 = __half2float(h[3]);
-        } else {
-            const float4 c = reinterpret_cast<const float4*>(dst)[x];
-            d0 = c.x; d1 = c.y; d2 = c.z; d3 = c.w;
-        }
-    }
+    if (!p.clear && inside) load_dst<FMT>(st, dst, x, p.bgra);
 
     for (uint32_t k = 0; k < batches; k++) {
         const uint32_t s = k & 1u;
@@ -285,94 +404,98 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterKernelParams p)
         }
         mbar_wait(&full_bar[s], (k >> 1) & 1u);
         const uint32_t cnt = min((uint32_t)kBatch, total - k * kBatch);
-        const float4* recs = stage[s];
-        // Warp-level culling: each lane tests one splat's alive-region bbox against this warp's
-        // 8x4 pixel patch; only splats that can touch the patch are evaluated, in list order.
-        for (uint32_t base = 0; base < cnt; base += 32) {
-            const uint32_t jl = base + lane;
-            bool hit = false;
-            if (jl < cnt) {
-                const float4 c0 = recs[jl * 3 + 0];
-                const float4 c1 = recs[jl * 3 + 1];
-                hit = fabsf(c0.x - pcx) <= c1.z + 3.51f && fabsf(c0.y - pcy) <= c1.w + 1.51f;
-            }
-            uint32_t todo = __ballot_sync(0xffffffffu, hit);
-            while (todo) {
-                const uint32_t j = base + (uint32_t)(__ffs(todo) - 1);
-                todo &= todo - 1;
-                const float4 q0 = recs[j * 3 + 0];
-                const float4 q1 = recs[j * 3 + 1];
-                const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
-                const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
-                const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
-                if constexpr (COUNT) n_eval += inside ? 1u : 0u;
-                float alpha;
-                if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
-                    if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
-                    alpha = 1.0f;
-                } else {
-                    const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
-                    if (!(r2 <= p.sd2)) continue;  // discard: render.wesl:145,155
-                    const float a = recs[j * 3 + 2].w;
-                    if constexpr (MODE == SB_MODE_SPLAT) {
-                        const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
-                        alpha = __fmul_rn(a, e);  // render.wesl:149
-                    } else {
-                        const float ol = r2 > p.outline ? 1.0f : 0.0f;  // render.wesl:159-160
-                        alpha = __fadd_rn(a, __fmul_rn(__fsub_rn(1.0f, a), ol));
-                    }
-                }
-                const float4 q2 = recs[j * 3 + 2];
-                if constexpr (COUNT) n_alive += inside ? 1u : 0u;
-                const float om = __fsub_rn(1.0f, alpha);
-                if constexpr (FMT == FMT_UNORM8) {
-                    d0 = rint_small(fminf(__fmaf_rn(d0, om, __fmul_rn(q2.x, alpha)), 255.0f));
-                    d1 = rint_small(fminf(__fmaf_rn(d1, om, __fmul_rn(q2.y, alpha)), 255.0f));
-                    d2 = rint_small(fminf(__fmaf_rn(d2, om, __fmul_rn(q2.z, alpha)), 255.0f));
-                } else {
-                    d0 = __fmaf_rn(d0, om, __fmul_rn(q2.x, alpha));
-                    d1 = __fmaf_rn(d1, om, __fmul_rn(q2.y, alpha));
-                    d2 = __fmaf_rn(d2, om, __fmul_rn(q2.z, alpha));
-                    d3 = __fmaf_rn(d3, om, alpha);
-                    if constexpr (FMT == FMT_F16) {
-                        d0 = __half2float(__float2half_rn(d0)); d1 = __half2float(__float2half_rn(d1));
-                        d2 = __half2float(__float2half_rn(d2)); d3 = __half2float(__float2half_rn(d3));
-                    }
-                }
-            }
-        }
+        composite_batch<MODE, FMT, STRICT, COUNT, false>(stage[s], cnt, px, py, pcx, pcy, lane, inside, p.sd2, p.outline, st);
         __syncthreads();  // everyone is done with stage[s] before it is refilled
     }
+    flush_counters<COUNT>(st, lane, p.counters);
+    if (inside) store_dst<FMT>(st, dst, x, p.bgra);
+}
 
-    if constexpr (COUNT) {
+// K6 (b): no gathered copy of the records at all.  A producer warp reads the tile's Gaussian indices
+// (coalesced) and fetches the 48-byte records straight from the per-Gaussian array with TMA
+// tile::gather4 (cp.async.bulk.tensor.2d ... tile::gather4 -> UTMALDG, four rows per instruction, two
+// instructions per lane and batch) into a double-buffered ring; eight consumer warps composite.
+template <int MODE, int FMT, bool STRICT, bool COUNT>
+__global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelParams p, const __grid_constant__ CUtensorMap recs_map) {
+    __shared__ __align__(256) float4 stage[kG4Stages][kG4StageF4];
+    __shared__ __align__(8) uint64_t full_bar[kG4Stages];
+    __shared__ __align__(8) uint64_t empty_bar[kG4Stages];
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
+    const uint32_t tile = tile_y * p.tiles_x + tile_x;
+    const uint32_t begin = p.tile_ranges[2 * tile], end = p.tile_ranges[2 * tile + 1];
+    const uint32_t total = end - begin;
+    const uint32_t batches = (total + kBatchG4 - 1) / kBatchG4;
+
+    if (tid == 0) {
+        for (int s = 0; s < kG4Stages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ---------------- producer warp: lanes 0..30 fetch 8 records each (two gather4s) per batch
+        for (uint32_t k = 0; k < batches; k++) {
+            const uint32_t s = k % kG4Stages;
+            mbar_wait(&empty_bar[s], ((k / kG4Stages) & 1u) ^ 1u);
+            const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
+            const uint32_t* idx = p.dup_vals + begin + (size_t)k * kBatchG4;
+            const uint32_t g_first = __ldg(idx);  // padding index for rows past the end of the list
+            uint32_t g[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n_alive += __shfl_xor_sync(0xffffffffu, n_alive, o);
-            n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+            for (int q = 0; q < 8; q++) {
+                const uint32_t j = lane + (uint32_t)kG4Lanes * q;
+                g[q] = (lane < kG4Lanes && j < cnt) ? __ldg(idx + j) : g_first;
+            }
+            // gather #0 holds records q = 0..3 of the lane, #1 holds q = 4..7; only gathers with a valid first
+            // record are issued and the barrier is armed with exactly the bytes that will land
+            const bool need0 = lane < kG4Lanes && lane < cnt;
+            const bool need1 = lane < kG4Lanes && lane + 4u * kG4Lanes < cnt;
+            const uint32_t n0 = min((uint32_t)kG4Lanes, cnt);
+            const uint32_t n1 = cnt > 4u * kG4Lanes ? min((uint32_t)kG4Lanes, cnt - 4u * kG4Lanes) : 0u;
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (n0 + n1) * 4u * (uint32_t)sizeof(SplatRec));
+            __syncwarp();
+            const uint32_t dst0 = smem_u32(&stage[s][g4_row_f4(lane, 0)]);
+            if (need0) tma_gather4(dst0, &recs_map, &full_bar[s], g[0], g[1], g[2], g[3]);
+            if (need1) tma_gather4(dst0 + 256u, &recs_map, &full_bar[s], g[4], g[5], g[6], g[7]);
         }
-        if (lane == 0 && p.counters) {
-            atomicAdd(&p.counters[0], (unsigned long long)n_alive);
-            atomicAdd(&p.counters[1], (unsigned long long)n_eval);
-        }
+        return;
     }
 
-    if (inside) {
-        if constexpr (FMT == FMT_UNORM8) {
-            uchar4 c;
-            c.x = (unsigned char)(p.bgra ? d2 : d0);
-            c.y = (unsigned char)d1;
-            c.z = (unsigned char)(p.bgra ? d0 : d2);
-            c.w = 255;
-            reinterpret_cast<uchar4*>(dst)[x] = c;
-        } else if constexpr (FMT == FMT_F16) {
-            __half2 lo = __floats2half2_rn(d0, d1), hi = __floats2half2_rn(d2, d3);
-            uint2 o;
-            o.x = *reinterpret_cast<uint32_t*>(&lo);
-            o.y = *reinterpret_cast<uint32_t*>(&hi);
-            reinterpret_cast<uint2*>(dst)[x] = o;
-        } else {
-            reinterpret_cast<float4*>(dst)[x] = make_float4(d0, d1, d2, d3);
-        }
+    // ---------------- consumers: each warp owns an 8x4 pixel patch
+    const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane & 7u);
+    const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+    const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 4.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
+    PixelState st;
+    uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
+    if (!p.clear && inside) load_dst<FMT>(st, dst, x, p.bgra);
+
+    for (uint32_t k = 0; k < batches; k++) {
+        const uint32_t s = k % kG4Stages;
+        mbar_wait(&full_bar[s], (k / kG4Stages) & 1u);
+        const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
+        composite_batch<MODE, FMT, STRICT, COUNT, true>(stage[s], cnt, px, py, pcx, pcy, lane, inside, p.sd2, p.outline, st);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    flush_counters<COUNT>(st, lane, p.counters);
+    if (inside) store_dst<FMT>(st, dst, x, p.bgra);
+}
+
+// tile ranges from the tile-sorted keys (gather4 path: no record copy)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ dup_keys, const uint32_t* __restrict__ dup_count,
+                                                          uint32_t* __restrict__ tile_ranges) {
+    const uint32_t d = *dup_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+        const uint32_t t = dup_keys[i];
+        if (i == 0 || dup_keys[i - 1] != t) tile_ranges[2 * t] = i;
+        if (i == d - 1 || dup_keys[i + 1] != t) tile_ranges[2 * t + 1] = i + 1;
     }
 }
 
@@ -391,9 +514,14 @@ __global__ void clear_kernel(uint8_t* pixels, uint32_t pitch, uint32_t width, ui
 }
 
 template <int MODE, int FMT, bool STRICT>
-void launch_raster(const RasterKernelParams& kp, dim3 grid, cudaStream_t stream) {
-    if (kp.counters) raster_kernel<MODE, FMT, STRICT, true><<<grid, 256, 0, stream>>>(kp);
-    else raster_kernel<MODE, FMT, STRICT, false><<<grid, 256, 0, stream>>>(kp);
+void launch_raster(const RasterKernelParams& kp, const CUtensorMap* recs_map, dim3 grid, cudaStream_t stream) {
+    if (recs_map) {
+        if (kp.counters) raster_gather4_kernel<MODE, FMT, STRICT, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
+        else raster_gather4_kernel<MODE, FMT, STRICT, false><<<grid, 288, 0, stream>>>(kp, *recs_map);
+    } else {
+        if (kp.counters) raster_bulk_kernel<MODE, FMT, STRICT, true><<<grid, 256, 0, stream>>>(kp);
+        else raster_bulk_kernel<MODE, FMT, STRICT, false><<<grid, 256, 0, stream>>>(kp);
+    }
 }
 
 }  // namespace
@@ -454,12 +582,16 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     if (e != cudaSuccess) return e;
     if (p.events) cudaEventRecord(p.events[1], stream);
 
-    gather_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, p.recs, p.buf.tile_recs,
-                                                  p.buf.tile_ranges);
+    if (p.recs_map)
+        tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_count, p.buf.tile_ranges);
+    else
+        gather_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, p.recs, p.buf.tile_recs,
+                                                      p.buf.tile_ranges);
     if (p.events) cudaEventRecord(p.events[2], stream);
 
     RasterKernelParams kp;
     kp.tile_recs = p.buf.tile_recs;
+    kp.dup_vals = p.buf.dup_vals;
     kp.tile_ranges = p.buf.tile_ranges;
     kp.pixels = reinterpret_cast<uint8_t*>(t.d_pixels);
     kp.pitch = t.pitch_bytes;
@@ -480,8 +612,8 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
                                                                                                : FMT_F32;
 #define SB_RASTER(M, F)                                                        \
     if (u.mode == M && fmt == F) {                                             \
-        if (M == SB_MODE_SPLAT && p.strict_exp) launch_raster<M, F, true>(kp, grid, stream); \
-        else launch_raster<M, F, false>(kp, grid, stream);                     \
+        if (M == SB_MODE_SPLAT && p.strict_exp) launch_raster<M, F, true>(kp, p.recs_map, grid, stream); \
+        else launch_raster<M, F, false>(kp, p.recs_map, grid, stream);                     \
     }
     SB_RASTER(SB_MODE_SPLAT, FMT_UNORM8)
     SB_RASTER(SB_MODE_SPLAT, FMT_F16)

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_preprocess", "sb_viewer_sort", "sb_viewer_draw", "sb_viewer_render_to_host", "sb_viewer_gaussians_ptr",
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
-    "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_set_strict_exp",
+    "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_raster_path", "sb_viewer_set_strict_exp",
     "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times", "sb_viewer_set_raster_counting",
     "sb_viewer_read_raster_counters",
     "sb_viewer_reserve_duplicates", "sb_sorter_create", "sb_sorter_destroy", "sb_sorter_sort", "sb_mm_create",
@@ -155,6 +155,7 @@ def load() -> C.CDLL:
     sig("sb_viewer_read_indices", i32, vp, vp, vp, u64)
     sig("sb_viewer_read_depth_keys", i32, vp, vp, vp, u64)
     sig("sb_viewer_read_frame_stats", i32, vp, vp, P(u64), P(u64), P(u32))
+    sig("sb_viewer_raster_path", i32, vp, P(i32))
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
     sig("sb_viewer_set_raster_counting", i32, vp, i32)
     sig("sb_viewer_read_raster_counters", i32, vp, vp, P(u64), P(u64))
@@ -403,6 +404,11 @@ class Viewer:
         _check(l.sb_viewer_gaussians_depth_ptr(self._h, C.byref(p), C.byref(b)), self.ctx._h)
         out["gaussians_depth"] = (p.value, b.value)
         return out
+
+    def raster_path(self) -> str:
+        f = C.c_int32()
+        _check(load().sb_viewer_raster_path(self._h, C.byref(f)), self.ctx._h)
+        return "tma_gather4" if f.value else "bulk"
 
     def set_strict_exp(self, strict: bool):
         _check(load().sb_viewer_set_strict_exp(self._h, int(strict)), self.ctx._h)
