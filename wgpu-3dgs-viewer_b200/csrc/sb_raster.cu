@@ -180,15 +180,14 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------- K6 rasterizer
 
 constexpr int kBatch = 256;  // splat records per shared-memory stage (12 KB)
-// gather4 path: 256 records per batch = 32 producer lanes x 8 records (two gather4s per lane).  Each
-// gather4 (4 rows x 48 B) is written at a 256-byte pitch (the TMA destination must be 128-byte aligned).
-// float4 index of record q (0..7) of lane l: l * 32 + g4_q_off(q)
-constexpr int kG4Lanes = 32;
-constexpr int kBatchG4 = kG4Lanes * 8;
+// gather4 path: 256 records per batch = 64 gather4s (two per producer lane).  Gather m holds the
+// consecutive records 4m..4m+3 (4 rows x 48 B) and is written at a 256-byte pitch (the TMA destination
+// must be 128-byte aligned), so record j of the batch starts at float4 index (j >> 2) * 16 + (j & 3) * 3
+// = 3 j + (j & ~3): a cull round's 32 consecutive records spread over the banks (2-way conflicts).
+constexpr int kBatchG4 = 256;
 constexpr int kG4Stages = 2;
-constexpr int kG4StageF4 = kG4Lanes * 2 * 16;
-__device__ __forceinline__ uint32_t g4_q_off(uint32_t q) { return (q >> 2) * 16 + (q & 3u) * 3; }
-__device__ __forceinline__ uint32_t g4_row_f4(uint32_t owner_lane, uint32_t q) { return owner_lane * 32 + g4_q_off(q); }
+constexpr int kG4StageF4 = (kBatchG4 / 4) * 16;
+__device__ __forceinline__ uint32_t g4_row_f4(uint32_t j) { return 3u * j + (j & ~3u); }
 
 enum { FMT_UNORM8 = 0, FMT_F16 = 1, FMT_F32 = 2 };
 
@@ -278,19 +277,17 @@ __device__ __forceinline__ void store_dst(const PixelState& st, uint8_t* row, ui
 }
 
 // Composites one staged batch onto this thread's pixel, in list order.  PERM: record j of the batch
-// was fetched by producer lane j % 31 as its q = j / 31 -th record (layout: g4_row_f4).
+// sits at float4 index g4_row_f4(j) (the layout the gather4 producer writes).
 // Warp-level culling: each lane tests one splat's alive-region bbox against the warp's 8x4 pixel
 // patch; only splats that can touch the patch are evaluated.
 template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, float px, float py, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd2, float outline, PixelState& st) {
-    constexpr uint32_t kRound = PERM ? kG4Lanes : 32;  // records tested per warp round
-    for (uint32_t base = 0, q = 0; base < cnt; base += kRound, ++q) {
+    for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t jl = base + lane;
-        const uint32_t qoff = PERM ? g4_q_off(q) : base * 3;  // per round, so the survivor loop adds one shift/mad
         bool hit = false;
-        if (lane < kRound && jl < cnt) {
-            const uint32_t r4 = PERM ? (lane * 32 + qoff) : jl * 3;
+        if (jl < cnt) {
+            const uint32_t r4 = PERM ? g4_row_f4(jl) : jl * 3;
             const float4 c0 = recs[r4 + 0];
             const float4 c1 = recs[r4 + 1];
             hit = fabsf(c0.x - pcx) <= c1.z + 3.51f && fabsf(c0.y - pcy) <= c1.w + 1.51f;
@@ -299,7 +296,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
         while (todo) {
             const uint32_t b = (uint32_t)(__ffs(todo) - 1);
             todo &= todo - 1;
-            const uint32_t r4 = PERM ? (b * 32 + qoff) : (b * 3 + qoff);
+            const uint32_t r4 = PERM ? g4_row_f4(base + b) : (base + b) * 3;
             const float4 q0 = recs[r4 + 0];
             const float4 q1 = recs[r4 + 1];
             const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
@@ -438,7 +435,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelP
     __syncthreads();
 
     if (warp == 8) {
-        // ---------------- producer warp: lanes 0..30 fetch 8 records each (two gather4s) per batch
+        // ---------------- producer warp: lane t issues gather4 #t (records 4t..4t+3) and #t+32
         for (uint32_t k = 0; k < batches; k++) {
             const uint32_t s = k % kG4Stages;
             mbar_wait(&empty_bar[s], ((k / kG4Stages) & 1u) ^ 1u);
@@ -447,21 +444,20 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelP
             const uint32_t g_first = __ldg(idx);  // padding index for rows past the end of the list
             uint32_t g[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const uint32_t j = lane + (uint32_t)kG4Lanes * q;
-                g[q] = (lane < kG4Lanes && j < cnt) ? __ldg(idx + j) : g_first;
-            }
-            // gather #0 holds records q = 0..3 of the lane, #1 holds q = 4..7; only gathers with a valid first
-            // record are issued and the barrier is armed with exactly the bytes that will land
-            const bool need0 = lane < kG4Lanes && lane < cnt;
-            const bool need1 = lane < kG4Lanes && lane + 4u * kG4Lanes < cnt;
-            const uint32_t n0 = min((uint32_t)kG4Lanes, cnt);
-            const uint32_t n1 = cnt > 4u * kG4Lanes ? min((uint32_t)kG4Lanes, cnt - 4u * kG4Lanes) : 0u;
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (n0 + n1) * 4u * (uint32_t)sizeof(SplatRec));
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t j = 4u * (lane + 32u * h) + i;
+                    g[h * 4 + i] = j < cnt ? __ldg(idx + j) : g_first;
+                }
+            // only gathers whose first record exists are issued; the barrier is armed with exactly the
+            // bytes that will land
+            const uint32_t gathers = (cnt + 3u) / 4u;
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], gathers * 4u * (uint32_t)sizeof(SplatRec));
             __syncwarp();
-            const uint32_t dst0 = smem_u32(&stage[s][g4_row_f4(lane, 0)]);
-            if (need0) tma_gather4(dst0, &recs_map, &full_bar[s], g[0], g[1], g[2], g[3]);
-            if (need1) tma_gather4(dst0 + 256u, &recs_map, &full_bar[s], g[4], g[5], g[6], g[7]);
+            const uint32_t dst0 = smem_u32(&stage[s][lane * 16]);
+            if (lane < gathers) tma_gather4(dst0, &recs_map, &full_bar[s], g[0], g[1], g[2], g[3]);
+            if (lane + 32u < gathers) tma_gather4(dst0 + 32u * 256u, &recs_map, &full_bar[s], g[4], g[5], g[6], g[7]);
         }
         return;
     }
