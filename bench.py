@@ -105,7 +105,7 @@ def ncu_traffic():
         val, unit = txt.split()[:2]
         return float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
-    for key, stage in (("preprocess_kernel", "preprocess"), ("raster_kernel", "raster")):
+    for key, stage in (("preprocess_kernel", "preprocess"), ("raster_gather4_kernel", "raster")):
         rows = summ.get(key) or []
         vals = [to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"]) for r in rows
                 if "dram__bytes_read.sum" in r and "dram__bytes_write.sum" in r]
@@ -244,7 +244,7 @@ def run_cuda(args):
     raster_ops = alive * 27.0
     raster_gops = raster_ops / stage["raster"] / 1e6
     roofs = {
-        "raster": {"bound": "fp32", "kernel": "raster_kernel<splat,unorm8> (K6)", "achieved": raster_gops, "peak": fp32_peak,
+        "raster": {"bound": "fp32", "kernel": "raster_gather4_kernel<splat,unorm8> (K6)", "achieved": raster_gops, "peak": fp32_peak,
                    "unit": "Gop/s (FP32 lane-ops, FMA = 1)", "frac": raster_gops / fp32_peak, "traffic": None,
                    "peak_source": f"nominal 148 SMs x 128 lanes x {sm_clock:.0f} MHz sampled under load (no measured FP32 peak in MEASURED_PEAKS.json)",
                    "algorithmic_ops": raster_ops, "alive_fragments": alive, "evaluated_lane_pairs": evaluated,

@@ -18,8 +18,8 @@ for line in out.splitlines():
             if op.startswith(k):
                 counts[fn][k] += 1
 print("# cuobjdump -sass", lib)
-print("# UBLKCP = cp.async.bulk (TMA 1-D bulk copy); SYNCS = mbarrier; VOTE/MATCH = warp ballots; ATOMS = shared atomics;")
-print("# HMMA / UTC*MMA / LDTM / UTMALDG (tensor cores, TMEM, tensor-map TMA) are absent by design: no stage is a dense contraction.")
+print("# UBLKCP = cp.async.bulk (TMA 1-D bulk copy); UTMALDG = cp.async.bulk.tensor (here: tile::gather4); SYNCS = mbarrier;")
+print("# VOTE = warp ballots; ATOMS = shared atomics.  HMMA / UTC*MMA / LDTM (tensor cores, TMEM) are absent by design: no stage is a dense contraction.")
 want = sys.argv[1:] or ["preprocess_kernel<0, 0>", "preprocess_kernel<1, 1>", "preprocess_kernel<2, 1>", "onesweep_kernel<8>", "onesweep_kernel<5>",
                         "histogram_kernel", "raster_kernel<0, 0, false, false>", "raster_kernel<1, 0, false, false>", "raster_kernel<0, 3, true, false>",
                         "dup_scan_kernel", "dup_emit_kernel", "gather_kernel", "select_rect_kernel", "sort_init_kernel", "sort_finish_kernel"]
