@@ -353,9 +353,11 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         int win = -2;  // -2: look-back of tile res_it not started
         bool pub_done = false;
         for (;;) {
+            bool progress = false;
             // warp-uniform probe: lanes may observe the phase flip at different instants
             const bool counted = !pub_done && __all_sync(0xffffffffu, mbar_test_wait(&counted_bar[pub_it % R], (pub_it / R) & 1u));
             if (counted) {
+                progress = true;
                 const uint32_t ring = pub_it % R;
                 const uint32_t tile = ring_tile[ring];
                 if (tile == 0xffffffffu) {
@@ -391,6 +393,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
                         acc += contrib;
+                        progress = true;
                         if (pm) resolved = true;
                         else win -= 32;
                     }
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
                 }
             }
             if (pub_done && res_it == pub_it) break;
+            if (!progress) __nanosleep(64);  // do not steal issue slots from the consumer warps while idle
         }
         return;
     }
