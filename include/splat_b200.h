@@ -201,6 +201,15 @@ SB_API SbStatus sb_viewer_draw(SbViewer* v, void* stream, const SbTarget* target
 SB_API SbStatus sb_viewer_render_to_host(SbViewer* v, void* stream, const SbCameraPod* cam,
                                          void* host_pixels, uint64_t host_bytes);
 
+/* A batch of camera views of the same scene (BASELINE config 5a; the reference would call
+ * update_camera + render once per view, tests/e2e/viewer.rs:23-34).  View i is rendered with cams[i]
+ * into targets[i]; if `targets` is NULL each frame is rendered into an internal target and copied to
+ * host_pixels[i] (pinned recommended).  Views are pipelined two deep on internal streams over a twin
+ * set of frame buffers — the latency-bound stages of one view overlap the rasterizer of the other —
+ * forked from and joined back to `stream`, so the call is ordered on `stream` like any other. */
+SB_API SbStatus sb_viewer_render_batch(SbViewer* v, void* stream, const SbCameraPod* cams, const SbTarget* targets,
+                                       void* const* host_pixels, uint32_t count);
+
 /* Public buffers of the Viewer (src/lib.rs:65-82) as device pointers */
 SB_API SbStatus sb_viewer_gaussians_ptr(SbViewer* v, const void** d_pods, uint64_t* bytes);
 SB_API SbStatus sb_viewer_indirect_args_ptr(SbViewer* v, const SbDrawIndirectArgs** d_args);

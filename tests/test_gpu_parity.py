@@ -448,3 +448,46 @@ assert d == 0
     out = subprocess.run([sys.executable, "-c", code, os.path.join(root, "wgpu-3dgs-viewer_b200"), root], env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_render_batch_equals_single_frames(sb, ob, ctx):
+    """sb_viewer_render_batch (views pipelined two deep on internal streams) is bit-identical to
+    update_camera + render per view, for device targets and for host frames; artefacts stay exact."""
+    torch = _torch()
+    n, w, h = 30000, 640, 360
+    g, pods = make_scene(sb, ob, n, 44)
+    v = sb.Viewer(ctx, pods, n)
+    rng = np.random.default_rng(8)
+    sel = rng.integers(0, 2**32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32)
+    v.enable_selection(True)
+    v.set_selection(sel)
+    v.update_model_transform((0.5, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0), (1.1, 1.0, 0.9))
+    cams = [sb.camera_pod(*sb.scenes.orbit_camera(k, 7), w, h) for k in range(7)]
+    singles = []
+    for c in cams:
+        t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        v.update_camera_with_pod(c)
+        v.render(t, w, h)
+        singles.append(t)
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream()
+    outs = [torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda") for _ in cams]
+    v.render_batch(cams, targets=outs, width=w, height=h, stream=stream)
+    stream.synchronize()
+    for a, b in zip(singles, outs):
+        assert torch.equal(a, b)
+    hosts = [torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory() for _ in cams]
+    v.render_batch(cams, host_ptrs=[t.data_ptr() for t in hosts], stream=stream)
+    stream.synchronize()
+    for a, b in zip(singles, hosts):
+        assert torch.equal(a.cpu(), b)
+    # the primary viewer's artefacts belong to the last even-indexed view (slot 0) and stay oracle-exact
+    om = ob.OracleModel(pods, n, model_transform=ob.model_transform_pod((0.5, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0), (1.1, 1.0, 0.9)),
+                        selection=sel, invert_selection=1)
+    pos, yaw, pitch = sb.scenes.orbit_camera(6, 7)
+    pre = ob.preprocess(om, ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod())
+    draw, _ = v.read_indirect_args(stream)
+    assert int(draw[1]) == pre["count"]
+    _, oi = ob.radix_sort(pre["keys"][: pre["count"]].view(np.uint32), pre["indices"][: pre["count"]])
+    assert np.array_equal(v.read_indices(pre["count"], stream), oi)
+    v.close()

@@ -170,6 +170,12 @@ struct SbViewer {
     int strict_exp = 0;
     CUtensorMap recs_map;        // 2-D view of recs[] (12 x n floats, 48-byte rows) for TMA gather4
     bool use_gather4 = false;
+    // view-batch pipelining (sb_viewer_render_batch): a twin set of frame buffers over the same pods,
+    // two internal streams forked from / joined to the caller's stream
+    SbViewer* twin = nullptr;
+    const uint32_t* selection_override = nullptr;  // twin: the primary's selection words
+    cudaStream_t bstream[2] = {nullptr, nullptr};
+    cudaEvent_t bevent[3] = {nullptr, nullptr, nullptr};
     bool timing = false;
     bool counting = false;
     DeviceBuf counters;
@@ -288,7 +294,7 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     std::memset(&p, 0, sizeof p);
     p.gaussians = static_cast<const uint8_t*>(v->d_gaussians);
     p.n = v->n;
-    p.selection = v->selection_enabled ? v->selection.as<uint32_t>() : nullptr;
+    p.selection = v->selection_enabled ? (v->selection_override ? v->selection_override : v->selection.as<uint32_t>()) : nullptr;
     p.invert_selection = v->invert_selection;
     p.indices = v->indices.as<uint32_t>();
     p.keys = v->keys.as<float>();
@@ -452,6 +458,11 @@ SbStatus sb_viewer_create_from_device(SbContext* ctx, int32_t sh_fmt, int32_t co
 
 void sb_viewer_destroy(SbViewer* v) {
     if (!v) return;
+    if (v->twin) sb_viewer_destroy(v->twin);
+    for (cudaStream_t s : v->bstream)
+        if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : v->bevent)
+        if (e) cudaEventDestroy(e);
     for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->tboxes, &v->pre_scratch, &v->sort_keys_alt,
                          &v->sort_vals_alt, &v->sort_internal, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
                          &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target, &v->counters})
@@ -595,6 +606,86 @@ SbStatus sb_viewer_render_to_host(SbViewer* v, void* stream, const SbCameraPod* 
     SbStatus s = sb_viewer_render(v, stream, &t);
     if (s != SB_OK) return s;
     SB_CUDA(v->ctx, cudaMemcpyAsync(host_pixels, v->internal_target.p, need, cudaMemcpyDeviceToHost, st));
+    return SB_OK;
+}
+
+namespace {
+
+SbStatus batch_setup(SbViewer* v) {
+    if (v->twin) return SB_OK;
+    SbViewer* t = nullptr;
+    SbStatus s = sb_viewer_create_from_device(v->ctx, v->sh_fmt, v->cov_fmt, v->target_format, v->d_gaussians, (uint64_t)v->n * v->stride,
+                                              v->n, &t);
+    if (s != SB_OK) return s;
+    for (cudaStream_t& st : v->bstream) SB_CUDA(v->ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : v->bevent) SB_CUDA(v->ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    v->twin = t;
+    return SB_OK;
+}
+
+// copies the per-frame state the reference keeps in uniform buffers / the selection buffer
+void sync_twin(SbViewer* v) {
+    SbViewer* t = v->twin;
+    t->model_transform = v->model_transform;
+    t->gaussian_transform = v->gaussian_transform;
+    t->selection_enabled = v->selection_enabled;
+    t->invert_selection = v->invert_selection;
+    t->selection_override = v->selection.as<uint32_t>();
+    t->strict_exp = v->strict_exp;
+}
+
+}  // namespace
+
+SbStatus sb_viewer_render_batch(SbViewer* v, void* stream, const SbCameraPod* cams, const SbTarget* targets, void* const* host_pixels,
+                                uint32_t count) {
+    if (!v || (count && (!cams || (!targets && !host_pixels)))) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (count == 0) return SB_OK;
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    SbStatus s = batch_setup(v);
+    if (s != SB_OK) return s;
+    sync_twin(v);
+    // validate every target before enqueuing anything
+    const uint32_t bpp = bytes_per_pixel(v->target_format);
+    std::vector<SbTarget> tg(count);
+    for (uint32_t i = 0; i < count; i++) {
+        SbViewer* slot = (i & 1u) ? v->twin : v;
+        const uint32_t w = (uint32_t)cams[i].size[0], h = (uint32_t)cams[i].size[1];
+        if (targets) {
+            tg[i] = targets[i];
+        } else {  // render into the slot's internal target, then copy to host_pixels[i]
+            const uint64_t need = (uint64_t)w * h * bpp;
+            if (!host_pixels[i]) return fail(v->ctx, SB_ERR_INVALID_ARG, "null host frame");
+            if (slot->internal_target.bytes < need) {
+                SB_CUDA(v->ctx, cudaDeviceSynchronize());
+                SB_CUDA(v->ctx, slot->internal_target.alloc(need));
+            }
+            tg[i] = SbTarget{slot->internal_target.p, w * bpp, w, h, v->target_format, 0, 0};
+        }
+        const sb::Uniforms u = make_uniforms(cams[i], v->model_transform, v->gaussian_transform, v->target_format);
+        s = check_target(v, &tg[i], u);
+        if (s != SB_OK) return s;
+    }
+    // fork: both internal streams start after everything already enqueued on the caller's stream
+    SB_CUDA(v->ctx, cudaEventRecord(v->bevent[2], user));
+    for (int k = 0; k < 2; k++) SB_CUDA(v->ctx, cudaStreamWaitEvent(v->bstream[k], v->bevent[2], 0));
+    for (uint32_t i = 0; i < count; i++) {
+        SbViewer* slot = (i & 1u) ? v->twin : v;
+        cudaStream_t st = v->bstream[i & 1u];
+        s = do_preprocess(slot, cams[i], v->gaussian_transform, st);
+        if (s == SB_OK) s = do_sort(slot, st);
+        if (s == SB_OK) s = do_draw(slot, cams[i], v->gaussian_transform, &tg[i], 1, st);
+        if (s != SB_OK) return s;
+        if (!targets) {
+            const uint64_t need = (uint64_t)tg[i].width * tg[i].height * bpp;
+            SB_CUDA(v->ctx, cudaMemcpyAsync(host_pixels[i], tg[i].d_pixels, need, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    // join: the caller's stream continues once both slots are done
+    for (int k = 0; k < 2; k++) {
+        SB_CUDA(v->ctx, cudaEventRecord(v->bevent[k], v->bstream[k]));
+        SB_CUDA(v->ctx, cudaStreamWaitEvent(user, v->bevent[k], 0));
+    }
+    v->camera = cams[count - 1];
     return SB_OK;
 }
 

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_update_model_transform_with_pod", "sb_viewer_update_gaussian_transform",
     "sb_viewer_update_gaussian_transform_with_pod", "sb_viewer_enable_selection", "sb_viewer_selection_ptr",
     "sb_viewer_set_selection", "sb_viewer_read_selection", "sb_viewer_set_invert_selection", "sb_viewer_select_rect", "sb_viewer_render",
-    "sb_viewer_preprocess", "sb_viewer_sort", "sb_viewer_draw", "sb_viewer_render_to_host", "sb_viewer_gaussians_ptr",
+    "sb_viewer_preprocess", "sb_viewer_sort", "sb_viewer_draw", "sb_viewer_render_to_host", "sb_viewer_render_batch", "sb_viewer_gaussians_ptr",
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
     "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_raster_path", "sb_viewer_set_strict_exp",
@@ -146,6 +146,7 @@ def load() -> C.CDLL:
     sig("sb_viewer_sort", i32, vp, vp)
     sig("sb_viewer_draw", i32, vp, vp, P(Target))
     sig("sb_viewer_render_to_host", i32, vp, vp, P(CameraPod), vp, u64)
+    sig("sb_viewer_render_batch", i32, vp, vp, P(CameraPod), P(Target), P(vp), u32)
     sig("sb_viewer_gaussians_ptr", i32, vp, P(vp), P(u64))
     sig("sb_viewer_indirect_args_ptr", i32, vp, P(vp))
     sig("sb_viewer_radix_sort_indirect_args_ptr", i32, vp, P(vp))
@@ -365,6 +366,17 @@ class Viewer:
 
     def render_to_host(self, cam: CameraPod, host_ptr: int, host_bytes: int, stream=None):
         _check(load().sb_viewer_render_to_host(self._h, _stream_handle(stream), C.byref(cam), host_ptr, host_bytes), self.ctx._h)
+
+    def render_batch(self, cams, targets=None, width=None, height=None, host_ptrs=None, stream=None):
+        """Render len(cams) views (pipelined two deep).  targets: device tensors/pointers, or host_ptrs: pinned host pointers."""
+        n = len(cams)
+        cam_arr = (CameraPod * n)(*cams)
+        if targets is not None:
+            tg = (Target * n)(*[make_target(t, width, height, self.target_format) for t in targets])
+            _check(load().sb_viewer_render_batch(self._h, _stream_handle(stream), cam_arr, tg, None, n), self.ctx._h)
+        else:
+            hp = (C.c_void_p * n)(*host_ptrs)
+            _check(load().sb_viewer_render_batch(self._h, _stream_handle(stream), cam_arr, None, hp, n), self.ctx._h)
 
     # --- artefact read-back (synchronising)
     def read_indirect_args(self, stream=None):
