@@ -160,24 +160,34 @@ def run_cuda(args):
         if world > 1:
             dist.barrier()
 
-    def step_device(i):
-        viewer.update_camera_with_pod(cams[(i * world + rank) % N_VIEWS])
+    def cam_of(i):
+        return cams[(i * world + rank) % N_VIEWS]
+
+    def step_device(i):  # one view, strictly one frame in flight (latency path)
+        viewer.update_camera_with_pod(cam_of(i))
         viewer.render(target, WIDTH, HEIGHT, stream=stream)
 
-    def step_e2e(i):
-        viewer.render_to_host(cams[(i * world + rank) % N_VIEWS], host_frame.data_ptr(), host_frame.numel(), stream=stream)
+    # the headline path: the steps of a run are the views of a camera batch (config 5a) and go
+    # through sb_viewer_render_batch, which keeps two views in flight on internal streams
+    targets2 = [target, torch.zeros_like(target)]
+    hosts2 = [host_frame, torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory()]
 
-    def timed(step_fn, steps, warmup, sample_clocks=False):
-        for i in range(warmup):
-            step_fn(i)
+    def run_batch(first, count, to_host):
+        cs = [cam_of(first + i) for i in range(count)]
+        if to_host:
+            viewer.render_batch(cs, host_ptrs=[hosts2[i & 1].data_ptr() for i in range(count)], stream=stream)
+        else:
+            viewer.render_batch(cs, targets=[targets2[i & 1] for i in range(count)], width=WIDTH, height=HEIGHT, stream=stream)
+
+    def timed(run_fn, steps, warmup, sample_clocks=False):
+        run_fn(0, warmup)
         stream.synchronize()
         torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(steps):
-            step_fn(warmup + i)
+        run_fn(warmup, steps)
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -190,8 +200,13 @@ def run_cuda(args):
             ms = float(t.item())
         return ms, clocks
 
-    ms, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    def run_single(first, count):
+        for i in range(count):
+            step_device(first + i)
+
+    ms, clocks = timed(lambda f, c: run_batch(f, c, False), args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _ = timed(lambda f, c: run_batch(f, c, True), args.steps, max(args.warmup, 3))
+    ms_single, _ = timed(run_single, args.steps, args.warmup)
     frames = args.steps * world
 
     # per-stage device times of the same frames (cudaEvents inside the library, same stream)
@@ -267,10 +282,14 @@ def run_cuda(args):
                                f"{N_VIEWS}-view orbit, one view per step per GPU (BASELINE.json config 2b / 5a)",
                    "gaussians": n, "resolution": [WIDTH, HEIGHT], "pod_stride": stride, "scene_bytes": int(scene_bytes),
                    "l2_policy": "scene (1.34 GB) is larger than L2; no explicit flush",
-                   "parallelism": f"views sharded over {world} GPU(s), scene replicated"},
+                   "parallelism": f"views sharded over {world} GPU(s), scene replicated",
+                   "api": "sb_viewer_render_batch: the K steps are K views of the batch, two views in flight per GPU"},
         "clocks": clocks,
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 144, "d2h_bytes_per_step": int(host_frame.numel())},
+                "h2d_bytes_per_step": 144, "d2h_bytes_per_step": int(host_frame.numel()),
+                "api": "sb_viewer_render_batch(host_pixels): camera pods in, every frame copied to pinned host memory"},
+        "single_frame": {"frames_per_s": frames / (ms_single / 1e3), "ms_per_frame": ms_single / args.steps,
+                         "api": "sb_viewer_update_camera_with_pod + sb_viewer_render, one frame in flight"},
         "gpu_launches": KERNELS_PER_FRAME * args.steps,
         # dominant kernel of the frame (largest share of device time) first; the two HBM-bound
         # stages the north star grades follow in roofline_stages
