@@ -315,7 +315,7 @@ def cpu_frames_per_sec(sample_n: int, steps: int, warmup: int):
     pods = build_scene(sample_n)
     model = ob.OracleModel(pods, sample_n)
     gt = ob.gaussian_transform_pod()
-    threads = ob.lib().so_max_threads()
+    threads = ob.use_all_host_threads()
     times = []
     for i in range(warmup + steps):
         pos, yaw, pitch = sb.scenes.orbit_camera(i % N_VIEWS, N_VIEWS)

@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         l.so_exp_neg_poly.argtypes = [C.c_float]
         l.so_select_rect.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         l.so_max_threads.restype = C.c_int
+        l.so_set_threads.argtypes = [C.c_int]
         _lib = l
     return _lib
 
@@ -216,3 +217,10 @@ def select_rect(model: OracleModel, cam: CameraPod, x0, y0, x1, y1) -> np.ndarra
 
 def exp_neg_poly(x: float) -> float:
     return lib().so_exp_neg_poly(x)
+
+
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every core the process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().so_set_threads(n)
+    return lib().so_max_threads()

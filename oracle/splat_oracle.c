@@ -679,6 +679,14 @@ static void raster_band(const SoSplat* sp, uint32_t count, const Uniforms* u, in
     *bbox_px += nb; *alive_px += na;
 }
 
+void so_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int so_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

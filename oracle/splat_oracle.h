@@ -147,6 +147,7 @@ void so_select_rect(const SoModel* model, const SoCameraPod* cam,
                     float x0, float y0, float x1, float y1, uint32_t* dest);
 
 int so_max_threads(void);
+void so_set_threads(int n);   /* override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */
 int so_unorm8_newton_mismatches(void);
 
 #ifdef __cplusplus
