@@ -416,26 +416,38 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
 
     // ---------------- consumers: one Gaussian per thread per tile; warps never block on each other.
     // The (index, key) writes of a tile need its base from the decoupled look-back; they are
-    // deferred by two iterations so that latency hides behind the next tiles' work.
+    // deferred by three iterations so that latency hides behind the next tiles' work.
     const float sd_size = smul(u.std_dev, u.gsize);
     struct Deferred {
         bool vis = false;
-        uint32_t g = 0, rank = 0, tile = 0xffffffffu, ring = 0, par = 0, total = 0;
+        uint32_t g = 0, lane_rank = 0, tile = 0xffffffffu, ring = 0, par = 0;
         float key = 0.0f;
     };
-    Deferred d1, d2;  // outputs of the previous tile (d1) and of the one before (d2)
+    Deferred d1, d2, d3;  // outputs of the previous three tiles, oldest = d3
 
+    // Writes a tile's (index, key) pairs.  Everything that depends on other warps (the warp prefix inside
+    // the tile) or other CTAs (the tile base from the look-back) is read here, three tiles late.
     auto flush = [&](const Deferred& d) {
         if (d.tile == 0xffffffffu) return;
-        mbar_wait(&based_bar[d.ring], d.par);
+        mbar_wait(&based_bar[d.ring], d.par);  // implies counted
         const uint32_t base = tile_base[d.ring];
+        const uint32_t c = lane < NW ? warp_counts[d.ring * NW + lane] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t warp_excl = __shfl_sync(0xffffffffu, inc - c, warp);
         if (d.vis) {
-            p.indices[base + d.rank] = d.g;
-            p.keys[base + d.rank] = d.key;
+            const uint32_t slot = base + warp_excl + d.lane_rank;
+            p.indices[slot] = d.g;
+            p.keys[slot] = d.key;
         }
         if (d.tile == p.num_tiles - 1) {
             // post: preprocess.wesl:108-126 — indirect args + pad keys with 2.0
-            const uint32_t v = base + d.total;
+            const uint32_t v = base + total;
             const uint32_t blocks = (v + kHistoBlockKvs - 1) / kHistoBlockKvs;
             if (tid == 0) {
                 p.draw_args->vertex_count = 6;
@@ -518,8 +530,9 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
             warp_counts[ring * NW + warp] = __popc(bal);
             mbar_arrive(&counted_bar[ring]);
         }
-        // ---- (index, key) pairs of the tile two iterations back: its base has had time to arrive
-        flush(d2);
+        // ---- (index, key) pairs of the tile three iterations back: its base has had time to arrive
+        flush(d3);
+        d3 = d2;
         d2 = d1;
 
         // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
@@ -585,26 +598,15 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s * NW + warp]);
 
-        // ---- compaction, phase 2: ranks inside the tile (the other warps' counts are there by now)
-        mbar_wait(&counted_bar[ring], rpar);
-        {
-            const uint32_t c = lane < NW ? warp_counts[ring * NW + lane] : 0u;
-            uint32_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)lane >= o) inc += t;
-            }
-            d1.total = __shfl_sync(0xffffffffu, inc, 31);
-            d1.rank = __shfl_sync(0xffffffffu, inc - c, warp) + __popc(bal & lanemask_lt());
-        }
         d1.vis = vis;
         d1.g = g;
+        d1.lane_rank = __popc(bal & lanemask_lt());
         d1.key = ssub(1.0f, nz);  // preprocess.wesl:105
         d1.tile = tile;
         d1.ring = ring;
         d1.par = rpar;
     }
+    flush(d3);
     flush(d2);
     flush(d1);
 }
