@@ -241,6 +241,8 @@ SB_API SbStatus sb_viewer_read_stage_times(SbViewer* v, void* stream, float ms[6
  * frame — the pair counts the FP32 roofline of the rasterizer is computed from. */
 SB_API SbStatus sb_viewer_set_raster_counting(SbViewer* v, int32_t enabled);
 SB_API SbStatus sb_viewer_read_raster_counters(SbViewer* v, void* stream, uint64_t* alive, uint64_t* evaluated);
+/* same instrumented build: (warp, splat) evaluations issued, and how many of them had at least one alive lane */
+SB_API SbStatus sb_viewer_read_raster_warp_counters(SbViewer* v, void* stream, uint64_t* warp_evals, uint64_t* warp_evals_alive);
 /* capacity (in duplicates) of the tile-binning buffers; default 8*n + tiles */
 SB_API SbStatus sb_viewer_reserve_duplicates(SbViewer* v, uint64_t capacity);
 

@@ -635,7 +635,12 @@ static void raster_band(const SoSplat* sp, uint32_t count, const Uniforms* u, in
         uint32_t x1 = fx1 >= (float)width ? width - 1 : (uint32_t)fx1;
         uint32_t y0 = fy0 < (float)y_lo ? y_lo : (uint32_t)fy0;
         uint32_t y1 = fy1 >= (float)y_hi ? y_hi - 1 : (uint32_t)fy1;
-        float c255[3] = { s->r * 255.0f, s->g * 255.0f, s->b * 255.0f };
+        /* Fixed-point attachments clamp the SOURCE colour to [0,1] before the blend equation
+           (Vulkan 1.3 spec 29.1 "Blending": "If the color attachment is fixed-point, the components of
+           the source and destination values and blend factors are each clamped to [0,1]"); SH colours
+           can exceed 1 (utils.wesl:82-135 only clamps below).  With c, d <= 255 and alpha in [0,1] the
+           post-blend clamp below can never bind after rounding, it is kept as a statement of the spec. */
+        float c255[3] = { fminf(s->r * 255.0f, 255.0f), fminf(s->g * 255.0f, 255.0f), fminf(s->b * 255.0f, 255.0f) };
         float cf[3] = { s->r, s->g, s->b };
         for (uint32_t py = y0; py <= y1; py++) {
             float dy = ((float)py + 0.5f) - s->cy;

@@ -20,6 +20,7 @@ ap.add_argument("--sh", type=int, default=0)
 ap.add_argument("--cov", type=int, default=0)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--count", action="store_true", help="one extra instrumented frame: fragment / warp-evaluation counters")
 args = ap.parse_args()
 
 ctx = sb.Context(0)
@@ -64,6 +65,11 @@ for n in args.n:
                    preprocess_GBs=pre_bytes / med["preprocess"] / 1e6, sort_Gkeys=V / med["depth_sort"] / 1e6,
                    sort_GBs=V * 68 / med["depth_sort"] / 1e6, pairs_G=D * 256 / 1e9,
                    raster_Gpairs_s=D * 256 / med["raster"] / 1e6)
+        if args.count:
+            v.set_raster_counting(True)
+            v.render(target, w, h, stream=stream)
+            out["counters"] = v.read_raster_counters(stream)
+            v.set_raster_counting(False)
         print(json.dumps(out), flush=True)
     v.close()
     del target

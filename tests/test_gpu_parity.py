@@ -201,6 +201,24 @@ def test_deep_low_alpha_stack(sb, ob, ctx):
     assert np.abs(f8 - r["img"][..., :3].astype(np.int32)).max() > 3
 
 
+@pytest.mark.parametrize("target_format", [0, 3])
+def test_overbright_sh_colours(sb, ob, ctx, target_format):
+    """SH lobes push view_color far above 1 (utils.wesl:82-135 clamps only below).  A fixed-point target clamps the
+    SOURCE colour to [0,1] before the blend (Vulkan 1.3 spec 29.1); a float target keeps the over-bright value."""
+    n = 5000
+    g = sb.scenes.synthetic_gaussians(n, 321)
+    g["sh"] *= 12.0
+    pods = sb.pack_gaussians(g)
+    r = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, 480, 270, target_format=target_format)
+    check_artifacts(ob, r, n)
+    if target_format == 0:
+        assert img_diff(r) == 0
+    else:
+        assert r["img"][..., :3].max() > 1.5, "float target must keep over-bright colours"
+        d = np.abs(r["img"].astype(np.float64) - r["oimg"].astype(np.float64))
+        assert (d <= 1e-3 * np.maximum(1.0, np.abs(r["oimg"]))).all()
+
+
 def test_equal_depth_ties_keep_index_order(sb, ob, ctx):
     """equal keys are the norm; the canonical order inside a run is ascending index."""
     n = 5000
@@ -445,6 +463,43 @@ assert d == 0
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, SB_RASTER_PATH="bulk")
+    out = subprocess.run([sys.executable, "-c", code, os.path.join(root, "wgpu-3dgs-viewer_b200"), root], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_bbox_only_cull_is_bit_identical(sb, ob):
+    """SB_RASTER_CULL=bbox switches the warp-level cull back to the alive-region bbox alone; the separating-axis cull
+    of the default path may only drop (patch, splat) pairs with no alive fragment, so the frames are identical."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import splat_b200 as sb
+from oracle import binding as ob
+n, w, h = 20000, 640, 360
+g = sb.scenes.synthetic_gaussians(n, 77, log_scale=(-5.0, -2.0))
+pods = sb.pack_gaussians(g)
+ctx = sb.Context(0)
+for cam in (sb.scenes.CAMERA_INSIDE, sb.scenes.CAMERA_OUTSIDE):
+    v = sb.Viewer(ctx, pods, n)
+    v.set_strict_exp(True)
+    v.set_raster_counting(True)
+    pos, yaw, pitch = cam
+    v.update_camera(pos, yaw, pitch, w, h)
+    t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    v.render(t, w, h)
+    c = v.read_raster_counters()
+    oimg, ost = ob.render(ob.OracleModel(pods, n), ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(), strict_exp=True)
+    d = np.abs(t.cpu().numpy().astype(np.int32) - oimg.astype(np.int32)).max()
+    print("maxdiff", d, c, ost)
+    assert d == 0 and c["alive"] == ost["alive_pixels"]
+    v.close()
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SB_RASTER_CULL="bbox")
     out = subprocess.run([sys.executable, "-c", code, os.path.join(root, "wgpu-3dgs-viewer_b200"), root], env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr

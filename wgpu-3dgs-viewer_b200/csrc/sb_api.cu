@@ -373,10 +373,15 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.target = *target;
     p.strict_exp = v->strict_exp;
     p.clear = clear;
+    {
+        // SB_RASTER_CULL=bbox keeps the warp-level cull on the alive-region bbox only (A/B measurements)
+        static const bool bbox_only = [] { const char* c = std::getenv("SB_RASTER_CULL"); return c && std::string(c) == "bbox"; }();
+        p.obb_cull = bbox_only ? 0 : 1;
+    }
     p.events = v->timing ? &v->ev[3] : nullptr;
     p.recs_map = v->use_gather4 ? &v->recs_map : nullptr;
     p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
-    if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 16, stream));
+    if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 32, stream));
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
     return SB_OK;
 }
@@ -765,7 +770,7 @@ SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
 
 SbStatus sb_viewer_set_raster_counting(SbViewer* v, int32_t enabled) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
-    if (enabled && !v->counters.p) SB_CUDA(v->ctx, v->counters.alloc(16));
+    if (enabled && !v->counters.p) SB_CUDA(v->ctx, v->counters.alloc(32));
     v->counting = enabled != 0;
     return SB_OK;
 }
@@ -778,6 +783,17 @@ SbStatus sb_viewer_read_raster_counters(SbViewer* v, void* stream, uint64_t* ali
     SB_CUDA(v->ctx, cudaMemcpy(c, v->counters.p, 16, cudaMemcpyDeviceToHost));
     if (alive) *alive = c[0];
     if (evaluated) *evaluated = c[1];
+    return SB_OK;
+}
+
+SbStatus sb_viewer_read_raster_warp_counters(SbViewer* v, void* stream, uint64_t* warp_evals, uint64_t* warp_evals_alive) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    if (!v->counters.p) return fail(v->ctx, SB_ERR_INVALID_ARG, "raster counting was never enabled");
+    SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    unsigned long long c[4] = {0, 0, 0, 0};
+    SB_CUDA(v->ctx, cudaMemcpy(c, v->counters.p, 32, cudaMemcpyDeviceToHost));
+    if (warp_evals) *warp_evals = c[2];
+    if (warp_evals_alive) *warp_evals_alive = c[3];
     return SB_OK;
 }
 

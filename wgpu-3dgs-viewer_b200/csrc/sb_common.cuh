@@ -35,12 +35,14 @@ struct Uniforms {
 
 // Projected splat = everything vert_main (render.wesl:76-130) hands to the fragment stage,
 // computed once per visible Gaussian instead of 6x per quad.  48 bytes, 3 x 128-bit.
+// The axis rows are stored column-wise, (ax, bx) and (ay, by), so the rasterizer evaluates both
+// quad_offset components with one packed FMUL2 + one packed FFMA2 (sb_raster.cu).
 struct __align__(16) SplatRec {
     float cx, cy;   // pixel-space centre
-    float ax, ay;   // quad_offset.x = dx*ax + dy*ay
-    float bx, by;   // quad_offset.y = dx*bx + dy*by
+    float ax, bx;   // quad_offset.x = dx*ax + dy*ay
+    float ay, by;   // quad_offset.y = dx*bx + dy*by
     float ex, ey;   // half extent (pixels) of the alive region: used for warp-level culling
-    float r, g;     // colour * color_scale
+    float r, g;     // colour * color_scale (clamped to 255 on unorm8 targets: source-colour clamp)
     float b, a;
 };
 // Tile bbox of a splat, kept in a separate 8-byte array so the binning gathers (random, in depth

@@ -74,6 +74,7 @@ struct RasterParams {
     SbTarget target;
     int strict_exp;
     int clear;                       // 1: clear to BLACK first (first model of a frame)
+    int obb_cull;                    // 1: warp-level cull also tests the ellipse axes (SAT), 0: bbox only
     const CUtensorMap* recs_map;     // non-null: fetch records with TMA gather4 (no gathered copy); host pointer, passed by value
     unsigned long long* counters;    // optional instrumentation: [0] alive fragments, [1] evaluated lane pairs
     cudaEvent_t* events;             // optional: [0]=after scan+emit, [1]=after tile sort, [2]=after gather, [3]=after raster

@@ -550,9 +550,13 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
             float rgb[3];
             const uint32_t packed = __float_as_uint(head.w);
             view_color<SH>(u, rec, packed, -smul(md[0], inv_ml), -smul(md[1], inv_ml), -smul(md[2], inv_ml), rgb);
-            out.r = smul(rgb[0], u.color_scale);
-            out.g = smul(rgb[1], u.color_scale);
-            out.b = smul(rgb[2], u.color_scale);
+            // Fixed-point colour attachments clamp the SOURCE colour to [0,1] before the blend equation
+            // (Vulkan 1.3 spec 29.1 "Blending"; the reference renders to Rgba8Unorm, src/renderer.rs:296-300):
+            // done here once per splat, which also makes the post-blend clamp redundant (d, c <= 255, alpha <= 1).
+            const float cmax = u.color_scale == 255.0f ? 255.0f : __int_as_float(0x7f800000);
+            out.r = fminf(smul(rgb[0], u.color_scale), cmax);
+            out.g = fminf(smul(rgb[1], u.color_scale), cmax);
+            out.b = fminf(smul(rgb[2], u.color_scale), cmax);
             out.a = unorm8(packed >> 24);
             bool valid;
             if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
@@ -588,8 +592,8 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
                 out.ex = out.ey = 0.0f;
             }
             float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
-            dst[0] = make_float4(out.cx, out.cy, out.ax, out.ay);
-            dst[1] = make_float4(out.bx, out.by, out.ex, out.ey);
+            dst[0] = make_float4(out.cx, out.cy, out.ax, out.bx);
+            dst[1] = make_float4(out.ay, out.by, out.ex, out.ey);
             dst[2] = make_float4(out.r, out.g, out.b, out.a);
             *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(tb.tmin, tb.tmax);
         }

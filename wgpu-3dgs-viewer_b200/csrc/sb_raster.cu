@@ -216,7 +216,40 @@ __device__ __forceinline__ float exp_neg_fast(float x) {
 }
 
 // round-to-nearest-even of x in [0, 2^22) without the (quarter-rate) FRND instruction
-__device__ __forceinline__ float rint_small(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
+constexpr float kRintMagic = 12582912.0f;  // 1.5 * 2^23
+__device__ __forceinline__ float rint_small(float x) { return __fadd_rn(__fadd_rn(x, kRintMagic), -kRintMagic); }
+
+// ---- packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2): two individually rounded IEEE f32 operations
+// per issued instruction, so results stay bit-identical to the scalar oracle.  A pair lives in an
+// aligned register pair; ptxas folds a pair built from one scalar into the broadcast operand form
+// (`R.F32`) and immediates, so no moves are spent on (alpha, alpha) or the rounding constant.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 struct RasterKernelParams {
     const SplatRec* tile_recs;      // bulk path: records gathered into tile order
@@ -228,112 +261,156 @@ struct RasterKernelParams {
     uint32_t row0, rows;
     uint32_t tiles_x;
     uint32_t ty_lo;
+    float sd;       // std_dev
     float sd2;      // std_dev^2
     float outline;  // (std_dev - 0.1)^2
     int bgra;
     int clear;
-    unsigned long long* counters;  // COUNT builds: [0] alive fragments, [1] evaluated (pixel,splat) lane pairs
+    int obb_cull;   // 1: cull a splat against the warp's patch along the ellipse axes too
+    unsigned long long* counters;  // COUNT builds: [0] alive fragments, [1] evaluated (pixel,splat) lane pairs,
+                                   // [2] (warp,splat) evaluations, [3] of those with at least one alive lane
 };
 
+// Destination pixel, kept as two packed pairs: (d0, d1) and (d2, d3); 0..255 units on unorm8 targets.
 struct PixelState {
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 1.0f;  // destination; 0..255 units on unorm8 targets
-    uint32_t n_alive = 0, n_eval = 0;
+    f32x2 d01, d23;
+    uint32_t n_alive = 0, n_eval = 0, n_warp_eval = 0, n_warp_alive = 0;
+    __device__ __forceinline__ PixelState() { d01 = pk2(0.0f, 0.0f); d23 = pk2(0.0f, 1.0f); }
 };
 
 template <int FMT>
 __device__ __forceinline__ void load_dst(PixelState& st, const uint8_t* row, uint32_t x, int bgra) {
     if constexpr (FMT == FMT_UNORM8) {
         const uchar4 c = reinterpret_cast<const uchar4*>(row)[x];
-        st.d0 = bgra ? c.z : c.x;
-        st.d1 = c.y;
-        st.d2 = bgra ? c.x : c.z;
+        st.d01 = pk2(bgra ? c.z : c.x, c.y);
+        st.d23 = pk2(bgra ? c.x : c.z, 1.0f);
     } else if constexpr (FMT == FMT_F16) {
         const __half* h = reinterpret_cast<const __half*>(row) + 4 * x;
-        st.d0 = __half2float(h[0]); st.d1 = __half2float(h[1]); st.d2 = __half2float(h[2]); st.d3 = __half2float(h[3]);
+        st.d01 = pk2(__half2float(h[0]), __half2float(h[1]));
+        st.d23 = pk2(__half2float(h[2]), __half2float(h[3]));
     } else {
         const float4 c = reinterpret_cast<const float4*>(row)[x];
-        st.d0 = c.x; st.d1 = c.y; st.d2 = c.z; st.d3 = c.w;
+        st.d01 = pk2(c.x, c.y);
+        st.d23 = pk2(c.z, c.w);
     }
 }
 
 template <int FMT>
 __device__ __forceinline__ void store_dst(const PixelState& st, uint8_t* row, uint32_t x, int bgra) {
+    float d0, d1, d2, d3;
+    upk2(st.d01, d0, d1);
+    upk2(st.d23, d2, d3);
     if constexpr (FMT == FMT_UNORM8) {
         uchar4 c;
-        c.x = (unsigned char)(bgra ? st.d2 : st.d0);
-        c.y = (unsigned char)st.d1;
-        c.z = (unsigned char)(bgra ? st.d0 : st.d2);
+        c.x = (unsigned char)(bgra ? d2 : d0);
+        c.y = (unsigned char)d1;
+        c.z = (unsigned char)(bgra ? d0 : d2);
         c.w = 255;
         reinterpret_cast<uchar4*>(row)[x] = c;
     } else if constexpr (FMT == FMT_F16) {
-        __half2 lo = __floats2half2_rn(st.d0, st.d1), hi = __floats2half2_rn(st.d2, st.d3);
+        __half2 lo = __floats2half2_rn(d0, d1), hi = __floats2half2_rn(d2, d3);
         uint2 o;
         o.x = *reinterpret_cast<uint32_t*>(&lo);
         o.y = *reinterpret_cast<uint32_t*>(&hi);
         reinterpret_cast<uint2*>(row)[x] = o;
     } else {
-        reinterpret_cast<float4*>(row)[x] = make_float4(st.d0, st.d1, st.d2, st.d3);
+        reinterpret_cast<float4*>(row)[x] = make_float4(d0, d1, d2, d3);
     }
 }
 
 // Composites one staged batch onto this thread's pixel, in list order.  PERM: record j of the batch
 // sits at float4 index g4_row_f4(j) (the layout the gather4 producer writes).
-// Warp-level culling: each lane tests one splat's alive-region bbox against the warp's 8x4 pixel
-// patch; only splats that can touch the patch are evaluated.
+// Warp-level culling: each lane tests one splat against the warp's 8x4 pixel patch — the bbox of its
+// alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of the patch
+// rectangle against the ellipse's oriented bounding box; only survivors are evaluated.
 template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
-__device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, float px, float py, float pcx, float pcy,
-                                                uint32_t lane, bool inside, float sd2, float outline, PixelState& st) {
-    for (uint32_t base = 0; base < cnt; base += 32) {
-        const uint32_t jl = base + lane;
+__device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
+                                                uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
+                                                PixelState& st) {
+    // Byte addressing.  PERM: record j sits at 64 j - 16 (j & 3) (four 48-byte rows per 256-byte gather);
+    // otherwise at 48 j.  A round is 32 consecutive records starting at a multiple of 32.
+    const char* rb = reinterpret_cast<const char*>(recs);
+    const char* mine = rb + (PERM ? 64u * lane - 16u * (lane & 3u) : 48u * lane);
+    constexpr uint32_t kRound = PERM ? 2048u : 1536u;
+    for (uint32_t base = 0; base < cnt; base += 32, mine += kRound, rb += kRound) {
         bool hit = false;
-        if (jl < cnt) {
-            const uint32_t r4 = PERM ? g4_row_f4(jl) : jl * 3;
-            const float4 c0 = recs[r4 + 0];
-            const float4 c1 = recs[r4 + 1];
-            hit = fabsf(c0.x - pcx) <= c1.z + 3.51f && fabsf(c0.y - pcy) <= c1.w + 1.51f;
+        if (base + lane < cnt) {
+            const float4 c0 = *reinterpret_cast<const float4*>(mine);       // cx cy ax bx
+            const float4 c1 = *reinterpret_cast<const float4*>(mine + 16);  // ay by ex ey
+            const float ddx = pcx - c0.x, ddy = pcy - c0.y;
+            hit = fabsf(ddx) <= c1.z + 3.51f && fabsf(ddy) <= c1.w + 1.51f;
+            if (obb) {
+                // |q(p)| <= |q(pc)| + 3.5|a_x| + 1.5|a_y| over the patch's pixel centres; alive needs |q| <= sd
+                const float qcx = fmaf(ddx, c0.z, ddy * c1.x), qcy = fmaf(ddx, c0.w, ddy * c1.y);
+                const float mx = fmaf(3.5f, fabsf(c0.z), fmaf(1.5f, fabsf(c1.x), sd));
+                const float my = fmaf(3.5f, fabsf(c0.w), fmaf(1.5f, fabsf(c1.y), sd));
+                hit = hit && fabsf(qcx) <= fmaf(mx, 1.0001f, 1.0e-3f) && fabsf(qcy) <= fmaf(my, 1.0001f, 1.0e-3f);
+            }
         }
-        uint32_t todo = __ballot_sync(0xffffffffu, hit);
+        // bit hb = 31 - b <-> splat b of the round: FLO finds the next splat, no BREV per iteration
+        uint32_t todo = __brev(__ballot_sync(0xffffffffu, hit));
+        // address of splat b = 31 - hb: rb + 64 b - 16 (b & 3) = last - 64 hb + 16 (hb & 3)   (PERM)
+        //                                 rb + 48 b                = last - 48 hb               (else)
+        const char* last = rb + (PERM ? 64u * 31u - 48u : 48u * 31u);
         while (todo) {
-            const uint32_t b = (uint32_t)(__ffs(todo) - 1);
-            todo &= todo - 1;
-            const uint32_t r4 = PERM ? g4_row_f4(base + b) : (base + b) * 3;
-            const float4 q0 = recs[r4 + 0];
-            const float4 q1 = recs[r4 + 1];
-            const float dx = __fsub_rn(px, q0.x), dy = __fsub_rn(py, q0.y);
-            const float qx = __fmaf_rn(dx, q0.z, __fmul_rn(dy, q0.w));
-            const float qy = __fmaf_rn(dx, q1.x, __fmul_rn(dy, q1.y));
+            uint32_t hb;  // FLO directly; `31 - __clz` is canonicalised back into a clz and costs five more integer ops
+            asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
+            todo ^= 1u << hb;
+            const char* rp = PERM ? last - 64u * hb + 16u * (hb & 3u) : last - 48u * hb;
+            const float4 q0 = *reinterpret_cast<const float4*>(rp);       // cx cy ax bx
+            const float2 q1 = *reinterpret_cast<const float2*>(rp + 16);  // ay by
+            // quad offset (render.wesl:125-128 inverted): q = (fma(dx,ax,dy*ay), fma(dx,bx,dy*by))
+            float dx, dy, qx, qy;
+            upk2(sub2(pxy, pk2(q0.x, q0.y)), dx, dy);
+            upk2(fma2(pk2(q0.z, q0.w), pk2(dx, dx), mul2(pk2(q1.x, q1.y), pk2(dy, dy))), qx, qy);
             if constexpr (COUNT) st.n_eval += inside ? 1u : 0u;
             float alpha;
+            bool alive;
+            const float4 q2 = *reinterpret_cast<const float4*>(rp + 32);  // r g b a
             if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
-                if (!(fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f)) continue;
+                alive = fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f;
                 alpha = 1.0f;
             } else {
                 const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
-                if (!(r2 <= sd2)) continue;  // discard: render.wesl:145,155
-                const float a = recs[r4 + 2].w;
+                alive = r2 <= sd2;  // discard otherwise: render.wesl:145,155
                 if constexpr (MODE == SB_MODE_SPLAT) {
                     const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
-                    alpha = __fmul_rn(a, e);  // render.wesl:149
+                    alpha = __fmul_rn(q2.w, e);  // render.wesl:149
                 } else {
                     const float ol = r2 > outline ? 1.0f : 0.0f;  // render.wesl:159-160
-                    alpha = __fadd_rn(a, __fmul_rn(__fsub_rn(1.0f, a), ol));
+                    alpha = __fadd_rn(q2.w, __fmul_rn(__fsub_rn(1.0f, q2.w), ol));
                 }
             }
-            const float4 q2 = recs[r4 + 2];
-            if constexpr (COUNT) st.n_alive += inside ? 1u : 0u;
+            if constexpr (COUNT) {
+                st.n_alive += (inside && alive) ? 1u : 0u;
+                const bool any = __any_sync(__activemask(), alive);
+                st.n_warp_eval += 1u;
+                st.n_warp_alive += any ? 1u : 0u;
+            }
+            // A discarded fragment blends with alpha = 0, which is the identity EXACTLY (d*1 + c*0 = d, and d is
+            // already an integer on unorm8 targets): the loop body stays branch-free.
+            alpha = alive ? alpha : 0.0f;
             const float om = __fsub_rn(1.0f, alpha);
+            const f32x2 om2 = pk2(om, om), al2 = pk2(alpha, alpha);
             if constexpr (FMT == FMT_UNORM8) {
-                st.d0 = rint_small(fminf(__fmaf_rn(st.d0, om, __fmul_rn(q2.x, alpha)), 255.0f));
-                st.d1 = rint_small(fminf(__fmaf_rn(st.d1, om, __fmul_rn(q2.y, alpha)), 255.0f));
-                st.d2 = rint_small(fminf(__fmaf_rn(st.d2, om, __fmul_rn(q2.z, alpha)), 255.0f));
+                // d <- rint(fma(d, 1-alpha, c255*alpha)); the source colour is clamped to 255 per splat (K1) and
+                // alpha <= 1, so the blend cannot exceed 255 + rounding and the post-blend clamp never binds
+                const f32x2 m = pk2(kRintMagic, kRintMagic), nm = pk2(-kRintMagic, -kRintMagic);
+                st.d01 = add2(add2(fma2(st.d01, om2, mul2(pk2(q2.x, q2.y), al2)), m), nm);
+                float d2, d3;
+                upk2(st.d23, d2, d3);
+                d2 = rint_small(__fmaf_rn(d2, om, __fmul_rn(q2.z, alpha)));
+                st.d23 = pk2(d2, d3);
             } else {
-                st.d0 = __fmaf_rn(st.d0, om, __fmul_rn(q2.x, alpha));
-                st.d1 = __fmaf_rn(st.d1, om, __fmul_rn(q2.y, alpha));
-                st.d2 = __fmaf_rn(st.d2, om, __fmul_rn(q2.z, alpha));
-                st.d3 = __fmaf_rn(st.d3, om, alpha);
+                // (b*alpha, 1*alpha): 1*alpha is exact, so d3 = fma(d3, 1-alpha, alpha) as in the oracle
+                st.d01 = fma2(st.d01, om2, mul2(pk2(q2.x, q2.y), al2));
+                st.d23 = fma2(st.d23, om2, mul2(pk2(q2.z, 1.0f), al2));
                 if constexpr (FMT == FMT_F16) {
-                    st.d0 = __half2float(__float2half_rn(st.d0)); st.d1 = __half2float(__float2half_rn(st.d1));
-                    st.d2 = __half2float(__float2half_rn(st.d2)); st.d3 = __half2float(__float2half_rn(st.d3));
+                    float d0, d1, d2, d3;
+                    upk2(st.d01, d0, d1);
+                    upk2(st.d23, d2, d3);
+                    st.d01 = pk2(__half2float(__float2half_rn(d0)), __half2float(__float2half_rn(d1)));
+                    st.d23 = pk2(__half2float(__float2half_rn(d2)), __half2float(__float2half_rn(d3)));
                 }
             }
         }
@@ -351,6 +428,8 @@ __device__ __forceinline__ void flush_counters(PixelState& st, uint32_t lane, un
         if (lane == 0 && counters) {
             atomicAdd(&counters[0], (unsigned long long)st.n_alive);
             atomicAdd(&counters[1], (unsigned long long)st.n_eval);
+            atomicAdd(&counters[2], (unsigned long long)st.n_warp_eval);
+            atomicAdd(&counters[3], (unsigned long long)st.n_warp_alive);
         }
     }
 }
@@ -401,7 +480,7 @@ __global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelPara
         }
         mbar_wait(&full_bar[s], (k >> 1) & 1u);
         const uint32_t cnt = min((uint32_t)kBatch, total - k * kBatch);
-        composite_batch<MODE, FMT, STRICT, COUNT, false>(stage[s], cnt, px, py, pcx, pcy, lane, inside, p.sd2, p.outline, st);
+        composite_batch<MODE, FMT, STRICT, COUNT, false>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline, p.obb_cull != 0, st);
         __syncthreads();  // everyone is done with stage[s] before it is refilled
     }
     flush_counters<COUNT>(st, lane, p.counters);
@@ -476,7 +555,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelP
         const uint32_t s = k % kG4Stages;
         mbar_wait(&full_bar[s], (k / kG4Stages) & 1u);
         const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
-        composite_batch<MODE, FMT, STRICT, COUNT, true>(stage[s], cnt, px, py, pcx, pcy, lane, inside, p.sd2, p.outline, st);
+        composite_batch<MODE, FMT, STRICT, COUNT, true>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline, p.obb_cull != 0, st);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
@@ -597,10 +676,12 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     kp.rows = rows;
     kp.tiles_x = u.tiles_x;
     kp.ty_lo = ty_lo;
+    kp.sd = u.std_dev;
     kp.sd2 = u.std_dev * u.std_dev;
     kp.outline = (u.std_dev - 0.1f) * (u.std_dev - 0.1f);
     kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
     kp.clear = p.clear;
+    kp.obb_cull = p.obb_cull;
     kp.counters = p.counters;
     const dim3 grid(u.tiles_x, ty_hi - ty_lo + 1);
     const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8

@@ -10,6 +10,9 @@
 // The sort is STABLE (ties keep input order) like the reference's (radix_sort.wgsl:325-343),
 // which is what makes the final order canonical (ascending Gaussian index within equal keys).
 // The number of keys is read from device memory (the reference's indirect dispatch).
+#include <cstdlib>
+#include <string>
+
 #include "sb_internal.h"
 
 namespace sb {
@@ -343,6 +346,276 @@ __global__ void __launch_bounds__(kSortThreads, 4)
     }
 }
 
+
+constexpr size_t kPlanOffset = kHistWords + 4;  // [kPlanOffset + pass]: bit 0 = skip, bit 1 = input lives in the alt buffers
+
+// lanes of the warp whose NBITS-bit digit equals this lane's: one vote per digit bit
+template <int NBITS>
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+    // differ |= lanes whose bit b differs from mine = vote ^ (my bit replicated).  Written in PTX: ptxas turns it
+    // into one R2P for all bits + VOTE + predicated NOT + OR per bit; the C form costs six instructions per bit.
+    uint32_t differ = 0u;
+#pragma unroll
+    for (int b = 0; b < NBITS; b++) {
+        uint32_t x;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, m, r;\n"
+            "and.b32 t, %1, %2;\n"
+            "setp.ne.u32 p, t, 0;\n"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+            "selp.b32 r, -1, 0, p;\n"
+            "xor.b32 %0, m, r;\n"
+            "}\n"
+            : "=r"(x)
+            : "r"(d), "r"(1u << b));
+        differ |= x;
+    }
+    return ~differ;
+}
+
+// ================================================================ K3 (v3): small-footprint one-tile-per-CTA pass
+//
+// Lessons of three persistent variants that were built and measured (profiles/r01_sort_variants.txt): any scheme in which a CTA holds
+// a ticket while it still has to wait on another tile's look-back feeds that wait back into everybody's look-back and
+// ends up slower than the plain kernel.  So: one tile per CTA, ticket at the start, nothing between ticket and
+// aggregate but the key load and the ranking — and as many tiles in flight per SM as shared memory allows:
+//   256 threads x 16 pairs (4096-pair tiles), <= 40 registers, 34 KB of shared memory -> six CTAs (48 warps) per SM;
+//   the payload never enters registers: once a pair's tile-sorted position is known, cp.async (LDGSTS, 4 bytes)
+//   moves it from global memory straight to its staging slot, overlapping the look-back;
+//   count, plan, digit totals and the ticket are fetched in one round trip; ranking without shared-memory atomics.
+constexpr int kV3Threads = 256;
+constexpr int kV3Items = 16;
+constexpr int kV3Tile = kV3Threads * kV3Items;  // 4096
+constexpr int kV3Warps = kV3Threads / 32;
+constexpr int kV3CtasPerSm = 6;
+
+struct Sort3Smem {
+    union {
+        uint32_t warp_hist[kV3Warps][kRadix];
+        struct {
+            uint32_t keys[kV3Tile];
+            uint32_t vals[kV3Tile];
+        } stage;
+    };
+    uint32_t digit_local[kRadix];
+    uint32_t digit_base[kRadix];
+    uint32_t scan_a[kV3Warps];
+    uint32_t scan_b[kV3Warps];
+    uint32_t tile;
+};
+
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NBITS, bool FULL>
+__device__ __forceinline__ void onesweep3_tile(Sort3Smem& sm, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t count,
+                                               int shift, uint32_t gcount, uint32_t* __restrict__ lookback, uint32_t tile) {
+    constexpr uint32_t kMask = (1u << NBITS) - 1u;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tile_base = tile * kV3Tile;
+    const uint32_t tile_count = FULL ? (uint32_t)kV3Tile : (count - tile_base);
+
+    uint32_t key[kV3Items];
+    const uint32_t woff = warp * (32 * kV3Items) + lane;
+    const uint32_t* kp = keys_in + tile_base + woff;
+#pragma unroll
+    for (int i = 0; i < kV3Items; i++) key[i] = (FULL || woff + i * 32 < tile_count) ? __ldg(kp + i * 32) : 0xffffffffu;
+
+    uint32_t* wh = sm.warp_hist[warp];
+    {
+        uint4* z = reinterpret_cast<uint4*>(wh);
+        z[lane] = make_uint4(0, 0, 0, 0);
+        z[lane + 32] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+
+    uint32_t rank2[kV3Items / 2];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < kV3Items; i++) {
+        const bool ok = FULL || (woff + i * 32) < tile_count;
+        const uint32_t d = (key[i] >> shift) & kMask;
+        uint32_t peers = match_digit<NBITS>(d);
+        if (!FULL) {
+            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            peers &= ok ? okm : ~okm;
+        }
+        const uint32_t below = __popc(peers & lt);
+        uint32_t pre = 0;
+        if (below == 0 && ok) {
+            pre = wh[d];
+            wh[d] = pre + (uint32_t)__popc(peers);
+        }
+        __syncwarp();
+        pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
+        if (i & 1) rank2[i >> 1] |= (pre + below) << 16;
+        else rank2[i >> 1] = pre + below;
+    }
+    __syncthreads();
+
+    // ---- thread d owns digit d: scan over warps, publish the tile aggregate, scans over digits
+    uint32_t digit_count, local_excl, global_excl, nearest = 0;
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kV3Warps; w++) {
+            const uint32_t t = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = run;
+            run += t;
+        }
+        digit_count = run;
+        st_relaxed_u32(&lookback[(size_t)tile * kRadix + tid], (tile == 0 ? kLbPrefix : kLbAggregate) | digit_count);
+        if (tile > 0) nearest = ld_relaxed_u32(&lookback[(size_t)(tile - 1) * kRadix + tid]);
+        uint32_t a = digit_count, b = gcount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o);
+            const uint32_t tb = __shfl_up_sync(0xffffffffu, b, o);
+            if ((int)lane >= o) {
+                a += ta;
+                b += tb;
+            }
+        }
+        if (lane == 31) {
+            sm.scan_a[warp] = a;
+            sm.scan_b[warp] = b;
+        }
+        __syncthreads();
+        uint32_t wa = 0, wb = 0;
+#pragma unroll
+        for (int w = 0; w < kV3Warps; w++) {
+            if (w < (int)warp) {
+                wa += sm.scan_a[w];
+                wb += sm.scan_b[w];
+            }
+        }
+        local_excl = a - digit_count + wa;
+        global_excl = b - gcount + wb;
+        sm.digit_local[tid] = local_excl;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < kV3Items; i++) {
+        const uint32_t d = (key[i] >> shift) & kMask;
+        rank2[i >> 1] += (wh[d] + sm.digit_local[d]) << (16 * (i & 1));
+    }
+    __syncthreads();  // histograms dead: the storage becomes the staging buffer
+    const uint32_t vals_smem = smem_u32(sm.stage.vals);
+    const uint32_t* vp = vals_in + tile_base + woff;
+#pragma unroll
+    for (int i = 0; i < kV3Items; i++) {
+        if (FULL || (woff + i * 32) < tile_count) {
+            const uint32_t pos = (rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            sm.stage.keys[pos] = key[i];
+            cp_async_4(vals_smem + pos * 4u, vp + i * 32);  // payload: global -> staging slot, no register
+        }
+    }
+
+    {
+        uint32_t tile_excl = 0;
+        int t = (int)tile - 1;
+        bool have = true;
+        while (t >= 0) {
+            const uint32_t v0 = have ? nearest : ld_relaxed_u32(&lookback[(size_t)t * kRadix + tid]);
+            have = false;
+            if ((v0 >> 30) == 0) {
+                __nanosleep(40);
+                continue;
+            }
+            tile_excl += v0 & kLbValueMask;
+            --t;
+            if ((v0 >> 30) == 2) break;
+            uint32_t v[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) v[j] = (t - j) >= 0 ? ld_relaxed_u32(&lookback[(size_t)(t - j) * kRadix + tid]) : kLbPrefix;
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                if (done) break;
+                if ((v[j] >> 30) == 0) break;
+                tile_excl += v[j] & kLbValueMask;
+                --t;
+                if ((v[j] >> 30) == 2) {
+                    done = true;
+                    t = -1;
+                }
+            }
+        }
+        if (tile > 0) st_relaxed_u32(&lookback[(size_t)tile * kRadix + tid], kLbPrefix | (tile_excl + digit_count));
+        sm.digit_base[tid] = global_excl + tile_excl - local_excl;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kV3Items; i++) {
+        const uint32_t j = i * kV3Threads + tid;
+        if (FULL || j < tile_count) {
+            const uint32_t k = sm.stage.keys[j];
+            const uint32_t dst = sm.digit_base[(k >> shift) & kMask] + j;
+            keys_out[dst] = k;
+            vals_out[dst] = sm.stage.vals[j];
+        }
+    }
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(kV3Threads, kV3CtasPerSm)
+    onesweep3_kernel(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
+                     uint32_t* __restrict__ vals_b, const uint32_t* __restrict__ d_count, uint32_t max_count, int shift,
+                     const uint32_t* __restrict__ ghist, uint32_t* __restrict__ ticket, uint32_t* __restrict__ lookback,
+                     const uint32_t* __restrict__ plan) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Sort3Smem& sm = *reinterpret_cast<Sort3Smem*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    // one round trip: ticket, count, plan and this digit's total are all in flight together
+    uint32_t q = 0;
+    if (tid == 0) q = atomicAdd(ticket, 1u);
+    const uint32_t count = min(*d_count, max_count);
+    const uint32_t pl = *plan;
+    const uint32_t gcount = ghist[tid];
+    if (pl & 1u) return;
+    if (tid == 0) sm.tile = q;
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile * kV3Tile >= count) return;  // surplus CTA
+    const bool alt_in = (pl >> 1) & 1u;
+    const uint32_t* kin = alt_in ? keys_b : keys_a;
+    const uint32_t* vin = alt_in ? vals_b : vals_a;
+    uint32_t* kout = alt_in ? keys_a : keys_b;
+    uint32_t* vout = alt_in ? vals_a : vals_b;
+    if ((tile + 1) * kV3Tile <= count)
+        onesweep3_tile<NBITS, true>(sm, kin, vin, kout, vout, count, shift, gcount, lookback, tile);
+    else
+        onesweep3_tile<NBITS, false>(sm, kin, vin, kout, vout, count, shift, gcount, lookback, tile);
+}
+
+// One block after the histograms: which passes are the identity (one digit holds every key) and where each
+// remaining pass reads its input; state[0] = 1 when the result ends in the alt buffers.
+__global__ void sort_plan_kernel(uint32_t* __restrict__ internal, const uint32_t* __restrict__ d_count, uint32_t max_count, int num_passes) {
+    __shared__ int skip[kMaxPasses];
+    const uint32_t count = min(*d_count, max_count);
+    if (threadIdx.x < kMaxPasses) skip[threadIdx.x] = 0;
+    __syncthreads();
+    for (int p = 0; p < num_passes; p++)
+        if (internal[p * kRadix + threadIdx.x] == count) skip[p] = 1;  // threadIdx.x < 256
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t parity = 0;
+        for (int p = 0; p < num_passes; p++) {
+            const uint32_t s = (count == 0 || skip[p]) ? 1u : 0u;
+            internal[kPlanOffset + p] = s | (parity << 1);
+            if (!s) parity ^= 1u;
+        }
+        internal[kStateOffset] = parity;
+    }
+}
+
 // brings the result home when an odd number of passes ran (parity == 1)
 __global__ void sort_finish_kernel(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ keys_b,
                                    const uint32_t* __restrict__ vals_b, const uint32_t* __restrict__ d_count, uint32_t max_count,
@@ -367,9 +640,9 @@ __global__ void sort_finish_kernel(uint32_t* __restrict__ keys_a, uint32_t* __re
 
 // zeroes the histograms, tickets and the part of the look-back tables this sort will use
 __global__ void sort_init_kernel(uint32_t* __restrict__ internal, const uint32_t* __restrict__ d_count, uint32_t max_count,
-                                 int num_passes, uint32_t tiles_alloc) {
+                                 int num_passes, uint32_t tiles_alloc, uint32_t tile_size) {
     const uint32_t count = min(*d_count, max_count);
-    const uint32_t tiles = (count + kSortTile - 1) / kSortTile;
+    const uint32_t tiles = (count + tile_size - 1) / tile_size;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < kLookbackOffset; i += gridDim.x * blockDim.x) internal[i] = 0;
     for (int p = 0; p < num_passes; p++) {
         uint32_t* lb = internal + kLookbackOffset + (size_t)p * tiles_alloc * kRadix;
@@ -397,18 +670,52 @@ void launch_pass(int nbits, unsigned tiles, cudaStream_t stream, uint32_t* kin, 
     }
 }
 
+template <int NBITS>
+void launch_pass3_n(unsigned grid, cudaStream_t stream, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb,
+                    const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket, uint32_t* lb,
+                    const uint32_t* plan) {
+    onesweep3_kernel<NBITS><<<grid, kV3Threads, sizeof(Sort3Smem), stream>>>(ka, va, kb, vb, d_count, max_count, shift, ghist, ticket, lb, plan);
+}
+
+void launch_pass3(int nbits, unsigned grid, cudaStream_t stream, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb,
+                  const uint32_t* d_count, uint32_t max_count, int shift, const uint32_t* ghist, uint32_t* ticket, uint32_t* lb,
+                  const uint32_t* plan) {
+    switch (nbits) {
+#define SB_PASS(N) case N: launch_pass3_n<N>(grid, stream, ka, va, kb, vb, d_count, max_count, shift, ghist, ticket, lb, plan); break;
+        SB_PASS(1) SB_PASS(2) SB_PASS(3) SB_PASS(4) SB_PASS(5) SB_PASS(6) SB_PASS(7)
+        default: launch_pass3_n<8>(grid, stream, ka, va, kb, vb, d_count, max_count, shift, ghist, ticket, lb, plan); break;
+#undef SB_PASS
+    }
+}
+
 cudaError_t set_smem_all() {
     cudaError_t e = cudaSuccess;
-#define SB_ATTR(N) if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+#define SB_ATTR(N)                                                                                                                   \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)); \
+    if (e == cudaSuccess)                                                                                                            \
+        e = cudaFuncSetAttribute(onesweep3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sort3Smem));
     SB_ATTR(1) SB_ATTR(2) SB_ATTR(3) SB_ATTR(4) SB_ATTR(5) SB_ATTR(6) SB_ATTR(7) SB_ATTR(8)
 #undef SB_ATTR
     return e;
 }
 
+// SB_SORT_IMPL = v1 (8192-pair tiles, three CTAs per SM, shared-memory peer masks) | v3 (4096-pair tiles, six CTAs per SM,
+// vote ranking, cp.async payload).  Default: v3 for sorts of three or more digit passes (the depth sort: +5 % at 64 M keys),
+// v1 for the two-pass tile sort, whose 5-bit second pass measured 8 % faster with the larger tiles.
+int sort_impl(int num_passes) {
+    static const int forced = [] {
+        const char* c = std::getenv("SB_SORT_IMPL");
+        if (c && std::string(c) == "v1") return 1;
+        if (c && std::string(c) == "v3") return 3;
+        return 0;
+    }();
+    return forced ? forced : (num_passes >= 3 ? 3 : 1);
+}
+
 }  // namespace
 
 size_t sort_internal_bytes(uint32_t capacity) {
-    const size_t tiles = ((size_t)capacity + kSortTile - 1) / kSortTile;
+    const size_t tiles = ((size_t)capacity + kV3Tile - 1) / kV3Tile;  // the smaller of the two tile sizes
     return (kLookbackOffset + (size_t)kMaxPasses * tiles * kRadix) * sizeof(uint32_t);
 }
 
@@ -417,7 +724,10 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
     if (max_count == 0) return cudaSuccess;
     const int num_passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
     if (num_passes < 1 || num_passes > kMaxPasses) return cudaErrorInvalidValue;
-    const size_t tiles = ((size_t)max_count + kSortTile - 1) / kSortTile;
+    const int impl = sort_impl(num_passes);
+    const bool v2 = impl == 3;
+    const size_t tile_size = impl == 3 ? kV3Tile : kSortTile;
+    const size_t tiles = ((size_t)max_count + tile_size - 1) / tile_size;
     const size_t need = (kLookbackOffset + (size_t)num_passes * tiles * kRadix) * sizeof(uint32_t);
     if (need > scratch.internal_bytes) return cudaErrorInvalidValue;
     cudaError_t e;
@@ -427,19 +737,30 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    sort_init_kernel<<<num_sms * 2, 256, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, (uint32_t)tiles);
+    sort_init_kernel<<<num_sms * 2, 256, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, (uint32_t)tiles, (uint32_t)tile_size);
     uint32_t* ghist = scratch.internal;
     uint32_t* tickets = scratch.internal + kTicketOffset;
     uint32_t* lookback = scratch.internal + kLookbackOffset;
 
-    const int hist_grid = (int)min((size_t)num_sms * 2, (tiles * kSortTile / 4 + 511) / 512);
+    const int hist_grid = (int)min((size_t)num_sms * 2, (tiles * tile_size / 4 + 511) / 512);
     histogram_kernel<<<hist_grid > 0 ? hist_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, begin_bit, end_bit, num_passes, ghist);
 
     uint32_t* state = scratch.internal + kStateOffset;
-    for (int p = 0; p < num_passes; p++) {
-        const int nbits = min(kRadixBits, end_bit - (begin_bit + p * kRadixBits));
-        launch_pass(nbits, (unsigned)tiles, stream, keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count,
-                    begin_bit + p * kRadixBits, ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix, state, p);
+    if (v2) {
+        sort_plan_kernel<<<1, kRadix, 0, stream>>>(scratch.internal, d_count, max_count, num_passes);
+        const unsigned grid = (unsigned)tiles;
+        for (int p = 0; p < num_passes; p++) {
+            const int nbits = min(kRadixBits, end_bit - (begin_bit + p * kRadixBits));
+            launch_pass3(nbits, grid, stream, keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count,
+                         begin_bit + p * kRadixBits, ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix,
+                         scratch.internal + kPlanOffset + p);
+        }
+    } else {
+        for (int p = 0; p < num_passes; p++) {
+            const int nbits = min(kRadixBits, end_bit - (begin_bit + p * kRadixBits));
+            launch_pass(nbits, (unsigned)tiles, stream, keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count,
+                        begin_bit + p * kRadixBits, ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix, state, p);
+        }
     }
     // result sits in the alt buffers when an odd number of passes actually ran: bring it home
     sort_finish_kernel<<<num_sms * 4, 256, 0, stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count, state);

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_raster_path", "sb_viewer_set_strict_exp",
     "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times", "sb_viewer_set_raster_counting",
     "sb_viewer_read_raster_counters",
+    "sb_viewer_read_raster_warp_counters",
     "sb_viewer_reserve_duplicates", "sb_sorter_create", "sb_sorter_destroy", "sb_sorter_sort", "sb_mm_create",
     "sb_mm_destroy", "sb_mm_insert_model", "sb_mm_remove_model", "sb_mm_update_camera_with_pod",
     "sb_mm_update_model_transform_with_pod", "sb_mm_update_gaussian_transform_with_pod", "sb_mm_set_selection",
@@ -160,6 +161,7 @@ def load() -> C.CDLL:
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
     sig("sb_viewer_set_raster_counting", i32, vp, i32)
     sig("sb_viewer_read_raster_counters", i32, vp, vp, P(u64), P(u64))
+    sig("sb_viewer_read_raster_warp_counters", i32, vp, vp, P(u64), P(u64))
     sig("sb_viewer_set_stage_timing", i32, vp, i32)
     sig("sb_viewer_read_stage_times", i32, vp, vp, P(f32))
     sig("sb_viewer_reserve_duplicates", i32, vp, u64)
@@ -433,7 +435,9 @@ class Viewer:
     def read_raster_counters(self, stream=None) -> dict:
         a, e = C.c_uint64(), C.c_uint64()
         _check(load().sb_viewer_read_raster_counters(self._h, _stream_handle(stream), C.byref(a), C.byref(e)), self.ctx._h)
-        return dict(alive=a.value, evaluated=e.value)
+        w, wa = C.c_uint64(), C.c_uint64()
+        _check(load().sb_viewer_read_raster_warp_counters(self._h, _stream_handle(stream), C.byref(w), C.byref(wa)), self.ctx._h)
+        return dict(alive=a.value, evaluated=e.value, warp_evals=w.value, warp_evals_alive=wa.value)
 
     def set_stage_timing(self, enabled: bool):
         _check(load().sb_viewer_set_stage_timing(self._h, int(enabled)), self.ctx._h)
