@@ -13,6 +13,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+#include <string>
+
 #include "sb_internal.h"
 
 namespace sb {
@@ -184,8 +187,15 @@ constexpr int kBatch = 256;  // splat records per shared-memory stage (12 KB)
 // consecutive records 4m..4m+3 (4 rows x 48 B) and is written at a 256-byte pitch (the TMA destination
 // must be 128-byte aligned), so record j of the batch starts at float4 index (j >> 2) * 16 + (j & 3) * 3
 // = 3 j + (j & ~3): a cull round's 32 consecutive records spread over the banks (2-way conflicts).
-constexpr int kBatchG4 = 256;
-constexpr int kG4Stages = 2;
+#ifndef SB_G4_BATCH
+#define SB_G4_BATCH 256
+#endif
+#ifndef SB_G4_STAGES
+#define SB_G4_STAGES 2
+#endif
+constexpr int kBatchG4 = SB_G4_BATCH;  // 128 or 256: one or two gather4 per producer lane
+constexpr int kG4Stages = SB_G4_STAGES;
+constexpr int kG4PerLane = kBatchG4 / 128;
 constexpr int kG4StageF4 = (kBatchG4 / 4) * 16;
 __device__ __forceinline__ uint32_t g4_row_f4(uint32_t j) { return 3u * j + (j & ~3u); }
 
@@ -318,11 +328,74 @@ __device__ __forceinline__ void store_dst(const PixelState& st, uint8_t* row, ui
     }
 }
 
+// One (pixel, splat) evaluation + blend: splat 31 - hb of the current round.  Branch-free.
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
+__device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 pxy, bool inside, float sd2, float outline, PixelState& st) {
+    const char* rp = PERM ? last - 64u * hb + 16u * (hb & 3u) : last - 48u * hb;
+    const float4 q0 = *reinterpret_cast<const float4*>(rp);       // cx cy ax bx
+    const float2 q1 = *reinterpret_cast<const float2*>(rp + 16);  // ay by
+    // quad offset (render.wesl:125-128 inverted): q = (fma(dx,ax,dy*ay), fma(dx,bx,dy*by))
+    float dx, dy, qx, qy;
+    upk2(sub2(pxy, pk2(q0.x, q0.y)), dx, dy);
+    upk2(fma2(pk2(q0.z, q0.w), pk2(dx, dx), mul2(pk2(q1.x, q1.y), pk2(dy, dy))), qx, qy);
+    if constexpr (COUNT) st.n_eval += inside ? 1u : 0u;
+    float alpha;
+    bool alive;
+    const float4 q2 = *reinterpret_cast<const float4*>(rp + 32);  // r g b a
+    if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
+        alive = fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f;
+        alpha = 1.0f;
+    } else {
+        const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
+        alive = r2 <= sd2;  // discard otherwise: render.wesl:145,155
+        if constexpr (MODE == SB_MODE_SPLAT) {
+            const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
+            alpha = __fmul_rn(q2.w, e);  // render.wesl:149
+        } else {
+            const float ol = r2 > outline ? 1.0f : 0.0f;  // render.wesl:159-160
+            alpha = __fadd_rn(q2.w, __fmul_rn(__fsub_rn(1.0f, q2.w), ol));
+        }
+    }
+    if constexpr (COUNT) {
+        st.n_alive += (inside && alive) ? 1u : 0u;
+        const uint32_t act = __activemask();  // one or both halves
+        const bool any = __any_sync(act, alive);
+        st.n_warp_eval += 1u;
+        st.n_warp_alive += any ? 1u : 0u;
+    }
+    // A discarded fragment blends with alpha = 0, which is the identity EXACTLY (d*1 + c*0 = d, and d is
+    // already an integer on unorm8 targets): the loop body stays branch-free.
+    alpha = alive ? alpha : 0.0f;
+    const float om = __fsub_rn(1.0f, alpha);
+    const f32x2 om2 = pk2(om, om), al2 = pk2(alpha, alpha);
+    if constexpr (FMT == FMT_UNORM8) {
+        // d <- rint(fma(d, 1-alpha, c255*alpha)); the source colour is clamped to 255 per splat (K1) and
+        // alpha <= 1, so the blend cannot exceed 255 + rounding and the post-blend clamp never binds
+        const f32x2 m = pk2(kRintMagic, kRintMagic), nm = pk2(-kRintMagic, -kRintMagic);
+        st.d01 = add2(add2(fma2(st.d01, om2, mul2(pk2(q2.x, q2.y), al2)), m), nm);
+        float d2, d3;
+        upk2(st.d23, d2, d3);
+        d2 = rint_small(__fmaf_rn(d2, om, __fmul_rn(q2.z, alpha)));
+        st.d23 = pk2(d2, d3);
+    } else {
+        // (b*alpha, 1*alpha): 1*alpha is exact, so d3 = fma(d3, 1-alpha, alpha) as in the oracle
+        st.d01 = fma2(st.d01, om2, mul2(pk2(q2.x, q2.y), al2));
+        st.d23 = fma2(st.d23, om2, mul2(pk2(q2.z, 1.0f), al2));
+        if constexpr (FMT == FMT_F16) {
+            float d0, d1, d2, d3;
+            upk2(st.d01, d0, d1);
+            upk2(st.d23, d2, d3);
+            st.d01 = pk2(__half2float(__float2half_rn(d0)), __half2float(__float2half_rn(d1)));
+            st.d23 = pk2(__half2float(__float2half_rn(d2)), __half2float(__float2half_rn(d3)));
+        }
+    }
+}
+
 // Composites one staged batch onto this thread's pixel, in list order.  PERM: record j of the batch
 // sits at float4 index g4_row_f4(j) (the layout the gather4 producer writes).
-// Warp-level culling: each lane tests one splat against the warp's 8x4 pixel patch — the bbox of its
-// alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of the patch
-// rectangle against the ellipse's oriented bounding box; only survivors are evaluated.
+// Warp-level culling: each lane tests one splat against the two 4x4 halves of the warp's 8x4 pixel patch — the
+// bbox of its alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of a half's
+// rectangle against the ellipse's oriented bounding box; each half-warp then evaluates only its own survivors.
 template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
@@ -333,85 +406,49 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
     const char* mine = rb + (PERM ? 64u * lane - 16u * (lane & 3u) : 48u * lane);
     constexpr uint32_t kRound = PERM ? 2048u : 1536u;
     for (uint32_t base = 0; base < cnt; base += 32, mine += kRound, rb += kRound) {
-        bool hit = false;
+        // each lane tests ONE splat against BOTH 4x4 halves of the warp's 8x4 patch (pcx: centre of the left half)
+        bool hit_l = false, hit_r = false;
         if (base + lane < cnt) {
             const float4 c0 = *reinterpret_cast<const float4*>(mine);       // cx cy ax bx
             const float4 c1 = *reinterpret_cast<const float4*>(mine + 16);  // ay by ex ey
-            const float ddx = pcx - c0.x, ddy = pcy - c0.y;
-            hit = fabsf(ddx) <= c1.z + 3.51f && fabsf(ddy) <= c1.w + 1.51f;
+            const float dl = pcx - c0.x, dr = dl + 4.0f, ddy = pcy - c0.y;
+            const bool hy = fabsf(ddy) <= c1.w + 1.51f;
+            hit_l = hy && fabsf(dl) <= c1.z + 1.51f;
+            hit_r = hy && fabsf(dr) <= c1.z + 1.51f;
             if (obb) {
-                // |q(p)| <= |q(pc)| + 3.5|a_x| + 1.5|a_y| over the patch's pixel centres; alive needs |q| <= sd
-                const float qcx = fmaf(ddx, c0.z, ddy * c1.x), qcy = fmaf(ddx, c0.w, ddy * c1.y);
-                const float mx = fmaf(3.5f, fabsf(c0.z), fmaf(1.5f, fabsf(c1.x), sd));
-                const float my = fmaf(3.5f, fabsf(c0.w), fmaf(1.5f, fabsf(c1.y), sd));
-                hit = hit && fabsf(qcx) <= fmaf(mx, 1.0001f, 1.0e-3f) && fabsf(qcy) <= fmaf(my, 1.0001f, 1.0e-3f);
+                // |q(p)| <= |q(pc)| + 1.5|a_x| + 1.5|a_y| over a half's pixel centres; alive needs |q| <= sd
+                const float tx = ddy * c1.x, ty = ddy * c1.y;
+                const float mx = fmaf(1.5f, fabsf(c0.z) + fabsf(c1.x), sd), my = fmaf(1.5f, fabsf(c0.w) + fabsf(c1.y), sd);
+                const float lx = fmaf(mx, 1.0001f, 1.0e-3f), ly = fmaf(my, 1.0001f, 1.0e-3f);
+                hit_l = hit_l && fabsf(fmaf(dl, c0.z, tx)) <= lx && fabsf(fmaf(dl, c0.w, ty)) <= ly;
+                hit_r = hit_r && fabsf(fmaf(dr, c0.z, tx)) <= lx && fabsf(fmaf(dr, c0.w, ty)) <= ly;
             }
         }
-        // bit hb = 31 - b <-> splat b of the round: FLO finds the next splat, no BREV per iteration
-        uint32_t todo = __brev(__ballot_sync(0xffffffffu, hit));
+        // Two independent splat streams per warp: lanes 0-15 (left half) walk the splats that touch the left 4x4 pixels,
+        // lanes 16-31 those of the right half; a splat of a few pixels usually touches only one of them, so the loop runs
+        // max(n_left, n_right) times instead of n_left-or-right.  Bit hb = 31 - b <-> splat b of the round.
+        const uint32_t ml = __ballot_sync(0xffffffffu, hit_l), mr = __ballot_sync(0xffffffffu, hit_r);
         // address of splat b = 31 - hb: rb + 64 b - 16 (b & 3) = last - 64 hb + 16 (hb & 3)   (PERM)
         //                                 rb + 48 b                = last - 48 hb               (else)
         const char* last = rb + (PERM ? 64u * 31u - 48u : 48u * 31u);
-        while (todo) {
-            uint32_t hb;  // FLO directly; `31 - __clz` is canonicalised back into a clz and costs five more integer ops
-            asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
-            todo ^= 1u << hb;
-            const char* rp = PERM ? last - 64u * hb + 16u * (hb & 3u) : last - 48u * hb;
-            const float4 q0 = *reinterpret_cast<const float4*>(rp);       // cx cy ax bx
-            const float2 q1 = *reinterpret_cast<const float2*>(rp + 16);  // ay by
-            // quad offset (render.wesl:125-128 inverted): q = (fma(dx,ax,dy*ay), fma(dx,bx,dy*by))
-            float dx, dy, qx, qy;
-            upk2(sub2(pxy, pk2(q0.x, q0.y)), dx, dy);
-            upk2(fma2(pk2(q0.z, q0.w), pk2(dx, dx), mul2(pk2(q1.x, q1.y), pk2(dy, dy))), qx, qy);
-            if constexpr (COUNT) st.n_eval += inside ? 1u : 0u;
-            float alpha;
-            bool alive;
-            const float4 q2 = *reinterpret_cast<const float4*>(rp + 32);  // r g b a
-            if constexpr (MODE == SB_MODE_POINT) {  // render.wesl:164-166
-                alive = fabsf(qx) <= 1.0f && fabsf(qy) <= 1.0f;
-                alpha = 1.0f;
-            } else {
-                const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
-                alive = r2 <= sd2;  // discard otherwise: render.wesl:145,155
-                if constexpr (MODE == SB_MODE_SPLAT) {
-                    const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
-                    alpha = __fmul_rn(q2.w, e);  // render.wesl:149
-                } else {
-                    const float ol = r2 > outline ? 1.0f : 0.0f;  // render.wesl:159-160
-                    alpha = __fadd_rn(q2.w, __fmul_rn(__fsub_rn(1.0f, q2.w), ol));
-                }
+        // Big splats touch both halves: then one warp-uniform walk over the union costs the same number of iterations
+        // and keeps the loop control on the uniform datapath.  Split only when it saves at least two iterations.
+        const uint32_t un = ml | mr;
+        if (__popc(un) >= max(__popc(ml), __popc(mr)) + 2) {
+            uint32_t todo = __brev(lane < 16 ? ml : mr);
+            while (todo) {
+                uint32_t hb;  // FLO directly; `31 - __clz` is canonicalised back into a clz and costs five more integer ops
+                asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
+                todo ^= 1u << hb;
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM>(last, hb, pxy, inside, sd2, outline, st);
             }
-            if constexpr (COUNT) {
-                st.n_alive += (inside && alive) ? 1u : 0u;
-                const bool any = __any_sync(__activemask(), alive);
-                st.n_warp_eval += 1u;
-                st.n_warp_alive += any ? 1u : 0u;
-            }
-            // A discarded fragment blends with alpha = 0, which is the identity EXACTLY (d*1 + c*0 = d, and d is
-            // already an integer on unorm8 targets): the loop body stays branch-free.
-            alpha = alive ? alpha : 0.0f;
-            const float om = __fsub_rn(1.0f, alpha);
-            const f32x2 om2 = pk2(om, om), al2 = pk2(alpha, alpha);
-            if constexpr (FMT == FMT_UNORM8) {
-                // d <- rint(fma(d, 1-alpha, c255*alpha)); the source colour is clamped to 255 per splat (K1) and
-                // alpha <= 1, so the blend cannot exceed 255 + rounding and the post-blend clamp never binds
-                const f32x2 m = pk2(kRintMagic, kRintMagic), nm = pk2(-kRintMagic, -kRintMagic);
-                st.d01 = add2(add2(fma2(st.d01, om2, mul2(pk2(q2.x, q2.y), al2)), m), nm);
-                float d2, d3;
-                upk2(st.d23, d2, d3);
-                d2 = rint_small(__fmaf_rn(d2, om, __fmul_rn(q2.z, alpha)));
-                st.d23 = pk2(d2, d3);
-            } else {
-                // (b*alpha, 1*alpha): 1*alpha is exact, so d3 = fma(d3, 1-alpha, alpha) as in the oracle
-                st.d01 = fma2(st.d01, om2, mul2(pk2(q2.x, q2.y), al2));
-                st.d23 = fma2(st.d23, om2, mul2(pk2(q2.z, 1.0f), al2));
-                if constexpr (FMT == FMT_F16) {
-                    float d0, d1, d2, d3;
-                    upk2(st.d01, d0, d1);
-                    upk2(st.d23, d2, d3);
-                    st.d01 = pk2(__half2float(__float2half_rn(d0)), __half2float(__float2half_rn(d1)));
-                    st.d23 = pk2(__half2float(__float2half_rn(d2)), __half2float(__float2half_rn(d3)));
-                }
+        } else {
+            uint32_t todo = __brev(un);
+            while (todo) {
+                uint32_t hb;
+                asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
+                todo ^= 1u << hb;
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM>(last, hb, pxy, inside, sd2, outline, st);
             }
         }
     }
@@ -444,12 +481,13 @@ __global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelPara
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
     const uint32_t tile = tile_y * p.tiles_x + tile_x;
-    // each warp owns an 8x4 pixel patch (pixel centres: half extents 3.5 x 1.5 around pcx, pcy)
-    const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane & 7u);
-    const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    // each warp owns an 8x4 pixel patch: lanes 0-15 its left 4x4 half, lanes 16-31 the right one (pixel centres:
+    // half extents 1.5 x 1.5 around the half's centre; pcx = centre of the LEFT half)
+    const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane >> 4) * 4 + (lane & 3u);
+    const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + ((lane >> 2) & 3u);
     const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-    const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 4.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
+    const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 2.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
 
     const uint32_t begin = p.tile_ranges[2 * tile], end = p.tile_ranges[2 * tile + 1];
     const uint32_t total = end - begin;
@@ -514,39 +552,48 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelP
     __syncthreads();
 
     if (warp == 8) {
-        // ---------------- producer warp: lane t issues gather4 #t (records 4t..4t+3) and #t+32
-        for (uint32_t k = 0; k < batches; k++) {
-            const uint32_t s = k % kG4Stages;
-            mbar_wait(&empty_bar[s], ((k / kG4Stages) & 1u) ^ 1u);
+        // ---------------- producer warp: lane t issues gather4 #t (records 4t..4t+3) and #t+32.  The Gaussian
+        // indices of batch k+1 are fetched right after the gathers of batch k were issued, so a refill costs one
+        // gather round trip, not an index load followed by one.
+        uint32_t g[4 * kG4PerLane];
+        auto load_indices = [&](uint32_t k) {
             const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
             const uint32_t* idx = p.dup_vals + begin + (size_t)k * kBatchG4;
             const uint32_t g_first = __ldg(idx);  // padding index for rows past the end of the list
-            uint32_t g[8];
 #pragma unroll
-            for (int h = 0; h < 2; h++)
+            for (int h = 0; h < kG4PerLane; h++)
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const uint32_t j = 4u * (lane + 32u * h) + i;
                     g[h * 4 + i] = j < cnt ? __ldg(idx + j) : g_first;
                 }
+        };
+        if (batches > 0) load_indices(0);
+        for (uint32_t k = 0; k < batches; k++) {
+            const uint32_t s = k % kG4Stages;
+            mbar_wait(&empty_bar[s], ((k / kG4Stages) & 1u) ^ 1u);
+            const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
             // only gathers whose first record exists are issued; the barrier is armed with exactly the
             // bytes that will land
             const uint32_t gathers = (cnt + 3u) / 4u;
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], gathers * 4u * (uint32_t)sizeof(SplatRec));
             __syncwarp();
             const uint32_t dst0 = smem_u32(&stage[s][lane * 16]);
-            if (lane < gathers) tma_gather4(dst0, &recs_map, &full_bar[s], g[0], g[1], g[2], g[3]);
-            if (lane + 32u < gathers) tma_gather4(dst0 + 32u * 256u, &recs_map, &full_bar[s], g[4], g[5], g[6], g[7]);
+#pragma unroll
+            for (int h = 0; h < kG4PerLane; h++)
+                if (lane + 32u * h < gathers)
+                    tma_gather4(dst0 + 32u * 256u * h, &recs_map, &full_bar[s], g[4 * h], g[4 * h + 1], g[4 * h + 2], g[4 * h + 3]);
+            if (k + 1 < batches) load_indices(k + 1);
         }
         return;
     }
 
-    // ---------------- consumers: each warp owns an 8x4 pixel patch
-    const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane & 7u);
-    const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    // ---------------- consumers: each warp owns an 8x4 pixel patch, lanes 0-15 its left 4x4 half, lanes 16-31 the right one
+    const uint32_t x = tile_x * kTile + (warp & 1u) * 8 + (lane >> 4) * 4 + (lane & 3u);
+    const uint32_t y = tile_y * kTile + (warp >> 1) * 4 + ((lane >> 2) & 3u);
     const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-    const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 4.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
+    const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 2.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
     PixelState st;
     uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
     if (!p.clear && inside) load_dst<FMT>(st, dst, x, p.bgra);

@@ -8,7 +8,8 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_LIB = os.path.join(_PKG, "lib", "libsplat_b200.so")
+# SB_LIB: load a tuning variant built next to the default library (Makefile EXTRA/BUILD/LIB); never a fallback
+_LIB = os.environ.get("SB_LIB") or os.path.join(_PKG, "lib", "libsplat_b200.so")
 
 SH_SINGLE, SH_HALF, SH_NORM8, SH_NONE = 0, 1, 2, 3
 COV_SINGLE, COV_HALF, COV_ROT_SCALE = 0, 1, 2
