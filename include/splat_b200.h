@@ -99,6 +99,19 @@ typedef struct {
                                d_pixels + 0); rows == 0 means the full frame */
 } SbTarget;
 
+/* wgpu::CompareFunction of a DepthStencilState (ViewerCreateOptions.depth_stencil, src/lib.rs:279-284) */
+enum {
+    SB_COMPARE_NEVER = 1, SB_COMPARE_LESS = 2, SB_COMPARE_EQUAL = 3, SB_COMPARE_LESS_EQUAL = 4,
+    SB_COMPARE_GREATER = 5, SB_COMPARE_NOT_EQUAL = 6, SB_COMPARE_GREATER_EQUAL = 7, SB_COMPARE_ALWAYS = 8
+};
+/* Depth attachment of a caller's render pass: Depth32Float, same width/height/strip as the colour target. */
+typedef struct SbDepthAttachment {
+    void* d_depth;            /* device pointer, f32 per pixel */
+    uint32_t pitch_bytes;
+    int32_t compare;          /* SB_COMPARE_* (depth_compare) */
+    int32_t write_enabled;    /* depth_write_enabled */
+} SbDepthAttachment;
+
 typedef struct SbContext SbContext;
 typedef struct SbViewer SbViewer;
 typedef struct SbMultiModelViewer SbMultiModelViewer;
@@ -185,6 +198,14 @@ SB_API SbStatus sb_viewer_set_invert_selection(SbViewer* v, int32_t invert);
 /* selection::viewport evaluation with an analytic rectangle mask:
  * src/shader/selection/viewport.wesl:37-69 + viewport_texture_rectangle.wesl; pixels [x0,x1)x[y0,y1) */
 SB_API SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float y0, float x1, float y1);
+/* selection::viewport evaluation with an analytic brush mask: src/shader/selection/viewport_texture_brush.wesl draws,
+ * per stroke segment, a disc of `radius` at both ends and a quad between them into the mask texture — a capsule.  Texel
+ * (ix,iy) is set iff its centre lies within `radius` of a segment of the polyline points_xy[0..n_points) (host floats
+ * x0,y0,x1,y1,..; pixels; 1 <= n_points <= SB_BRUSH_MAX_POINTS, one point = a dab).  accumulate != 0 ORs the result into
+ * the selection words, the way successive strokes accumulate in the reference's texture; 0 replaces them. */
+#define SB_BRUSH_MAX_POINTS 64
+SB_API SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* points_xy, uint32_t n_points, float radius,
+                                       int32_t accumulate);
 
 /* Viewer::render(encoder, texture_view): src/lib.rs:266-275 — enqueue the whole frame */
 SB_API SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target);
@@ -195,6 +216,13 @@ SB_API SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* targ
 SB_API SbStatus sb_viewer_preprocess(SbViewer* v, void* stream);
 SB_API SbStatus sb_viewer_sort(SbViewer* v, void* stream);
 SB_API SbStatus sb_viewer_draw(SbViewer* v, void* stream, const SbTarget* target);
+/* Renderer::render_with_pass (src/renderer.rs:187-195) inside a caller's render pass, with the pipeline's optional
+ * depth_stencil state (src/renderer.rs:123, 304): the splats composite over what the target already holds when
+ * load != 0 (LoadOp::Load; 0 = clear to BLACK first), and every fragment that survives the shader's discard is depth
+ * tested against `depth` (nullable) with its splat's depth = the centre's ndc z (render.wesl:123), writing it back when
+ * write_enabled.  Runs the preprocess and sort stages too when run_stages != 0 (Viewer::render), else only the draw. */
+SB_API SbStatus sb_viewer_render_with_pass(SbViewer* v, void* stream, const SbTarget* target, const SbDepthAttachment* depth,
+                                           int32_t load, int32_t run_stages);
 
 /* Convenience for host-resident callers: update camera, render into an internal device
  * target, copy the frame to host_pixels (pinned recommended) — all enqueued on `stream`. */

@@ -94,6 +94,9 @@ def lib() -> C.CDLL:
         l.so_exp_neg_poly.restype = C.c_float
         l.so_exp_neg_poly.argtypes = [C.c_float]
         l.so_select_rect.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        l.so_render_pass.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.POINTER(GaussianTransformPod), C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        l.so_select_brush.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_void_p]
         l.so_max_threads.restype = C.c_int
         l.so_set_threads.argtypes = [C.c_int]
         _lib = l
@@ -209,10 +212,31 @@ def render(models, cam: CameraPod, gt: GaussianTransformPod, target_format=TARGE
     return out, dict(visible=st.visible, bbox_pixels=st.bbox_pixels, alive_pixels=st.alive_pixels)
 
 
+def render_pass(model: OracleModel, cam: CameraPod, gt: GaussianTransformPod, target: np.ndarray, load: bool, depth: np.ndarray | None = None,
+                compare: int = 8, depth_write: bool = False, target_format=TARGET_RGBA8, strict_exp=False, n_threads=0):
+    """Renderer::render_with_pass: composites `model` into `target` (in place; loaded or cleared) against the optional
+    f32 depth attachment `depth` (updated in place when depth_write)."""
+    assert target.flags["C_CONTIGUOUS"] and (depth is None or (depth.dtype == np.float32 and depth.flags["C_CONTIGUOUS"]))
+    buf = target.view(np.uint16) if target.dtype == np.float16 else target
+    lib().so_render_pass(C.byref(model.c), C.byref(cam), C.byref(gt), target_format, int(strict_exp), int(load), buf.ctypes.data,
+                         None if depth is None else depth.ctypes.data, compare, int(depth_write), n_threads)
+    return target
+
+
 def select_rect(model: OracleModel, cam: CameraPod, x0, y0, x1, y1) -> np.ndarray:
     out = np.zeros(max((model.n + 31) // 32, 1), dtype=np.uint32)
     lib().so_select_rect(C.byref(model.c), C.byref(cam), x0, y0, x1, y1, out.ctypes.data)
     return out[: (model.n + 31) // 32]
+
+
+def select_brush(model: OracleModel, cam: CameraPod, points, radius, accumulate=False, dest: np.ndarray | None = None) -> np.ndarray:
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+    words = (model.n + 31) // 32
+    out = np.zeros(max(words, 1), dtype=np.uint32)
+    if dest is not None:
+        out[:words] = dest[:words]
+    lib().so_select_brush(C.byref(model.c), C.byref(cam), pts.ctypes.data, len(pts), radius, int(accumulate), out.ctypes.data)
+    return out[:words]
 
 
 def exp_neg_poly(x: float) -> float:

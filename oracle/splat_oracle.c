@@ -548,6 +548,7 @@ static void project_one(const Uniforms* u, const SoModel* model, uint32_t index,
     project_centre(u, pos, world, clip);
     float nx = clip[0] / clip[3], ny = clip[1] / clip[3];
     memset(s, 0, sizeof *s);
+    s->z = clip[2] / clip[3];
     s->cx = (nx + 1.0f) * 0.5f * u->size[0];
     s->cy = (1.0f - ny) * 0.5f * u->size[1];
     /* color(): render.wesl:58-73 */
@@ -618,9 +619,23 @@ float so_exp_neg_poly(float x) {
     return p;
 }
 
+static int depth_passes(int compare, float z, float d) {
+    switch (compare) {
+        case 1: return 0;
+        case 2: return z < d;
+        case 3: return z == d;
+        case 4: return z <= d;
+        case 5: return z > d;
+        case 6: return z != d;
+        case 7: return z >= d;
+        default: return 1;
+    }
+}
+
 static void raster_band(const SoSplat* sp, uint32_t count, const Uniforms* u, int strict_exp,
                         int is_unorm, int is_f16, uint32_t width, uint32_t y_lo, uint32_t y_hi,
-                        uint32_t row0, float* acc, uint64_t* bbox_px, uint64_t* alive_px) {
+                        uint32_t row0, float* acc, uint64_t* bbox_px, uint64_t* alive_px,
+                        float* depth, int depth_compare, int depth_write) {
     const float sd = u->std_dev;
     const float sd2 = sd * sd;
     const float ol = (sd - 0.1f) * (sd - 0.1f);
@@ -666,6 +681,11 @@ static void raster_band(const SoSplat* sp, uint32_t count, const Uniforms* u, in
                     }
                 }
                 na++;
+                if (depth) { /* depth test after the shader's discard: src/renderer.rs:304 */
+                    float* dz = depth + (size_t)(py - row0) * width + px;
+                    if (!depth_passes(depth_compare, s->z, *dz)) continue;
+                    if (depth_write) *dz = s->z;
+                }
                 float om = 1.0f - alpha;
                 float* d = row + (size_t)px * 4;
                 if (is_unorm) {
@@ -733,7 +753,7 @@ void so_render(const SoModel* models, uint32_t n_models, const SoCameraPod* cam,
             uint32_t y_lo = row0 + (uint32_t)((uint64_t)rows * (uint32_t)t / (uint32_t)n_threads);
             uint32_t y_hi = row0 + (uint32_t)((uint64_t)rows * ((uint32_t)t + 1) / (uint32_t)n_threads);
             if (y_hi > y_lo)
-                raster_band(sp, v, &u, strict_exp, is_unorm, is_f16, width, y_lo, y_hi, row0, acc, &nb, &na);
+                raster_band(sp, v, &u, strict_exp, is_unorm, is_f16, width, y_lo, y_hi, row0, acc, &nb, &na, NULL, 0, 0);
         }
         st.bbox_pixels += nb; st.alive_pixels += na;
         free(sp); free(keys); free(idx);
@@ -755,6 +775,109 @@ void so_render(const SoModel* models, uint32_t n_models, const SoCameraPod* cam,
         memcpy(target, acc, npx * 4 * sizeof(float));
     }
     if (stats) *stats = st;
+    free(acc);
+}
+
+/* squared distance from p to the segment a-b; every step one IEEE op in this order */
+static float so_seg_dist2(float px, float py, float ax, float ay, float bx, float by) {
+    float ex = bx - ax, ey = by - ay, wx = px - ax, wy = py - ay;
+    float len2 = ex * ex + ey * ey;
+    float t = 0.0f;
+    if (len2 > 0.0f) t = fminf(fmaxf((wx * ex + wy * ey) / len2, 0.0f), 1.0f);
+    float dx = wx - t * ex, dy = wy - t * ey;
+    return dx * dx + dy * dy;
+}
+
+/* viewport selection with the brush mask: viewport.wesl:37-69 fed by viewport_texture_brush.wesl, which draws a disc of
+ * `radius` at both ends of a stroke segment (frag_main discards dot(uv,uv) > 1) and a quad of half-width `radius`
+ * between them: a capsule.  Texel (ix,iy) is taken as set iff its centre is within `radius` of a segment of the
+ * polyline; successive strokes accumulate in the texture (accumulate != 0: OR into dest). */
+void so_select_brush(const SoModel* model, const SoCameraPod* cam, const float* points_xy, uint32_t n_points,
+                     float radius, int accumulate, uint32_t* dest) {
+    SoGaussianTransformPod gt = { 1.0f, 0, 0, 0, 255 };
+    Uniforms u = make_uniforms(cam, &model->model_transform, &gt);
+    uint32_t n = model->n, words = (n + 31u) / 32u;
+    uint32_t stride = so_pod_stride(model->sh_fmt, model->cov_fmt);
+    float r2 = radius * radius;
+    for (uint32_t w = 0; w < words; w++) {
+        uint32_t bits = 0;
+        for (uint32_t b = 0; b < 32 && w * 32u + b < n; b++) {
+            const uint8_t* pod = (const uint8_t*)model->pods + (size_t)stride * (w * 32u + b);
+            float pos[3]; memcpy(pos, pod, 12);
+            float world[3], clip[4];
+            project_centre(&u, pos, world, clip);
+            float nx = clip[0] / clip[3], ny = clip[1] / clip[3], nz = clip[2] / clip[3];
+            if (cull(nx, ny, nz)) continue;
+            float tx = (nx * 1.0f + 1.0f) * u.size[0] * 0.5f;
+            float ty = (ny * -1.0f + 1.0f) * u.size[1] * 0.5f;
+            int32_t ix = (int32_t)tx, iy = (int32_t)ty;
+            if (ix < 0 || iy < 0 || ix >= (int32_t)u.size[0] || iy >= (int32_t)u.size[1]) continue;
+            float px = (float)ix + 0.5f, py = (float)iy + 0.5f;
+            int sel = 0;
+            if (n_points == 1) sel = so_seg_dist2(px, py, points_xy[0], points_xy[1], points_xy[0], points_xy[1]) <= r2;
+            for (uint32_t i = 0; i + 1 < n_points && !sel; i++)
+                sel = so_seg_dist2(px, py, points_xy[2 * i], points_xy[2 * i + 1], points_xy[2 * i + 2], points_xy[2 * i + 3]) <= r2;
+            if (sel) bits |= 1u << b;
+        }
+        dest[w] = accumulate ? (dest[w] | bits) : bits;
+    }
+}
+
+void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
+                    int target_format, int strict_exp, int load, void* target, float* depth, int depth_compare,
+                    int depth_write, int n_threads) {
+    uint32_t width = (uint32_t)cam->size[0], height = (uint32_t)cam->size[1];
+    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_f16 = target_format == SO_TARGET_RGBA16F;
+    int ri = target_format == SO_TARGET_BGRA8 ? 2 : 0, bi = 2 - ri;
+    if (n_threads <= 0) n_threads = so_max_threads();
+    size_t npx = (size_t)height * width;
+    float* acc = (float*)malloc((npx ? npx : 1) * 4 * sizeof(float));
+    for (size_t i = 0; i < npx; i++) {
+        if (!load) {
+            acc[i * 4 + 0] = acc[i * 4 + 1] = acc[i * 4 + 2] = 0.0f; acc[i * 4 + 3] = 1.0f;
+        } else if (is_unorm) { /* 0..255 units, as the blend keeps them */
+            const uint8_t* t = (const uint8_t*)target + i * 4;
+            acc[i * 4 + 0] = t[ri]; acc[i * 4 + 1] = t[1]; acc[i * 4 + 2] = t[bi]; acc[i * 4 + 3] = 1.0f;
+        } else if (is_f16) {
+            const uint16_t* t = (const uint16_t*)target + i * 4;
+            for (int c = 0; c < 4; c++) acc[i * 4 + c] = f16_to_f32(t[c]);
+        } else {
+            memcpy(acc + i * 4, (const float*)target + i * 4, 16);
+        }
+    }
+    uint32_t n = model->n;
+    uint32_t cap = ((n + 3839u) / 3840u) * 3840u;
+    uint32_t* idx = (uint32_t*)malloc((size_t)(cap ? cap : 1) * 4);
+    float* keys = (float*)malloc((size_t)(cap ? cap : 1) * 4);
+    uint32_t v = so_preprocess(model, cam, gt, idx, keys, NULL, NULL, NULL);
+    so_radix_sort((uint32_t*)keys, idx, v);
+    SoSplat* sp = (SoSplat*)malloc((size_t)(v ? v : 1) * sizeof(SoSplat));
+    so_project(model, cam, gt, idx, v, sp);
+    Uniforms u = make_uniforms(cam, &model->model_transform, gt);
+    uint64_t nb = 0, na = 0;
+    #pragma omp parallel for schedule(static) num_threads(n_threads) reduction(+ : nb, na)
+    for (int t = 0; t < n_threads; t++) {
+        uint32_t y_lo = (uint32_t)((uint64_t)height * (uint32_t)t / (uint32_t)n_threads);
+        uint32_t y_hi = (uint32_t)((uint64_t)height * ((uint32_t)t + 1) / (uint32_t)n_threads);
+        if (y_hi > y_lo)
+            raster_band(sp, v, &u, strict_exp, is_unorm, is_f16, width, y_lo, y_hi, 0, acc, &nb, &na, depth, depth_compare, depth_write);
+    }
+    free(sp); free(keys); free(idx);
+    if (is_unorm) {
+        uint8_t* out = (uint8_t*)target;
+        for (size_t i = 0; i < npx; i++) {
+            out[i * 4 + ri] = (uint8_t)acc[i * 4 + 0];
+            out[i * 4 + 1] = (uint8_t)acc[i * 4 + 1];
+            out[i * 4 + bi] = (uint8_t)acc[i * 4 + 2];
+            out[i * 4 + 3] = 255;
+        }
+    } else if (is_f16) {
+        uint16_t* out = (uint16_t*)target;
+        for (size_t i = 0; i < npx * 4; i++) out[i] = f32_to_f16(acc[i]);
+    } else {
+        memcpy(target, acc, npx * 4 * sizeof(float));
+    }
     free(acc);
 }
 

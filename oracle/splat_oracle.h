@@ -125,6 +125,7 @@ typedef struct {
     float r, g, b, a;       /* colour (rgb >= 0, un-clamped above) and opacity */
     float ext_x, ext_y;     /* half extent of the quad's alive region in pixels */
     int32_t valid;          /* 0 = degenerate (axes == 0 or NaN): nothing drawn */
+    float z;                /* ndc z of the centre = the depth of every fragment of the quad (render.wesl:123) */
 } SoSplat;
 
 void so_project(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
@@ -138,6 +139,15 @@ void so_render(const SoModel* models, uint32_t n_models, const SoCameraPod* cam,
                const SoGaussianTransformPod* gt, int target_format, int strict_exp,
                uint32_t row0, uint32_t rows, void* target, SoStats* stats, int n_threads);
 
+/* Renderer::render_with_pass with an optional depth_stencil state (src/renderer.rs:123, 187-195, 304): one model drawn
+ * inside a caller's pass.  load != 0: `target` already holds the pass's colour (LoadOp::Load), else it is cleared to
+ * BLACK.  depth (nullable): f32[h*w] attachment; a fragment that survives the shader's discard passes when
+ * compare(splat z, depth) holds (1 never, 2 less, 3 equal, 4 less-equal, 5 greater, 6 not-equal, 7 greater-equal,
+ * 8 always) and writes its z back when depth_write != 0.  Full frames only. */
+void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
+                    int target_format, int strict_exp, int load, void* target, float* depth, int depth_compare,
+                    int depth_write, int n_threads);
+
 /* exp(-x) for x in [0, ~88] from exactly-rounded fma steps (bit-reproducible on GPU). */
 float so_exp_neg_poly(float x);
 
@@ -145,6 +155,9 @@ float so_exp_neg_poly(float x);
  * with an analytic rectangle mask [x0,x1) x [y0,y1) in pixels.  Writes ceil(n/32) words. */
 void so_select_rect(const SoModel* model, const SoCameraPod* cam,
                     float x0, float y0, float x1, float y1, uint32_t* dest);
+/* same with the brush mask (viewport_texture_brush.wesl): texel centres within `radius` of the stroke polyline */
+void so_select_brush(const SoModel* model, const SoCameraPod* cam, const float* points_xy, uint32_t n_points,
+                     float radius, int accumulate, uint32_t* dest);
 
 int so_max_threads(void);
 void so_set_threads(int n);   /* override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */

@@ -330,6 +330,89 @@ def test_viewport_rect_selection(sb, ob, ctx):
     v.close()
 
 
+def test_viewport_brush_selection(sb, ob, ctx):
+    """selection::viewport with the brush mask (viewport_texture_brush.wesl: capsules along the stroke), strokes
+    accumulating like in the reference's mask texture; the mask then drives the preprocess cull."""
+    n, w, h = 30000, 800, 450
+    g, pods = make_scene(sb, ob, n, 58)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.enable_selection(True)
+    om = ob.OracleModel(pods, n)
+    ocam = ob.camera_pod(pos, yaw, pitch, w, h)
+    stroke1 = [(100.0, 80.0), (380.5, 200.25), (420.0, 400.0)]
+    stroke2 = [(600.0, 120.0)]  # a dab
+    v.select_brush(stroke1, 37.5)
+    m1 = v.read_selection()
+    o1 = ob.select_brush(om, ocam, stroke1, 37.5)
+    assert np.array_equal(m1, o1) and m1.any()
+    v.select_brush(stroke2, 60.0, accumulate=True)
+    m2 = v.read_selection()
+    o2 = ob.select_brush(om, ocam, stroke2, 60.0, accumulate=True, dest=o1)
+    assert np.array_equal(m2, o2) and (m2 & ~m1).any()
+    # zero radius: only texel centres exactly on the stroke; degenerate segment
+    v.select_brush([(10.5, 10.5), (10.5, 10.5)], 0.0)
+    assert np.array_equal(v.read_selection(), ob.select_brush(om, ocam, [(10.5, 10.5), (10.5, 10.5)], 0.0))
+    with pytest.raises(sb.SplatError):
+        v.select_brush(np.zeros((65, 2)), 1.0)
+    v.close()
+
+
+@pytest.mark.parametrize("compare,write", [(2, True), (4, False), (5, True), (8, False), (1, True)])
+@pytest.mark.parametrize("target_format", [0, 3])
+def test_render_with_pass_depth_stencil(sb, ob, ctx, compare, write, target_format):
+    """Renderer::render_with_pass inside a caller's pass (src/renderer.rs:187-195) with the pipeline's depth_stencil state
+    (:123, :304): LoadOp::Load of an existing colour target, fragments depth-tested with the splat's centre z against a
+    Depth32Float attachment the caller filled, depth written back when depth_write_enabled."""
+    torch = _torch()
+    n, w, h = 12000, 512, 288
+    g, pods = make_scene(sb, ob, n, 140 + compare)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    rng = np.random.default_rng(5)
+    # caller's pass so far: a colour gradient and a depth "wall" cutting through the cloud (ndc z of the cloud ~ 0.9966..0.9975)
+    if target_format == 0:
+        colour = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        colour[..., 3] = 255
+    else:
+        colour = rng.random(size=(h, w, 4), dtype=np.float32)
+        colour[..., 3] = 1.0
+    zz = np.linspace(0.9962, 0.9978, w, dtype=np.float32)[None, :].repeat(h, 0).copy()
+    zz[::7] = 1.0  # some rows wide open
+    v = sb.Viewer(ctx, pods, n, target_format=target_format)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.set_strict_exp(True)
+    t = torch.from_numpy(colour.copy()).cuda()
+    d = torch.from_numpy(zz.copy()).cuda()
+    v.render_with_pass(t, w, h, depth=d, compare=compare, depth_write=write, load_target=True)
+    torch.cuda.synchronize()
+    om = ob.OracleModel(pods, n)
+    ocol, oz = colour.copy(), zz.copy()
+    ob.render_pass(om, ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(), ocol, True, depth=oz, compare=compare,
+                   depth_write=write, target_format=target_format, strict_exp=True)
+    got, gz = t.cpu().numpy(), d.cpu().numpy()
+    if target_format == 0:
+        assert np.array_equal(got, ocol)
+    else:
+        assert np.abs(got - ocol).max() <= 1e-3
+    assert np.array_equal(gz, oz), "depth attachment differs"
+    if compare == 1:
+        assert np.array_equal(got, colour) and np.array_equal(gz, zz)  # Never: nothing drawn
+    elif write:
+        assert (gz != zz).any()
+    else:
+        assert np.array_equal(gz, zz)
+    if compare in (2, 5):
+        assert (got != colour).any()
+    # without a depth attachment and with LoadOp::Clear the pass equals Viewer::render
+    t2, t3 = torch.zeros_like(t), torch.zeros_like(t)
+    v.render_with_pass(t2, w, h, load_target=False)
+    v.render(t3, w, h)
+    torch.cuda.synchronize()
+    assert torch.equal(t2, t3)
+    v.close()
+
+
 def test_standalone_radix_sorter(sb, ctx):
     """RadixSorter<()>: stable ascending (key, payload) sort with a device-side count."""
     torch = _torch()

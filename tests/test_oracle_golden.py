@@ -195,3 +195,24 @@ def test_multi_model_order_matters(ob, sb):
 def test_unorm8_newton_identity(ob):
     """The kernel's division-free u8/255 is exact for every byte (see sb_preprocess.cu: unorm8)."""
     assert ob.lib().so_unorm8_newton_mismatches() == 0
+
+
+def test_oracle_brush_mask_is_a_capsule():
+    """so_select_brush: a Gaussian is selected iff the texel under its centre lies within `radius` of the stroke."""
+    from oracle import binding as ob
+    import numpy as np
+    g = np.zeros(4, dtype=ob.GAUSSIAN_DTYPE)
+    g["rot"][:, 3] = 1
+    g["scale"][:] = 0.01
+    g["color"][:] = 255
+    # camera at the origin looking down +z (yaw = pitch = 0): x right, y up; 200x100 target
+    g["pos"] = [(0, 0, 5), (0.5, 0, 5), (0, 0.5, 5), (0, 0, -5)]
+    pods = ob.pack_gaussians(g, 0, 0)
+    m = ob.OracleModel(pods, 4)
+    cam = ob.camera_pod((0.0, 0.0, 0.0), 0.0, 0.0, 200, 100)
+    centre = ob.select_brush(m, cam, [(100.0, 50.0)], 3.0)
+    assert centre[0] == 0b0001  # only the Gaussian under the dab; the one behind the camera is culled
+    stroke = ob.select_brush(m, cam, [(90.0, 50.0), (140.0, 50.0)], 1.0)
+    assert stroke[0] & 0b0001 and not stroke[0] & 0b0100 and not stroke[0] & 0b1000
+    both = ob.select_brush(m, cam, [(100.0, 0.0), (100.0, 99.0)], 1.0, accumulate=True, dest=stroke)
+    assert both[0] & 0b0100 and both[0] & stroke[0] == stroke[0]

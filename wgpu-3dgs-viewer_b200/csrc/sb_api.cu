@@ -329,7 +329,7 @@ SbStatus do_sort(SbViewer* v, cudaStream_t stream) {
 }
 
 SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, const SbTarget* target, int clear,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const SbDepthAttachment* depth = nullptr) {
     sb::RasterParams p;
     std::memset(&p, 0, sizeof p);
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
@@ -380,6 +380,17 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     }
     p.events = v->timing ? &v->ev[3] : nullptr;
     p.recs_map = v->use_gather4 ? &v->recs_map : nullptr;
+    if (depth && depth->d_depth) {
+        if (!v->use_gather4) return fail(v->ctx, SB_ERR_INVALID_ARG, "a depth attachment needs the default (TMA gather4) raster path");
+        if (depth->compare < SB_COMPARE_NEVER || depth->compare > SB_COMPARE_ALWAYS) return fail(v->ctx, SB_ERR_INVALID_ARG, "bad compare function");
+        if (depth->pitch_bytes < target->width * 4u) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "depth pitch too small");
+        p.depth = static_cast<float*>(depth->d_depth);
+        p.depth_pitch = depth->pitch_bytes;
+        p.depth_compare = depth->compare;
+        p.depth_write = depth->write_enabled != 0;
+        p.pods = static_cast<const uint8_t*>(v->d_gaussians);
+        p.pod_stride = v->stride;
+    }
     p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
     if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 32, stream));
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
@@ -558,6 +569,28 @@ SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float y0, fl
     SB_CUDA(v->ctx, sb::launch_select_rect(static_cast<const uint8_t*>(v->d_gaussians), v->n, v->stride, u, x0, y0, x1, y1,
                                            v->selection.as<uint32_t>(), static_cast<cudaStream_t>(stream)));
     return SB_OK;
+}
+
+SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* points_xy, uint32_t n_points, float radius, int32_t accumulate) {
+    if (!v || !points_xy) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (n_points == 0 || n_points > SB_BRUSH_MAX_POINTS || !(radius >= 0.0f))
+        return fail(v->ctx, SB_ERR_INVALID_ARG, "brush stroke needs 1..SB_BRUSH_MAX_POINTS points and a non-negative radius");
+    const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    SB_CUDA(v->ctx, sb::launch_select_brush(static_cast<const uint8_t*>(v->d_gaussians), v->n, v->stride, u, points_xy, n_points, radius,
+                                            accumulate, v->selection.as<uint32_t>(), static_cast<cudaStream_t>(stream)));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_render_with_pass(SbViewer* v, void* stream, const SbTarget* target, const SbDepthAttachment* depth, int32_t load,
+                                    int32_t run_stages) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (run_stages) {
+        SbStatus s = do_preprocess(v, v->camera, v->gaussian_transform, st);
+        if (s == SB_OK) s = do_sort(v, st);
+        if (s != SB_OK) return s;
+    }
+    return do_draw(v, v->camera, v->gaussian_transform, target, load ? 0 : 1, st, depth);
 }
 
 SbStatus sb_viewer_preprocess(SbViewer* v, void* stream) {

@@ -75,6 +75,11 @@ struct RasterParams {
     int strict_exp;
     int clear;                       // 1: clear to BLACK first (first model of a frame)
     int obb_cull;                    // 1: warp-level cull also tests the ellipse axes (SAT), 0: bbox only
+    float* depth;                    // optional f32 depth attachment (strip geometry of the target); needs recs_map
+    uint32_t depth_pitch;
+    int depth_compare, depth_write;
+    const uint8_t* pods;             // pod array + stride: the depth-tested pass recomputes each splat's ndc z
+    uint32_t pod_stride;
     const CUtensorMap* recs_map;     // non-null: fetch records with TMA gather4 (no gathered copy); host pointer, passed by value
     unsigned long long* counters;    // optional instrumentation: [0] alive fragments, [1] evaluated lane pairs
     cudaEvent_t* events;             // optional: [0]=after scan+emit, [1]=after tile sort, [2]=after gather, [3]=after raster
@@ -86,5 +91,10 @@ cudaError_t launch_clear(const SbTarget& target, cudaStream_t stream);
 // selection::viewport::main with an analytic rectangle mask; writes ceil(n/32) words.
 cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, float x0, float y0, float x1,
                                float y1, uint32_t* words, cudaStream_t stream);
+
+// selection::viewport::main with an analytic brush mask: texels within `radius` of the stroke polyline
+// (n_points <= SB_BRUSH_MAX_POINTS host floats x,y); accumulate != 0 ORs into the existing words.
+cudaError_t launch_select_brush(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, const float* points_xy,
+                                uint32_t n_points, float radius, int accumulate, uint32_t* words, cudaStream_t stream);
 
 }  // namespace sb

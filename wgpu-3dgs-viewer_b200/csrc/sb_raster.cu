@@ -277,6 +277,14 @@ struct RasterKernelParams {
     int bgra;
     int clear;
     int obb_cull;   // 1: cull a splat against the warp's patch along the ellipse axes too
+    // depth attachment of a caller's render pass (Renderer::render_with_pass + depth_stencil: src/renderer.rs:123,187-195,304)
+    float* depth;              // f32 depth, same strip geometry as pixels; nullptr = no depth test
+    uint32_t depth_pitch;      // bytes
+    int depth_compare;         // SB_COMPARE_*
+    int depth_write;
+    const uint8_t* pods;       // the fragment depth of a splat is its centre's ndc z (render.wesl:123: clip_pos.zw = proj_pos.zw),
+    uint32_t pod_stride;       //   recomputed from the pod position by the producer warp, exactly as K1 computes it
+    float pv[16], model[16];
     unsigned long long* counters;  // COUNT builds: [0] alive fragments, [1] evaluated (pixel,splat) lane pairs,
                                    // [2] (warp,splat) evaluations, [3] of those with at least one alive lane
 };
@@ -284,6 +292,7 @@ struct RasterKernelParams {
 // Destination pixel, kept as two packed pairs: (d0, d1) and (d2, d3); 0..255 units on unorm8 targets.
 struct PixelState {
     f32x2 d01, d23;
+    float depth = 1.0f;  // depth attachment value under this pixel (DEPTH builds)
     uint32_t n_alive = 0, n_eval = 0, n_warp_eval = 0, n_warp_alive = 0;
     __device__ __forceinline__ PixelState() { d01 = pk2(0.0f, 0.0f); d23 = pk2(0.0f, 1.0f); }
 };
@@ -329,8 +338,27 @@ __device__ __forceinline__ void store_dst(const PixelState& st, uint8_t* row, ui
 }
 
 // One (pixel, splat) evaluation + blend: splat 31 - hb of the current round.  Branch-free.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
-__device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 pxy, bool inside, float sd2, float outline, PixelState& st) {
+__device__ __forceinline__ bool depth_passes(int compare, float z, float d) {
+    switch (compare) {
+        case SB_COMPARE_NEVER: return false;
+        case SB_COMPARE_LESS: return z < d;
+        case SB_COMPARE_EQUAL: return z == d;
+        case SB_COMPARE_LESS_EQUAL: return z <= d;
+        case SB_COMPARE_GREATER: return z > d;
+        case SB_COMPARE_NOT_EQUAL: return z != d;
+        case SB_COMPARE_GREATER_EQUAL: return z >= d;
+        default: return true;
+    }
+}
+
+struct DepthArgs {
+    const float* zs;  // ndc z of the 32 splats of the current round (shared memory), nullptr when DEPTH is off
+    int compare, write;
+};
+
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH>
+__device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 pxy, bool inside, float sd2, float outline, PixelState& st,
+                                           const DepthArgs& da) {
     const char* rp = PERM ? last - 64u * hb + 16u * (hb & 3u) : last - 48u * hb;
     const float4 q0 = *reinterpret_cast<const float4*>(rp);       // cx cy ax bx
     const float2 q1 = *reinterpret_cast<const float2*>(rp + 16);  // ay by
@@ -362,6 +390,12 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
         const bool any = __any_sync(act, alive);
         st.n_warp_eval += 1u;
         st.n_warp_alive += any ? 1u : 0u;
+    }
+    if constexpr (DEPTH) {
+        // depth test AFTER the shader's discard, against the attachment as earlier fragments of this frame left it
+        const float z = da.zs[31u - hb];
+        alive = alive && depth_passes(da.compare, z, st.depth);
+        if (da.write && alive) st.depth = z;
     }
     // A discarded fragment blends with alpha = 0, which is the identity EXACTLY (d*1 + c*0 = d, and d is
     // already an integer on unorm8 targets): the loop body stays branch-free.
@@ -396,16 +430,16 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
 // Warp-level culling: each lane tests one splat against the two 4x4 halves of the warp's 8x4 pixel patch — the
 // bbox of its alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of a half's
 // rectangle against the ellipse's oriented bounding box; each half-warp then evaluates only its own survivors.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM>
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false>
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
-                                                PixelState& st) {
+                                                PixelState& st, DepthArgs da = DepthArgs{nullptr, 0, 0}) {
     // Byte addressing.  PERM: record j sits at 64 j - 16 (j & 3) (four 48-byte rows per 256-byte gather);
     // otherwise at 48 j.  A round is 32 consecutive records starting at a multiple of 32.
     const char* rb = reinterpret_cast<const char*>(recs);
     const char* mine = rb + (PERM ? 64u * lane - 16u * (lane & 3u) : 48u * lane);
     constexpr uint32_t kRound = PERM ? 2048u : 1536u;
-    for (uint32_t base = 0; base < cnt; base += 32, mine += kRound, rb += kRound) {
+    for (uint32_t base = 0; base < cnt; base += 32, mine += kRound, rb += kRound, da.zs += DEPTH ? 32 : 0) {
         // each lane tests ONE splat against BOTH 4x4 halves of the warp's 8x4 patch (pcx: centre of the left half)
         bool hit_l = false, hit_r = false;
         if (base + lane < cnt) {
@@ -440,7 +474,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
                 uint32_t hb;  // FLO directly; `31 - __clz` is canonicalised back into a clz and costs five more integer ops
                 asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
                 todo ^= 1u << hb;
-                eval_splat<MODE, FMT, STRICT, COUNT, PERM>(last, hb, pxy, inside, sd2, outline, st);
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH>(last, hb, pxy, inside, sd2, outline, st, da);
             }
         } else {
             uint32_t todo = __brev(un);
@@ -448,7 +482,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
                 uint32_t hb;
                 asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
                 todo ^= 1u << hb;
-                eval_splat<MODE, FMT, STRICT, COUNT, PERM>(last, hb, pxy, inside, sd2, outline, st);
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH>(last, hb, pxy, inside, sd2, outline, st, da);
             }
         }
     }
@@ -529,9 +563,10 @@ __global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelPara
 // (coalesced) and fetches the 48-byte records straight from the per-Gaussian array with TMA
 // tile::gather4 (cp.async.bulk.tensor.2d ... tile::gather4 -> UTMALDG, four rows per instruction, two
 // instructions per lane and batch) into a double-buffered ring; eight consumer warps composite.
-template <int MODE, int FMT, bool STRICT, bool COUNT>
-__global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelParams p, const __grid_constant__ CUtensorMap recs_map) {
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool DEPTH = false>
+__global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_constant__ RasterKernelParams p, const __grid_constant__ CUtensorMap recs_map) {
     __shared__ __align__(256) float4 stage[kG4Stages][kG4StageF4];
+    __shared__ float zs[DEPTH ? kG4Stages : 1][DEPTH ? kBatchG4 : 1];  // ndc z per staged record (depth-tested passes only)
     __shared__ __align__(8) uint64_t full_bar[kG4Stages];
     __shared__ __align__(8) uint64_t empty_bar[kG4Stages];
 
@@ -576,6 +611,24 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelP
             // only gathers whose first record exists are issued; the barrier is armed with exactly the
             // bytes that will land
             const uint32_t gathers = (cnt + 3u) / 4u;
+            if constexpr (DEPTH) {
+                // fragment depth = the centre's ndc z, recomputed from the pod position with K1's strict arithmetic
+#pragma unroll
+                for (int h = 0; h < kG4PerLane; h++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float4 head = __ldg(reinterpret_cast<const float4*>(p.pods + (size_t)g[4 * h + i] * p.pod_stride));
+                        float world[3], cz, cw;
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            world[c] = sadd(sadd(sadd(smul(p.model[c], head.x), smul(p.model[4 + c], head.y)), smul(p.model[8 + c], head.z)),
+                                            p.model[12 + c]);
+                        cz = sadd(sadd(sadd(smul(p.pv[2], world[0]), smul(p.pv[6], world[1])), smul(p.pv[10], world[2])), p.pv[14]);
+                        cw = sadd(sadd(sadd(smul(p.pv[3], world[0]), smul(p.pv[7], world[1])), smul(p.pv[11], world[2])), p.pv[15]);
+                        zs[s][4u * (lane + 32u * h) + i] = sdiv(cz, cw);
+                    }
+                __syncwarp();
+            }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], gathers * 4u * (uint32_t)sizeof(SplatRec));
             __syncwarp();
             const uint32_t dst0 = smem_u32(&stage[s][lane * 16]);
@@ -597,17 +650,25 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const RasterKernelP
     PixelState st;
     uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
     if (!p.clear && inside) load_dst<FMT>(st, dst, x, p.bgra);
+    float* zdst = nullptr;
+    if constexpr (DEPTH) {
+        zdst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.depth) + (size_t)(y - p.row0) * p.depth_pitch) + x;
+        if (inside) st.depth = *zdst;
+    }
 
     for (uint32_t k = 0; k < batches; k++) {
         const uint32_t s = k % kG4Stages;
         mbar_wait(&full_bar[s], (k / kG4Stages) & 1u);
         const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
-        composite_batch<MODE, FMT, STRICT, COUNT, true>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline, p.obb_cull != 0, st);
+        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline,
+                                                               p.obb_cull != 0, st, DepthArgs{DEPTH ? zs[s] : nullptr, p.depth_compare, p.depth_write});
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
     flush_counters<COUNT>(st, lane, p.counters);
     if (inside) store_dst<FMT>(st, dst, x, p.bgra);
+    if constexpr (DEPTH)
+        if (inside && p.depth_write) *zdst = st.depth;
 }
 
 // tile ranges from the tile-sorted keys (gather4 path: no record copy)
@@ -637,7 +698,9 @@ __global__ void clear_kernel(uint8_t* pixels, uint32_t pitch, uint32_t width, ui
 
 template <int MODE, int FMT, bool STRICT>
 void launch_raster(const RasterKernelParams& kp, const CUtensorMap* recs_map, dim3 grid, cudaStream_t stream) {
-    if (recs_map) {
+    if (recs_map && kp.depth) {
+        raster_gather4_kernel<MODE, FMT, STRICT, false, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
+    } else if (recs_map) {
         if (kp.counters) raster_gather4_kernel<MODE, FMT, STRICT, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
         else raster_gather4_kernel<MODE, FMT, STRICT, false><<<grid, 288, 0, stream>>>(kp, *recs_map);
     } else {
@@ -729,6 +792,16 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
     kp.clear = p.clear;
     kp.obb_cull = p.obb_cull;
+    kp.depth = p.depth;
+    kp.depth_pitch = p.depth_pitch;
+    kp.depth_compare = p.depth_compare;
+    kp.depth_write = p.depth_write;
+    kp.pods = p.pods;
+    kp.pod_stride = p.pod_stride;
+    for (int i = 0; i < 16; i++) {
+        kp.pv[i] = u.pv[i];
+        kp.model[i] = u.model[i];
+    }
     kp.counters = p.counters;
     const dim3 grid(u.tiles_x, ty_hi - ty_lo + 1);
     const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8

@@ -4,12 +4,70 @@
 // rectangle mask texture (src/shader/selection/viewport_texture_rectangle.wesl): a Gaussian is
 // selected iff its centre passes cull() and the mask texel under it is set.  The rectangle is
 // evaluated analytically: texel (ix,iy) is set iff its centre lies in [x0,x1) x [y0,y1).
+// The brush mask (src/shader/selection/viewport_texture_brush.wesl: two discs + a quad per stroke segment,
+// i.e. a capsule) is evaluated analytically too: a texel is set iff its centre is within `radius` of a segment
+// of the stroke polyline; strokes accumulate like they do in the reference's mask texture (op = union).
 // One warp owns one 32-bit selection word, so no atomics are needed.
 #include "sb_internal.h"
 
 namespace sb {
 
 namespace {
+
+// texel under a Gaussian's centre (viewport.wesl:44-60); false when the centre is culled or off the texture
+__device__ __forceinline__ bool centre_texel(const uint8_t* __restrict__ gaussians, uint32_t g, uint32_t stride, const Uniforms& u,
+                                             float& px, float& py) {
+    const float4 head = __ldg(reinterpret_cast<const float4*>(gaussians + (size_t)g * stride));
+    float world[3], clip[4];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        world[i] = sadd(sadd(sadd(smul(u.model[i], head.x), smul(u.model[4 + i], head.y)), smul(u.model[8 + i], head.z)), u.model[12 + i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        clip[i] = sadd(sadd(sadd(smul(u.pv[i], world[0]), smul(u.pv[4 + i], world[1])), smul(u.pv[8 + i], world[2])), u.pv[12 + i]);
+    const float nx = sdiv(clip[0], clip[3]), ny = sdiv(clip[1], clip[3]), nz = sdiv(clip[2], clip[3]);
+    if (!((nx >= -1.0f && ny >= -1.0f && nz >= 0.0f) && (nx <= 1.0f && ny <= 1.0f && nz <= 1.0f))) return false;
+    // ndc_to_camera_texture (camera.wesl:18-20) then vec2<i32>() truncation (viewport.wesl:60)
+    const float tx = smul(smul(sadd(smul(nx, 1.0f), 1.0f), u.size[0]), 0.5f);
+    const float ty = smul(smul(sadd(smul(ny, -1.0f), 1.0f), u.size[1]), 0.5f);
+    const int ix = (int)tx, iy = (int)ty;
+    if (!(ix >= 0 && iy >= 0 && ix < (int)u.size[0] && iy < (int)u.size[1])) return false;
+    px = (float)ix + 0.5f;
+    py = (float)iy + 0.5f;
+    return true;
+}
+
+// squared distance from p to the segment a-b, every step individually rounded (mirrors so_seg_dist2 in the oracle)
+__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by) {
+    const float ex = ssub(bx, ax), ey = ssub(by, ay), wx = ssub(px, ax), wy = ssub(py, ay);
+    const float len2 = sadd(smul(ex, ex), smul(ey, ey));
+    float t = 0.0f;
+    if (len2 > 0.0f) t = fminf(fmaxf(sdiv(sadd(smul(wx, ex), smul(wy, ey)), len2), 0.0f), 1.0f);
+    const float dx = ssub(wx, smul(t, ex)), dy = ssub(wy, smul(t, ey));
+    return sadd(smul(dx, dx), smul(dy, dy));
+}
+
+struct BrushStroke {
+    float xy[2 * SB_BRUSH_MAX_POINTS];
+    uint32_t n_points;
+    float radius;
+};
+
+__global__ void __launch_bounds__(256) select_brush_kernel(const uint8_t* __restrict__ gaussians, uint32_t n, uint32_t stride,
+                                                           const __grid_constant__ Uniforms u, const __grid_constant__ BrushStroke b,
+                                                           int accumulate, uint32_t* __restrict__ words) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool sel = false;
+    float px, py;
+    if (g < n && centre_texel(gaussians, g, stride, u, px, py)) {
+        const float r2 = smul(b.radius, b.radius);
+        if (b.n_points == 1) sel = seg_dist2(px, py, b.xy[0], b.xy[1], b.xy[0], b.xy[1]) <= r2;
+        for (uint32_t i = 0; i + 1 < b.n_points; i++)
+            sel = sel || seg_dist2(px, py, b.xy[2 * i], b.xy[2 * i + 1], b.xy[2 * i + 2], b.xy[2 * i + 3]) <= r2;
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, sel);
+    if ((threadIdx.x & 31u) == 0 && g < n) words[g >> 5] = accumulate ? (words[g >> 5] | bits) : bits;
+}
 
 __global__ void __launch_bounds__(256) select_rect_kernel(const uint8_t* __restrict__ gaussians, uint32_t n, uint32_t stride,
                                                           const __grid_constant__ Uniforms u, float x0, float y0, float x1, float y1,
@@ -50,6 +108,19 @@ cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t st
                                float y1, uint32_t* words, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     select_rect_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, u, x0, y0, x1, y1, words);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_brush(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, const float* points_xy,
+                                uint32_t n_points, float radius, int accumulate, uint32_t* words, cudaStream_t stream) {
+    if (n == 0 || n_points == 0) return cudaSuccess;
+    if (n_points > SB_BRUSH_MAX_POINTS) return cudaErrorInvalidValue;
+    BrushStroke b;
+    for (uint32_t i = 0; i < 2 * n_points; i++) b.xy[i] = points_xy[i];
+    for (uint32_t i = 2 * n_points; i < 2 * SB_BRUSH_MAX_POINTS; i++) b.xy[i] = 0.0f;
+    b.n_points = n_points;
+    b.radius = radius;
+    select_brush_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, u, b, accumulate, words);
     return cudaGetLastError();
 }
 

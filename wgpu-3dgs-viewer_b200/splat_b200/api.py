@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_update_camera_with_pod", "sb_viewer_update_camera", "sb_viewer_update_model_transform",
     "sb_viewer_update_model_transform_with_pod", "sb_viewer_update_gaussian_transform",
     "sb_viewer_update_gaussian_transform_with_pod", "sb_viewer_enable_selection", "sb_viewer_selection_ptr",
-    "sb_viewer_set_selection", "sb_viewer_read_selection", "sb_viewer_set_invert_selection", "sb_viewer_select_rect", "sb_viewer_render",
+    "sb_viewer_set_selection", "sb_viewer_read_selection", "sb_viewer_set_invert_selection", "sb_viewer_select_rect",
+    "sb_viewer_select_brush", "sb_viewer_render", "sb_viewer_render_with_pass",
     "sb_viewer_preprocess", "sb_viewer_sort", "sb_viewer_draw", "sb_viewer_render_to_host", "sb_viewer_render_batch", "sb_viewer_gaussians_ptr",
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
@@ -67,6 +68,10 @@ class DispatchIndirectArgs(C.Structure):
 class Target(C.Structure):
     _fields_ = [("d_pixels", C.c_void_p), ("pitch_bytes", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
                 ("format", C.c_int32), ("row0", C.c_uint32), ("rows", C.c_uint32)]
+
+
+class DepthAttachment(C.Structure):
+    _fields_ = [("d_depth", C.c_void_p), ("pitch_bytes", C.c_uint32), ("compare", C.c_int32), ("write_enabled", C.c_int32)]
 
 
 assert C.sizeof(CameraPod) == 144 and C.sizeof(ModelTransformPod) == 48 and C.sizeof(GaussianTransformPod) == 8
@@ -143,6 +148,8 @@ def load() -> C.CDLL:
     sig("sb_viewer_read_selection", i32, vp, vp, vp, u64)
     sig("sb_viewer_set_invert_selection", i32, vp, i32)
     sig("sb_viewer_select_rect", i32, vp, vp, f32, f32, f32, f32)
+    sig("sb_viewer_select_brush", i32, vp, vp, P(f32), u32, f32, i32)
+    sig("sb_viewer_render_with_pass", i32, vp, vp, P(Target), P(DepthAttachment), i32, i32)
     sig("sb_viewer_render", i32, vp, vp, P(Target))
     sig("sb_viewer_preprocess", i32, vp, vp)
     sig("sb_viewer_sort", i32, vp, vp)
@@ -257,6 +264,9 @@ def _stream_handle(stream) -> int:
     return int(stream.cuda_stream)  # torch.cuda.Stream
 
 
+COMPARE_NEVER, COMPARE_LESS, COMPARE_EQUAL, COMPARE_LESS_EQUAL, COMPARE_GREATER, COMPARE_NOT_EQUAL, COMPARE_GREATER_EQUAL, COMPARE_ALWAYS = range(1, 9)
+
+
 def make_target(tensor_or_ptr, width, height, fmt, pitch=None, row0=0, rows=0) -> Target:
     ptr = tensor_or_ptr if isinstance(tensor_or_ptr, int) else tensor_or_ptr.data_ptr()
     t = Target()
@@ -347,6 +357,11 @@ class Viewer:
     def select_rect(self, x0, y0, x1, y1, stream=None):
         _check(load().sb_viewer_select_rect(self._h, _stream_handle(stream), x0, y0, x1, y1), self.ctx._h)
 
+    def select_brush(self, points, radius, accumulate=False, stream=None):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        _check(load().sb_viewer_select_brush(self._h, _stream_handle(stream), pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts),
+                                             float(radius), int(accumulate)), self.ctx._h)
+
     def read_selection(self, stream=None) -> np.ndarray:
         out = np.zeros((self.n + 31) // 32, dtype=np.uint32)
         _check(load().sb_viewer_read_selection(self._h, _stream_handle(stream), out.ctypes.data, len(out)), self.ctx._h)
@@ -356,6 +371,20 @@ class Viewer:
     def render(self, target, width, height, stream=None, row0=0, rows=0, pitch=None):
         t = make_target(target, width, height, self.target_format, pitch, row0, rows)
         _check(load().sb_viewer_render(self._h, _stream_handle(stream), C.byref(t)), self.ctx._h)
+
+    def render_with_pass(self, target, width, height, depth=None, compare=COMPARE_ALWAYS, depth_write=False, load_target=True,
+                         run_stages=True, stream=None):
+        """Renderer::render_with_pass + depth_stencil: composite over the target's contents against an f32 depth tensor."""
+        t = make_target(target, width, height, self.target_format)
+        d = None
+        if depth is not None:
+            d = DepthAttachment()
+            d.d_depth = depth.data_ptr()
+            d.pitch_bytes = width * 4
+            d.compare = compare
+            d.write_enabled = int(depth_write)
+        _check(load().sb_viewer_render_with_pass(self._h, _stream_handle(stream), C.byref(t), C.byref(d) if d is not None else None,
+                                                 int(load_target), int(run_stages)), self.ctx._h)
 
     def preprocess(self, stream=None):
         _check(load().sb_viewer_preprocess(self._h, _stream_handle(stream)), self.ctx._h)
