@@ -82,6 +82,15 @@ public:
     void preprocess(void* stream) { check(sb_viewer_preprocess(h_, stream), ctx_.raw()); }                      // viewer.preprocessor.preprocess
     void sort(void* stream) { check(sb_viewer_sort(h_, stream), ctx_.raw()); }                                  // viewer.radix_sorter.sort
     void draw(void* stream, const SbTarget& t) { check(sb_viewer_draw(h_, stream, &t), ctx_.raw()); }           // viewer.renderer.render
+    // viewer.renderer.render_with_pass inside the caller's pass (+ ViewerCreateOptions.depth_stencil): src/renderer.rs:187-195
+    void render_with_pass(void* stream, const SbTarget& t, const SbDepthAttachment* depth = nullptr, bool load = true, bool run_stages = false) {
+        check(sb_viewer_render_with_pass(h_, stream, &t, depth, load, run_stages), ctx_.raw());
+    }
+    // selection::ViewportSelector evaluation with an analytic rectangle / brush mask
+    void select_rect(void* stream, float x0, float y0, float x1, float y1) { check(sb_viewer_select_rect(h_, stream, x0, y0, x1, y1), ctx_.raw()); }
+    void select_brush(void* stream, const std::vector<float>& points_xy, float radius, bool accumulate = false) {
+        check(sb_viewer_select_brush(h_, stream, points_xy.data(), (uint32_t)(points_xy.size() / 2), radius, accumulate), ctx_.raw());
+    }
     SbViewer* raw() const { return h_; }
 private:
     Context& ctx_;

@@ -33,6 +33,11 @@ pub mod ffi {
     #[repr(C)] #[derive(Clone, Copy, Debug)]
     pub struct Target { pub d_pixels: *mut c_void, pub pitch_bytes: u32, pub width: u32, pub height: u32, pub format: i32, pub row0: u32, pub rows: u32 }
 
+    /// `wgpu::DepthStencilState` of `ViewerCreateOptions::depth_stencil` reduced to what the draw needs, plus the
+    /// pass's Depth32Float attachment (reference src/lib.rs:279-284, src/renderer.rs:123,304).
+    #[repr(C)] #[derive(Clone, Copy, Debug)]
+    pub struct DepthAttachment { pub d_depth: *mut c_void, pub pitch_bytes: u32, pub compare: i32, pub write_enabled: i32 }
+
     #[link(name = "splat_b200")]
     extern "C" {
         pub fn sb_last_error_string(ctx: *const SbContext) -> *const c_char;
@@ -50,7 +55,10 @@ pub mod ffi {
         pub fn sb_viewer_enable_selection(v: *mut SbViewer, enabled: i32) -> i32;
         pub fn sb_viewer_set_selection(v: *mut SbViewer, stream: *mut c_void, words: *const u32, n_words: u64) -> i32;
         pub fn sb_viewer_set_invert_selection(v: *mut SbViewer, invert: i32) -> i32;
+        pub fn sb_viewer_select_rect(v: *mut SbViewer, stream: *mut c_void, x0: f32, y0: f32, x1: f32, y1: f32) -> i32;
+        pub fn sb_viewer_select_brush(v: *mut SbViewer, stream: *mut c_void, points_xy: *const f32, n_points: u32, radius: f32, accumulate: i32) -> i32;
         pub fn sb_viewer_render(v: *mut SbViewer, stream: *mut c_void, target: *const Target) -> i32;
+        pub fn sb_viewer_render_with_pass(v: *mut SbViewer, stream: *mut c_void, target: *const Target, depth: *const DepthAttachment, load: i32, run_stages: i32) -> i32;
         pub fn sb_viewer_preprocess(v: *mut SbViewer, stream: *mut c_void) -> i32;
         pub fn sb_viewer_sort(v: *mut SbViewer, stream: *mut c_void) -> i32;
         pub fn sb_viewer_draw(v: *mut SbViewer, stream: *mut c_void, target: *const Target) -> i32;
@@ -135,6 +143,19 @@ impl<'c, G: GaussianPod> Viewer<'c, G> {
     pub fn preprocess(&self, stream: Stream) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_preprocess(self.raw, stream.0) }, self.ctx.0) }
     pub fn sort(&self, stream: Stream) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_sort(self.raw, stream.0) }, self.ctx.0) }
     pub fn draw(&self, stream: Stream, target: &Target) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_draw(self.raw, stream.0, target) }, self.ctx.0) }
+    /// `Renderer::render_with_pass(pass, indirect_args)` (src/renderer.rs:187-195): draw inside the caller's pass —
+    /// over the colour the target already holds, depth-tested against the pass's depth attachment when the viewer
+    /// was created with `ViewerCreateOptions { depth_stencil: Some(..) }`.
+    pub fn render_with_pass(&self, stream: Stream, target: &Target, depth: Option<&ffi::DepthAttachment>) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_render_with_pass(self.raw, stream.0, target, depth.map_or(std::ptr::null(), |d| d as *const _), 1, 0) }, self.ctx.0)
+    }
+    /// `selection::ViewportSelector` evaluation with a rectangle / brush mask (src/selection/viewport_selector.rs:250-301).
+    pub fn select_rect(&mut self, stream: Stream, min: glam::Vec2, max: glam::Vec2) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_select_rect(self.raw, stream.0, min.x, min.y, max.x, max.y) }, self.ctx.0)
+    }
+    pub fn select_brush(&mut self, stream: Stream, stroke: &[glam::Vec2], radius: f32, accumulate: bool) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_select_brush(self.raw, stream.0, stroke.as_ptr().cast(), stroke.len() as u32, radius, accumulate as i32) }, self.ctx.0)
+    }
 }
 impl<G: GaussianPod> Drop for Viewer<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_viewer_destroy(self.raw) } } }
 
