@@ -352,6 +352,9 @@ constexpr size_t kPlanOffset = kHistWords + 4;  // [kPlanOffset + pass]: bit 0 =
 // lanes of the warp whose NBITS-bit digit equals this lane's: one vote per digit bit
 template <int NBITS>
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+#ifdef SB_SORT_USE_MATCH
+    return __match_any_sync(0xffffffffu, d);  // tuning variant, measured: 64 M keys 2.38 ms against 1.85 ms with the votes
+#endif
     // differ |= lanes whose bit b differs from mine = vote ^ (my bit replicated).  Written in PTX: ptxas turns it
     // into one R2P for all bits + VOTE + predicated NOT + OR per bit; the C form costs six instructions per bit.
     uint32_t differ = 0u;
