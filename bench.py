@@ -363,7 +363,18 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+    stdout at communicator creation), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+    saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
