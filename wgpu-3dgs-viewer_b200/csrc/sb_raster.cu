@@ -567,6 +567,7 @@ template <int MODE, int FMT, bool STRICT, bool COUNT, bool DEPTH = false>
 __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_constant__ RasterKernelParams p, const __grid_constant__ CUtensorMap recs_map) {
     __shared__ __align__(256) float4 stage[kG4Stages][kG4StageF4];
     __shared__ float zs[DEPTH ? kG4Stages : 1][DEPTH ? kBatchG4 : 1];  // ndc z per staged record (depth-tested passes only)
+    __shared__ __align__(8) uint64_t z_bar[kG4Stages];  // DEPTH: producer's generic stores to zs -> consumers (plain arrive/wait pair)
     __shared__ __align__(8) uint64_t full_bar[kG4Stages];
     __shared__ __align__(8) uint64_t empty_bar[kG4Stages];
 
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
         for (int s = 0; s < kG4Stages; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 8);
+            mbar_init(&z_bar[s], 32);  // every producer lane arrives for its own stores
         }
         fence_mbar_init();
     }
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
                         cw = sadd(sadd(sadd(smul(p.pv[3], world[0]), smul(p.pv[7], world[1])), smul(p.pv[11], world[2])), p.pv[15]);
                         zs[s][4u * (lane + 32u * h) + i] = sdiv(cz, cw);
                     }
-                __syncwarp();
+                mbar_arrive(&z_bar[s]);
             }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], gathers * 4u * (uint32_t)sizeof(SplatRec));
             __syncwarp();
@@ -659,6 +661,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
     for (uint32_t k = 0; k < batches; k++) {
         const uint32_t s = k % kG4Stages;
         mbar_wait(&full_bar[s], (k / kG4Stages) & 1u);
+        if constexpr (DEPTH) mbar_wait(&z_bar[s], (k / kG4Stages) & 1u);
         const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
         composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline,
                                                                p.obb_cull != 0, st, DepthArgs{DEPTH ? zs[s] : nullptr, p.depth_compare, p.depth_write});

@@ -169,6 +169,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem& sm, const uint32_t* __re
         if (ok) atomicOr(&plane[d], my_bit);
         __syncwarp();
         const uint32_t peers = ok ? plane[d] : my_bit;
+        __syncwarp();  // every peer has read the mask before its leader clears it (racecheck: read/write hazard otherwise)
         const uint32_t below = __popc(peers & lt);
         uint32_t pre = 0;
         if (below == 0 && ok) {
