@@ -434,6 +434,56 @@ def test_standalone_radix_sorter(sb, ctx):
         s.close()
 
 
+@pytest.mark.parametrize("impl", ["v1", "v3"])
+def test_radix_sorter_both_pass_kernels(sb, impl):
+    """Both digit-pass kernels (SB_SORT_IMPL=v1: 8192-pair tiles, shared-memory peer masks; v3: 4096-pair tiles, vote ranking,
+    cp.async payload) forced on every shape: odd bit ranges, begin_bit > 0, a device count below the capacity, an empty
+    input, constant keys (every pass is the identity and is skipped) and sorted / reversed inputs.  Subprocess: the choice is
+    read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import splat_b200 as sb
+ctx = sb.Context(0)
+rng = np.random.default_rng(23)
+cases = [(1, 0, 32, 1), (4097, 0, 32, 4097), (12289, 0, 17, 12289), (50000, 0, 20, 50000), (50000, 0, 25, 50000),
+         (65536, 4, 21, 65536), (300000, 0, 32, 123457), (5000, 0, 32, 0), (40000, 8, 16, 40000), (33333, 0, 1, 33333)]
+for n, b0, b1, count in cases:
+    for kind in ("random", "constant", "sorted", "reversed"):
+        if kind == "random":
+            keys = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        elif kind == "constant":
+            keys = np.full(n, 0xDEADBEEF, dtype=np.uint32)
+        else:
+            keys = np.sort(rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32))
+            if kind == "reversed":
+                keys = keys[::-1].copy()
+        vals = rng.permutation(n).astype(np.uint32)
+        dk = torch.from_numpy(keys.view(np.int32)).cuda()
+        dv = torch.from_numpy(vals.view(np.int32)).cuda()
+        cnt = torch.tensor([count], dtype=torch.int32, device="cuda")
+        s = sb.RadixSorter(ctx, n)
+        s.sort(dk.data_ptr(), dv.data_ptr(), cnt.data_ptr(), n, b0, b1)
+        torch.cuda.synchronize()
+        mask = np.uint32(((1 << (b1 - b0)) - 1) << b0) if b1 - b0 < 32 else np.uint32(0xffffffff)
+        order = np.argsort(keys[:count] & mask, kind="stable")
+        gk, gv = dk.cpu().numpy().view(np.uint32), dv.cpu().numpy().view(np.uint32)
+        assert np.array_equal(gk[:count], keys[:count][order]), (n, b0, b1, count, kind)
+        assert np.array_equal(gv[:count], vals[:count][order]), (n, b0, b1, count, kind)
+        assert np.array_equal(gk[count:], keys[count:]) and np.array_equal(gv[count:], vals[count:]), "pairs beyond the count must stay"
+        s.close()
+print("ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SB_SORT_IMPL=impl)
+    out = subprocess.run([sys.executable, "-c", code, os.path.join(root, "wgpu-3dgs-viewer_b200")], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_errors(sb, ctx):
     pods = sb.pack_gaussians(sb.scenes.synthetic_gaussians(10, 1))
     v = sb.Viewer(ctx, pods, 10)
