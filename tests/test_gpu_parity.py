@@ -537,6 +537,22 @@ def test_full_size_properties(sb, ctx):
     v.close()
 
 
+@pytest.mark.parametrize("camera", ["outside", "inside"])
+def test_config2_1M_1080p_against_oracle(sb, ob, ctx, camera):
+    """BASELINE.json configs[1] at full size — 1 M Gaussians, single/single pods, 1920x1080, splat mode — against the
+    oracle: visible set, counts, keys and order bit-exact, framebuffer bit-exact with the reproducible exp and within
+    2/255 with the MUFU path (deep per-pixel stacks: ~100 blended layers per pixel with the outside camera)."""
+    n, w, h = 1_000_000, 1920, 1080
+    g, pods = make_scene(sb, ob, n, sb.scenes.BASE_SEED + 1)
+    cam = sb.scenes.CAMERA_OUTSIDE if camera == "outside" else sb.scenes.CAMERA_INSIDE
+    r = run_frame(sb, ob, ctx, pods, n, cam, w, h, strict=True)
+    check_artifacts(ob, r, n)
+    assert not r["stats"]["overflowed"]
+    assert img_diff(r) == 0
+    fast = run_frame(sb, ob, ctx, pods, n, cam, w, h, strict=False)
+    assert img_diff(fast) <= 2
+
+
 def test_raster_counters_and_stage_timing(sb, ob, ctx):
     """The instrumented rasterizer counts exactly the fragments the oracle blends; stage timers work."""
     torch = _torch()
