@@ -285,6 +285,60 @@ SB_API void sb_sorter_destroy(SbRadixSorter* s);
 SB_API SbStatus sb_sorter_sort(SbRadixSorter* s, void* stream, uint32_t* d_keys, uint32_t* d_payload,
                                const uint32_t* d_count, uint32_t max_count, int32_t begin_bit, int32_t end_bit);
 
+/* ---------------------------------------------------------------- standalone Preprocessor / Renderer (the B = () variants) */
+
+/* Preprocessor::new_without_bind_group + create_bind_group + preprocess(encoder, bind_group, gaussian_count):
+ * src/preprocessor.rs:375-435, 37-68, 438-450.  The bind group (layout src/preprocessor.rs:104-221) is this struct of
+ * caller-owned device buffers plus the three uniform pods (bindings 0-2), passed per call; sizes are validated
+ * the way TryFrom<wgpu::Buffer> validates them (SB_ERR_BAD_BUFFER_SIZE). */
+typedef struct SbPreprocessorBindGroup {
+    SbCameraPod camera;                                   /* binding 0 */
+    SbModelTransformPod model_transform;                  /* binding 1 */
+    SbGaussianTransformPod gaussian_transform;            /* binding 2 */
+    const void* d_gaussians;                              /* binding 3: GaussiansBuffer<G> */
+    uint64_t gaussians_bytes;                             /*   must equal n * size_of::<G>() */
+    SbDrawIndirectArgs* d_indirect_args;                  /* binding 4: 16 bytes */
+    SbDispatchIndirectArgs* d_radix_sort_indirect_args;   /* binding 5: 12 bytes */
+    uint32_t* d_indirect_indices;                         /* binding 6: IndirectIndicesBuffer */
+    uint64_t indirect_indices_bytes;                      /*   >= 4 * n */
+    float* d_gaussians_depth;                             /* binding 7: GaussiansDepthBuffer */
+    uint64_t gaussians_depth_bytes;                       /*   >= 4 * sb_padded_key_count(n) (the reference allocates 4x that) */
+    const uint32_t* d_selection;                          /* binding 8: ceil(n/32) words; NULL = feature off */
+    uint32_t invert_selection;                            /* binding 9 */
+} SbPreprocessorBindGroup;
+typedef struct SbPreprocessor SbPreprocessor;
+SB_API SbStatus sb_preprocessor_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, uint64_t n, SbPreprocessor** out);
+SB_API void sb_preprocessor_destroy(SbPreprocessor* p);
+/* enqueue pre+main+post over the first gaussian_count (<= n) Gaussians: visible indices (ascending), depth keys,
+ * pad keys, {6,V,0,0} and {ceil(V/3840),1,1}.  The visible count for a following sb_sorter_sort is
+ * &d_indirect_args->instance_count. */
+SB_API SbStatus sb_preprocessor_preprocess(SbPreprocessor* p, void* stream, const SbPreprocessorBindGroup* bind_group,
+                                           uint32_t gaussian_count);
+
+/* Renderer::new_without_bind_group + create_bind_group + render(encoder, view, bind_group, indirect_args) /
+ * render_with_pass: src/renderer.rs:247-318, 23-41, 321-356.  Bind group layout src/renderer.rs:56-116. */
+typedef struct SbRendererBindGroup {
+    SbCameraPod camera;                                   /* binding 0 */
+    SbModelTransformPod model_transform;                  /* binding 1 */
+    SbGaussianTransformPod gaussian_transform;            /* binding 2 */
+    const void* d_gaussians;                              /* binding 3 */
+    uint64_t gaussians_bytes;
+    const uint32_t* d_indirect_indices;                   /* binding 4: instance i draws Gaussian indices[i] */
+    uint64_t indirect_indices_bytes;
+} SbRendererBindGroup;
+typedef struct SbRenderer SbRenderer;
+SB_API SbStatus sb_renderer_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, uint64_t n,
+                                   SbRenderer** out);
+SB_API void sb_renderer_destroy(SbRenderer* r);
+/* One indirect instanced draw: instances 0..d_indirect_args->instance_count-1 in order, whatever produced the indices
+ * (the vertex stage runs here for exactly those Gaussians; a quad whose centre has w <= 0 or ndc z outside [0,1] is
+ * clipped as a whole, as the fixed-function clipper does with render.wesl:123's flat z/w).  load == 0 clears to BLACK
+ * first (Renderer::render), load != 0 composites over the target (render_with_pass inside a caller's pass); depth is
+ * the optional depth_stencil attachment as in sb_viewer_render_with_pass. */
+SB_API SbStatus sb_renderer_render(SbRenderer* r, void* stream, const SbRendererBindGroup* bind_group, const SbTarget* target,
+                                   const SbDrawIndirectArgs* d_indirect_args, const SbDepthAttachment* depth, int32_t load);
+SB_API SbStatus sb_renderer_set_strict_exp(SbRenderer* r, int32_t strict);
+
 /* ---------------------------------------------------------------- MultiModelViewer (src/multi_model.rs:291-531) */
 
 SB_API SbStatus sb_mm_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format,

@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
         l.so_select_rect.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         l.so_render_pass.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.POINTER(GaussianTransformPod), C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        l.so_draw.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.POINTER(GaussianTransformPod), C.c_void_p, C.c_uint32, C.c_int,
+                              C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         l.so_select_brush.argtypes = [C.POINTER(Model), C.POINTER(CameraPod), C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_void_p]
         l.so_max_threads.restype = C.c_int
         l.so_set_threads.argtypes = [C.c_int]
@@ -220,6 +222,19 @@ def render_pass(model: OracleModel, cam: CameraPod, gt: GaussianTransformPod, ta
     buf = target.view(np.uint16) if target.dtype == np.float16 else target
     lib().so_render_pass(C.byref(model.c), C.byref(cam), C.byref(gt), target_format, int(strict_exp), int(load), buf.ctypes.data,
                          None if depth is None else depth.ctypes.data, compare, int(depth_write), n_threads)
+    return target
+
+
+def draw(model: OracleModel, cam: CameraPod, gt: GaussianTransformPod, indices: np.ndarray, target: np.ndarray, load: bool = False,
+         depth: np.ndarray | None = None, compare: int = 8, depth_write: bool = False, target_format=TARGET_RGBA8, strict_exp=False,
+         n_threads=0):
+    """Renderer<G, ()>::render on a caller's indices: instance i = Gaussian indices[i], drawn in that order into `target`
+    (in place; loaded or cleared), no preprocess and no sort."""
+    idx = np.ascontiguousarray(indices, dtype=np.uint32)
+    assert target.flags["C_CONTIGUOUS"] and (depth is None or (depth.dtype == np.float32 and depth.flags["C_CONTIGUOUS"]))
+    buf = target.view(np.uint16) if target.dtype == np.float16 else target
+    lib().so_draw(C.byref(model.c), C.byref(cam), C.byref(gt), idx.ctypes.data, len(idx), target_format, int(strict_exp), int(load),
+                  buf.ctypes.data, None if depth is None else depth.ctypes.data, compare, int(depth_write), n_threads)
     return target
 
 

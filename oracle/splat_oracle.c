@@ -823,15 +823,11 @@ void so_select_brush(const SoModel* model, const SoCameraPod* cam, const float* 
     }
 }
 
-void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
-                    int target_format, int strict_exp, int load, void* target, float* depth, int depth_compare,
-                    int depth_write, int n_threads) {
-    uint32_t width = (uint32_t)cam->size[0], height = (uint32_t)cam->size[1];
+/* target <-> the f32 accumulator the blend runs in (unorm8: 0..255 units) */
+static float* acc_load(int target_format, int load, const void* target, size_t npx) {
     int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
     int is_f16 = target_format == SO_TARGET_RGBA16F;
     int ri = target_format == SO_TARGET_BGRA8 ? 2 : 0, bi = 2 - ri;
-    if (n_threads <= 0) n_threads = so_max_threads();
-    size_t npx = (size_t)height * width;
     float* acc = (float*)malloc((npx ? npx : 1) * 4 * sizeof(float));
     for (size_t i = 0; i < npx; i++) {
         if (!load) {
@@ -846,24 +842,13 @@ void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussi
             memcpy(acc + i * 4, (const float*)target + i * 4, 16);
         }
     }
-    uint32_t n = model->n;
-    uint32_t cap = ((n + 3839u) / 3840u) * 3840u;
-    uint32_t* idx = (uint32_t*)malloc((size_t)(cap ? cap : 1) * 4);
-    float* keys = (float*)malloc((size_t)(cap ? cap : 1) * 4);
-    uint32_t v = so_preprocess(model, cam, gt, idx, keys, NULL, NULL, NULL);
-    so_radix_sort((uint32_t*)keys, idx, v);
-    SoSplat* sp = (SoSplat*)malloc((size_t)(v ? v : 1) * sizeof(SoSplat));
-    so_project(model, cam, gt, idx, v, sp);
-    Uniforms u = make_uniforms(cam, &model->model_transform, gt);
-    uint64_t nb = 0, na = 0;
-    #pragma omp parallel for schedule(static) num_threads(n_threads) reduction(+ : nb, na)
-    for (int t = 0; t < n_threads; t++) {
-        uint32_t y_lo = (uint32_t)((uint64_t)height * (uint32_t)t / (uint32_t)n_threads);
-        uint32_t y_hi = (uint32_t)((uint64_t)height * ((uint32_t)t + 1) / (uint32_t)n_threads);
-        if (y_hi > y_lo)
-            raster_band(sp, v, &u, strict_exp, is_unorm, is_f16, width, y_lo, y_hi, 0, acc, &nb, &na, depth, depth_compare, depth_write);
-    }
-    free(sp); free(keys); free(idx);
+    return acc;
+}
+
+static void acc_store(int target_format, const float* acc, void* target, size_t npx) {
+    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_f16 = target_format == SO_TARGET_RGBA16F;
+    int ri = target_format == SO_TARGET_BGRA8 ? 2 : 0, bi = 2 - ri;
     if (is_unorm) {
         uint8_t* out = (uint8_t*)target;
         for (size_t i = 0; i < npx; i++) {
@@ -878,6 +863,68 @@ void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussi
     } else {
         memcpy(target, acc, npx * 4 * sizeof(float));
     }
+}
+
+/* one indirect instanced draw of `count` instances, instance i = Gaussian indices[i], in that order */
+static void draw_instances(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
+                           const uint32_t* indices, uint32_t count, int clip_quads, int target_format, int strict_exp,
+                           float* acc, float* depth, int depth_compare, int depth_write, int n_threads) {
+    uint32_t width = (uint32_t)cam->size[0], height = (uint32_t)cam->size[1];
+    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_f16 = target_format == SO_TARGET_RGBA16F;
+    if (n_threads <= 0) n_threads = so_max_threads();
+    SoSplat* sp = (SoSplat*)malloc((size_t)(count ? count : 1) * sizeof(SoSplat));
+    so_project(model, cam, gt, indices, count, sp);
+    Uniforms u = make_uniforms(cam, &model->model_transform, gt);
+    if (clip_quads) {
+        /* The four vertices of a quad share clip z and w (render.wesl:123), so the fixed-function clipper keeps or drops
+         * the quad as a whole: kept iff w > 0 and 0 <= z <= w.  x/y are clipped per pixel by the viewport. */
+        uint32_t stride = so_pod_stride(model->sh_fmt, model->cov_fmt);
+        for (uint32_t i = 0; i < count; i++) {
+            float pos[3], world[3], clip[4];
+            memcpy(pos, (const uint8_t*)model->pods + (size_t)stride * indices[i], 12);
+            project_centre(&u, pos, world, clip);
+            float nz = clip[2] / clip[3];
+            if (!(clip[3] > 0.0f && nz >= 0.0f && nz <= 1.0f)) sp[i].valid = 0;
+        }
+    }
+    uint64_t nb = 0, na = 0;
+    #pragma omp parallel for schedule(static) num_threads(n_threads) reduction(+ : nb, na)
+    for (int t = 0; t < n_threads; t++) {
+        uint32_t y_lo = (uint32_t)((uint64_t)height * (uint32_t)t / (uint32_t)n_threads);
+        uint32_t y_hi = (uint32_t)((uint64_t)height * ((uint32_t)t + 1) / (uint32_t)n_threads);
+        if (y_hi > y_lo)
+            raster_band(sp, count, &u, strict_exp, is_unorm, is_f16, width, y_lo, y_hi, 0, acc, &nb, &na, depth, depth_compare, depth_write);
+    }
+    free(sp);
+}
+
+void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
+                    int target_format, int strict_exp, int load, void* target, float* depth, int depth_compare,
+                    int depth_write, int n_threads) {
+    size_t npx = (size_t)(uint32_t)cam->size[1] * (uint32_t)cam->size[0];
+    float* acc = acc_load(target_format, load, target, npx);
+    uint32_t n = model->n;
+    uint32_t cap = ((n + 3839u) / 3840u) * 3840u;
+    uint32_t* idx = (uint32_t*)malloc((size_t)(cap ? cap : 1) * 4);
+    float* keys = (float*)malloc((size_t)(cap ? cap : 1) * 4);
+    uint32_t v = so_preprocess(model, cam, gt, idx, keys, NULL, NULL, NULL);
+    so_radix_sort((uint32_t*)keys, idx, v);
+    draw_instances(model, cam, gt, idx, v, 0, target_format, strict_exp, acc, depth, depth_compare, depth_write, n_threads);
+    free(keys); free(idx);
+    acc_store(target_format, acc, target, npx);
+    free(acc);
+}
+
+/* Renderer<G, ()>::render / render_with_pass on a caller's bind group (src/renderer.rs:321-356): instances
+ * 0..count-1 of `indices` in order, no preprocess, no sort. */
+void so_draw(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
+             const uint32_t* indices, uint32_t count, int target_format, int strict_exp, int load, void* target,
+             float* depth, int depth_compare, int depth_write, int n_threads) {
+    size_t npx = (size_t)(uint32_t)cam->size[1] * (uint32_t)cam->size[0];
+    float* acc = acc_load(target_format, load, target, npx);
+    draw_instances(model, cam, gt, indices, count, 1, target_format, strict_exp, acc, depth, depth_compare, depth_write, n_threads);
+    acc_store(target_format, acc, target, npx);
     free(acc);
 }
 

@@ -148,6 +148,13 @@ void so_render_pass(const SoModel* model, const SoCameraPod* cam, const SoGaussi
                     int target_format, int strict_exp, int load, void* target, float* depth, int depth_compare,
                     int depth_write, int n_threads);
 
+/* Renderer<G, ()>::render / render_with_pass on a caller's bind group (src/renderer.rs:321-356): one indirect instanced
+ * draw of instances 0..count-1, instance i = Gaussian indices[i], composited in that order — no preprocess, no sort.
+ * A quad whose centre has clip w <= 0 or z outside [0, w] is clipped as a whole (flat z/w, render.wesl:123). */
+void so_draw(const SoModel* model, const SoCameraPod* cam, const SoGaussianTransformPod* gt,
+             const uint32_t* indices, uint32_t count, int target_format, int strict_exp, int load, void* target,
+             float* depth, int depth_compare, int depth_write, int n_threads);
+
 /* exp(-x) for x in [0, ~88] from exactly-rounded fma steps (bit-reproducible on GPU). */
 float so_exp_neg_poly(float x);
 

@@ -174,6 +174,9 @@ struct SbViewer {
     // two internal streams forked from / joined to the caller's stream
     SbViewer* twin = nullptr;
     const uint32_t* selection_override = nullptr;  // twin: the primary's selection words
+    // standalone Renderer: the caller's IndirectIndicesBuffer / IndirectArgsBuffer.instance_count
+    const uint32_t* ext_indices = nullptr;
+    const uint32_t* ext_count = nullptr;
     cudaStream_t bstream[2] = {nullptr, nullptr};
     cudaEvent_t bevent[3] = {nullptr, nullptr, nullptr};
     bool timing = false;
@@ -355,8 +358,8 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     }
     p.recs = v->recs.as<sb::SplatRec>();
     p.tboxes = v->tboxes.as<sb::TileBox>();
-    p.sorted_indices = v->indices.as<uint32_t>();
-    p.visible_count = v->d_visible();
+    p.sorted_indices = v->ext_indices ? v->ext_indices : v->indices.as<uint32_t>();
+    p.visible_count = v->ext_count ? v->ext_count : v->d_visible();
     p.max_visible = v->n;
     p.buf.dup_offsets = v->dup_offsets.as<uint32_t>();
     p.buf.dup_keys = v->dup_keys.as<uint32_t>();
@@ -899,6 +902,143 @@ SbStatus sb_sorter_sort(SbRadixSorter* s, void* stream, uint32_t* d_keys, uint32
     SB_CUDA(s->ctx, sb::launch_sort(d_keys, d_payload, d_count, max_count, begin_bit, end_bit, sc, s->ctx->num_sms,
                                     static_cast<cudaStream_t>(stream)));
     return SB_OK;
+}
+
+// ---------------------------------------------------------------- standalone Preprocessor (Preprocessor<G, ()>)
+
+struct SbPreprocessor {
+    SbContext* ctx;
+    int sh_fmt, cov_fmt;
+    uint32_t stride, n;
+    DeviceBuf scratch;  // tile tickets + look-back table, and the V word the kernel also writes
+    DeviceBuf visible;
+};
+
+SbStatus sb_preprocessor_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, uint64_t n, SbPreprocessor** out) {
+    if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    const uint32_t stride = sb_pod_stride(sh_fmt, cov_fmt);
+    if (stride == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
+    if (n > 0x3fffffffull) return fail(ctx, SB_ERR_MODEL_TOO_LARGE, "more than 2^30 gaussians");
+    if (n * stride > ctx->model_size_limit) return fail(ctx, SB_ERR_MODEL_TOO_LARGE, "model size exceeds the device limit");  // src/preprocessor.rs:381-388
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    SbPreprocessor* p = new SbPreprocessor();
+    p->ctx = ctx;
+    p->sh_fmt = sh_fmt;
+    p->cov_fmt = cov_fmt;
+    p->stride = stride;
+    p->n = (uint32_t)n;
+    cudaError_t e = p->scratch.alloc(sb::preprocess_scratch_bytes(p->n, sh_fmt, cov_fmt));
+    if (e == cudaSuccess) e = p->visible.alloc(16);
+    if (e != cudaSuccess) {
+        sb_preprocessor_destroy(p);
+        return fail_cuda(ctx, e, "preprocessor alloc");
+    }
+    *out = p;
+    return SB_OK;
+}
+
+void sb_preprocessor_destroy(SbPreprocessor* p) {
+    if (!p) return;
+    p->scratch.release();
+    p->visible.release();
+    delete p;
+}
+
+SbStatus sb_preprocessor_preprocess(SbPreprocessor* pre, void* stream, const SbPreprocessorBindGroup* bg, uint32_t gaussian_count) {
+    if (!pre || !bg) return fail(pre ? pre->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    SbContext* ctx = pre->ctx;
+    if (gaussian_count > pre->n) return fail(ctx, SB_ERR_INVALID_ARG, "gaussian_count exceeds the preprocessor's model size");
+    if (bg->gaussians_bytes != (uint64_t)pre->n * pre->stride) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians buffer size != n * size_of::<G>()");
+    if (bg->indirect_indices_bytes < (uint64_t)pre->n * 4) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "indirect indices buffer smaller than 4 * n");
+    const uint32_t padded = sb_padded_key_count(pre->n);
+    if (bg->gaussians_depth_bytes < (uint64_t)padded * 4) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians depth buffer smaller than 4 * ceil(n/3840)*3840");
+    if (!bg->d_indirect_args || !bg->d_radix_sort_indirect_args || (pre->n && (!bg->d_gaussians || !bg->d_indirect_indices || !bg->d_gaussians_depth)))
+        return fail(ctx, SB_ERR_INVALID_ARG, "null buffer in bind group");
+    if (reinterpret_cast<uintptr_t>(bg->d_gaussians) & 15u) return fail(ctx, SB_ERR_INVALID_ARG, "device pods must be 16-byte aligned");
+    if (bg->gaussian_transform.display_mode > 2 || bg->gaussian_transform.sh_deg > 3) return fail(ctx, SB_ERR_INVALID_ARG, "bad gaussian transform pod");
+    sb::PreParams p;
+    std::memset(&p, 0, sizeof p);
+    p.gaussians = static_cast<const uint8_t*>(bg->d_gaussians);
+    p.n = gaussian_count;
+    p.selection = bg->d_selection;
+    p.invert_selection = bg->invert_selection;
+    p.indices = bg->d_indirect_indices;
+    p.keys = bg->d_gaussians_depth;
+    p.keys_capacity = (uint32_t)std::min<uint64_t>(bg->gaussians_depth_bytes / 4, 0xffffffffull);  // arrayLength(&gaussians_depth), preprocess.wesl:119-122
+    p.draw_args = bg->d_indirect_args;
+    p.sort_args = bg->d_radix_sort_indirect_args;
+    p.recs = nullptr;  // the vertex-stage work belongs to the Renderer here
+    p.tboxes = nullptr;
+    p.visible_count = pre->visible.as<uint32_t>();
+    p.u = make_uniforms(bg->camera, bg->model_transform, bg->gaussian_transform, SB_TARGET_RGBA8_UNORM);
+    SB_CUDA(ctx, sb::launch_preprocess(pre->sh_fmt, pre->cov_fmt, p, pre->scratch.p, pre->scratch.bytes, ctx->num_sms,
+                                       static_cast<cudaStream_t>(stream)));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- standalone Renderer (Renderer<G, ()>)
+
+struct SbRenderer {
+    SbViewer* v;  // owns the record / binning buffers; pods, indices and the count are the caller's
+};
+
+SbStatus sb_renderer_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, uint64_t n, SbRenderer** out) {
+    if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    SbViewer* v = nullptr;
+    SbStatus s = viewer_new(ctx, sh_fmt, cov_fmt, target_format, n, &v);
+    if (s != SB_OK) return s;
+    if (!v->use_gather4) {  // the standalone renderer has no gathered-copy path
+        sb_viewer_destroy(v);
+        return fail(ctx, SB_ERR_INVALID_ARG, "sb_renderer needs the default (TMA gather4) raster path");
+    }
+    SbRenderer* r = new SbRenderer();
+    r->v = v;
+    *out = r;
+    return SB_OK;
+}
+
+void sb_renderer_destroy(SbRenderer* r) {
+    if (!r) return;
+    sb_viewer_destroy(r->v);
+    delete r;
+}
+
+SbStatus sb_renderer_set_strict_exp(SbRenderer* r, int32_t strict) {
+    if (!r) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    r->v->strict_exp = strict != 0;
+    return SB_OK;
+}
+
+SbStatus sb_renderer_render(SbRenderer* r, void* stream, const SbRendererBindGroup* bg, const SbTarget* target,
+                            const SbDrawIndirectArgs* d_indirect_args, const SbDepthAttachment* depth, int32_t load) {
+    if (!r || !bg || !d_indirect_args) return fail(r ? r->v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    SbViewer* v = r->v;
+    SbContext* ctx = v->ctx;
+    if (bg->gaussians_bytes != (uint64_t)v->n * v->stride) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians buffer size != n * size_of::<G>()");
+    if (bg->indirect_indices_bytes < (uint64_t)v->n * 4) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "indirect indices buffer smaller than 4 * n");
+    if (v->n && (!bg->d_gaussians || !bg->d_indirect_indices)) return fail(ctx, SB_ERR_INVALID_ARG, "null buffer in bind group");
+    if (reinterpret_cast<uintptr_t>(bg->d_gaussians) & 15u) return fail(ctx, SB_ERR_INVALID_ARG, "device pods must be 16-byte aligned");
+    if (bg->gaussian_transform.display_mode > 2 || bg->gaussian_transform.sh_deg > 3) return fail(ctx, SB_ERR_INVALID_ARG, "bad gaussian transform pod");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    v->d_gaussians = bg->d_gaussians;
+    v->camera = bg->camera;
+    v->model_transform = bg->model_transform;
+    v->gaussian_transform = bg->gaussian_transform;
+    v->ext_indices = bg->d_indirect_indices;
+    v->ext_count = &d_indirect_args->instance_count;
+    sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    SbStatus s = check_target(v, target, u);  // validate before enqueuing anything
+    if (s != SB_OK) return s;
+    // vertex stage (render.wesl:76-130) for exactly the instances the draw names
+    sb::PreParams p;
+    std::memset(&p, 0, sizeof p);
+    p.gaussians = static_cast<const uint8_t*>(bg->d_gaussians);
+    p.n = v->n;
+    p.recs = v->recs.as<sb::SplatRec>();
+    p.tboxes = v->tboxes.as<sb::TileBox>();
+    p.u = u;
+    SB_CUDA(ctx, sb::launch_vertex_stage(v->sh_fmt, v->cov_fmt, p, v->ext_indices, v->ext_count, ctx->num_sms, st));
+    return do_draw(v, v->camera, v->gaussian_transform, target, load ? 0 : 1, st, depth);
 }
 
 // ---------------------------------------------------------------- MultiModelViewer

@@ -33,6 +33,11 @@ size_t preprocess_scratch_bytes(uint32_t n, int sh_fmt, int cov_fmt);
 cudaError_t launch_preprocess(int sh_fmt, int cov_fmt, PreParams& p, void* scratch, size_t scratch_bytes,
                               int num_sms, cudaStream_t stream);
 
+// Vertex stage alone (standalone Renderer on caller-owned buffers): recs/tboxes of the first *count Gaussians named by
+// `indices`; p needs gaussians, n, recs, tboxes and u only.
+cudaError_t launch_vertex_stage(int sh_fmt, int cov_fmt, PreParams& p, const uint32_t* indices, const uint32_t* count, int num_sms,
+                                cudaStream_t stream);
+
 // ---------------------------------------------------------------- radix sort (sb_sort.cu)
 struct SortScratch {
     uint32_t* keys_alt;

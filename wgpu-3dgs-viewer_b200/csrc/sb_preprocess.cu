@@ -266,6 +266,143 @@ __device__ __forceinline__ bool finite4(float a, float b, float c, float d) {
     return isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d);
 }
 
+// ---- per-Gaussian work shared by the fused preprocess kernel and the standalone Renderer's vertex stage ----------
+// Phase 1 (preprocess.wesl:60-106): selection, projection, frustum cull (+ the border cull for centres just
+// outside).  `rec` points at the pod — in shared memory (K1) or global memory (vertex_kernel).
+struct CullOut {
+    float4 head;
+    float world[3];
+    float nx, ny, nz, cw;
+    float axes[4];
+};
+template <int SH, int COV>
+__device__ __forceinline__ bool cull_gaussian(const PreParams& p, const Uniforms& u, uint32_t g, const uint8_t* rec, float sd_size,
+                                              bool vis, CullOut& o) {
+    float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vis) head = *reinterpret_cast<const float4*>(rec);
+    // selection: preprocess.wesl:68-78
+    if (p.selection != nullptr && vis) {
+        const uint32_t word = __ldg(&p.selection[g >> 5]);
+        const bool bit = (word >> (g & 31u)) & 1u;
+        const bool inverted = p.invert_selection != 0u;
+        if (inverted == bit) vis = false;
+    }
+
+    // model_to_world + world_to_camera: preprocess.wesl:82-84 (strict)
+    float world[3], clip[4];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        world[i] = sadd(sadd(sadd(smul(u.model[i], head.x), smul(u.model[4 + i], head.y)), smul(u.model[8 + i], head.z)),
+                        u.model[12 + i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        clip[i] = sadd(sadd(sadd(smul(u.pv[i], world[0]), smul(u.pv[4 + i], world[1])), smul(u.pv[8 + i], world[2])),
+                       u.pv[12 + i]);
+    const float nx = sdiv(clip[0], clip[3]), ny = sdiv(clip[1], clip[3]), nz = sdiv(clip[2], clip[3]);
+
+    // cov2d_axes is needed by the border cull (centre outside) and by every survivor in
+    // splat/ellipse mode: evaluate it once, here, for whoever needs it.
+    const bool centre_out = cull(nx, ny, nz);
+    float axes[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vis && (centre_out || u.mode != SB_MODE_POINT)) {
+        float cov[6];
+        unpack_cov3d<SH, COV>(rec, cov);
+        cov2d_axes(u, head.x, head.y, head.z, cov, sd_size, axes);
+    }
+    if (vis && centre_out) {  // preprocess.wesl:87-99
+        const float mx = sdiv(smul(axes[0], u.std_dev), u.size[0]);
+        const float my = sdiv(smul(axes[1], u.std_dev), u.size[1]);
+        const float ndc_major_len = ssqrt(sadd(smul(mx, mx), smul(my, my)));
+        const float l = ssqrt(sadd(smul(nx, nx), smul(ny, ny)));
+        const float dirx = sdiv(-nx, l), diry = sdiv(-ny, l);
+        const float m = fminf(ndc_major_len, l);
+        const float bx = sadd(nx, smul(m, dirx)), by = sadd(ny, smul(m, diry));
+        if (cull(bx, by, nz)) vis = false;
+    }
+
+    o.head = head;
+#pragma unroll
+    for (int i = 0; i < 3; i++) o.world[i] = world[i];
+    o.nx = nx;
+    o.ny = ny;
+    o.nz = nz;
+    o.cw = clip[3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) o.axes[i] = axes[i];
+    return vis;
+}
+
+// Phase 2 (render.wesl:76-130): the vertex-stage work of a splat, written once per splat.
+template <int SH, int COV>
+__device__ __forceinline__ void emit_splat(const PreParams& p, const Uniforms& u, uint32_t g, const uint8_t* rec, const CullOut& o) {
+    const float4 head = o.head;
+    const float nx = o.nx, ny = o.ny;
+    const float* world = o.world;
+    const float* axes = o.axes;
+    {
+        SplatRec out;
+        out.cx = smul(smul(sadd(nx, 1.0f), 0.5f), u.size[0]);
+        out.cy = smul(smul(ssub(1.0f, ny), 0.5f), u.size[1]);
+        // color(): render.wesl:58-73; -normalize(v) = -(v * (1/|v|))
+        const float vdx = ssub(u.cam_pos[0], world[0]), vdy = ssub(u.cam_pos[1], world[1]), vdz = ssub(u.cam_pos[2], world[2]);
+        float md[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            md[i] = sadd(sadd(smul(u.inv_sr[i], vdx), smul(u.inv_sr[3 + i], vdy)), smul(u.inv_sr[6 + i], vdz));
+        const float inv_ml = sdiv(1.0f, ssqrt(sadd(sadd(smul(md[0], md[0]), smul(md[1], md[1])), smul(md[2], md[2]))));
+        float rgb[3];
+        const uint32_t packed = __float_as_uint(head.w);
+        view_color<SH>(u, rec, packed, -smul(md[0], inv_ml), -smul(md[1], inv_ml), -smul(md[2], inv_ml), rgb);
+        // Fixed-point colour attachments clamp the SOURCE colour to [0,1] before the blend equation
+        // (Vulkan 1.3 spec 29.1 "Blending"; the reference renders to Rgba8Unorm, src/renderer.rs:296-300):
+        // done here once per splat, which also makes the post-blend clamp redundant (d, c <= 255, alpha <= 1).
+        const float cmax = u.color_scale == 255.0f ? 255.0f : __int_as_float(0x7f800000);
+        out.r = fminf(smul(rgb[0], u.color_scale), cmax);
+        out.g = fminf(smul(rgb[1], u.color_scale), cmax);
+        out.b = fminf(smul(rgb[2], u.color_scale), cmax);
+        out.a = unorm8(packed >> 24);
+        bool valid;
+        if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
+            float vp[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                vp[i] = sadd(sadd(sadd(smul(u.vm[i], head.x), smul(u.vm[4 + i], head.y)), smul(u.vm[8 + i], head.z)),
+                             u.vm[12 + i]);
+            const float len = ssqrt(sadd(sadd(smul(vp[0], vp[0]), smul(vp[1], vp[1])), smul(vp[2], vp[2])));
+            const float half = sdiv(smul(smul(smul(0.01f, u.gsize), 0.5f), u.size[1]), len);
+            const float inv = sdiv(1.0f, half);
+            out.ax = inv; out.ay = 0.0f; out.bx = 0.0f; out.by = inv;
+            out.ex = half; out.ey = half;
+            valid = (half > 0.0f) && isfinite(inv) && isfinite(out.cx) && isfinite(out.cy);
+        } else {
+            const float mm = sadd(smul(axes[0], axes[0]), smul(axes[1], axes[1]));
+            const float nn = sadd(smul(axes[2], axes[2]), smul(axes[3], axes[3]));
+            out.ax = sdiv(smul(2.0f, axes[0]), mm);
+            out.ay = -sdiv(smul(2.0f, axes[1]), mm);
+            out.bx = sdiv(smul(2.0f, axes[2]), nn);
+            out.by = -sdiv(smul(2.0f, axes[3]), nn);
+            const float hs = smul(0.5f, u.std_dev);
+            out.ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
+            out.ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
+            valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, out.ex, out.ey);
+        }
+        TileBox tb;
+        if (valid) {
+            tile_bbox(u, out.cx, out.cy, out.ex, out.ey, tb.tmin, tb.tmax);
+        } else {
+            tb.tmin = 1u | (1u << 16);
+            tb.tmax = 0u;
+            out.ex = out.ey = 0.0f;
+        }
+        float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
+        dst[0] = make_float4(out.cx, out.cy, out.ax, out.bx);
+        dst[1] = make_float4(out.ay, out.by, out.ex, out.ey);
+        dst[2] = make_float4(out.r, out.g, out.b, out.a);
+        *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(tb.tmin, tb.tmax);
+    }
+
+}
+
 template <int SH, int COV>
 __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
     preprocess_kernel(const __grid_constant__ PreParams p) {
@@ -481,48 +618,9 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         const uint32_t g = tile * T + tid;
         const uint8_t* rec = smem + s * STAGE_BYTES + tid * STRIDE;
         bool vis = g < p.n;
-        float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vis) head = *reinterpret_cast<const float4*>(rec);
-
-        // selection: preprocess.wesl:68-78
-        if (p.selection != nullptr && vis) {
-            const uint32_t word = __ldg(&p.selection[g >> 5]);
-            const bool bit = (word >> (g & 31u)) & 1u;
-            const bool inverted = p.invert_selection != 0u;
-            if (inverted == bit) vis = false;
-        }
-
-        // model_to_world + world_to_camera: preprocess.wesl:82-84 (strict)
-        float world[3], clip[4];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            world[i] = sadd(sadd(sadd(smul(u.model[i], head.x), smul(u.model[4 + i], head.y)), smul(u.model[8 + i], head.z)),
-                            u.model[12 + i]);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            clip[i] = sadd(sadd(sadd(smul(u.pv[i], world[0]), smul(u.pv[4 + i], world[1])), smul(u.pv[8 + i], world[2])),
-                           u.pv[12 + i]);
-        const float nx = sdiv(clip[0], clip[3]), ny = sdiv(clip[1], clip[3]), nz = sdiv(clip[2], clip[3]);
-
-        // cov2d_axes is needed by the border cull (centre outside) and by every survivor in
-        // splat/ellipse mode: evaluate it once, here, for whoever needs it.
-        const bool centre_out = cull(nx, ny, nz);
-        float axes[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vis && (centre_out || u.mode != SB_MODE_POINT)) {
-            float cov[6];
-            unpack_cov3d<SH, COV>(rec, cov);
-            cov2d_axes(u, head.x, head.y, head.z, cov, sd_size, axes);
-        }
-        if (vis && centre_out) {  // preprocess.wesl:87-99
-            const float mx = sdiv(smul(axes[0], u.std_dev), u.size[0]);
-            const float my = sdiv(smul(axes[1], u.std_dev), u.size[1]);
-            const float ndc_major_len = ssqrt(sadd(smul(mx, mx), smul(my, my)));
-            const float l = ssqrt(sadd(smul(nx, nx), smul(ny, ny)));
-            const float dirx = sdiv(-nx, l), diry = sdiv(-ny, l);
-            const float m = fminf(ndc_major_len, l);
-            const float bx = sadd(nx, smul(m, dirx)), by = sadd(ny, smul(m, diry));
-            if (cull(bx, by, nz)) vis = false;
-        }
+        CullOut co;
+        vis = cull_gaussian<SH, COV>(p, u, g, rec, sd_size, vis, co);
+        const float nz = co.nz;
 
         // ---- order-preserving compaction, phase 1: publish this warp's count (non-blocking)
         const uint32_t bal = __ballot_sync(0xffffffffu, vis);
@@ -536,67 +634,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         d2 = d1;
 
         // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
-        if (vis) {
-            SplatRec out;
-            out.cx = smul(smul(sadd(nx, 1.0f), 0.5f), u.size[0]);
-            out.cy = smul(smul(ssub(1.0f, ny), 0.5f), u.size[1]);
-            // color(): render.wesl:58-73; -normalize(v) = -(v * (1/|v|))
-            const float vdx = ssub(u.cam_pos[0], world[0]), vdy = ssub(u.cam_pos[1], world[1]), vdz = ssub(u.cam_pos[2], world[2]);
-            float md[3];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-                md[i] = sadd(sadd(smul(u.inv_sr[i], vdx), smul(u.inv_sr[3 + i], vdy)), smul(u.inv_sr[6 + i], vdz));
-            const float inv_ml = sdiv(1.0f, ssqrt(sadd(sadd(smul(md[0], md[0]), smul(md[1], md[1])), smul(md[2], md[2]))));
-            float rgb[3];
-            const uint32_t packed = __float_as_uint(head.w);
-            view_color<SH>(u, rec, packed, -smul(md[0], inv_ml), -smul(md[1], inv_ml), -smul(md[2], inv_ml), rgb);
-            // Fixed-point colour attachments clamp the SOURCE colour to [0,1] before the blend equation
-            // (Vulkan 1.3 spec 29.1 "Blending"; the reference renders to Rgba8Unorm, src/renderer.rs:296-300):
-            // done here once per splat, which also makes the post-blend clamp redundant (d, c <= 255, alpha <= 1).
-            const float cmax = u.color_scale == 255.0f ? 255.0f : __int_as_float(0x7f800000);
-            out.r = fminf(smul(rgb[0], u.color_scale), cmax);
-            out.g = fminf(smul(rgb[1], u.color_scale), cmax);
-            out.b = fminf(smul(rgb[2], u.color_scale), cmax);
-            out.a = unorm8(packed >> 24);
-            bool valid;
-            if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
-                float vp[3];
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-                    vp[i] = sadd(sadd(sadd(smul(u.vm[i], head.x), smul(u.vm[4 + i], head.y)), smul(u.vm[8 + i], head.z)),
-                                 u.vm[12 + i]);
-                const float len = ssqrt(sadd(sadd(smul(vp[0], vp[0]), smul(vp[1], vp[1])), smul(vp[2], vp[2])));
-                const float half = sdiv(smul(smul(smul(0.01f, u.gsize), 0.5f), u.size[1]), len);
-                const float inv = sdiv(1.0f, half);
-                out.ax = inv; out.ay = 0.0f; out.bx = 0.0f; out.by = inv;
-                out.ex = half; out.ey = half;
-                valid = (half > 0.0f) && isfinite(inv) && isfinite(out.cx) && isfinite(out.cy);
-            } else {
-                const float mm = sadd(smul(axes[0], axes[0]), smul(axes[1], axes[1]));
-                const float nn = sadd(smul(axes[2], axes[2]), smul(axes[3], axes[3]));
-                out.ax = sdiv(smul(2.0f, axes[0]), mm);
-                out.ay = -sdiv(smul(2.0f, axes[1]), mm);
-                out.bx = sdiv(smul(2.0f, axes[2]), nn);
-                out.by = -sdiv(smul(2.0f, axes[3]), nn);
-                const float hs = smul(0.5f, u.std_dev);
-                out.ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
-                out.ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
-                valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, out.ex, out.ey);
-            }
-            TileBox tb;
-            if (valid) {
-                tile_bbox(u, out.cx, out.cy, out.ex, out.ey, tb.tmin, tb.tmax);
-            } else {
-                tb.tmin = 1u | (1u << 16);
-                tb.tmax = 0u;
-                out.ex = out.ey = 0.0f;
-            }
-            float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
-            dst[0] = make_float4(out.cx, out.cy, out.ax, out.bx);
-            dst[1] = make_float4(out.ay, out.by, out.ex, out.ey);
-            dst[2] = make_float4(out.r, out.g, out.b, out.a);
-            *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(tb.tmin, tb.tmax);
-        }
+        if (vis && p.recs != nullptr) emit_splat<SH, COV>(p, u, g, rec, co);  // a standalone Preprocessor has no record buffer
 
         // the pods of this chunk are no longer needed: let the producer refill the slot
         __syncwarp();
@@ -613,6 +651,32 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
     flush(d3);
     flush(d2);
     flush(d1);
+}
+
+// ================================================================ vertex stage of a standalone Renderer
+// Renderer::render(encoder, view, indirect_args) on caller-owned buffers (src/renderer.rs:163-195): the splat records
+// K1 normally produces are computed here for the `*count` Gaussians the indirect indices name, whatever produced them.
+// A quad whose w <= 0 or whose (flat) depth lies outside [0,1] is clipped as a whole, as the fixed-function rasterizer
+// clips it (render.wesl:123: clip_pos.zw = proj_pos.zw for all four vertices); x/y are not culled.
+template <int SH, int COV>
+__global__ void __launch_bounds__(256) vertex_kernel(const __grid_constant__ PreParams p, const uint32_t* __restrict__ indices,
+                                                     const uint32_t* __restrict__ count) {
+    constexpr int STRIDE = pod_stride(SH, COV);
+    const Uniforms& u = p.u;
+    const float sd_size = smul(u.std_dev, u.gsize);
+    const uint32_t v = min(*count, p.n);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < v; i += gridDim.x * blockDim.x) {
+        const uint32_t g = indices[i];
+        if (g >= p.n) continue;
+        const uint8_t* rec = p.gaussians + (size_t)g * STRIDE;
+        CullOut co;
+        cull_gaussian<SH, COV>(p, u, g, rec, sd_size, true, co);
+        if (co.cw > 0.0f && co.nz >= 0.0f && co.nz <= 1.0f) {
+            emit_splat<SH, COV>(p, u, g, rec, co);
+        } else {
+            *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(1u | (1u << 16), 0u);  // no tiles
+        }
+    }
 }
 
 template <int SH, int COV>
@@ -633,7 +697,35 @@ cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+template <int SH, int COV>
+cudaError_t launch_vertex_one(const PreParams& p, const uint32_t* indices, const uint32_t* count, int num_sms, cudaStream_t stream) {
+    vertex_kernel<SH, COV><<<num_sms * 8, 256, 0, stream>>>(p, indices, count);
+    return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t launch_vertex_stage(int sh_fmt, int cov_fmt, PreParams& p, const uint32_t* indices, const uint32_t* count, int num_sms,
+                                cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    p.selection = nullptr;  // the selection mask belongs to the Preprocessor
+#define SB_CASE(SHV, COVV) \
+    if (sh_fmt == SHV && cov_fmt == COVV) return launch_vertex_one<SHV, COVV>(p, indices, count, num_sms, stream);
+    SB_CASE(SB_SH_SINGLE, SB_COV_SINGLE)
+    SB_CASE(SB_SH_SINGLE, SB_COV_HALF)
+    SB_CASE(SB_SH_SINGLE, SB_COV_ROT_SCALE)
+    SB_CASE(SB_SH_HALF, SB_COV_SINGLE)
+    SB_CASE(SB_SH_HALF, SB_COV_HALF)
+    SB_CASE(SB_SH_HALF, SB_COV_ROT_SCALE)
+    SB_CASE(SB_SH_NORM8, SB_COV_SINGLE)
+    SB_CASE(SB_SH_NORM8, SB_COV_HALF)
+    SB_CASE(SB_SH_NORM8, SB_COV_ROT_SCALE)
+    SB_CASE(SB_SH_NONE, SB_COV_SINGLE)
+    SB_CASE(SB_SH_NONE, SB_COV_HALF)
+    SB_CASE(SB_SH_NONE, SB_COV_ROT_SCALE)
+#undef SB_CASE
+    return cudaErrorInvalidValue;
+}
 
 int preprocess_records_per_tile(int sh_fmt, int cov_fmt) { return tile_records(pod_stride(sh_fmt, cov_fmt)); }
 

@@ -13,6 +13,6 @@ from .api import (  # noqa: F401
     build, camera_pod, gaussian_transform_pod, lib_path, load, model_transform_pod, pack_gaussians,
     pod_stride, read_ply, padded_key_count, keys_buffer_size_bytes, EXPORTED_SYMBOLS, DepthAttachment,
     COMPARE_NEVER, COMPARE_LESS, COMPARE_EQUAL, COMPARE_LESS_EQUAL, COMPARE_GREATER, COMPARE_NOT_EQUAL, COMPARE_GREATER_EQUAL,
-    COMPARE_ALWAYS,
+    COMPARE_ALWAYS, Preprocessor, Renderer, PreprocessorBindGroup, RendererBindGroup, DrawIndirectArgs, DispatchIndirectArgs,
 )
 from . import scenes, sharding  # noqa: F401

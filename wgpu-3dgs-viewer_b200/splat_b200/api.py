@@ -38,7 +38,9 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times", "sb_viewer_set_raster_counting",
     "sb_viewer_read_raster_counters",
     "sb_viewer_read_raster_warp_counters",
-    "sb_viewer_reserve_duplicates", "sb_sorter_create", "sb_sorter_destroy", "sb_sorter_sort", "sb_mm_create",
+    "sb_viewer_reserve_duplicates", "sb_sorter_create", "sb_sorter_destroy", "sb_sorter_sort",
+    "sb_preprocessor_create", "sb_preprocessor_destroy", "sb_preprocessor_preprocess",
+    "sb_renderer_create", "sb_renderer_destroy", "sb_renderer_render", "sb_renderer_set_strict_exp", "sb_mm_create",
     "sb_mm_destroy", "sb_mm_insert_model", "sb_mm_remove_model", "sb_mm_update_camera_with_pod",
     "sb_mm_update_model_transform_with_pod", "sb_mm_update_gaussian_transform_with_pod", "sb_mm_set_selection",
     "sb_mm_render", "sb_mm_read_model_indices",
@@ -72,6 +74,20 @@ class Target(C.Structure):
 
 class DepthAttachment(C.Structure):
     _fields_ = [("d_depth", C.c_void_p), ("pitch_bytes", C.c_uint32), ("compare", C.c_int32), ("write_enabled", C.c_int32)]
+
+
+class PreprocessorBindGroup(C.Structure):
+    _fields_ = [("camera", CameraPod), ("model_transform", ModelTransformPod), ("gaussian_transform", GaussianTransformPod),
+                ("d_gaussians", C.c_void_p), ("gaussians_bytes", C.c_uint64), ("d_indirect_args", C.c_void_p),
+                ("d_radix_sort_indirect_args", C.c_void_p), ("d_indirect_indices", C.c_void_p), ("indirect_indices_bytes", C.c_uint64),
+                ("d_gaussians_depth", C.c_void_p), ("gaussians_depth_bytes", C.c_uint64), ("d_selection", C.c_void_p),
+                ("invert_selection", C.c_uint32)]
+
+
+class RendererBindGroup(C.Structure):
+    _fields_ = [("camera", CameraPod), ("model_transform", ModelTransformPod), ("gaussian_transform", GaussianTransformPod),
+                ("d_gaussians", C.c_void_p), ("gaussians_bytes", C.c_uint64), ("d_indirect_indices", C.c_void_p),
+                ("indirect_indices_bytes", C.c_uint64)]
 
 
 assert C.sizeof(CameraPod) == 144 and C.sizeof(ModelTransformPod) == 48 and C.sizeof(GaussianTransformPod) == 8
@@ -176,6 +192,13 @@ def load() -> C.CDLL:
     sig("sb_sorter_create", i32, vp, u32, P(vp))
     sig("sb_sorter_destroy", None, vp)
     sig("sb_sorter_sort", i32, vp, vp, vp, vp, vp, u32, i32, i32)
+    sig("sb_preprocessor_create", i32, vp, i32, i32, u64, P(vp))
+    sig("sb_preprocessor_destroy", None, vp)
+    sig("sb_preprocessor_preprocess", i32, vp, vp, P(PreprocessorBindGroup), u32)
+    sig("sb_renderer_create", i32, vp, i32, i32, i32, u64, P(vp))
+    sig("sb_renderer_destroy", None, vp)
+    sig("sb_renderer_render", i32, vp, vp, P(RendererBindGroup), P(Target), vp, P(DepthAttachment), i32)
+    sig("sb_renderer_set_strict_exp", i32, vp, i32)
     sig("sb_mm_create", i32, vp, i32, i32, i32, P(vp))
     sig("sb_mm_destroy", None, vp)
     sig("sb_mm_insert_model", i32, vp, u64, vp, u64, P(i32))
@@ -495,6 +518,82 @@ class RadixSorter:
     def close(self):
         if self._h:
             load().sb_sorter_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def _nbytes(t) -> int:
+    return t.numel() * t.element_size()
+
+
+class Preprocessor:
+    """`Preprocessor<G, ()>` (reference src/preprocessor.rs:370-450): the stage alone, on the caller's device buffers
+    (torch tensors here)."""
+
+    def __init__(self, ctx: Context, n: int, sh_fmt=SH_SINGLE, cov_fmt=COV_SINGLE):
+        self.ctx, self.n = ctx, n
+        self._h = C.c_void_p()
+        _check(load().sb_preprocessor_create(ctx._h, sh_fmt, cov_fmt, n, C.byref(self._h)), ctx._h)
+
+    @staticmethod
+    def create_bind_group(camera, model_transform, gaussian_transform, gaussians, indirect_args, radix_sort_indirect_args,
+                          indirect_indices, gaussians_depth, selection=None, invert_selection=1) -> PreprocessorBindGroup:
+        bg = PreprocessorBindGroup()
+        bg.camera, bg.model_transform, bg.gaussian_transform = camera, model_transform, gaussian_transform
+        bg.d_gaussians, bg.gaussians_bytes = gaussians.data_ptr(), _nbytes(gaussians)
+        bg.d_indirect_args = indirect_args.data_ptr()
+        bg.d_radix_sort_indirect_args = radix_sort_indirect_args.data_ptr()
+        bg.d_indirect_indices, bg.indirect_indices_bytes = indirect_indices.data_ptr(), _nbytes(indirect_indices)
+        bg.d_gaussians_depth, bg.gaussians_depth_bytes = gaussians_depth.data_ptr(), _nbytes(gaussians_depth)
+        bg.d_selection = selection.data_ptr() if selection is not None else None
+        bg.invert_selection = int(invert_selection)
+        bg._keepalive = (gaussians, indirect_args, radix_sort_indirect_args, indirect_indices, gaussians_depth, selection)
+        return bg
+
+    def preprocess(self, bind_group: PreprocessorBindGroup, gaussian_count: int | None = None, stream=None):
+        _check(load().sb_preprocessor_preprocess(self._h, _stream_handle(stream), C.byref(bind_group),
+                                                 self.n if gaussian_count is None else gaussian_count), self.ctx._h)
+
+    def close(self):
+        if self._h:
+            load().sb_preprocessor_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Renderer:
+    """`Renderer<G, ()>` (reference src/renderer.rs:242-356): one indirect instanced draw of the caller's indices."""
+
+    def __init__(self, ctx: Context, n: int, sh_fmt=SH_SINGLE, cov_fmt=COV_SINGLE, target_format=TARGET_RGBA8):
+        self.ctx, self.n, self.target_format = ctx, n, target_format
+        self._h = C.c_void_p()
+        _check(load().sb_renderer_create(ctx._h, sh_fmt, cov_fmt, target_format, n, C.byref(self._h)), ctx._h)
+
+    @staticmethod
+    def create_bind_group(camera, model_transform, gaussian_transform, gaussians, indirect_indices) -> RendererBindGroup:
+        bg = RendererBindGroup()
+        bg.camera, bg.model_transform, bg.gaussian_transform = camera, model_transform, gaussian_transform
+        bg.d_gaussians, bg.gaussians_bytes = gaussians.data_ptr(), _nbytes(gaussians)
+        bg.d_indirect_indices, bg.indirect_indices_bytes = indirect_indices.data_ptr(), _nbytes(indirect_indices)
+        bg._keepalive = (gaussians, indirect_indices)
+        return bg
+
+    def set_strict_exp(self, strict: bool):
+        _check(load().sb_renderer_set_strict_exp(self._h, int(strict)), self.ctx._h)
+
+    def render(self, target, width, height, bind_group: RendererBindGroup, indirect_args, depth=None, compare=COMPARE_ALWAYS,
+               depth_write=False, load_target=False, stream=None):
+        """render (load_target False: clear to BLACK) / render_with_pass (load_target True) with `indirect_args` a device
+        tensor holding DrawIndirectArgs."""
+        t = make_target(target, width, height, self.target_format)
+        d = None
+        if depth is not None:
+            d = DepthAttachment()
+            d.d_depth, d.pitch_bytes, d.compare, d.write_enabled = depth.data_ptr(), width * 4, compare, int(depth_write)
+        _check(load().sb_renderer_render(self._h, _stream_handle(stream), C.byref(bind_group), C.byref(t), indirect_args.data_ptr(),
+                                         C.byref(d) if d is not None else None, int(load_target)), self.ctx._h)
+
+    def close(self):
+        if self._h:
+            load().sb_renderer_destroy(self._h)
             self._h = C.c_void_p()
 
 
