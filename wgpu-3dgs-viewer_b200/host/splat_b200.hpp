@@ -120,4 +120,41 @@ private:
     SbMultiModelViewer* h_ = nullptr;
 };
 
+// Preprocessor<G, ()> / RadixSorter<()> / Renderer<G, ()> on caller-owned device buffers
+// (reference src/preprocessor.rs:370-450, src/radix_sorter.rs:71-96, src/renderer.rs:242-356)
+class Preprocessor {
+public:
+    Preprocessor(Context& ctx, uint64_t n, int32_t sh_fmt = SB_SH_SINGLE, int32_t cov_fmt = SB_COV_SINGLE) : ctx_(ctx) { check(sb_preprocessor_create(ctx.raw(), sh_fmt, cov_fmt, n, &h_), ctx.raw()); }
+    ~Preprocessor() { sb_preprocessor_destroy(h_); }
+    void preprocess(void* stream, const SbPreprocessorBindGroup& bg, uint32_t gaussian_count) { check(sb_preprocessor_preprocess(h_, stream, &bg, gaussian_count), ctx_.raw()); }
+private:
+    Context& ctx_;
+    SbPreprocessor* h_ = nullptr;
+};
+
+class RadixSorter {
+public:
+    RadixSorter(Context& ctx, uint32_t capacity) : ctx_(ctx), cap_(capacity) { check(sb_sorter_create(ctx.raw(), capacity, &h_), ctx.raw()); }
+    ~RadixSorter() { sb_sorter_destroy(h_); }
+    // sort(encoder, bind_groups, args): the count is IndirectArgsBuffer.instance_count, read on the device
+    void sort(void* stream, float* d_depth_keys, uint32_t* d_indices, const SbDrawIndirectArgs* d_indirect_args) {
+        check(sb_sorter_sort(h_, stream, reinterpret_cast<uint32_t*>(d_depth_keys), d_indices, &d_indirect_args->instance_count, cap_, 0, 32), ctx_.raw());
+    }
+private:
+    Context& ctx_;
+    uint32_t cap_;
+    SbRadixSorter* h_ = nullptr;
+};
+
+class Renderer {
+public:
+    Renderer(Context& ctx, int32_t texture_format, uint64_t n, int32_t sh_fmt = SB_SH_SINGLE, int32_t cov_fmt = SB_COV_SINGLE) : ctx_(ctx) { check(sb_renderer_create(ctx.raw(), sh_fmt, cov_fmt, texture_format, n, &h_), ctx.raw()); }
+    ~Renderer() { sb_renderer_destroy(h_); }
+    void render(void* stream, const SbTarget& t, const SbRendererBindGroup& bg, const SbDrawIndirectArgs* d_indirect_args) { check(sb_renderer_render(h_, stream, &bg, &t, d_indirect_args, nullptr, 0), ctx_.raw()); }
+    void render_with_pass(void* stream, const SbTarget& t, const SbDepthAttachment* depth, const SbRendererBindGroup& bg, const SbDrawIndirectArgs* d_indirect_args) { check(sb_renderer_render(h_, stream, &bg, &t, d_indirect_args, depth, 1), ctx_.raw()); }
+private:
+    Context& ctx_;
+    SbRenderer* h_ = nullptr;
+};
+
 }  // namespace splat_b200

@@ -16,6 +16,9 @@ pub mod ffi {
     #[repr(C)] pub struct SbContext { _p: [u8; 0] }
     #[repr(C)] pub struct SbViewer { _p: [u8; 0] }
     #[repr(C)] pub struct SbMultiModelViewer { _p: [u8; 0] }
+    #[repr(C)] pub struct SbPreprocessor { _p: [u8; 0] }
+    #[repr(C)] pub struct SbRadixSorter { _p: [u8; 0] }
+    #[repr(C)] pub struct SbRenderer { _p: [u8; 0] }
 
     /// `CameraPod` — byte-identical to the reference (src/buffer/camera.rs:63-80).
     #[repr(C)] #[derive(Clone, Copy, Debug, PartialEq, bytemuck::Pod, bytemuck::Zeroable)]
@@ -38,8 +41,35 @@ pub mod ffi {
     #[repr(C)] #[derive(Clone, Copy, Debug)]
     pub struct DepthAttachment { pub d_depth: *mut c_void, pub pitch_bytes: u32, pub compare: i32, pub write_enabled: i32 }
 
+    /// The `Preprocessor` bind group (reference src/preprocessor.rs:104-221): bindings 0-9 on caller-owned device buffers.
+    #[repr(C)] #[derive(Clone, Copy)]
+    pub struct PreprocessorBindGroup {
+        pub camera: CameraPod, pub model_transform: ModelTransformPod, pub gaussian_transform: GaussianTransformPod,
+        pub d_gaussians: *const c_void, pub gaussians_bytes: u64,
+        pub d_indirect_args: *mut DrawIndirectArgs, pub d_radix_sort_indirect_args: *mut DispatchIndirectArgs,
+        pub d_indirect_indices: *mut u32, pub indirect_indices_bytes: u64,
+        pub d_gaussians_depth: *mut f32, pub gaussians_depth_bytes: u64,
+        pub d_selection: *const u32, pub invert_selection: u32,
+    }
+    /// The `Renderer` bind group (reference src/renderer.rs:56-116): bindings 0-4.
+    #[repr(C)] #[derive(Clone, Copy)]
+    pub struct RendererBindGroup {
+        pub camera: CameraPod, pub model_transform: ModelTransformPod, pub gaussian_transform: GaussianTransformPod,
+        pub d_gaussians: *const c_void, pub gaussians_bytes: u64,
+        pub d_indirect_indices: *const u32, pub indirect_indices_bytes: u64,
+    }
+
     #[link(name = "splat_b200")]
     extern "C" {
+        pub fn sb_preprocessor_create(ctx: *mut SbContext, sh: i32, cov: i32, n: u64, out: *mut *mut SbPreprocessor) -> i32;
+        pub fn sb_preprocessor_destroy(p: *mut SbPreprocessor);
+        pub fn sb_preprocessor_preprocess(p: *mut SbPreprocessor, stream: *mut c_void, bind_group: *const PreprocessorBindGroup, gaussian_count: u32) -> i32;
+        pub fn sb_sorter_create(ctx: *mut SbContext, capacity: u32, out: *mut *mut SbRadixSorter) -> i32;
+        pub fn sb_sorter_destroy(s: *mut SbRadixSorter);
+        pub fn sb_sorter_sort(s: *mut SbRadixSorter, stream: *mut c_void, d_keys: *mut u32, d_payload: *mut u32, d_count: *const u32, max_count: u32, begin_bit: i32, end_bit: i32) -> i32;
+        pub fn sb_renderer_create(ctx: *mut SbContext, sh: i32, cov: i32, target_format: i32, n: u64, out: *mut *mut SbRenderer) -> i32;
+        pub fn sb_renderer_destroy(r: *mut SbRenderer);
+        pub fn sb_renderer_render(r: *mut SbRenderer, stream: *mut c_void, bind_group: *const RendererBindGroup, target: *const Target, d_indirect_args: *const DrawIndirectArgs, depth: *const DepthAttachment, load: i32) -> i32;
         pub fn sb_last_error_string(ctx: *const SbContext) -> *const c_char;
         pub fn sb_pod_stride(sh_fmt: i32, cov_fmt: i32) -> u32;
         pub fn sb_pack_gaussians(src: *const Gaussian, n: u64, sh_fmt: i32, cov_fmt: i32, out: *mut c_void) -> i32;
@@ -179,3 +209,32 @@ impl<'c, G: GaussianPod> MultiModelViewer<'c, G> {
     pub fn render(&self, stream: Stream, target: &Target, keys: &[u64]) -> Result<(), Error> { check(unsafe { ffi::sb_mm_render(self.raw, stream.0, target, keys.as_ptr(), keys.len() as u32) }, self.ctx.0) }
 }
 impl<G: GaussianPod> Drop for MultiModelViewer<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_mm_destroy(self.raw) } } }
+
+/// `Preprocessor<G, ()>` (src/preprocessor.rs:370-450): `new_without_bind_group` + `preprocess(encoder, bind_group, n)`.
+pub struct Preprocessor<'c, G: GaussianPod = DefaultGaussianPod> { raw: *mut ffi::SbPreprocessor, ctx: &'c Context, _g: PhantomData<G> }
+impl<'c, G: GaussianPod> Preprocessor<'c, G> {
+    pub fn new_without_bind_group(ctx: &'c Context, gaussian_capacity: u64) -> Result<Self, Error> { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::sb_preprocessor_create(ctx.0, G::SH, G::COV, gaussian_capacity, &mut raw) }, ctx.0)?; Ok(Self { raw, ctx, _g: PhantomData }) }
+    pub fn preprocess(&self, stream: Stream, bind_group: &ffi::PreprocessorBindGroup, gaussian_count: u32) -> Result<(), Error> { check(unsafe { ffi::sb_preprocessor_preprocess(self.raw, stream.0, bind_group, gaussian_count) }, self.ctx.0) }
+}
+impl<G: GaussianPod> Drop for Preprocessor<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_preprocessor_destroy(self.raw) } } }
+
+/// `RadixSorter<()>` (src/radix_sorter.rs:71-96): stable ascending sort of (depth key, index); the count is read on the
+/// device from `IndirectArgsBuffer.instance_count`.
+pub struct RadixSorter<'c> { raw: *mut ffi::SbRadixSorter, ctx: &'c Context }
+impl<'c> RadixSorter<'c> {
+    pub fn new_without_bind_groups(ctx: &'c Context, capacity: u32) -> Result<Self, Error> { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::sb_sorter_create(ctx.0, capacity, &mut raw) }, ctx.0)?; Ok(Self { raw, ctx }) }
+    pub fn sort(&self, stream: Stream, d_depth_keys: *mut f32, d_indices: *mut u32, d_indirect_args: *const ffi::DrawIndirectArgs, capacity: u32) -> Result<(), Error> {
+        let d_count = unsafe { std::ptr::addr_of!((*d_indirect_args).instance_count) };
+        check(unsafe { ffi::sb_sorter_sort(self.raw, stream.0, d_depth_keys.cast(), d_indices, d_count, capacity, 0, 32) }, self.ctx.0)
+    }
+}
+impl Drop for RadixSorter<'_> { fn drop(&mut self) { unsafe { ffi::sb_sorter_destroy(self.raw) } } }
+
+/// `Renderer<G, ()>` (src/renderer.rs:242-356): `render` clears to BLACK, `render_with_pass` composites over the target.
+pub struct Renderer<'c, G: GaussianPod = DefaultGaussianPod> { raw: *mut ffi::SbRenderer, ctx: &'c Context, _g: PhantomData<G> }
+impl<'c, G: GaussianPod> Renderer<'c, G> {
+    pub fn new_without_bind_group(ctx: &'c Context, texture_format: i32, gaussian_capacity: u64) -> Result<Self, Error> { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::sb_renderer_create(ctx.0, G::SH, G::COV, texture_format, gaussian_capacity, &mut raw) }, ctx.0)?; Ok(Self { raw, ctx, _g: PhantomData }) }
+    pub fn render(&self, stream: Stream, target: &Target, bind_group: &ffi::RendererBindGroup, d_indirect_args: *const ffi::DrawIndirectArgs) -> Result<(), Error> { check(unsafe { ffi::sb_renderer_render(self.raw, stream.0, bind_group, target, d_indirect_args, std::ptr::null(), 0) }, self.ctx.0) }
+    pub fn render_with_pass(&self, stream: Stream, target: &Target, depth: Option<&ffi::DepthAttachment>, bind_group: &ffi::RendererBindGroup, d_indirect_args: *const ffi::DrawIndirectArgs) -> Result<(), Error> { check(unsafe { ffi::sb_renderer_render(self.raw, stream.0, bind_group, target, d_indirect_args, depth.map_or(std::ptr::null(), |d| d as *const _), 1) }, self.ctx.0) }
+}
+impl<G: GaussianPod> Drop for Renderer<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_renderer_destroy(self.raw) } } }
