@@ -259,6 +259,11 @@ SB_API SbStatus sb_viewer_raster_path(SbViewer* v, int32_t* tma_gather4);
 /* testing knob: 1 = bit-reproducible polynomial exp in the fragment stage (matches the
  * oracle's strict_exp); 0 (default) = MUFU ex2 fast path */
 SB_API SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict);
+/* Exact alpha cut-off (default on): in splat mode on a unorm8 target a blend with alpha < 0.5/255 returns the destination
+ * unchanged after re-quantisation, so each splat is shrunk to the radius beyond which alpha = a*exp(-r^2) stays below that:
+ * fewer (splat, tile) duplicates and fragments, bit-identical frames.  Never applied to float targets, ellipse/point modes
+ * or depth-tested passes.  0 switches it off (the instrumented fragment counts then equal the reference's). */
+SB_API SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled);
 /* Tracing (the reference has none: every pass has timestamp_writes: None, src/radix_sorter.rs:504-507).
  * When enabled, cudaEvents are recorded on the launching stream between the stages of a frame;
  * ms[0..5] = preprocess, depth sort, tile count+emit, tile sort, gather, raster. */

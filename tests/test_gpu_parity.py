@@ -564,6 +564,7 @@ def test_raster_counters_and_stage_timing(sb, ob, ctx):
     v.update_camera(pos, yaw, pitch, w, h)
     v.set_stage_timing(True)
     v.set_raster_counting(True)
+    v.set_exact_cutoff(False)  # count every fragment the reference's fragment stage blends, identity blends included
     t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
     v.render(t, w, h)
     times = v.read_stage_times()
@@ -580,6 +581,54 @@ def test_raster_counters_and_stage_timing(sb, ob, ctx):
     torch.cuda.synchronize()
     assert torch.equal(t, t2)
     v.close()
+
+
+@pytest.mark.parametrize("camera", ["outside", "inside"])
+@pytest.mark.parametrize("strict", [True, False])
+def test_exact_alpha_cutoff_is_bit_identical(sb, ob, ctx, camera, strict):
+    """The alpha cut-off (splat mode, unorm8) only drops blends that are the identity after re-quantisation: frames with
+    and without it are equal bit for bit — with the strict and with the fast exp — while duplicates and evaluated
+    fragments shrink; opacities around the threshold (bytes 0..3) and opaque splats are all present."""
+    torch = _torch()
+    n, w, h = 40000, 800, 450
+    g = sb.scenes.synthetic_gaussians(n, 67)
+    g["color"][: n // 8, 3] = np.arange(n // 8) % 6          # alpha bytes 0..5: at and around the cut
+    g["color"][n // 8: n // 4, 3] = 255
+    pods = sb.pack_gaussians(g)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE if camera == "outside" else sb.scenes.CAMERA_INSIDE
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.set_strict_exp(strict)
+    v.set_raster_counting(True)
+    frames, stats, counters = [], [], []
+    for cut in (True, False):
+        v.set_exact_cutoff(cut)
+        t = torch.full((h, w, 4), 3, dtype=torch.uint8, device="cuda")
+        v.render(t, w, h)
+        torch.cuda.synchronize()
+        frames.append(t)
+        stats.append(v.read_frame_stats())
+        counters.append(v.read_raster_counters())
+    assert torch.equal(frames[0], frames[1])
+    assert stats[0]["visible"] == stats[1]["visible"]            # the visible set / sort are untouched
+    assert stats[0]["duplicates"] < stats[1]["duplicates"]
+    assert counters[0]["evaluated"] < counters[1]["evaluated"] and counters[0]["alive"] <= counters[1]["alive"]
+    if strict:
+        oimg, ost = ob.render(ob.OracleModel(pods, n), ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(), strict_exp=True)
+        assert np.array_equal(frames[0].cpu().numpy(), oimg)
+        assert counters[1]["alive"] == ost["alive_pixels"]
+    # float targets never cut: the flag changes nothing there
+    vf = sb.Viewer(ctx, pods, n, target_format=sb.TARGET_RGBA32F)
+    vf.update_camera(pos, yaw, pitch, w, h)
+    dups = []
+    for cut in (True, False):
+        vf.set_exact_cutoff(cut)
+        tf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        vf.render(tf, w, h)
+        torch.cuda.synchronize()
+        dups.append(vf.read_frame_stats()["duplicates"])
+    assert dups[0] == dups[1] == stats[1]["duplicates"]
+    v.close(); vf.close()
 
 
 def test_bulk_raster_path_parity(sb, ob):
@@ -636,6 +685,7 @@ for cam in (sb.scenes.CAMERA_INSIDE, sb.scenes.CAMERA_OUTSIDE):
     v = sb.Viewer(ctx, pods, n)
     v.set_strict_exp(True)
     v.set_raster_counting(True)
+    v.set_exact_cutoff(False)
     pos, yaw, pitch = cam
     v.update_camera(pos, yaw, pitch, w, h)
     t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")

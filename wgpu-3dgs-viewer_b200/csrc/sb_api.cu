@@ -52,7 +52,8 @@ void mat4_mul(const float* a, const float* b, float* r) {  // column-major
             r[j * 4 + i] = ((a[i] * b[j * 4] + a[4 + i] * b[j * 4 + 1]) + a[8 + i] * b[j * 4 + 2]) + a[12 + i] * b[j * 4 + 3];
 }
 
-sb::Uniforms make_uniforms(const SbCameraPod& cam, const SbModelTransformPod& mt, const SbGaussianTransformPod& gt, int target_format) {
+sb::Uniforms make_uniforms(const SbCameraPod& cam, const SbModelTransformPod& mt, const SbGaussianTransformPod& gt, int target_format,
+                           bool alpha_cut = false) {
     sb::Uniforms u;
     std::memset(&u, 0, sizeof u);
     // Mat3::from_quat
@@ -87,6 +88,8 @@ sb::Uniforms make_uniforms(const SbCameraPod& cam, const SbModelTransformPod& mt
     u.std_dev = (float)gt.max_std_dev / 255.0f * 3.0f;
     u.gsize = gt.size;
     u.color_scale = is_unorm(target_format) ? 255.0f : 1.0f;
+    // exact alpha cut-off: only where a blend below the threshold is provably the identity (sb_common.cuh)
+    u.cut_k = (alpha_cut && is_unorm(target_format) && gt.display_mode == SB_MODE_SPLAT) ? 1.0f / sb::kAlphaCut : 0.0f;
     u.mode = gt.display_mode;
     u.sh_deg = gt.sh_deg;
     u.no_sh0 = gt.no_sh0;
@@ -168,6 +171,8 @@ struct SbViewer {
     bool selection_enabled = false;
     uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
     int strict_exp = 0;
+    bool exact_cutoff = true;    // shrink splats to the radius beyond which a unorm8 blend is exactly the identity
+    bool recs_cut = false;       // recs/tboxes currently hold cut extents (a depth-tested pass needs the full ones)
     CUtensorMap recs_map;        // 2-D view of recs[] (12 x n floats, 48-byte rows) for TMA gather4
     bool use_gather4 = false;
     // view-batch pipelining (sb_viewer_render_batch): a twin set of frame buffers over the same pods,
@@ -307,7 +312,8 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.recs = v->recs.as<sb::SplatRec>();
     p.tboxes = v->tboxes.as<sb::TileBox>();
     p.visible_count = v->d_visible();
-    p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
+    p.u = make_uniforms(cam, v->model_transform, gt, v->target_format, v->exact_cutoff);
+    v->recs_cut = p.u.cut_k > 0.0f;
     if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[0], stream));
     SB_CUDA(v->ctx, sb::launch_preprocess(v->sh_fmt, v->cov_fmt, p, v->pre_scratch.p, v->pre_scratch.bytes, v->ctx->num_sms, stream));
     if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[1], stream));
@@ -393,6 +399,19 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
         p.depth_write = depth->write_enabled != 0;
         p.pods = static_cast<const uint8_t*>(v->d_gaussians);
         p.pod_stride = v->stride;
+        if (v->recs_cut) {
+            // a fragment the cut-off would drop still takes part in the depth test and may write depth: redo the vertex
+            // stage of the visible splats with their full extents
+            sb::PreParams vp;
+            std::memset(&vp, 0, sizeof vp);
+            vp.gaussians = p.pods;
+            vp.n = v->n;
+            vp.recs = v->recs.as<sb::SplatRec>();
+            vp.tboxes = v->tboxes.as<sb::TileBox>();
+            vp.u = p.u;  // cut_k = 0
+            SB_CUDA(v->ctx, sb::launch_vertex_stage(v->sh_fmt, v->cov_fmt, vp, p.sorted_indices, p.visible_count, v->ctx->num_sms, stream));
+            v->recs_cut = false;
+        }
     }
     p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
     if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 32, stream));
@@ -673,6 +692,7 @@ void sync_twin(SbViewer* v) {
     t->invert_selection = v->invert_selection;
     t->selection_override = v->selection.as<uint32_t>();
     t->strict_exp = v->strict_exp;
+    t->exact_cutoff = v->exact_cutoff;
 }
 
 }  // namespace
@@ -801,6 +821,12 @@ SbStatus sb_viewer_raster_path(SbViewer* v, int32_t* tma_gather4) {
 SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     v->strict_exp = strict != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    v->exact_cutoff = enabled != 0;
     return SB_OK;
 }
 
@@ -1026,7 +1052,9 @@ SbStatus sb_renderer_render(SbRenderer* r, void* stream, const SbRendererBindGro
     v->gaussian_transform = bg->gaussian_transform;
     v->ext_indices = bg->d_indirect_indices;
     v->ext_count = &d_indirect_args->instance_count;
-    sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    const bool depth_pass = depth && depth->d_depth;
+    sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format, v->exact_cutoff && !depth_pass);
+    v->recs_cut = false;  // the vertex stage below already matches the pass
     SbStatus s = check_target(v, target, u);  // validate before enqueuing anything
     if (s != SB_OK) return s;
     // vertex stage (render.wesl:76-130) for exactly the instances the draw names

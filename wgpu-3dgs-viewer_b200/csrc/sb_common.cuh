@@ -28,10 +28,18 @@ struct Uniforms {
     float std_dev;     // gaussian_transform_max_std_dev
     float gsize;       // gaussian_transform.size
     float color_scale; // 255 for unorm8 targets, 1 for float targets
+    float cut_k;       // exact alpha cut-off (splat mode on unorm8 targets): 1 / kAlphaCut, 0 = off
     uint32_t mode, sh_deg, no_sh0;
     uint32_t width, height;
     uint32_t tiles_x, tiles_y;
 };
+
+// On a unorm8 target a blend with alpha < 0.5/255 is the identity EXACTLY: d is an integer in 0..255, the source colour
+// c255 <= 255, so |fma(d, 1-alpha, c255*alpha) - d| <= alpha*255 + 1.6e-5 < 0.5 and rint() returns d.  In splat mode
+// alpha = a*exp(-r^2) falls below kAlphaCut for r^2 > ln(a / kAlphaCut); the vertex stage shrinks the splat's cull
+// extents (and with them its tile bbox) to that radius, so those fragments are never generated.  Bit-identical output.
+constexpr float kAlphaCut = 0.00195f;      // < 0.5/255 = 0.0019608 with room for the rounding of the blend
+constexpr float kAlphaCutMargin = 0.01f;   // added to ln(a / kAlphaCut): covers the rounding of r^2 and of exp (1 %)
 
 // Projected splat = everything vert_main (render.wesl:76-130) hands to the fragment stage,
 // computed once per visible Gaussian instead of 6x per quad.  48 bytes, 3 x 128-bit.

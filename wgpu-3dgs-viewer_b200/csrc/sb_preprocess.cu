@@ -385,6 +385,16 @@ __device__ __forceinline__ void emit_splat(const PreParams& p, const Uniforms& u
             out.ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
             out.ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
             valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, out.ex, out.ey);
+            if (u.cut_k > 0.0f) {  // exact alpha cut-off (sb_common.cuh): splat mode on a unorm8 target
+                const float rc2 = logf(out.a * u.cut_k) + kAlphaCutMargin;  // a = 0 -> -inf
+                if (!(rc2 > 0.0f)) {
+                    valid = false;  // a < kAlphaCut: every blend of this splat is the identity
+                } else if (rc2 < u.std_dev * u.std_dev) {
+                    const float s = sqrtf(rc2) / u.std_dev * 1.0001f;
+                    out.ex *= s;
+                    out.ey *= s;
+                }
+            }
         }
         TileBox tb;
         if (valid) {

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
     "sb_viewer_read_depth_keys", "sb_viewer_read_frame_stats", "sb_viewer_raster_path", "sb_viewer_set_strict_exp",
+    "sb_viewer_set_exact_cutoff",
     "sb_viewer_set_stage_timing", "sb_viewer_read_stage_times", "sb_viewer_set_raster_counting",
     "sb_viewer_read_raster_counters",
     "sb_viewer_read_raster_warp_counters",
@@ -183,6 +184,7 @@ def load() -> C.CDLL:
     sig("sb_viewer_read_frame_stats", i32, vp, vp, P(u64), P(u64), P(u32))
     sig("sb_viewer_raster_path", i32, vp, P(i32))
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
+    sig("sb_viewer_set_exact_cutoff", i32, vp, i32)
     sig("sb_viewer_set_raster_counting", i32, vp, i32)
     sig("sb_viewer_read_raster_counters", i32, vp, vp, P(u64), P(u64))
     sig("sb_viewer_read_raster_warp_counters", i32, vp, vp, P(u64), P(u64))
@@ -479,6 +481,9 @@ class Viewer:
 
     def set_strict_exp(self, strict: bool):
         _check(load().sb_viewer_set_strict_exp(self._h, int(strict)), self.ctx._h)
+
+    def set_exact_cutoff(self, enabled: bool):
+        _check(load().sb_viewer_set_exact_cutoff(self._h, int(enabled)), self.ctx._h)
 
     STAGES = ("preprocess", "depth_sort", "tile_emit", "tile_sort", "gather", "raster")
 
