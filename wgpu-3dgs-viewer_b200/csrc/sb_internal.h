@@ -49,8 +49,13 @@ size_t sort_internal_bytes(uint32_t capacity);
 // Stable ascending LSD sort of the first *d_count (clamped to max_count) (key,payload) pairs over
 // bits [begin_bit, end_bit).  Result lands in keys/payload when the pass count is even, and is
 // copied back otherwise.
+// parity_out (device word, nullable): the result is left where the last pass wrote it — *parity_out = 1: in the alt
+// buffers — and launch_sort_finish brings it home when somebody needs it there.
 cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count,
-                        int begin_bit, int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream);
+                        int begin_bit, int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream,
+                        uint32_t* parity_out = nullptr);
+cudaError_t launch_sort_finish(uint32_t* keys, uint32_t* payload, const SortScratch& scratch, const uint32_t* d_count, uint32_t max_count,
+                               const uint32_t* parity, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- binning + raster (sb_raster.cu)
 struct RasterBuffers {
@@ -71,6 +76,8 @@ struct RasterParams {
     const SplatRec* recs;            // indexed by Gaussian index
     const TileBox* tboxes;
     const uint32_t* sorted_indices;  // depth order
+    const uint32_t* sorted_indices_alt;  // where the depth sort left them when *sort_parity != 0 (both nullable)
+    const uint32_t* sort_parity;
     const uint32_t* visible_count;
     uint32_t max_visible;            // n
     RasterBuffers buf;

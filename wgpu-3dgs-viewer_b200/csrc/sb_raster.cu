@@ -29,6 +29,8 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 struct BinParams {
     const TileBox* tboxes;
     const uint32_t* sorted_indices;
+    const uint32_t* sorted_indices_alt;  // the depth sort's alt payload buffer: holds the result when *sort_parity != 0
+    const uint32_t* sort_parity;         // nullable: result is in sorted_indices
     const uint32_t* visible_count;
     uint32_t* dup_offsets;
     uint32_t* dup_keys;
@@ -71,13 +73,14 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t base = tile * kScanTile + tid * kScanItems;
+    const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
     uint32_t cnt[kScanItems];
     uint32_t sum = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
         const uint32_t r = base + i;
         uint32_t x0, y0, w;
-        cnt[i] = r < v ? splat_tiles(p.tboxes, p.sorted_indices[r], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
+        cnt[i] = r < v ? splat_tiles(p.tboxes, sorted[r], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
         sum += cnt[i];
     }
     uint32_t inc = sum;
@@ -127,11 +130,12 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
     const uint32_t v = *p.visible_count;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = gridDim.x * (blockDim.x / 32);
+    const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
     for (uint32_t wbase = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * 32; wbase < v; wbase += warps_total * 32) {
         const uint32_t r = wbase + lane;
         uint32_t g = 0, n = 0, x0 = 0, y0 = 0, w = 1, off = 0;
         if (r < v) {
-            g = p.sorted_indices[r];
+            g = sorted[r];
             n = splat_tiles(p.tboxes, g, p.ty_lo, p.ty_hi, x0, y0, w);
             off = p.dup_offsets[r];
         }
@@ -674,14 +678,27 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
         if (inside && p.depth_write) *zdst = st.depth;
 }
 
-// tile ranges from the tile-sorted keys (gather4 path: no record copy)
+// tile ranges from the tile-sorted keys (gather4 path: no record copy): four keys per thread, one 128-bit load
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ dup_keys, const uint32_t* __restrict__ dup_count,
                                                           uint32_t* __restrict__ tile_ranges) {
     const uint32_t d = *dup_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
-        const uint32_t t = dup_keys[i];
-        if (i == 0 || dup_keys[i - 1] != t) tile_ranges[2 * t] = i;
-        if (i == d - 1 || dup_keys[i + 1] != t) tile_ranges[2 * t + 1] = i + 1;
+    const uint32_t nvec = (d + 3) / 4;  // the buffer is padded to a multiple of four keys
+    const uint4* kv = reinterpret_cast<const uint4*>(dup_keys);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        const uint4 q = kv[i];
+        const uint32_t base = 4 * i;
+        const uint32_t k[6] = {base > 0 ? dup_keys[base - 1] : 0xffffffffu, q.x, q.y, q.z, q.w,
+                               base + 4 < d ? dup_keys[base + 4] : 0xffffffffu};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t idx = base + j;
+            if (idx < d) {
+                const uint32_t t = k[j + 1];
+                const uint32_t next = idx + 1 < d ? k[j + 2] : 0xffffffffu;
+                if (k[j] != t) tile_ranges[2 * t] = idx;
+                if (next != t) tile_ranges[2 * t + 1] = idx + 1;
+            }
+        }
     }
 }
 
@@ -741,10 +758,14 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(p.buf.tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
+    int bits = 1;
+    while ((1u << bits) < num_tiles) bits++;
 
     BinParams bp;
     bp.tboxes = p.tboxes;
     bp.sorted_indices = p.sorted_indices;
+    bp.sorted_indices_alt = p.sorted_indices_alt;
+    bp.sort_parity = p.sort_parity;
     bp.visible_count = p.visible_count;
     bp.dup_offsets = p.buf.dup_offsets;
     bp.dup_keys = p.buf.dup_keys;
@@ -764,8 +785,6 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     dup_emit_kernel<<<num_sms * 8, 256, 0, stream>>>(bp);
     if (p.events) cudaEventRecord(p.events[0], stream);
 
-    int bits = 1;
-    while ((1u << bits) < num_tiles) bits++;
     e = launch_sort(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, (uint32_t)p.buf.dup_capacity, 0, bits, p.sort, num_sms, stream);
     if (e != cudaSuccess) return e;
     if (p.events) cudaEventRecord(p.events[1], stream);

@@ -601,7 +601,8 @@ __global__ void __launch_bounds__(kV3Threads, kV3CtasPerSm)
 
 // One block after the histograms: which passes are the identity (one digit holds every key) and where each
 // remaining pass reads its input; state[0] = 1 when the result ends in the alt buffers.
-__global__ void sort_plan_kernel(uint32_t* __restrict__ internal, const uint32_t* __restrict__ d_count, uint32_t max_count, int num_passes) {
+__global__ void sort_plan_kernel(uint32_t* __restrict__ internal, const uint32_t* __restrict__ d_count, uint32_t max_count, int num_passes,
+                                 uint32_t* __restrict__ parity_out) {
     __shared__ int skip[kMaxPasses];
     const uint32_t count = min(*d_count, max_count);
     if (threadIdx.x < kMaxPasses) skip[threadIdx.x] = 0;
@@ -617,6 +618,7 @@ __global__ void sort_plan_kernel(uint32_t* __restrict__ internal, const uint32_t
             if (!s) parity ^= 1u;
         }
         internal[kStateOffset] = parity;
+        if (parity_out) *parity_out = parity;
     }
 }
 
@@ -723,8 +725,15 @@ size_t sort_internal_bytes(uint32_t capacity) {
     return (kLookbackOffset + (size_t)kMaxPasses * tiles * kRadix) * sizeof(uint32_t);
 }
 
+cudaError_t launch_sort_finish(uint32_t* keys, uint32_t* payload, const SortScratch& scratch, const uint32_t* d_count, uint32_t max_count,
+                               const uint32_t* parity, int num_sms, cudaStream_t stream) {
+    if (max_count == 0) return cudaSuccess;
+    sort_finish_kernel<<<num_sms * 4, 256, 0, stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count, parity);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count, int begin_bit,
-                        int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream) {
+                        int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream, uint32_t* parity_out) {
     if (max_count == 0) return cudaSuccess;
     const int num_passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
     if (num_passes < 1 || num_passes > kMaxPasses) return cudaErrorInvalidValue;
@@ -741,17 +750,16 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    sort_init_kernel<<<num_sms * 2, 256, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, (uint32_t)tiles, (uint32_t)tile_size);
     uint32_t* ghist = scratch.internal;
     uint32_t* tickets = scratch.internal + kTicketOffset;
     uint32_t* lookback = scratch.internal + kLookbackOffset;
-
+    sort_init_kernel<<<num_sms * 2, 256, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, (uint32_t)tiles, (uint32_t)tile_size);
     const int hist_grid = (int)min((size_t)num_sms * 2, (tiles * tile_size / 4 + 511) / 512);
     histogram_kernel<<<hist_grid > 0 ? hist_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, begin_bit, end_bit, num_passes, ghist);
 
     uint32_t* state = scratch.internal + kStateOffset;
     if (v2) {
-        sort_plan_kernel<<<1, kRadix, 0, stream>>>(scratch.internal, d_count, max_count, num_passes);
+        sort_plan_kernel<<<1, kRadix, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, parity_out);
         const unsigned grid = (unsigned)tiles;
         for (int p = 0; p < num_passes; p++) {
             const int nbits = min(kRadixBits, end_bit - (begin_bit + p * kRadixBits));
@@ -766,8 +774,11 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
                         begin_bit + p * kRadixBits, ghist + p * kRadix, tickets + p, lookback + (size_t)p * tiles * kRadix, state, p);
         }
     }
-    // result sits in the alt buffers when an odd number of passes actually ran: bring it home
-    sort_finish_kernel<<<num_sms * 4, 256, 0, stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count, state);
+    // result sits in the alt buffers when an odd number of passes actually ran: bring it home — unless the caller takes
+    // the parity and reads the result where it lies (v3 plan only; launch_sort_finish brings it home later)
+    if (!(v2 && parity_out))
+        sort_finish_kernel<<<num_sms * 4, 256, 0, stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count, state);
+    if (!v2 && parity_out) return cudaMemsetAsync(parity_out, 0, 4, stream);
     return cudaGetLastError();
 }
 
