@@ -207,6 +207,16 @@ SB_API SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float
 SB_API SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* points_xy, uint32_t n_points, float radius,
                                        int32_t accumulate);
 
+/* Editor-style per-Gaussian edit feeding the buffer: the colour-override use of the editor crate's
+ * NonDestructiveModifier<BasicSelectionModifier> exactly as tests/e2e/selection.rs:54-116 drives it
+ * (BasicColorRgbOverrideOrHsvModifiersPod::new_rgb_override(rgb), alpha, contrast 0, exposure 0, gamma 1).  Every call
+ * starts from the source colours (snapshot taken at the first call): Gaussians whose selection bit is set get
+ * colour = pack4x8unorm(rgb, source alpha * alpha), all others their source colour again — in the viewer's Gaussian
+ * buffer, in place, like modifier.apply(..., &viewer.gaussians_buffer, ...).  SH coefficients are left untouched
+ * (the HSV / contrast / exposure / gamma edits of the external crate are not built).  restore drops the edit. */
+SB_API SbStatus sb_viewer_apply_rgb_override(SbViewer* v, void* stream, const float rgb[3], float alpha);
+SB_API SbStatus sb_viewer_restore_gaussians(SbViewer* v, void* stream);
+
 /* Viewer::render(encoder, texture_view): src/lib.rs:266-275 — enqueue the whole frame */
 SB_API SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target);
 /* The three public stages, individually (viewer.preprocessor / radix_sorter / renderer):

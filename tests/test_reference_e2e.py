@@ -113,6 +113,93 @@ def test_selection_default_invert_hides_nothing(sb, ctx):  # src/selection/buffe
     v.close()
 
 
+def select_modify_render(sb, ctx, select):
+    """tests/e2e/selection.rs:16-116: viewport selection -> NonDestructiveModifier (rgb override to blue) -> render."""
+    import torch
+    v = sb.Viewer(ctx, gaussians=sb.scenes.single_red_gaussian())
+    v.update_camera_with_pod(given_camera(sb))
+    select(v)
+    v.apply_rgb_override((0.0, 0.0, 1.0), alpha=1.0)
+    t = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    v.render(t, W, H)
+    torch.cuda.synchronize()
+    out = t.cpu().numpy()
+    # non-destructive: restoring brings the red Gaussian back
+    v.restore_gaussians()
+    v.render(t, W, H)
+    torch.cuda.synchronize()
+    r, g, b, a = sums(t.cpu().numpy())
+    assert r > 1 and g < 1 and b < 1 and a > 1
+    v.close()
+    return sums(out)
+
+
+BRUSH_RADIUS = 50.0  # ViewportSelector::DEFAULT_BRUSH_RADIUS, src/selection/viewport_selector.rs:201
+
+
+def test_selected_rectangle_is_modified(sb, ctx):  # tests/e2e/selection.rs:118-137
+    r, g, b, a = select_modify_render(sb, ctx, lambda v: v.select_rect(256.0, 256.0, 1024.0 - 256.0, 1024.0 - 256.0))
+    assert r < 1 and g < 1 and b > 1 and a > 1
+
+
+def test_unselected_rectangle_is_not_modified(sb, ctx):  # tests/e2e/selection.rs:139-158
+    r, g, b, a = select_modify_render(sb, ctx, lambda v: v.select_rect(0.0, 0.0, 256.0, 256.0))
+    assert r > 1 and g < 1 and b < 1 and a > 1
+
+
+def test_selected_brush_is_modified(sb, ctx):  # tests/e2e/selection.rs:160-179
+    r, g, b, a = select_modify_render(sb, ctx, lambda v: v.select_brush([(256.0, 256.0), (768.0, 768.0)], BRUSH_RADIUS))
+    assert r < 1 and g < 1 and b > 1 and a > 1
+
+
+def test_unselected_brush_is_not_modified(sb, ctx):  # tests/e2e/selection.rs:181-196
+    r, g, b, a = select_modify_render(sb, ctx, lambda v: v.select_brush([(0.0, 0.0), (256.0, 256.0)], BRUSH_RADIUS))
+    assert r > 1 and g < 1 and b < 1 and a > 1
+
+
+def test_zero_radius_brush_selects_nothing(sb, ctx):  # tests/e2e/selection.rs:198-214
+    r, g, b, a = select_modify_render(sb, ctx, lambda v: v.select_brush([(256.0, 256.0), (768.0, 768.0)], 0.0))
+    assert r > 1 and g < 1 and b < 1 and a > 1
+
+
+def test_cleared_selection_is_not_modified(sb, ctx):  # tests/e2e/selection.rs:216-236
+    def sel(v):
+        v.select_rect(256.0, 256.0, 768.0, 768.0)
+        v.set_selection(np.zeros(1, dtype=np.uint32))  # selector.clear
+    r, g, b, a = select_modify_render(sb, ctx, sel)
+    assert r > 1 and g < 1 and b < 1 and a > 1
+
+
+def test_rgb_override_matches_oracle_on_edited_pods(sb, ob, ctx):
+    """The edit is exactly a rewrite of the colour words: frames equal the oracle's on pods edited the same way on the host."""
+    import torch
+    n, w, h = 20000, 640, 360
+    g = sb.scenes.synthetic_gaussians(n, 31)
+    pods = sb.pack_gaussians(g, 1, 1)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v = sb.Viewer(ctx, pods, n, sh_fmt=1, cov_fmt=1)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.set_strict_exp(True)
+    v.select_rect(200.0, 100.0, 450.0, 300.0)
+    sel = v.read_selection()
+    v.apply_rgb_override((0.25, 1.0, 0.5), alpha=0.5)
+    t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    v.render(t, w, h)
+    torch.cuda.synchronize()
+    stride = sb.pod_stride(1, 1)
+    edited = pods.copy().reshape(n, stride)
+    bits = ((sel[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+    assert 0 < bits.sum() < n
+    a = np.float32(edited[bits, 15].astype(np.float32) / np.float32(255.0)) * np.float32(0.5)
+    edited[bits, 12] = np.uint8(np.rint(np.float32(0.25) * np.float32(255)))
+    edited[bits, 13] = 255
+    edited[bits, 14] = np.uint8(np.rint(np.float32(0.5) * np.float32(255)))
+    edited[bits, 15] = np.rint(a * np.float32(255)).astype(np.uint8)
+    oimg, _ = ob.render(ob.OracleModel(edited.reshape(-1), n, 1, 1), ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(), strict_exp=True)
+    assert np.array_equal(t.cpu().numpy(), oimg)
+    v.close()
+
+
 def test_cpp_host_mirror_e2e(sb):
     """The typed C++ host mirror (host/splat_b200.hpp) runs the reference's viewer e2e test."""
     import os

@@ -160,6 +160,7 @@ struct SbViewer {
     DeviceBuf depth_keys_alt, depth_vals_alt;  // the depth sort's own ping-pong buffers: its result may stay there (sorted_pending)
     DeviceBuf dup_offsets, dup_keys, dup_vals, tile_recs, tile_ranges, bin_state;
     DeviceBuf selection;
+    DeviceBuf orig_colors;  // NonDestructiveModifier's source copy (colour words), taken at the first edit
     DeviceBuf internal_target;
     uint64_t dup_capacity = 0;
     uint32_t tile_capacity = 0;
@@ -540,7 +541,7 @@ void sb_viewer_destroy(SbViewer* v) {
         if (e) cudaEventDestroy(e);
     for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->tboxes, &v->pre_scratch, &v->sort_keys_alt,
                          &v->sort_vals_alt, &v->sort_internal, &v->depth_keys_alt, &v->depth_vals_alt, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
-                         &v->tile_ranges, &v->bin_state, &v->selection, &v->internal_target, &v->counters})
+                         &v->tile_ranges, &v->bin_state, &v->selection, &v->orig_colors, &v->internal_target, &v->counters})
         b->release();
     if (v->h_needed) cudaFreeHost(const_cast<uint32_t*>(v->h_needed));
     for (cudaEvent_t e : v->ev)
@@ -637,6 +638,27 @@ SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* points_x
     const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
     SB_CUDA(v->ctx, sb::launch_select_brush(static_cast<const uint8_t*>(v->d_gaussians), v->n, v->stride, u, points_xy, n_points, radius,
                                             accumulate, v->selection.as<uint32_t>(), static_cast<cudaStream_t>(stream)));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_apply_rgb_override(SbViewer* v, void* stream, const float rgb[3], float alpha) {
+    if (!v || !rgb) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* pods = const_cast<uint8_t*>(static_cast<const uint8_t*>(v->d_gaussians));  // the reference edits viewer.gaussians_buffer in place
+    if (!v->orig_colors.p) {
+        SB_CUDA(v->ctx, v->orig_colors.alloc((size_t)(v->n ? v->n : 1) * 4));
+        SB_CUDA(v->ctx, sb::launch_snapshot_colors(pods, v->n, v->stride, v->orig_colors.as<uint32_t>(), st));
+    }
+    SB_CUDA(v->ctx, sb::launch_rgb_override(pods, v->n, v->stride, v->orig_colors.as<uint32_t>(), v->selection.as<uint32_t>(), rgb, alpha, st));
+    return SB_OK;
+}
+
+SbStatus sb_viewer_restore_gaussians(SbViewer* v, void* stream) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    if (!v->orig_colors.p) return SB_OK;  // never edited
+    uint8_t* pods = const_cast<uint8_t*>(static_cast<const uint8_t*>(v->d_gaussians));
+    const float rgb[3] = {0.0f, 0.0f, 0.0f};
+    SB_CUDA(v->ctx, sb::launch_rgb_override(pods, v->n, v->stride, v->orig_colors.as<uint32_t>(), nullptr, rgb, 1.0f, static_cast<cudaStream_t>(stream)));
     return SB_OK;
 }
 

@@ -109,4 +109,9 @@ cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t st
 cudaError_t launch_select_brush(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, const float* points_xy,
                                 uint32_t n_points, float radius, int accumulate, uint32_t* words, cudaStream_t stream);
 
+// editor-style colour override: snapshot of the colour words, then selected -> override / others -> source
+cudaError_t launch_snapshot_colors(const uint8_t* gaussians, uint32_t n, uint32_t stride, uint32_t* orig, cudaStream_t stream);
+cudaError_t launch_rgb_override(uint8_t* gaussians, uint32_t n, uint32_t stride, const uint32_t* orig, const uint32_t* selection,
+                                const float rgb[3], float alpha, cudaStream_t stream);
+
 }  // namespace sb

@@ -102,6 +102,33 @@ __global__ void __launch_bounds__(256) select_rect_kernel(const uint8_t* __restr
     if ((threadIdx.x & 31u) == 0 && g < n) words[g >> 5] = bits;
 }
 
+// K8: the colour-override edit of the editor crate's BasicSelectionModifier in the shape the
+// reference's own test uses it (tests/e2e/selection.rs:54-116): NonDestructiveModifier keeps the source colours and, on every
+// apply, rewrites the colour word of each Gaussian — selected: the override rgb (pack4x8unorm) with the source alpha
+// scaled by `alpha`; not selected: the source colour again.  `orig` is the snapshot of the colour words (byte 12 of a pod).
+__global__ void __launch_bounds__(256) snapshot_colors_kernel(const uint8_t* __restrict__ gaussians, uint32_t n, uint32_t stride,
+                                                              uint32_t* __restrict__ orig) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) orig[g] = *reinterpret_cast<const uint32_t*>(gaussians + (size_t)g * stride + 12);
+}
+
+__device__ __forceinline__ uint32_t unorm8_pack(float x) {  // pack4x8unorm: round(clamp(x, 0, 1) * 255)
+    return (uint32_t)__float2int_rn(__fmul_rn(fminf(fmaxf(x, 0.0f), 1.0f), 255.0f));
+}
+
+__global__ void __launch_bounds__(256) rgb_override_kernel(uint8_t* __restrict__ gaussians, uint32_t n, uint32_t stride,
+                                                           const uint32_t* __restrict__ orig, const uint32_t* __restrict__ selection,
+                                                           float r, float g_, float b, float alpha) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t c = orig[g];
+    if (selection && ((selection[g >> 5] >> (g & 31u)) & 1u)) {
+        const float a = __fmul_rn(__fdiv_rn((float)(c >> 24), 255.0f), alpha);
+        c = unorm8_pack(r) | (unorm8_pack(g_) << 8) | (unorm8_pack(b) << 16) | (unorm8_pack(a) << 24);
+    }
+    *reinterpret_cast<uint32_t*>(gaussians + (size_t)g * stride + 12) = c;
+}
+
 }  // namespace
 
 cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, float x0, float y0, float x1,
@@ -121,6 +148,19 @@ cudaError_t launch_select_brush(const uint8_t* gaussians, uint32_t n, uint32_t s
     b.n_points = n_points;
     b.radius = radius;
     select_brush_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, u, b, accumulate, words);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_snapshot_colors(const uint8_t* gaussians, uint32_t n, uint32_t stride, uint32_t* orig, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    snapshot_colors_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, orig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rgb_override(uint8_t* gaussians, uint32_t n, uint32_t stride, const uint32_t* orig, const uint32_t* selection,
+                                const float rgb[3], float alpha, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    rgb_override_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, orig, selection, rgb[0], rgb[1], rgb[2], alpha);
     return cudaGetLastError();
 }
 

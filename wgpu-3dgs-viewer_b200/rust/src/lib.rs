@@ -87,6 +87,9 @@ pub mod ffi {
         pub fn sb_viewer_set_invert_selection(v: *mut SbViewer, invert: i32) -> i32;
         pub fn sb_viewer_select_rect(v: *mut SbViewer, stream: *mut c_void, x0: f32, y0: f32, x1: f32, y1: f32) -> i32;
         pub fn sb_viewer_select_brush(v: *mut SbViewer, stream: *mut c_void, points_xy: *const f32, n_points: u32, radius: f32, accumulate: i32) -> i32;
+        pub fn sb_viewer_apply_rgb_override(v: *mut SbViewer, stream: *mut c_void, rgb: *const f32, alpha: f32) -> i32;
+        pub fn sb_viewer_restore_gaussians(v: *mut SbViewer, stream: *mut c_void) -> i32;
+        pub fn sb_viewer_set_exact_cutoff(v: *mut SbViewer, enabled: i32) -> i32;
         pub fn sb_viewer_render(v: *mut SbViewer, stream: *mut c_void, target: *const Target) -> i32;
         pub fn sb_viewer_render_with_pass(v: *mut SbViewer, stream: *mut c_void, target: *const Target, depth: *const DepthAttachment, load: i32, run_stages: i32) -> i32;
         pub fn sb_viewer_preprocess(v: *mut SbViewer, stream: *mut c_void) -> i32;

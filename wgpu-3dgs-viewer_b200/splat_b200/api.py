@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "sb_viewer_update_model_transform_with_pod", "sb_viewer_update_gaussian_transform",
     "sb_viewer_update_gaussian_transform_with_pod", "sb_viewer_enable_selection", "sb_viewer_selection_ptr",
     "sb_viewer_set_selection", "sb_viewer_read_selection", "sb_viewer_set_invert_selection", "sb_viewer_select_rect",
-    "sb_viewer_select_brush", "sb_viewer_render", "sb_viewer_render_with_pass",
+    "sb_viewer_select_brush", "sb_viewer_apply_rgb_override", "sb_viewer_restore_gaussians", "sb_viewer_render", "sb_viewer_render_with_pass",
     "sb_viewer_preprocess", "sb_viewer_sort", "sb_viewer_draw", "sb_viewer_render_to_host", "sb_viewer_render_batch", "sb_viewer_gaussians_ptr",
     "sb_viewer_indirect_args_ptr", "sb_viewer_radix_sort_indirect_args_ptr", "sb_viewer_indirect_indices_ptr",
     "sb_viewer_gaussians_depth_ptr", "sb_viewer_read_indirect_args", "sb_viewer_read_indices",
@@ -166,6 +166,8 @@ def load() -> C.CDLL:
     sig("sb_viewer_set_invert_selection", i32, vp, i32)
     sig("sb_viewer_select_rect", i32, vp, vp, f32, f32, f32, f32)
     sig("sb_viewer_select_brush", i32, vp, vp, P(f32), u32, f32, i32)
+    sig("sb_viewer_apply_rgb_override", i32, vp, vp, P(f32), f32)
+    sig("sb_viewer_restore_gaussians", i32, vp, vp)
     sig("sb_viewer_render_with_pass", i32, vp, vp, P(Target), P(DepthAttachment), i32, i32)
     sig("sb_viewer_render", i32, vp, vp, P(Target))
     sig("sb_viewer_preprocess", i32, vp, vp)
@@ -386,6 +388,14 @@ class Viewer:
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
         _check(load().sb_viewer_select_brush(self._h, _stream_handle(stream), pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts),
                                              float(radius), int(accumulate)), self.ctx._h)
+
+    def apply_rgb_override(self, rgb, alpha=1.0, stream=None):
+        """editor NonDestructiveModifier + rgb override on the selected Gaussians (tests/e2e/selection.rs:54-116)."""
+        c = _f(rgb)
+        _check(load().sb_viewer_apply_rgb_override(self._h, _stream_handle(stream), c.ctypes.data_as(C.POINTER(C.c_float)), float(alpha)), self.ctx._h)
+
+    def restore_gaussians(self, stream=None):
+        _check(load().sb_viewer_restore_gaussians(self._h, _stream_handle(stream)), self.ctx._h)
 
     def read_selection(self, stream=None) -> np.ndarray:
         out = np.zeros((self.n + 31) // 32, dtype=np.uint32)
