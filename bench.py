@@ -34,8 +34,8 @@ SCENE_SEED = 0x3D65 + 2
 SH_FMT, COV_FMT = 0, 0           # pod single/single, 224 B
 N_VIEWS = 64                     # orbit cameras (config 5a)
 METRIC = "frames_per_sec_1080p_6M_gaussians"
-KERNELS_PER_FRAME = 18           # preprocess 1, depth sort 1+1+1+4+1 (init, hist, plan, passes, finish), scan 1, emit 1,
-                                 # tile sort 1+1+2+1, tile ranges 1, raster 1
+KERNELS_PER_FRAME = 17           # preprocess 1, depth sort 1+1+1+4 (init, hist, plan, passes; the result stays where the last pass
+                                 # wrote it), scan 1, emit 1, tile sort 1+1+2+1, tile ranges 1, raster 1
 
 
 def peaks():
@@ -226,14 +226,15 @@ def run_cuda(args):
     V, D = float(np.mean(vis)), float(np.mean(dup))
     # instrumented rasterizer build (outside every timed region): fragments blended / lane pairs evaluated
     viewer.set_raster_counting(True)
-    alive, evaluated = [], []
+    alive, evaluated, warp_evals = [], [], []
     for i in range(min(args.steps, 4)):
         step_device(args.warmup + i)
         c = viewer.read_raster_counters(stream)
         alive.append(c["alive"])
         evaluated.append(c["evaluated"])
+        warp_evals.append(c["warp_evals"])
     viewer.set_raster_counting(False)
-    alive, evaluated = float(np.mean(alive)), float(np.mean(evaluated))
+    alive, evaluated, warp_evals = float(np.mean(alive)), float(np.mean(evaluated)), float(np.mean(warp_evals))
 
     # sanity: the frame is not empty and alpha is opaque
     stream.synchronize()
@@ -258,12 +259,22 @@ def run_cuda(args):
     fp32_peak = 148 * 128 * sm_clock * 1e6 / 1e9           # G lane-ops/s at the clock sampled under load
     raster_ops = alive * 24.0
     raster_gops = raster_ops / stage["raster"] / 1e6
+    # shared memory: the datapath moves one 128-byte wavefront per clock and SM.  A (warp, splat) evaluation broadcasts the
+    # 48-byte record with three loads = 3 wavefronts; a cull round (32 splats, one per lane) reads 32 B per lane with two
+    # 128-bit loads = 8 wavefronts, and every one of a tile's 8 warps runs ceil(list / 32) rounds (>= D / 32 in total).
+    smem_wavefronts = 3.0 * warp_evals + 8.0 * 8.0 * D / 32.0
+    smem_gbs = smem_wavefronts * 128.0 / stage["raster"] / 1e6
+    smem_peak = 148 * 128 * sm_clock * 1e6 / 1e9              # GB/s
     roofs = {
         "raster": {"bound": "fp32", "kernel": "raster_gather4_kernel<splat,unorm8> (K6)", "achieved": raster_gops, "peak": fp32_peak,
                    "unit": "Gop/s (FP32 lane-ops, FMA = 1)", "frac": raster_gops / fp32_peak, "traffic": None,
                    "peak_source": f"nominal 148 SMs x 128 lanes x {sm_clock:.0f} MHz sampled under load (no measured FP32 peak in MEASURED_PEAKS.json)",
                    "algorithmic_ops": raster_ops, "alive_fragments": alive, "evaluated_lane_pairs": evaluated,
-                   "lane_efficiency": alive / evaluated if evaluated else None, "ms": stage["raster"]},
+                   "lane_efficiency": alive / evaluated if evaluated else None, "ms": stage["raster"],
+                   "warp_splat_evaluations": warp_evals,
+                   "smem": {"achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s (128-byte wavefronts)", "frac": smem_gbs / smem_peak,
+                            "wavefronts": smem_wavefronts,
+                            "peak_source": f"nominal 148 SMs x 128 B/clk x {sm_clock:.0f} MHz sampled under load"}},
         "preprocess": {"bound": "hbm", "kernel": "preprocess_kernel<single,single> (K1)", "achieved": pre_gbs, "peak": hbm_peak,
                        "unit": "GB/s", "frac": pre_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                        "algorithmic_bytes": pre_bytes, "ms": stage["preprocess"]},

@@ -50,7 +50,7 @@ class Stats(C.Structure):
 
 SPLAT_DTYPE = np.dtype(
     [("cx", "<f4"), ("cy", "<f4"), ("ax", "<f4"), ("ay", "<f4"), ("bx", "<f4"), ("by", "<f4"),
-     ("r", "<f4"), ("g", "<f4"), ("b", "<f4"), ("a", "<f4"), ("ext_x", "<f4"), ("ext_y", "<f4"), ("valid", "<i4")]
+     ("r", "<f4"), ("g", "<f4"), ("b", "<f4"), ("a", "<f4"), ("ext_x", "<f4"), ("ext_y", "<f4"), ("valid", "<i4"), ("z", "<f4")]
 )
 
 assert C.sizeof(CameraPod) == 144 and C.sizeof(ModelTransformPod) == 48 and C.sizeof(GaussianTransformPod) == 8

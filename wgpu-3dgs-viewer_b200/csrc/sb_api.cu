@@ -158,7 +158,7 @@ struct SbViewer {
     DeviceBuf indices, keys, args, recs, tboxes, pre_scratch;
     DeviceBuf sort_keys_alt, sort_vals_alt, sort_internal;
     DeviceBuf depth_keys_alt, depth_vals_alt;  // the depth sort's own ping-pong buffers: its result may stay there (sorted_pending)
-    DeviceBuf dup_offsets, dup_keys, dup_vals, tile_recs, tile_ranges, bin_state;
+    DeviceBuf dup_offsets, dup_keys, dup_vals, tile_recs, tile_ranges, tile_order, bin_state;
     DeviceBuf selection;
     DeviceBuf orig_colors;  // NonDestructiveModifier's source copy (colour words), taken at the first edit
     DeviceBuf internal_target;
@@ -389,6 +389,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     if (tiles > v->tile_capacity) {
         SB_CUDA(v->ctx, cudaStreamSynchronize(stream));
         SB_CUDA(v->ctx, v->tile_ranges.alloc((size_t)tiles * 8));
+        SB_CUDA(v->ctx, v->tile_order.alloc((size_t)tiles * 4));
         v->tile_capacity = tiles;
     }
     p.recs = v->recs.as<sb::SplatRec>();
@@ -409,6 +410,10 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.buf.dup_keys = v->dup_keys.as<uint32_t>();
     p.buf.dup_vals = v->dup_vals.as<uint32_t>();
     p.buf.tile_ranges = v->tile_ranges.as<uint32_t>();
+    {
+        static const bool row_major = [] { const char* c = std::getenv("SB_RASTER_ORDER"); return c && std::string(c) == "rows"; }();
+        p.buf.tile_order = row_major ? nullptr : v->tile_order.as<uint32_t>();
+    }
     p.buf.dup_count = v->d_dup_count();
     p.buf.overflow = v->d_overflow();
     p.buf.needed_host = v->d_needed;
@@ -424,6 +429,10 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
         // SB_RASTER_CULL=bbox keeps the warp-level cull on the alive-region bbox only (A/B measurements)
         static const bool bbox_only = [] { const char* c = std::getenv("SB_RASTER_CULL"); return c && std::string(c) == "bbox"; }();
         p.obb_cull = bbox_only ? 0 : 1;
+    }
+    {
+        static const int bands = [] { const char* c = std::getenv("SB_RASTER_BANDS"); return c ? std::atoi(c) : 1; }();
+        p.raster_bands = bands;
     }
     p.events = v->timing ? &v->ev[3] : nullptr;
     p.recs_map = v->use_gather4 ? &v->recs_map : nullptr;
@@ -541,7 +550,7 @@ void sb_viewer_destroy(SbViewer* v) {
         if (e) cudaEventDestroy(e);
     for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->tboxes, &v->pre_scratch, &v->sort_keys_alt,
                          &v->sort_vals_alt, &v->sort_internal, &v->depth_keys_alt, &v->depth_vals_alt, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
-                         &v->tile_ranges, &v->bin_state, &v->selection, &v->orig_colors, &v->internal_target, &v->counters})
+                         &v->tile_ranges, &v->tile_order, &v->bin_state, &v->selection, &v->orig_colors, &v->internal_target, &v->counters})
         b->release();
     if (v->h_needed) cudaFreeHost(const_cast<uint32_t*>(v->h_needed));
     for (cudaEvent_t e : v->ev)

@@ -63,6 +63,7 @@ struct RasterBuffers {
     uint32_t* dup_keys;       // [dup_capacity] tile id
     uint32_t* dup_vals;       // [dup_capacity] Gaussian index (in depth order within a tile)
     uint32_t* tile_ranges;    // [tiles*2] begin,end into dup arrays
+    uint32_t* tile_order;     // [tiles] raster schedule: tiles by descending list length (nullable: row-major)
     uint32_t* dup_count;      // D (device)
     uint32_t* overflow;       // flag
     uint32_t* needed_host;    // device alias of a mapped pinned word (may be null)
@@ -87,6 +88,7 @@ struct RasterParams {
     int strict_exp;
     int clear;                       // 1: clear to BLACK first (first model of a frame)
     int obb_cull;                    // 1: warp-level cull also tests the ellipse axes (SAT), 0: bbox only
+    int raster_bands;                // rasterize the tile rows as this many launches (<= 1: one)
     float* depth;                    // optional f32 depth attachment (strip geometry of the target); needs recs_map
     uint32_t depth_pitch;
     int depth_compare, depth_write;

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <string>
 
+#include <algorithm>
+
 #include "sb_internal.h"
 
 namespace sb {
@@ -269,6 +271,8 @@ struct RasterKernelParams {
     const SplatRec* tile_recs;      // bulk path: records gathered into tile order
     const uint32_t* dup_vals;       // gather4 path: Gaussian index per tile-sorted duplicate
     const uint32_t* tile_ranges;
+    const uint32_t* tile_order;     // nullable: CTA i of the launch rasterizes tile tile_order[order_base + i] (heaviest lists first)
+    uint32_t order_base;
     uint8_t* pixels;
     uint32_t pitch;
     uint32_t width, height;
@@ -517,7 +521,12 @@ __global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelPara
     __shared__ __align__(8) uint64_t full_bar[2];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
+    uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
+    if (p.tile_order) {  // longest-list-first schedule: the kernel's tail is made of short lists
+        const uint32_t t = p.tile_order[p.order_base + blockIdx.y * gridDim.x + blockIdx.x];
+        tile_x = t % p.tiles_x;
+        tile_y = t / p.tiles_x;
+    }
     const uint32_t tile = tile_y * p.tiles_x + tile_x;
     // each warp owns an 8x4 pixel patch: lanes 0-15 its left 4x4 half, lanes 16-31 the right one (pixel centres:
     // half extents 1.5 x 1.5 around the half's centre; pcx = centre of the LEFT half)
@@ -576,7 +585,12 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t empty_bar[kG4Stages];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
+    uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
+    if (p.tile_order) {  // longest-list-first schedule: the kernel's tail is made of short lists
+        const uint32_t t = p.tile_order[p.order_base + blockIdx.y * gridDim.x + blockIdx.x];
+        tile_x = t % p.tiles_x;
+        tile_y = t / p.tiles_x;
+    }
     const uint32_t tile = tile_y * p.tiles_x + tile_x;
     const uint32_t begin = p.tile_ranges[2 * tile], end = p.tile_ranges[2 * tile + 1];
     const uint32_t total = end - begin;
@@ -702,6 +716,61 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
     }
 }
 
+// Longest-processing-time-first schedule for the rasterizer: tiles of the strip ordered by descending list length
+// (counting sort on length / 32, one block).  A tile's CTA runs as long as its list, the heaviest 0.2-0.5 ms: started
+// in row-major order the late heavy tiles leave most of the machine idle at the end of the kernel.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_ranges, uint32_t first_tile, uint32_t nt,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ uint32_t hist[1024];
+    __shared__ uint32_t wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint2* rg = reinterpret_cast<const uint2*>(tile_ranges) + first_tile;
+    constexpr int kGroup = 8;  // tiles per thread whose ranges are fetched together (one round trip at 1080p)
+    auto bucket = [&](uint32_t i) { return i < nt ? 1023u - min((rg[i].y - rg[i].x) >> 5, 1023u) : 0xffffffffu; };
+    hist[tid] = 0;
+    __syncthreads();
+    // count, warp-aggregated: the empty tiles of a frame (most of them) all fall into one bucket
+    for (uint32_t g0 = 0; g0 < nt; g0 += kGroup * 1024u) {
+        uint32_t bk[kGroup];
+#pragma unroll
+        for (int k = 0; k < kGroup; k++) bk[k] = bucket(g0 + k * 1024u + tid);
+#pragma unroll
+        for (int k = 0; k < kGroup; k++) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, bk[k]);  // inactive lanes (0xffffffff) form their own group
+            if (bk[k] != 0xffffffffu && (peers & lt) == 0) atomicAdd(&hist[bk[k]], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    const uint32_t c = hist[tid];
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t base = inc - c;
+    for (uint32_t w = 0; w < warp; w++) base += wsum[w];
+    __syncthreads();
+    hist[tid] = base;
+    __syncthreads();
+    for (uint32_t g0 = 0; g0 < nt; g0 += kGroup * 1024u) {
+        uint32_t bk[kGroup];
+#pragma unroll
+        for (int k = 0; k < kGroup; k++) bk[k] = bucket(g0 + k * 1024u + tid);
+#pragma unroll
+        for (int k = 0; k < kGroup; k++) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, bk[k]);
+            uint32_t pos = 0;
+            if (bk[k] != 0xffffffffu && (peers & lt) == 0) pos = atomicAdd(&hist[bk[k]], (uint32_t)__popc(peers));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1);
+            if (bk[k] != 0xffffffffu) order[pos + __popc(peers & lt)] = first_tile + g0 + k * 1024u + tid;
+        }
+    }
+}
+
 // A render pass that only clears (Color::BLACK = 0,0,0,1): src/renderer.rs:171-177
 __global__ void clear_kernel(uint8_t* pixels, uint32_t pitch, uint32_t width, uint32_t rows, int fmt) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -794,9 +863,13 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     else
         gather_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, p.recs, p.buf.tile_recs,
                                                       p.buf.tile_ranges);
+    if (p.buf.tile_order)
+        tile_order_kernel<<<1, 1024, 0, stream>>>(p.buf.tile_ranges, ty_lo * u.tiles_x, (ty_hi - ty_lo + 1) * u.tiles_x, p.buf.tile_order);
     if (p.events) cudaEventRecord(p.events[2], stream);
 
     RasterKernelParams kp;
+    kp.tile_order = p.buf.tile_order;
+    kp.order_base = 0;
     kp.tile_recs = p.buf.tile_recs;
     kp.dup_vals = p.buf.dup_vals;
     kp.tile_ranges = p.buf.tile_ranges;
@@ -825,10 +898,18 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
         kp.model[i] = u.model[i];
     }
     kp.counters = p.counters;
-    const dim3 grid(u.tiles_x, ty_hi - ty_lo + 1);
+    // The tile rows can be rasterized as several launches (bands): in a pipelined view batch every band boundary is a
+    // point where the other view's kernels get SM slots, instead of queueing behind one 8160-CTA grid.
+    const uint32_t rows_total = ty_hi - ty_lo + 1;
+    const uint32_t bands = (uint32_t)std::min<int>(std::max(p.raster_bands, 1), (int)rows_total);
     const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
                     : t.format == SB_TARGET_RGBA16_FLOAT                                       ? FMT_F16
                                                                                                : FMT_F32;
+    for (uint32_t band = 0; band < bands; band++) {
+    const uint32_t y0 = ty_lo + rows_total * band / bands, y1 = ty_lo + rows_total * (band + 1) / bands;
+    kp.ty_lo = y0;
+    kp.order_base = (y0 - ty_lo) * u.tiles_x;  // with a schedule, a band is a slice of it
+    const dim3 grid(u.tiles_x, y1 - y0);
 #define SB_RASTER(M, F)                                                        \
     if (u.mode == M && fmt == F) {                                             \
         if (M == SB_MODE_SPLAT && p.strict_exp) launch_raster<M, F, true>(kp, p.recs_map, grid, stream); \
@@ -844,6 +925,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     SB_RASTER(SB_MODE_POINT, FMT_F16)
     SB_RASTER(SB_MODE_POINT, FMT_F32)
 #undef SB_RASTER
+    }
     if (p.events) cudaEventRecord(p.events[3], stream);
     return cudaGetLastError();
 }
