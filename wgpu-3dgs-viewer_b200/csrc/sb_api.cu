@@ -113,9 +113,12 @@ bool encode_recs_map(void* d_recs, uint64_t n, CUtensorMap* out) {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
         fn = reinterpret_cast<EncodeTiledFn>(p);
     }
-    const cuuint64_t gdim[2] = {12, n ? n : 1};
+    // Rows are declared 16 floats wide over the 48-byte record stride: each fetched row is a record plus the first 16 bytes
+    // of the next one, so the four rows of a gather4 land at a 64-byte pitch in shared memory and the rasterizer addresses
+    // record j at 64 j (the array is allocated 64 bytes longer for the last row's overhang).
+    const cuuint64_t gdim[2] = {16, n ? n : 1};
     const cuuint64_t gstride[1] = {sizeof(sb::SplatRec)};
-    const cuuint32_t box[2] = {12, 1};  // gather4 fetches four 1-row boxes (probed: scripts/probes/probe_gather4.cu)
+    const cuuint32_t box[2] = {16, 1};  // gather4 fetches four 1-row boxes (probed: scripts/probes/probe_gather4.cu)
     const cuuint32_t estr[2] = {1, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_recs, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -218,7 +221,7 @@ SbStatus viewer_alloc(SbViewer* v) {
     SB_CUDA(ctx, v->depth_keys_alt.alloc((size_t)(v->padded ? v->padded : 1) * 4));
     SB_CUDA(ctx, v->depth_vals_alt.alloc((size_t)(v->padded ? v->padded : 1) * 4));
     SB_CUDA(ctx, v->args.alloc(64));
-    SB_CUDA(ctx, v->recs.alloc((size_t)(n ? n : 1) * sizeof(sb::SplatRec)));
+    SB_CUDA(ctx, v->recs.alloc((size_t)(n ? n : 1) * sizeof(sb::SplatRec) + 64));
     SB_CUDA(ctx, v->tboxes.alloc((size_t)(n ? n : 1) * sizeof(sb::TileBox)));
     {
         // rasterizer record fetch: TMA gather4 from recs[] (default) or a gathered copy + 1-D bulk copies

@@ -203,7 +203,6 @@ constexpr int kBatchG4 = SB_G4_BATCH;  // 128 or 256: one or two gather4 per pro
 constexpr int kG4Stages = SB_G4_STAGES;
 constexpr int kG4PerLane = kBatchG4 / 128;
 constexpr int kG4StageF4 = (kBatchG4 / 4) * 16;
-__device__ __forceinline__ uint32_t g4_row_f4(uint32_t j) { return 3u * j + (j & ~3u); }
 
 enum { FMT_UNORM8 = 0, FMT_F16 = 1, FMT_F32 = 2 };
 
@@ -367,7 +366,7 @@ struct DepthArgs {
 template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH>
 __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 pxy, bool inside, float sd2, float outline, PixelState& st,
                                            const DepthArgs& da) {
-    const char* rp = PERM ? last - 64u * hb + 16u * (hb & 3u) : last - 48u * hb;
+    const char* rp = PERM ? last - 64u * hb : last - 48u * hb;
     const float4 q0 = *reinterpret_cast<const float4*>(rp);       // cx cy ax bx
     const float2 q1 = *reinterpret_cast<const float2*>(rp + 16);  // ay by
     // quad offset (render.wesl:125-128 inverted): q = (fma(dx,ax,dy*ay), fma(dx,bx,dy*by))
@@ -434,7 +433,7 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
 }
 
 // Composites one staged batch onto this thread's pixel, in list order.  PERM: record j of the batch
-// sits at float4 index g4_row_f4(j) (the layout the gather4 producer writes).
+// sits at float4 index 4 j (the layout the gather4 producer writes: rows fetched 64 bytes wide).
 // Warp-level culling: each lane tests one splat against the two 4x4 halves of the warp's 8x4 pixel patch — the
 // bbox of its alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of a half's
 // rectangle against the ellipse's oriented bounding box; each half-warp then evaluates only its own survivors.
@@ -442,10 +441,10 @@ template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = fa
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
                                                 PixelState& st, DepthArgs da = DepthArgs{nullptr, 0, 0}) {
-    // Byte addressing.  PERM: record j sits at 64 j - 16 (j & 3) (four 48-byte rows per 256-byte gather);
+    // Byte addressing.  PERM (gather4 path): record j sits at 64 j (rows are fetched 64 bytes wide, four per 256-byte gather);
     // otherwise at 48 j.  A round is 32 consecutive records starting at a multiple of 32.
     const char* rb = reinterpret_cast<const char*>(recs);
-    const char* mine = rb + (PERM ? 64u * lane - 16u * (lane & 3u) : 48u * lane);
+    const char* mine = rb + (PERM ? 64u * lane : 48u * lane);
     constexpr uint32_t kRound = PERM ? 2048u : 1536u;
     for (uint32_t base = 0; base < cnt; base += 32, mine += kRound, rb += kRound, da.zs += DEPTH ? 32 : 0) {
         // each lane tests ONE splat against BOTH 4x4 halves of the warp's 8x4 patch (pcx: centre of the left half)
@@ -470,9 +469,9 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
         // lanes 16-31 those of the right half; a splat of a few pixels usually touches only one of them, so the loop runs
         // max(n_left, n_right) times instead of n_left-or-right.  Bit hb = 31 - b <-> splat b of the round.
         const uint32_t ml = __ballot_sync(0xffffffffu, hit_l), mr = __ballot_sync(0xffffffffu, hit_r);
-        // address of splat b = 31 - hb: rb + 64 b - 16 (b & 3) = last - 64 hb + 16 (hb & 3)   (PERM)
+        // address of splat b = 31 - hb: rb + 64 b = last - 64 hb   (PERM)
         //                                 rb + 48 b                = last - 48 hb               (else)
-        const char* last = rb + (PERM ? 64u * 31u - 48u : 48u * 31u);
+        const char* last = rb + (PERM ? 64u * 31u : 48u * 31u);
         // Big splats touch both halves: then one warp-uniform walk over the union costs the same number of iterations
         // and keeps the loop control on the uniform datapath.  Split only when it saves at least two iterations.
         const uint32_t un = ml | mr;
@@ -649,7 +648,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
                     }
                 mbar_arrive(&z_bar[s]);
             }
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], gathers * 4u * (uint32_t)sizeof(SplatRec));
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], gathers * 4u * 64u);  // rows are fetched 64 bytes wide
             __syncwarp();
             const uint32_t dst0 = smem_u32(&stage[s][lane * 16]);
 #pragma unroll
