@@ -427,6 +427,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.sort = sort_scratch(v);
     p.target = *target;
     p.strict_exp = v->strict_exp;
+    p.no_discard = v->exact_cutoff ? 1 : 0;
     p.clear = clear;
     {
         // SB_RASTER_CULL=bbox keeps the warp-level cull on the alive-region bbox only (A/B measurements)

@@ -270,6 +270,7 @@ struct RasterKernelParams {
     const SplatRec* tile_recs;      // bulk path: records gathered into tile order
     const uint32_t* dup_vals;       // gather4 path: Gaussian index per tile-sorted duplicate
     const uint32_t* tile_ranges;
+    int no_discard;                 // ND instantiation (see eval_splat); only ever set for splat / unorm8 / fast exp / no depth
     const uint32_t* tile_order;     // nullable: CTA i of the launch rasterizes tile tile_order[order_base + i] (heaviest lists first)
     uint32_t order_base;
     uint8_t* pixels;
@@ -363,7 +364,10 @@ struct DepthArgs {
     int compare, write;
 };
 
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH>
+// ND ("no discard", splat mode on unorm8 targets with sd^2 >= 6.3 only): a fragment beyond the quad's alive radius has
+// alpha = a*exp(-r^2) < exp(-6.3) < kAlphaCut, so blending it is the identity exactly (sb_common.cuh) and the discard test
+// and its select can go.
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH, bool ND = false>
 __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 pxy, bool inside, float sd2, float outline, PixelState& st,
                                            const DepthArgs& da) {
     const char* rp = PERM ? last - 64u * hb : last - 48u * hb;
@@ -406,7 +410,7 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
     }
     // A discarded fragment blends with alpha = 0, which is the identity EXACTLY (d*1 + c*0 = d, and d is
     // already an integer on unorm8 targets): the loop body stays branch-free.
-    alpha = alive ? alpha : 0.0f;
+    if constexpr (!ND) alpha = alive ? alpha : 0.0f;
     const float om = __fsub_rn(1.0f, alpha);
     const f32x2 om2 = pk2(om, om), al2 = pk2(alpha, alpha);
     if constexpr (FMT == FMT_UNORM8) {
@@ -437,7 +441,7 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
 // Warp-level culling: each lane tests one splat against the two 4x4 halves of the warp's 8x4 pixel patch — the
 // bbox of its alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of a half's
 // rectangle against the ellipse's oriented bounding box; each half-warp then evaluates only its own survivors.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false>
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false, bool ND = false>
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
                                                 PixelState& st, DepthArgs da = DepthArgs{nullptr, 0, 0}) {
@@ -481,7 +485,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
                 uint32_t hb;  // FLO directly; `31 - __clz` is canonicalised back into a clz and costs five more integer ops
                 asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
                 todo ^= 1u << hb;
-                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH>(last, hb, pxy, inside, sd2, outline, st, da);
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH, ND>(last, hb, pxy, inside, sd2, outline, st, da);
             }
         } else {
             uint32_t todo = __brev(un);
@@ -489,7 +493,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
                 uint32_t hb;
                 asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
                 todo ^= 1u << hb;
-                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH>(last, hb, pxy, inside, sd2, outline, st, da);
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH, ND>(last, hb, pxy, inside, sd2, outline, st, da);
             }
         }
     }
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelPara
 // (coalesced) and fetches the 48-byte records straight from the per-Gaussian array with TMA
 // tile::gather4 (cp.async.bulk.tensor.2d ... tile::gather4 -> UTMALDG, four rows per instruction, two
 // instructions per lane and batch) into a double-buffered ring; eight consumer warps composite.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool DEPTH = false>
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool DEPTH = false, bool ND = false>
 __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_constant__ RasterKernelParams p, const __grid_constant__ CUtensorMap recs_map) {
     __shared__ __align__(256) float4 stage[kG4Stages][kG4StageF4];
     __shared__ float zs[DEPTH ? kG4Stages : 1][DEPTH ? kBatchG4 : 1];  // ndc z per staged record (depth-tested passes only)
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
         mbar_wait(&full_bar[s], (k / kG4Stages) & 1u);
         if constexpr (DEPTH) mbar_wait(&z_bar[s], (k / kG4Stages) & 1u);
         const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
-        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline,
+        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH, ND>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline,
                                                                p.obb_cull != 0, st, DepthArgs{DEPTH ? zs[s] : nullptr, p.depth_compare, p.depth_write});
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -789,8 +793,14 @@ void launch_raster(const RasterKernelParams& kp, const CUtensorMap* recs_map, di
     if (recs_map && kp.depth) {
         raster_gather4_kernel<MODE, FMT, STRICT, false, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
     } else if (recs_map) {
-        if (kp.counters) raster_gather4_kernel<MODE, FMT, STRICT, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
-        else raster_gather4_kernel<MODE, FMT, STRICT, false><<<grid, 288, 0, stream>>>(kp, *recs_map);
+        if (kp.counters) {
+            raster_gather4_kernel<MODE, FMT, STRICT, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
+        } else if (kp.no_discard) {
+            if constexpr (MODE == SB_MODE_SPLAT && FMT == FMT_UNORM8 && !STRICT)
+                raster_gather4_kernel<MODE, FMT, STRICT, false, false, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
+        } else {
+            raster_gather4_kernel<MODE, FMT, STRICT, false><<<grid, 288, 0, stream>>>(kp, *recs_map);
+        }
     } else {
         if (kp.counters) raster_bulk_kernel<MODE, FMT, STRICT, true><<<grid, 256, 0, stream>>>(kp);
         else raster_bulk_kernel<MODE, FMT, STRICT, false><<<grid, 256, 0, stream>>>(kp);
@@ -886,6 +896,8 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
     kp.clear = p.clear;
     kp.obb_cull = p.obb_cull;
+    kp.no_discard = p.no_discard && u.mode == SB_MODE_SPLAT && (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) &&
+                    !p.strict_exp && !p.depth && !p.counters && p.recs_map && u.std_dev * u.std_dev >= 6.3f;
     kp.depth = p.depth;
     kp.depth_pitch = p.depth_pitch;
     kp.depth_compare = p.depth_compare;
