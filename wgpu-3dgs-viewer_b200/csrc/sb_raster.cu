@@ -441,10 +441,53 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
 // Warp-level culling: each lane tests one splat against the two 4x4 halves of the warp's 8x4 pixel patch — the
 // bbox of its alive region and (obb) the two ellipse axes, i.e. the full separating-axis test of a half's
 // rectangle against the ellipse's oriented bounding box; each half-warp then evaluates only its own survivors.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false, bool ND = false>
+// CTA-level cull of the gather4 path: ONE thread tests a splat against all sixteen 4x4 blocks of the tile (bit 4 j + i <->
+// block column i, row j; bx0/by0 = centre of block (0, 0)) with the same tests a warp used to run for its own two blocks —
+// bbox of the alive region and the separating-axis test against the ellipse's oriented bounding box.  The eight warps then
+// pick their two bits from the mask instead of each loading and testing every splat of the list themselves.
+__device__ __forceinline__ uint32_t block_mask(const float4* __restrict__ rec, float bx0, float by0, float sd, bool obb) {
+    const float4 c0 = rec[0];  // cx cy ax bx
+    const float4 c1 = rec[1];  // ay by ex ey
+    const float ex = c1.z + 1.51f, ey = c1.w + 1.51f;
+    float dl[4], dy[4];
+    uint32_t cm = 0, rm = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        dl[i] = (bx0 + 4.0f * (float)i) - c0.x;
+        dy[i] = (by0 + 4.0f * (float)i) - c0.y;
+        cm |= (fabsf(dl[i]) <= ex ? 1u : 0u) << i;
+        rm |= (fabsf(dy[i]) <= ey ? 1u : 0u) << i;
+    }
+    if (cm == 0u || rm == 0u) return 0u;
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) m |= ((rm >> j) & 1u) ? (cm << (4 * j)) : 0u;
+    if (obb) {
+        // |q(p)| <= |q(pc)| + 1.5|a_x| + 1.5|a_y| over a block's pixel centres; alive needs |q| <= sd
+        const float mx = fmaf(1.5f, fabsf(c0.z) + fabsf(c1.x), sd), my = fmaf(1.5f, fabsf(c0.w) + fabsf(c1.y), sd);
+        const float lx = fmaf(mx, 1.0001f, 1.0e-3f), ly = fmaf(my, 1.0001f, 1.0e-3f);
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float tx = dy[j] * c1.x, ty = dy[j] * c1.y;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool h = fabsf(fmaf(dl[i], c0.z, tx)) <= lx && fabsf(fmaf(dl[i], c0.w, ty)) <= ly;
+                keep |= (h ? 1u : 0u) << (4 * j + i);
+            }
+        }
+        m &= keep;
+    }
+    return m;
+}
+
+// SHARED: the hit masks of the batch were computed once per CTA (block_mask) and sit in shared memory; `bl` = this warp's
+// left block's bit.
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false, bool ND = false, bool SHARED = false>
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
-                                                PixelState& st, DepthArgs da = DepthArgs{nullptr, 0, 0}) {
+                                                PixelState& st, DepthArgs da = DepthArgs{nullptr, 0, 0},
+                                                const uint16_t* __restrict__ masks = nullptr, uint32_t bl = 0) {
     // Byte addressing.  PERM (gather4 path): record j sits at 64 j (rows are fetched 64 bytes wide, four per 256-byte gather);
     // otherwise at 48 j.  A round is 32 consecutive records starting at a multiple of 32.
     const char* rb = reinterpret_cast<const char*>(recs);
@@ -453,7 +496,11 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
     for (uint32_t base = 0; base < cnt; base += 32, mine += kRound, rb += kRound, da.zs += DEPTH ? 32 : 0) {
         // each lane tests ONE splat against BOTH 4x4 halves of the warp's 8x4 patch (pcx: centre of the left half)
         bool hit_l = false, hit_r = false;
-        if (base + lane < cnt) {
+        if constexpr (SHARED) {
+            const uint32_t m = masks[base + lane] >> bl;  // masks past the end of the list are zero
+            hit_l = m & 1u;
+            hit_r = m & 2u;
+        } else if (base + lane < cnt) {
             const float4 c0 = *reinterpret_cast<const float4*>(mine);       // cx cy ax bx
             const float4 c1 = *reinterpret_cast<const float4*>(mine + 16);  // ay by ex ey
             const float dl = pcx - c0.x, dr = dl + 4.0f, ddy = pcy - c0.y;
@@ -586,6 +633,8 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t z_bar[kG4Stages];  // DEPTH: producer's generic stores to zs -> consumers (plain arrive/wait pair)
     __shared__ __align__(8) uint64_t full_bar[kG4Stages];
     __shared__ __align__(8) uint64_t empty_bar[kG4Stages];
+    __shared__ uint16_t cull_mask[kG4Stages][kBatchG4];  // block_mask of every staged record (consumer thread t owns record t)
+    static_assert(kBatchG4 == 256, "one consumer thread per staged record");
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     uint32_t tile_x = blockIdx.x, tile_y = p.ty_lo + blockIdx.y;
@@ -670,6 +719,8 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
     const bool inside = x < p.width && y >= p.row0 && y < p.row0 + p.rows;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
     const float pcx = (float)(tile_x * kTile + (warp & 1u) * 8) + 2.0f, pcy = (float)(tile_y * kTile + (warp >> 1) * 4) + 2.0f;
+    const float bx0 = (float)(tile_x * kTile) + 2.0f, by0 = (float)(tile_y * kTile) + 2.0f;  // centre of block (0, 0)
+    const uint32_t bl = (warp >> 1) * 4u + (warp & 1u) * 2u;                                   // bit of this warp's left block
     PixelState st;
     uint8_t* dst = p.pixels + (size_t)(y - p.row0) * p.pitch;
     if (!p.clear && inside) load_dst<FMT>(st, dst, x, p.bgra);
@@ -684,8 +735,14 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
         mbar_wait(&full_bar[s], (k / kG4Stages) & 1u);
         if constexpr (DEPTH) mbar_wait(&z_bar[s], (k / kG4Stages) & 1u);
         const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
-        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH, ND>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2, p.outline,
-                                                               p.obb_cull != 0, st, DepthArgs{DEPTH ? zs[s] : nullptr, p.depth_compare, p.depth_write});
+        // CTA-level cull: thread t tests record t of the batch against the tile's sixteen blocks, once for all warps.  The
+        // buffer of stage s is free: the stage was refilled only after every warp had released it (empty_bar).
+        cull_mask[s][tid] = tid < cnt ? (uint16_t)block_mask(&stage[s][4u * tid], bx0, by0, p.sd, p.obb_cull != 0) : (uint16_t)0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight consumer warps (the producer warp is not part of it)
+        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH, ND, true>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2,
+                                                                     p.outline, p.obb_cull != 0, st,
+                                                                     DepthArgs{DEPTH ? zs[s] : nullptr, p.depth_compare, p.depth_write},
+                                                                     cull_mask[s], bl);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
