@@ -428,6 +428,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.target = *target;
     p.strict_exp = v->strict_exp;
     p.no_discard = v->exact_cutoff ? 1 : 0;
+    p.cut_k = 0.0f;  // set below, once it is known whether the records keep their cut extents for this pass
     p.clear = clear;
     {
         // SB_RASTER_CULL=bbox keeps the warp-level cull on the alive-region bbox only (A/B measurements)
@@ -464,6 +465,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
             v->recs_cut = false;
         }
     }
+    p.cut_k = v->recs_cut ? 1.0f / sb::kAlphaCut : 0.0f;
     p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
     if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 32, stream));
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
@@ -1138,7 +1140,7 @@ SbStatus sb_renderer_render(SbRenderer* r, void* stream, const SbRendererBindGro
     v->ext_count = &d_indirect_args->instance_count;
     const bool depth_pass = depth && depth->d_depth;
     sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format, v->exact_cutoff && !depth_pass);
-    v->recs_cut = false;  // the vertex stage below already matches the pass
+    v->recs_cut = u.cut_k > 0.0f;  // the vertex stage below already matches the pass (no cut with a depth attachment)
     SbStatus s = check_target(v, target, u);  // validate before enqueuing anything
     if (s != SB_OK) return s;
     // vertex stage (render.wesl:76-130) for exactly the instances the draw names

@@ -88,6 +88,7 @@ struct RasterParams {
     int strict_exp;
     int clear;                       // 1: clear to BLACK first (first model of a frame)
     int obb_cull;                    // 1: warp-level cull also tests the ellipse axes (SAT), 0: bbox only
+    float cut_k;                     // 1 / kAlphaCut when recs carry cut extents (the cull may then use each splat's cut radius), else 0
     int no_discard;                  // allow the rasterizer to drop the discard test where it is provably redundant (exact cut-off on)
     int raster_bands;                // rasterize the tile rows as this many launches (<= 1: one)
     float* depth;                    // optional f32 depth attachment (strip geometry of the target); needs recs_map

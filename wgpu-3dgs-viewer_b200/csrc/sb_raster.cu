@@ -270,6 +270,7 @@ struct RasterKernelParams {
     const SplatRec* tile_recs;      // bulk path: records gathered into tile order
     const uint32_t* dup_vals;       // gather4 path: Gaussian index per tile-sorted duplicate
     const uint32_t* tile_ranges;
+    float cut_k;                    // 1 / kAlphaCut when the staged records carry cut extents (exact alpha cut-off), else 0
     int no_discard;                 // ND instantiation (see eval_splat); only ever set for splat / unorm8 / fast exp / no depth
     const uint32_t* tile_order;     // nullable: CTA i of the launch rasterizes tile tile_order[order_base + i] (heaviest lists first)
     uint32_t order_base;
@@ -445,7 +446,7 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
 // block column i, row j; bx0/by0 = centre of block (0, 0)) with the same tests a warp used to run for its own two blocks —
 // bbox of the alive region and the separating-axis test against the ellipse's oriented bounding box.  The eight warps then
 // pick their two bits from the mask instead of each loading and testing every splat of the list themselves.
-__device__ __forceinline__ uint32_t block_mask(const float4* __restrict__ rec, float bx0, float by0, float sd, bool obb) {
+__device__ __forceinline__ uint32_t block_mask(const float4* __restrict__ rec, float bx0, float by0, float sd, bool obb, float cut_k) {
     const float4 c0 = rec[0];  // cx cy ax bx
     const float4 c1 = rec[1];  // ay by ex ey
     const float ex = c1.z + 1.51f, ey = c1.w + 1.51f;
@@ -463,16 +464,27 @@ __device__ __forceinline__ uint32_t block_mask(const float4* __restrict__ rec, f
 #pragma unroll
     for (int j = 0; j < 4; j++) m |= ((rm >> j) & 1u) ? (cm << (4 * j)) : 0u;
     if (obb) {
-        // |q(p)| <= |q(pc)| + 1.5|a_x| + 1.5|a_y| over a block's pixel centres; alive needs |q| <= sd
-        const float mx = fmaf(1.5f, fabsf(c0.z) + fabsf(c1.x), sd), my = fmaf(1.5f, fabsf(c0.w) + fabsf(c1.y), sd);
+        // Radius of the region that can change a pixel, in quad-offset units: sd, or with the exact alpha cut-off
+        // (sb_common.cuh) the radius beyond which alpha = a*exp(-r^2) < kAlphaCut — a little more margin than the vertex
+        // stage takes, so this never cuts tighter than the extents it wrote.
+        float rc = sd;
+        if (cut_k > 0.0f) rc = sqrtf(fminf(fmaxf(__logf(rec[2].w * cut_k) + 1.5f * kAlphaCutMargin, 0.0f), sd * sd));
+        // separating axes of the ellipse's frame: |q(p)| <= |q(pc)| + 1.5|a_x| + 1.5|a_y| over a block's pixel centres
+        const float mx = fmaf(1.5f, fabsf(c0.z) + fabsf(c1.x), rc), my = fmaf(1.5f, fabsf(c0.w) + fabsf(c1.y), rc);
         const float lx = fmaf(mx, 1.0001f, 1.0e-3f), ly = fmaf(my, 1.0001f, 1.0e-3f);
+        // disc: |q(p) - q(pc)| <= R = 1.5 max |(ax, bx) +- (ay, by)| over the block, so a block with |q(pc)| > rc + R has
+        // no pixel inside the radius (cuts the corners the two axis tests leave)
+        const float sx = c0.z + c1.x, sy = c0.w + c1.y, tx_ = c0.z - c1.x, ty_ = c0.w - c1.y;
+        const float rr = fmaf(1.5f * 1.0001f, sqrtf(fmaxf(fmaf(sx, sx, sy * sy), fmaf(tx_, tx_, ty_ * ty_))), rc) + 1.0e-3f;
+        const float lim2 = rr * rr;
         uint32_t keep = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float tx = dy[j] * c1.x, ty = dy[j] * c1.y;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const bool h = fabsf(fmaf(dl[i], c0.z, tx)) <= lx && fabsf(fmaf(dl[i], c0.w, ty)) <= ly;
+                const float qx = fmaf(dl[i], c0.z, tx), qy = fmaf(dl[i], c0.w, ty);
+                const bool h = fabsf(qx) <= lx && fabsf(qy) <= ly && fmaf(qx, qx, qy * qy) <= lim2;
                 keep |= (h ? 1u : 0u) << (4 * j + i);
             }
         }
@@ -737,7 +749,7 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
         const uint32_t cnt = min((uint32_t)kBatchG4, total - k * kBatchG4);
         // CTA-level cull: thread t tests record t of the batch against the tile's sixteen blocks, once for all warps.  The
         // buffer of stage s is free: the stage was refilled only after every warp had released it (empty_bar).
-        cull_mask[s][tid] = tid < cnt ? (uint16_t)block_mask(&stage[s][4u * tid], bx0, by0, p.sd, p.obb_cull != 0) : (uint16_t)0;
+        cull_mask[s][tid] = tid < cnt ? (uint16_t)block_mask(&stage[s][4u * tid], bx0, by0, p.sd, p.obb_cull != 0, p.cut_k) : (uint16_t)0;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight consumer warps (the producer warp is not part of it)
         composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH, ND, true>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2,
                                                                      p.outline, p.obb_cull != 0, st,
@@ -953,6 +965,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
     kp.clear = p.clear;
     kp.obb_cull = p.obb_cull;
+    kp.cut_k = p.cut_k;
     kp.no_discard = p.no_discard && u.mode == SB_MODE_SPLAT && (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) &&
                     !p.strict_exp && !p.depth && !p.counters && p.recs_map && u.std_dev * u.std_dev >= 6.3f;
     kp.depth = p.depth;
