@@ -631,6 +631,52 @@ def test_exact_alpha_cutoff_is_bit_identical(sb, ob, ctx, camera, strict):
     v.close(); vf.close()
 
 
+@pytest.mark.parametrize("strict", [True, False])
+def test_exact_alpha_cutoff_adversarial(sb, ob, ctx, strict):
+    """The cut-off's rounding argument at its edge: screen-filling splats whose alpha sweeps continuously through the
+    threshold, pure black over pure white and pure white over black (|c - d| = 255, the worst case of the bound), opacity
+    bytes 1..4 as well as opaque ones.  Cut-off and no-discard build on/off give the same frame bit for bit; the strict frame
+    equals the oracle's."""
+    torch = _torch()
+    w, h = 320, 180
+    rng = np.random.default_rng(11)
+    n = 400
+    g = np.zeros(n, dtype=sb.GAUSSIAN_DTYPE)
+    g["rot"][:, 3] = 1.0
+    # all in front of the "outside" camera, near the view axis, big enough to cover the frame with slowly varying r^2
+    g["pos"][:, 0] = rng.uniform(-4, 4, n)
+    g["pos"][:, 1] = rng.uniform(-3, 3, n)
+    g["pos"][:, 2] = np.linspace(8, -8, n)            # far to near in index order too
+    g["scale"][:] = rng.uniform(1.0, 6.0, (n, 1))
+    g["scale"][:, 1] *= rng.uniform(0.3, 1.0, n)       # some anisotropy
+    white = (np.arange(n) // 7) % 2 == 0
+    g["color"][white, :3] = 255
+    g["color"][~white, :3] = 0
+    a = rng.choice([1, 2, 3, 4, 8, 40, 255], n, p=[0.2, 0.2, 0.15, 0.1, 0.1, 0.1, 0.15])
+    g["color"][:, 3] = a
+    g["color"][::50, 3] = 255                         # opaque layers that flip the destination to the other extreme
+    pods = sb.pack_gaussians(g)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.update_gaussian_transform(1.0, sb.MODE_SPLAT, 0, False, 3.0)   # sh_deg 0: colours exactly 0 / 255
+    v.set_strict_exp(strict)
+    frames = []
+    for cut in (True, False):
+        v.set_exact_cutoff(cut)
+        t = torch.full((h, w, 4), 9, dtype=torch.uint8, device="cuda")
+        v.render(t, w, h)
+        torch.cuda.synchronize()
+        frames.append(t.cpu().numpy())
+    assert np.array_equal(frames[0], frames[1])
+    assert frames[0][..., :3].min() < 30 and frames[0][..., :3].max() > 200   # both extremes are on screen
+    if strict:
+        oimg, _ = ob.render(ob.OracleModel(pods, n), ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(1.0, 0, 0, False, 3.0),
+                            strict_exp=True)
+        assert np.array_equal(frames[0], oimg)
+    v.close()
+
+
 def test_bulk_raster_path_parity(sb, ob):
     """SB_RASTER_PATH=bulk (gathered copy + 1-D TMA bulk copies) stays bit-identical to the default
     TMA gather4 path; run in a subprocess because the path is chosen at viewer creation."""
