@@ -25,7 +25,7 @@ namespace sb {
 namespace {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
+constexpr int kScanItems = 16;  // 4096 splats per tile: a quarter of the look-back hops of 1024 (the kernel is bound by the latency of that chain and of its gathers)
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 struct BinParams {
@@ -78,11 +78,24 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
     uint32_t cnt[kScanItems];
     uint32_t sum = 0;
+    static_assert(kScanItems % 4 == 0, "a thread's run of splats is read and written as 128-bit vectors");
+    uint32_t gidx[kScanItems];
+    const bool whole = base + kScanItems <= v;  // the run starts at a multiple of kScanItems: 16-byte aligned
+    if (whole) {
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; q++) {
+            const uint4 t = reinterpret_cast<const uint4*>(sorted + base)[q];
+            gidx[4 * q] = t.x; gidx[4 * q + 1] = t.y; gidx[4 * q + 2] = t.z; gidx[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) gidx[i] = base + i < v ? sorted[base + i] : 0u;
+    }
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
         const uint32_t r = base + i;
         uint32_t x0, y0, w;
-        cnt[i] = r < v ? splat_tiles(p.tboxes, sorted[r], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
+        cnt[i] = r < v ? splat_tiles(p.tboxes, gidx[i], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
         sum += cnt[i];
     }
     uint32_t inc = sum;
@@ -106,11 +119,23 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     }
     __syncthreads();
     uint32_t off = s_base + wexcl + inc - sum;
+    if (whole) {
 #pragma unroll
-    for (int i = 0; i < kScanItems; i++) {
-        const uint32_t r = base + i;
-        if (r < v) p.dup_offsets[r] = off;
-        off += cnt[i];
+        for (int q = 0; q < kScanItems / 4; q++) {
+            uint4 o;
+            o.x = off; off += cnt[4 * q];
+            o.y = off; off += cnt[4 * q + 1];
+            o.z = off; off += cnt[4 * q + 2];
+            o.w = off; off += cnt[4 * q + 3];
+            reinterpret_cast<uint4*>(p.dup_offsets + base)[q] = o;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            const uint32_t r = base + i;
+            if (r < v) p.dup_offsets[r] = off;
+            off += cnt[i];
+        }
     }
     const uint32_t last_tile = v == 0 ? 0 : (v - 1) / kScanTile;
     if (tile == last_tile && tid == 0) {
@@ -142,11 +167,18 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
             off = p.dup_offsets[r];
         }
         if (n > 0 && n <= 32) {
+            // row-major walk of the box without a division per tile
+            uint32_t key = y0 * p.tiles_x + x0, col = 0;
             for (uint32_t j = 0; j < n; j++) {
                 const uint32_t o = off + j;
                 if (o < p.dup_capacity) {
-                    p.dup_keys[o] = (y0 + j / w) * p.tiles_x + (x0 + j % w);
+                    p.dup_keys[o] = key;
                     p.dup_vals[o] = g;
+                }
+                ++key;
+                if (++col == w) {
+                    col = 0;
+                    key += p.tiles_x - w;
                 }
             }
         }
@@ -157,10 +189,15 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
             const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bg = __shfl_sync(0xffffffffu, g, src);
             const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src), boff = __shfl_sync(0xffffffffu, off, src);
+            // j / bw by multiplication: one division per big splat instead of one per tile.  floor(j / bw) ==
+            // umulhi(j, ceil(2^32 / bw)) whenever j * bw < 2^32 (checked; bw == 1 would need 2^32 as the multiplier)
+            const bool mul_ok = bw > 1u && (unsigned long long)bn * bw < (1ull << 32);
+            const uint32_t inv = mul_ok ? 0xffffffffu / bw + 1u : 0u;
             for (uint32_t j = lane; j < bn; j += 32) {
                 const uint32_t o = boff + j;
                 if (o < p.dup_capacity) {
-                    p.dup_keys[o] = (by0 + j / bw) * p.tiles_x + (bx0 + j % bw);
+                    const uint32_t q = mul_ok ? __umulhi(j, inv) : j / bw;
+                    p.dup_keys[o] = (by0 + q) * p.tiles_x + (bx0 + (j - q * bw));
                     p.dup_vals[o] = bg;
                 }
             }
