@@ -325,6 +325,7 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.recs = v->recs.as<sb::SplatRec>();
     p.tboxes = v->tboxes.as<sb::TileBox>();
     p.visible_count = v->d_visible();
+    p.visible_host = v->d_needed + 4;  // mapped pinned: the next frame's sort reads it (no synchronisation) as a size hint
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format, v->exact_cutoff);
     v->recs_cut = p.u.cut_k > 0.0f;
     v->sorted_pending = false;  // a new visible set replaces whatever a previous frame left behind
@@ -352,8 +353,9 @@ sb::SortScratch depth_sort_scratch(SbViewer* v) {
 
 SbStatus do_sort(SbViewer* v, cudaStream_t stream, bool defer_copy_home = false) {
     // keys = f32 depth bit patterns in [0, 0x3F800000]; pads (2.0) beyond V are left in place
+    // size hint = the visible count the previous preprocess of this viewer reported (0 = none yet): a heuristic only
     SB_CUDA(v->ctx, sb::launch_sort(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), v->d_visible(), v->n, 0, 32, depth_sort_scratch(v),
-                                    v->ctx->num_sms, stream, defer_copy_home ? v->d_sort_parity() : nullptr));
+                                    v->ctx->num_sms, stream, defer_copy_home ? v->d_sort_parity() : nullptr, v->h_needed[4]));
     v->sorted_pending = defer_copy_home;
     v->last_stream = stream;
     if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[2], stream));

@@ -24,6 +24,7 @@ struct PreParams {
     uint32_t* tile_counter;            // dynamic tile ticket (zeroed before launch)
     unsigned long long* tile_status;   // decoupled look-back state (zeroed before launch)
     uint32_t* visible_count;           // V for downstream kernels
+    uint32_t* visible_host;            // nullable: device alias of a mapped pinned word that also receives V
     Uniforms u;
 };
 
@@ -51,9 +52,11 @@ size_t sort_internal_bytes(uint32_t capacity);
 // copied back otherwise.
 // parity_out (device word, nullable): the result is left where the last pass wrote it — *parity_out = 1: in the alt
 // buffers — and launch_sort_finish brings it home when somebody needs it there.
+// expected_count (0 = unknown): a hint for the choice of pass kernel — small sorts are bound by the length of the look-back
+// chain and take the kernel with the larger tiles.
 cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count,
                         int begin_bit, int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream,
-                        uint32_t* parity_out = nullptr);
+                        uint32_t* parity_out = nullptr, uint32_t expected_count = 0);
 cudaError_t launch_sort_finish(uint32_t* keys, uint32_t* payload, const SortScratch& scratch, const uint32_t* d_count, uint32_t max_count,
                                const uint32_t* parity, int num_sms, cudaStream_t stream);
 

@@ -605,6 +605,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
                 p.sort_args->y = 1;
                 p.sort_args->z = 1;
                 *p.visible_count = v;
+                if (p.visible_host) *p.visible_host = v;
             }
             const uint32_t padded = min(blocks * kHistoBlockKvs, p.keys_capacity);
             for (uint32_t i = v + tid; i < padded; i += T) p.keys[i] = 2.0f;
