@@ -6,10 +6,12 @@
 //   K5 dup_emit    (tile id, Gaussian index) duplicates, emitted in depth order
 //      tile sort   stable onesweep over the tile-id bits only (sb_sort.cu): because the input is
 //                  already in the reference's draw order, stability alone preserves it per tile
-//   K5b gather     tile ranges + splat records gathered into tile order (contiguous batches)
-//   K6 raster      one CTA per 16x16 tile; batches staged into shared memory with TMA bulk
-//                  copies; one pixel per thread composites back-to-front in exactly the
-//                  reference's order, re-quantising after every blend on unorm8 targets.
+//   K5b ranges     per-tile ranges of the sorted duplicates + the rasterizer's longest-list-first tile schedule
+//                  (SB_RASTER_PATH=bulk: also a gathered copy of the records in tile order)
+//   K6 raster      one CTA per 16x16 tile; the tile's records are staged into shared memory by TMA gather4 straight
+//                  from the per-Gaussian array, culled once per CTA against the sixteen 4x4 blocks, and one pixel
+//                  per thread composites back-to-front in exactly the reference's order, re-quantising after every
+//                  blend on unorm8 targets.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -226,10 +228,9 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------- K6 rasterizer
 
 constexpr int kBatch = 256;  // splat records per shared-memory stage (12 KB)
-// gather4 path: 256 records per batch = 64 gather4s (two per producer lane).  Gather m holds the
-// consecutive records 4m..4m+3 (4 rows x 48 B) and is written at a 256-byte pitch (the TMA destination
-// must be 128-byte aligned), so record j of the batch starts at float4 index (j >> 2) * 16 + (j & 3) * 3
-// = 3 j + (j & ~3): a cull round's 32 consecutive records spread over the banks (2-way conflicts).
+// gather4 path: 256 records per batch = 64 gather4s (two per producer lane).  The tensor map declares rows 16 floats wide
+// over the 48-byte record stride, so gather m brings records 4m..4m+3 as four 64-byte rows (a record + 16 bytes of its
+// successor) into one 256-byte slot (the TMA destination must be 128-byte aligned): record j of the batch sits at 64 j.
 #ifndef SB_G4_BATCH
 #define SB_G4_BATCH 256
 #endif
