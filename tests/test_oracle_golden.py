@@ -216,3 +216,51 @@ def test_oracle_brush_mask_is_a_capsule():
     assert stroke[0] & 0b0001 and not stroke[0] & 0b0100 and not stroke[0] & 0b1000
     both = ob.select_brush(m, cam, [(100.0, 0.0), (100.0, 99.0)], 1.0, accumulate=True, dest=stroke)
     assert both[0] & 0b0100 and both[0] & stroke[0] == stroke[0]
+
+
+def test_oracle_draw_equals_render_and_clips_whole_quads(ob, sb):
+    """so_draw (Renderer<G, ()>::render on caller indices) fed with the preprocess + sort output reproduces so_render, and
+    drops the quads whose centre has w <= 0 or ndc z outside [0, 1] when it is handed indices no preprocess produced."""
+    n, w, h = 4000, 320, 180
+    g = sb.scenes.synthetic_gaussians(n, 5)
+    pods = ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE))
+    pos, yaw, pitch = sb.scenes.CAMERA_INSIDE
+    cam, gt = ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod()
+    om = ob.OracleModel(pods, n)
+    pre = ob.preprocess(om, cam, gt)
+    V = pre["count"]
+    _, idx = ob.radix_sort(pre["keys"][:V].view(np.uint32), pre["indices"][:V])
+    ref, _ = ob.render(om, cam, gt, strict_exp=True)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    ob.draw(om, cam, gt, idx, out, strict_exp=True)
+    assert np.array_equal(out, ref)
+    # every Gaussian in index order: the culled ones behind the camera must not draw, the ones beside the frustum may
+    sp = ob.project(om, cam, gt, np.arange(n, dtype=np.uint32))
+    behind = ~((sp["z"] >= 0) & (sp["z"] <= 1))
+    assert behind.sum() > n // 4
+    only_behind = np.flatnonzero(behind).astype(np.uint32)
+    out2 = np.full((h, w, 4), 7, dtype=np.uint8)
+    ob.draw(om, cam, gt, only_behind, out2, strict_exp=True)
+    assert (out2[..., :3] == 0).all() and (out2[..., 3] == 255).all()  # cleared to BLACK, nothing drawn
+
+
+def test_alpha_cutoff_identity_bound():
+    """The rounding argument behind the exact alpha cut-off (sb_common.cuh kAlphaCut = 0.00195): for every destination
+    d in 0..255, source colours c255 in [0, 255] and alpha <= kAlphaCut, rint(fma(d, 1 - alpha, c255 * alpha)) == d in the
+    f32 arithmetic the blend uses — and the no-discard build's premise exp(-6.3) < kAlphaCut."""
+    f32 = np.float32
+    cut = f32(0.00195)
+    assert np.exp(-6.3) < float(cut) * 0.99
+    rng = np.random.default_rng(1)
+    d = np.arange(256, dtype=np.float64)[:, None, None]
+    c = np.concatenate([np.array([0.0, 255.0, 254.99998, 1e-3]), rng.uniform(0, 255, 60)]).astype(f32).astype(np.float64)[None, :, None]
+    alphas = np.concatenate([np.array([cut, np.nextafter(cut, f32(0)), f32(1e-30), f32(0)], dtype=f32),
+                             (cut * rng.uniform(0, 1, 200).astype(f32)).astype(f32)])
+    om = (f32(1.0) - alphas).astype(f32).astype(np.float64)[None, None, :]          # 1 - alpha, rounded to f32
+    ca = (c.astype(f32) * alphas[None, None, :]).astype(f32).astype(np.float64)    # c255 * alpha, rounded to f32
+    x = (d * om + ca).astype(f32)                                                   # the fma: one rounding (f64 sum is exact enough: 1e-13)
+    assert np.array_equal(np.rint(x.astype(np.float64)), np.broadcast_to(d, x.shape))
+    # and just above the bound the identity does fail somewhere: the cut is not vacuous by orders of magnitude
+    a_big = f32(0.0021)
+    x2 = (d[:, 0, 0] * float(f32(1.0) - a_big) + float(f32(255.0) * a_big)).astype(f32)
+    assert (np.rint(x2) != d[:, 0, 0]).any()
