@@ -262,10 +262,13 @@ def test_screen_strips_match_full_frame(sb, ob, ctx):
     v.close()
 
 
-def test_multi_model_draw_order_and_selection(sb, ob, ctx):
+@pytest.mark.parametrize("explicit_stream", [False, True])
+def test_multi_model_draw_order_and_selection(sb, ob, ctx, explicit_stream):
     """Config 4: models composited in caller key order (multi_model.rs:505-527), per-model
-    transforms, per-model selection masks."""
+    transforms, per-model selection masks — on the legacy default stream and on a stream of the caller's (the models'
+    preprocess / sort / binning chains run on internal side streams, the rasters in key order on the caller's)."""
     torch = _torch()
+    stream = torch.cuda.Stream() if explicit_stream else None
     w, h, n = 640, 360, 6000
     pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
     cam = sb.camera_pod(pos, yaw, pitch, w, h)
@@ -290,7 +293,9 @@ def test_multi_model_draw_order_and_selection(sb, ob, ctx):
         omodels[k] = ob.OracleModel(pods, n, model_transform=ob.model_transform_pod(*mt), selection=sel, invert_selection=int(k == 1))
     for order in ([0, 1, 2, 3], [3, 1, 0, 2], [2], [1, 1, 0]):
         target = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
-        mm.render(target, w, h, order)
+        torch.cuda.synchronize()
+        mm.render(target, w, h, order, stream=stream)
+        mm.render(target, w, h, order, stream=stream)  # back to back: the second frame reuses every buffer of the first
         torch.cuda.synchronize()
         oimg, _ = ob.render([omodels[k] for k in order], ocam, ob.gaussian_transform_pod())
         d = np.abs(target.cpu().numpy().astype(np.int32) - oimg.astype(np.int32)).max()

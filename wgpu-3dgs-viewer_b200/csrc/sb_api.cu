@@ -372,9 +372,15 @@ SbStatus flush_sorted(SbViewer* v, cudaStream_t stream) {
 }
 
 SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, const SbTarget* target, int clear,
-                 cudaStream_t stream, const SbDepthAttachment* depth = nullptr) {
+                 cudaStream_t stream, const SbDepthAttachment* depth = nullptr, cudaStream_t raster_stream = nullptr,
+                 cudaEvent_t bin_done = nullptr) {
     sb::RasterParams p;
     std::memset(&p, 0, sizeof p);
+    p.split_raster = bin_done != nullptr;  // multi-model frames: binning on `stream`, the raster on the frame's draw-order stream
+    p.raster_stream = raster_stream;       // (may be the legacy default stream, i.e. null)
+    p.bin_done = bin_done;
+    // a reallocation below must wait for everything that may still read the old buffers, on either stream
+    auto quiesce = [&]() { return bin_done ? cudaDeviceSynchronize() : cudaStreamSynchronize(stream); };
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format);
     SbStatus s = check_target(v, target, p.u);
     if (s != SB_OK) return s;
@@ -384,7 +390,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     // frame that overflowed dropped its nearest splats and is flagged by read_frame_stats.
     const uint64_t want = std::max<uint64_t>(8ull * v->n + 128ull * tiles + (1ull << 20), (uint64_t)*v->h_needed * 3 / 2);
     if (*v->h_needed > v->dup_capacity || (v->tile_capacity == 0 && want > v->dup_capacity) || tiles > v->tile_capacity) {
-        SB_CUDA(v->ctx, cudaStreamSynchronize(stream));
+        SB_CUDA(v->ctx, quiesce());
         if (want > v->dup_capacity) {
             SbStatus gs = viewer_reserve(v, want);
             if (gs != SB_OK) return gs;
@@ -392,7 +398,7 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
         *v->h_needed = 0;
     }
     if (tiles > v->tile_capacity) {
-        SB_CUDA(v->ctx, cudaStreamSynchronize(stream));
+        SB_CUDA(v->ctx, quiesce());
         SB_CUDA(v->ctx, v->tile_ranges.alloc((size_t)tiles * 8));
         SB_CUDA(v->ctx, v->tile_order.alloc((size_t)tiles * 4));
         v->tile_capacity = tiles;
@@ -1167,6 +1173,12 @@ struct SbMultiModelViewer {
     SbCameraPod camera;
     SbGaussianTransformPod gaussian_transform;
     std::map<uint64_t, SbViewer*> models;  // HashMap<K, MultiModelViewerModel<G>>
+    // render(): the models' preprocess / sort / binning chains run on these side streams, forked from the caller's stream;
+    // only the rasters stay in draw order on the caller's stream
+    static constexpr int kSide = 4;
+    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr;
+    std::vector<cudaEvent_t> bin_done;
 };
 
 extern "C" {
@@ -1188,6 +1200,10 @@ SbStatus sb_mm_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t t
 void sb_mm_destroy(SbMultiModelViewer* mm) {
     if (!mm) return;
     for (auto& kv : mm->models) sb_viewer_destroy(kv.second);
+    for (cudaStream_t st : mm->side)
+        if (st) cudaStreamDestroy(st);
+    if (mm->fork) cudaEventDestroy(mm->fork);
+    for (cudaEvent_t e : mm->bin_done) cudaEventDestroy(e);
     delete mm;
 }
 
@@ -1265,6 +1281,42 @@ SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* targ
         auto it = mm->models.find(keys[i]);
         if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
         models.push_back(it->second);
+    }
+    // Several distinct models: their preprocess / sort / binning chains are independent (own buffers) and mostly latency-
+    // bound, so they run concurrently on side streams; the rasters keep the key order on the caller's stream.
+    bool concurrent = models.size() > 1;
+    for (size_t i = 0; i < models.size() && concurrent; i++)
+        for (size_t j = 0; j < i; j++)
+            if (models[i] == models[j]) concurrent = false;  // the same model twice shares its buffers: keep it sequential
+    if (concurrent) {
+        if (!mm->fork) {
+            for (cudaStream_t& sd : mm->side) SB_CUDA(mm->ctx, cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+            SB_CUDA(mm->ctx, cudaEventCreateWithFlags(&mm->fork, cudaEventDisableTiming));
+        }
+        while (mm->bin_done.size() < models.size()) {
+            cudaEvent_t e = nullptr;
+            SB_CUDA(mm->ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            mm->bin_done.push_back(e);
+        }
+        // validate before enqueuing anything
+        if (!target || !target->d_pixels) return fail(mm->ctx, SB_ERR_INVALID_ARG, "null target");
+        SB_CUDA(mm->ctx, cudaEventRecord(mm->fork, st));
+        for (cudaStream_t sd : mm->side) SB_CUDA(mm->ctx, cudaStreamWaitEvent(sd, mm->fork, 0));
+        for (size_t i = 0; i < models.size(); i++) {  // multi_model.rs:491-503
+            cudaStream_t sd = mm->side[i % SbMultiModelViewer::kSide];
+            SbStatus s = do_preprocess(models[i], mm->camera, mm->gaussian_transform, sd);
+            if (s == SB_OK) s = do_sort(models[i], sd, true);
+            if (s != SB_OK) return s;
+        }
+        int clr = 1;
+        for (size_t i = 0; i < models.size(); i++) {  // multi_model.rs:505-527: one pass, models in key order
+            SbStatus s = do_draw(models[i], mm->camera, mm->gaussian_transform, target, clr, mm->side[i % SbMultiModelViewer::kSide], nullptr, st,
+                                 mm->bin_done[i]);
+            if (s != SB_OK) return s;
+            models[i]->last_stream = st;  // ordered after this model's sort through bin_done
+            clr = 0;
+        }
+        return SB_OK;
     }
     for (SbViewer* v : models) {  // multi_model.rs:491-503
         SbStatus s = do_preprocess(v, mm->camera, mm->gaussian_transform, st);

@@ -102,6 +102,12 @@ struct RasterParams {
     const CUtensorMap* recs_map;     // non-null: fetch records with TMA gather4 (no gathered copy); host pointer, passed by value
     unsigned long long* counters;    // optional instrumentation: [0] alive fragments, [1] evaluated lane pairs
     cudaEvent_t* events;             // optional: [0]=after scan+emit, [1]=after tile sort, [2]=after gather, [3]=after raster
+    // Optional split (multi-model frames): binning runs on the stream passed to launch_bin_and_raster, `bin_done` is recorded
+    // there, and the raster kernel is enqueued on `raster_stream` after waiting for it — models are binned concurrently while
+    // their rasters stay in draw order on one stream.
+    bool split_raster;               // (a null raster_stream is the legacy default stream, so the split has its own flag)
+    cudaStream_t raster_stream;
+    cudaEvent_t bin_done;
 };
 cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_clear(const SbTarget& target, cudaStream_t stream);

@@ -982,6 +982,14 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     if (p.buf.tile_order)
         tile_order_kernel<<<1, 1024, 0, stream>>>(p.buf.tile_ranges, ty_lo * u.tiles_x, (ty_hi - ty_lo + 1) * u.tiles_x, p.buf.tile_order);
     if (p.events) cudaEventRecord(p.events[2], stream);
+    if (p.split_raster && p.bin_done != nullptr && p.raster_stream != stream) {
+        // binning done on this model's stream; its raster goes to the frame's draw-order stream
+        e = cudaEventRecord(p.bin_done, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(p.raster_stream, p.bin_done, 0);
+        if (e != cudaSuccess) return e;
+        stream = p.raster_stream;
+    }
 
     RasterKernelParams kp;
     kp.tile_order = p.buf.tile_order;
