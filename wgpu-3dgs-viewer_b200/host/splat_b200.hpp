@@ -91,6 +91,9 @@ public:
     void select_brush(void* stream, const std::vector<float>& points_xy, float radius, bool accumulate = false) {
         check(sb_viewer_select_brush(h_, stream, points_xy.data(), (uint32_t)(points_xy.size() / 2), radius, accumulate), ctx_.raw());
     }
+    // editor NonDestructiveModifier + rgb override on the selected Gaussians (tests/e2e/selection.rs:54-116)
+    void apply_rgb_override(void* stream, const float rgb[3], float alpha = 1.0f) { check(sb_viewer_apply_rgb_override(h_, stream, rgb, alpha), ctx_.raw()); }
+    void restore_gaussians(void* stream) { check(sb_viewer_restore_gaussians(h_, stream), ctx_.raw()); }
     SbViewer* raw() const { return h_; }
 private:
     Context& ctx_;
