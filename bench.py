@@ -34,6 +34,7 @@ SCENE_SEED = 0x3D65 + 2
 SH_FMT, COV_FMT = 0, 0           # pod single/single, 224 B
 N_VIEWS = 64                     # orbit cameras (config 5a)
 METRIC = "frames_per_sec_1080p_6M_gaussians"
+REPEATS = 5                      # timed regions per measurement (the median is reported)
 KERNELS_PER_FRAME = 17           # preprocess 1, depth sort 1+1+1+4 (init, hist, plan, passes; the result stays where the last pass
                                  # wrote it), scan 1, emit 1, tile sort 1+1+2+1, tile ranges 1, raster 1
 
@@ -121,9 +122,31 @@ def build_scene(n: int):
     return pods
 
 
+def workload_module():
+    """The synthetic-scene / camera definitions (splat_b200/scenes.py: pure numpy, no imports of the product) loaded BY PATH,
+    so the CPU arm never imports the product package or maps its shared library."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_scenes", os.path.join(ROOT, "wgpu-3dgs-viewer_b200", "splat_b200", "scenes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def view_camera(sb, k: int):
     pos, yaw, pitch = sb.scenes.orbit_camera(k % N_VIEWS, N_VIEWS)
     return sb.camera_pod(pos, yaw, pitch, WIDTH, HEIGHT)
+
+
+def workload_config(n, world, stride, scene_bytes, note=None):
+    """`config` of the JSON line — identical in both arms apart from `note`."""
+    cfg = {"workload": f"{n}-Gaussian SH3 scene (pod single/single, 224 B), 1920x1080 RGBA8, splat mode, "
+                       f"{N_VIEWS}-view orbit (yaw 2 pi k/64 + 0.1, pitch 0.1), one view per step per GPU (BASELINE.json config 2b / 5a)",
+           "gaussians": n, "resolution": [WIDTH, HEIGHT], "pod_stride": stride, "scene_bytes": int(scene_bytes),
+           "l2_policy": "scene (1.34 GB) is larger than L2; no explicit flush",
+           "parallelism": f"views sharded over {world} GPU(s), scene replicated"}
+    if note:
+        cfg["note"] = note
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------ own arm
@@ -180,25 +203,31 @@ def run_cuda(args):
             viewer.render_batch(cs, targets=[targets2[i & 1] for i in range(count)], width=WIDTH, height=HEIGHT, stream=stream)
 
     def timed(run_fn, steps, warmup, sample_clocks=False):
+        """W warm-up steps, then REPEATS regions of EXACTLY `steps` steps, each bracketed by barrier + synchronize on both
+        sides and timed with CUDA events on the launching stream (max over ranks); returns the median region."""
         run_fn(0, warmup)
         stream.synchronize()
         torch.cuda.synchronize()
-        barrier()
         sampler = ClockSampler(local_rank) if sample_clocks else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run_fn(warmup, steps)
-        e1.record(stream)
-        stream.synchronize()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        regions = []
+        for r in range(REPEATS):
+            barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run_fn(warmup + r * steps, steps)
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            barrier()
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            regions.append(ms)
         clocks = sampler.stop() if sampler else None
-        barrier()
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, clocks
+        return float(np.median(regions)), clocks
 
     def run_single(first, count):
         for i in range(count):
@@ -293,12 +322,9 @@ def run_cuda(args):
         "metric": METRIC, "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{n}-Gaussian SH3 scene (pod single/single, 224 B), 1920x1080 RGBA8, splat mode, "
-                               f"{N_VIEWS}-view orbit, one view per step per GPU (BASELINE.json config 2b / 5a)",
-                   "gaussians": n, "resolution": [WIDTH, HEIGHT], "pod_stride": stride, "scene_bytes": int(scene_bytes),
-                   "l2_policy": "scene (1.34 GB) is larger than L2; no explicit flush",
-                   "parallelism": f"views sharded over {world} GPU(s), scene replicated",
-                   "api": "sb_viewer_render_batch: the K steps are K views of the batch, two views in flight per GPU"},
+        "config": dict(workload_config(n, world, stride, scene_bytes),
+                       api="sb_viewer_render_batch: the K steps are K views of the batch, two views in flight per GPU",
+                       repeats=f"the K-step timed region is run {REPEATS} times back to back; value / ms_per_step are the median region"),
         "clocks": clocks,
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 144, "d2h_bytes_per_step": int(host_frame.numel()),
@@ -313,7 +339,7 @@ def run_cuda(args):
         "stages": {"ms": stage, "sum_ms": frame_stage_ms, "dominant": dominant, "visible": V, "tile_duplicates": D},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_sample(args.cpu_sample)
+        out["cpu_baseline"] = cpu_baseline_sample(pods, n)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -321,52 +347,61 @@ def run_cuda(args):
 
 # ------------------------------------------------------------------------------------------ CPU arm
 
-def cpu_frames_per_sec(sample_n: int, steps: int, warmup: int):
-    """Times the CPU oracle (faithful restatement of the reference's three stages; the unmodified
-    reference cannot be built here: no Rust toolchain, no Vulkan) on a `sample_n`-Gaussian scene
-    drawn from the bench scene's generator (same seed and distributions), all host threads."""
+def cpu_render_frames(model, frames, first_view, threads):
+    """Times `frames` whole frames of the CPU oracle (faithful restatement of the reference's three stages — per-Gaussian
+    preprocess, stable LSD radix sort, back-to-front compositing with per-blend re-quantisation; the unmodified crate cannot
+    be built here: no Rust toolchain, no Vulkan) on the bench scene itself, one orbit view per frame, all host threads."""
     from oracle import binding as ob
-    import splat_b200 as sb
-    pods = build_scene(sample_n)
-    model = ob.OracleModel(pods, sample_n)
+    scenes = workload_module()
     gt = ob.gaussian_transform_pod()
-    threads = ob.use_all_host_threads()
     times = []
-    for i in range(warmup + steps):
-        pos, yaw, pitch = sb.scenes.orbit_camera(i % N_VIEWS, N_VIEWS)
+    for i in range(frames):
+        pos, yaw, pitch = scenes.orbit_camera((first_view + i) % N_VIEWS, N_VIEWS)
         cam = ob.camera_pod(pos, yaw, pitch, WIDTH, HEIGHT)
         t0 = time.perf_counter()
         ob.render(model, cam, gt, ob.TARGET_RGBA8, n_threads=threads)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return float(np.sum(times)), threads
+        times.append(time.perf_counter() - t0)
+    return times
 
 
-def cpu_baseline_sample(sample_n: int):
-    secs, threads = cpu_frames_per_sec(sample_n, steps=2, warmup=1)
-    fps_sample = 2 / secs
-    return {"value": fps_sample * sample_n / N_GAUSSIANS, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"oracle render of a {sample_n}-Gaussian scene from the bench generator at 1920x1080, 2 frames, "
-                      f"{fps_sample:.3f} frames/s on the sample, scaled by {sample_n}/{N_GAUSSIANS} (cost is linear in splats)"}
+def cpu_baseline_sample(pods, n: int):
+    """cpu_baseline leg of the own arm: the oracle on the SAME pods (byte-identical layouts), bounded to 1 warm-up + 2 timed
+    frames of the full scene."""
+    from oracle import binding as ob
+    threads = ob.use_all_host_threads()
+    model = ob.OracleModel(pods, n, SH_FMT, COV_FMT)
+    times = cpu_render_frames(model, 3, 0, threads)[1:]
+    return {"value": len(times) / float(np.sum(times)), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/splat_oracle.c render of the bench scene itself ({n} Gaussians, 1920x1080, orbit views 1-2), "
+                      f"2 timed frames after 1 warm-up, {float(np.mean(times)):.3f} s/frame, no scaling"}
 
 
 def run_reference(args):
+    """--impl reference: the CPU arm.  Renders the actual bench scene (same generator, seed, size, cameras) with the oracle only:
+    packs with oracle.binding.pack_gaussians and never imports splat_b200 or maps libsplat_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_n = args.cpu_sample
-    secs, threads = cpu_frames_per_sec(sample_n, args.steps, args.warmup)
-    scale = sample_n / N_GAUSSIANS
-    value = args.steps / secs * scale
-    sample = (f"each step = oracle/splat_oracle.c render of a {sample_n}-Gaussian scene from the bench generator at 1920x1080 "
-              f"(all {threads} host threads); frames/s scaled by {sample_n}/{N_GAUSSIANS}")
+    from oracle import binding as ob
+    scenes = workload_module()
+    n = args.n
+    g = scenes.synthetic_gaussians(n, SCENE_SEED)
+    pods = ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE), SH_FMT, COV_FMT)
+    del g
+    model = ob.OracleModel(pods, n, SH_FMT, COV_FMT)
+    threads = ob.use_all_host_threads()
+    cpu_render_frames(model, args.warmup, 0, threads)
+    times = cpu_render_frames(model, args.steps, args.warmup, threads)
+    secs = float(np.sum(times))
+    value = args.steps / secs
+    sample = (f"each step = one whole frame of the bench scene ({n} Gaussians, 1920x1080, orbit view k) by oracle/splat_oracle.c "
+              f"on all {threads} host threads; no sampling, no scaling")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3 / scale, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{N_GAUSSIANS}-Gaussian SH3 scene (pod single/single, 224 B), 1920x1080 RGBA8, splat mode "
-                               "(CPU restatement of the reference algorithm, not lavapipe: the crate cannot be built here)",
-                   "gaussians": N_GAUSSIANS, "resolution": [WIDTH, HEIGHT]},
+        "config": workload_config(n, 1, ob.pod_stride(SH_FMT, COV_FMT), int(pods.nbytes),
+                                  note="CPU restatement of the reference algorithm (oracle), not lavapipe: the crate cannot be built here"),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -384,19 +419,23 @@ def _quiet_stdout():
     sys.stdout = os.fdopen(saved, "w", buffering=1)
 
 
-def main():
-    _quiet_stdout()
+def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--n", type=int, default=N_GAUSSIANS, help=argparse.SUPPRESS)
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    return args
+
+
+def main():
+    _quiet_stdout()
+    args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -369,9 +369,37 @@ SB_API SbStatus sb_mm_update_model_transform_with_pod(SbMultiModelViewer* mm, ui
 SB_API SbStatus sb_mm_update_gaussian_transform_with_pod(SbMultiModelViewer* mm, const SbGaussianTransformPod* pod);
 SB_API SbStatus sb_mm_set_selection(SbMultiModelViewer* mm, uint64_t key, void* stream, const uint32_t* words,
                                     uint64_t n_words, int32_t invert);
+/* update_camera / update_model_transform / update_gaussian_transform (non-pod variants): src/multi_model.rs:398-464 */
+SB_API SbStatus sb_mm_update_camera(SbMultiModelViewer* mm, const float pos[3], float yaw, float pitch, float z_near, float z_far,
+                                    float vertical_fov, uint32_t width, uint32_t height);
+SB_API SbStatus sb_mm_update_model_transform(SbMultiModelViewer* mm, uint64_t key, const float pos[3], const float rot_xyzw[4],
+                                             const float scale[3]);
+SB_API SbStatus sb_mm_update_gaussian_transform(SbMultiModelViewer* mm, float size, int32_t display_mode, int32_t sh_deg,
+                                                int32_t no_sh0, float max_std_dev);
+/* insert_model(device, key, &impl IterGaussian) packing source Gaussians on the host (src/multi_model.rs:353-362), and
+ * insert_model_with on a caller-owned device buffer (MultiModelViewerGaussianBuffers over an adopted GaussiansBuffer,
+ * src/multi_model.rs:366-391; never freed here; d_bytes must equal n * stride) */
+SB_API SbStatus sb_mm_insert_model_from_gaussians(SbMultiModelViewer* mm, uint64_t key, const SbGaussian* src, uint64_t n,
+                                                  int32_t* replaced);
+SB_API SbStatus sb_mm_insert_model_from_device(SbMultiModelViewer* mm, uint64_t key, const void* d_pods, uint64_t d_bytes, uint64_t n,
+                                               int32_t* replaced);
+/* models[key].gaussian_buffers.selection_buffer / invert_selection_buffer (src/multi_model.rs:81-84): viewport selection
+ * evaluated against the shared camera (selection::viewport, as sb_viewer_select_rect / _brush), the per-model switch of the
+ * preprocessor's mask test, and a synchronising read-back */
+SB_API SbStatus sb_mm_select_rect(SbMultiModelViewer* mm, uint64_t key, void* stream, float x0, float y0, float x1, float y1);
+SB_API SbStatus sb_mm_select_brush(SbMultiModelViewer* mm, uint64_t key, void* stream, const float* points_xy, uint32_t n_points,
+                                   float radius, int32_t accumulate);
+SB_API SbStatus sb_mm_enable_selection(SbMultiModelViewer* mm, uint64_t key, int32_t enabled, int32_t invert);
+SB_API SbStatus sb_mm_read_selection(SbMultiModelViewer* mm, uint64_t key, void* stream, uint32_t* out, uint64_t n_words);
 /* render(encoder, view, keys): models drawn in key order, model k+1 over model k */
 SB_API SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const uint64_t* keys,
                              uint32_t n_keys);
+/* MultiModelViewer::new_with_options(depth_stencil) (src/multi_model.rs:319-337): the shared Renderer then carries a
+ * DepthStencilState, and the models are drawn with renderer.render_with_pass inside a pass of the caller's that owns the depth
+ * attachment (MultiModelViewer::render itself attaches none, src/multi_model.rs:505-527).  Models composite in key order over the
+ * target (load != 0: LoadOp::Load, else cleared to BLACK) and are depth tested / written as in sb_viewer_render_with_pass. */
+SB_API SbStatus sb_mm_render_with_pass(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const SbDepthAttachment* depth,
+                                       int32_t load, const uint64_t* keys, uint32_t n_keys);
 SB_API SbStatus sb_mm_read_model_indices(SbMultiModelViewer* mm, uint64_t key, void* stream, uint32_t* out,
                                          uint64_t count, SbDrawIndirectArgs* draw);
 

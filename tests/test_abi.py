@@ -6,6 +6,7 @@ import re
 import subprocess
 
 import numpy as np
+import pytest
 
 
 def header_symbols():
@@ -107,3 +108,46 @@ def test_no_context_without_gpu(sb):
         assert e.status == 2 and "no CPU fallback" in str(e)
     else:
         raise AssertionError("sb_ctx_create must fail loudly without a CUDA device")
+
+
+def _write_ply(path, names, rows, vertex_count=None):
+    hdr = "ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % (len(rows) if vertex_count is None else vertex_count)
+    hdr += "".join(f"property float {n}\n" for n in names) + "end_header\n"
+    path.write_bytes(hdr.encode() + np.asarray(rows, dtype="<f4").tobytes())
+
+
+def test_ply_reader_rejects_incomplete_or_lying_files(sb, tmp_path):
+    """sb_read_ply must fail with SB_ERR_IO — never read out of bounds — when a required property is missing, the f_rest set is
+    partial in a way that is not a whole SH degree, or the header's vertex count exceeds the file."""
+    base = ["x", "y", "z", "f_dc_0", "f_dc_1", "f_dc_2", "opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    rng = np.random.default_rng(0)
+    rows = rng.standard_normal((5, len(base))).astype(np.float32)
+    p = tmp_path / "ok.ply"
+    _write_ply(p, base, rows)
+    g = sb.read_ply(str(p))
+    assert len(g) == 5 and np.all(g["sh"] == 0)
+    for missing in ("f_dc_1", "f_dc_2", "scale_2", "rot_3", "rot_1", "opacity", "z"):
+        names = [n for n in base if n != missing]
+        _write_ply(p, names, rows[:, : len(names)])
+        with pytest.raises(sb.SplatError) as e:
+            sb.read_ply(str(p))
+        assert e.value.status == 6, missing
+    # vertex count far beyond the data (and absurdly large): rejected before any allocation
+    for count in (6, 10**15):
+        _write_ply(p, base, rows, vertex_count=count)
+        with pytest.raises(sb.SplatError):
+            sb.read_ply(str(p))
+    # f_rest sets: 9 properties = SH degree 1 (3 per channel, channel-major) is read as such; 10 or a holey set is rejected
+    names9 = base + [f"f_rest_{i}" for i in range(9)]
+    rows9 = rng.standard_normal((4, len(names9))).astype(np.float32)
+    _write_ply(p, names9, rows9)
+    g = sb.read_ply(str(p))
+    rest = rows9[:, len(base):]
+    for k in range(3):
+        for c in range(3):
+            assert np.array_equal(g["sh"][:, k * 3 + c], rest[:, c * 3 + k])
+    assert np.all(g["sh"][:, 9:] == 0)
+    for bad in (base + [f"f_rest_{i}" for i in range(10)], base + ["f_rest_0", "f_rest_2", "f_rest_3"]):
+        _write_ply(p, bad, rng.standard_normal((2, len(bad))).astype(np.float32))
+        with pytest.raises(sb.SplatError):
+            sb.read_ply(str(p))

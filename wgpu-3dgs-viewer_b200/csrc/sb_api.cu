@@ -40,6 +40,22 @@ SbStatus fail_cuda(Ctx* ctx, cudaError_t e, const char* what) {
         if (_e != cudaSuccess) return fail_cuda(ctx, _e, #call);      \
     } while (0)
 
+// Every entry point that enqueues, allocates or copies runs on ITS context's device, whatever the calling thread's current
+// device is (several contexts — one per GPU — may live in one process); the previous device is restored on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const Ctx* c) {
+        if (!c) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 bool is_unorm(int fmt) { return fmt == SB_TARGET_RGBA8_UNORM || fmt == SB_TARGET_BGRA8_UNORM; }
 uint32_t bytes_per_pixel(int fmt) { return is_unorm(fmt) ? 4u : fmt == SB_TARGET_RGBA16_FLOAT ? 8u : 16u; }
 
@@ -167,8 +183,9 @@ struct SbViewer {
     DeviceBuf internal_target;
     uint64_t dup_capacity = 0;
     uint32_t tile_capacity = 0;
-    volatile uint32_t* h_needed = nullptr;  // mapped pinned: duplicates the last binned frame needed
-    uint32_t* d_needed = nullptr;
+    volatile uint32_t* h_needed = nullptr;  // mapped pinned: [0] duplicates the last binned frame needed (saturated), [1] overflow events,
+    uint32_t* d_needed = nullptr;           //                [4] visible count of the last preprocess (size hint for the sort)
+    uint32_t overflow_seen = 0;             // overflow events already reported to the caller
 
     SbCameraPod camera;
     SbModelTransformPod model_transform;
@@ -279,7 +296,6 @@ SbStatus viewer_new(SbContext* ctx, int sh_fmt, int cov_fmt, int target_format, 
                       (unsigned long long)ctx->model_size_limit);
         return fail(ctx, SB_ERR_MODEL_TOO_LARGE, msg);
     }
-    SB_CUDA(ctx, cudaSetDevice(ctx->device));
     SbViewer* v = new SbViewer();
     v->ctx = ctx;
     v->sh_fmt = sh_fmt;
@@ -299,6 +315,26 @@ SbStatus viewer_new(SbContext* ctx, int sh_fmt, int cov_fmt, int target_format, 
     }
     *out = v;
     return SB_OK;
+}
+
+// A frame whose (splat, tile) duplicates did not fit dropped its nearest splats.  The device reports it through a mapped pinned
+// word (no synchronisation); the NEXT enqueue that notices grows the buffers and returns SB_ERR_OVERFLOW WITHOUT enqueuing
+// anything, so the caller learns that an earlier frame was incomplete and simply renders again (now with room).
+SbStatus report_overflow(SbViewer* v) {
+    const uint32_t events = v->h_needed[1];
+    if (events == v->overflow_seen) return SB_OK;
+    v->overflow_seen = events;
+    const uint64_t need = v->h_needed[0];
+    SB_CUDA(v->ctx, cudaDeviceSynchronize());
+    if (need > v->dup_capacity) {
+        SbStatus gs = viewer_reserve(v, need + need / 2);
+        if (gs != SB_OK) return gs;
+    }
+    *v->h_needed = 0;
+    char msg[200];
+    std::snprintf(msg, sizeof msg, "a previous frame needed %s%llu tile duplicates and was rendered incompletely; capacity grown to %llu, render again",
+                  need == 0xffffffffull ? ">= " : "", (unsigned long long)need, (unsigned long long)v->dup_capacity);
+    return fail(v->ctx, SB_ERR_OVERFLOW, msg);
 }
 
 SbStatus check_target(SbViewer* v, const SbTarget* t, const sb::Uniforms& u) {
@@ -517,6 +553,7 @@ SbStatus sb_ctx_set_model_size_limit(SbContext* ctx, uint64_t bytes) {
 SbStatus sb_viewer_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, const void* packed_pods, uint64_t n,
                           SbViewer** out) {
     if (n && !packed_pods) return fail(ctx, SB_ERR_INVALID_ARG, "null pods");
+    DeviceGuard device_guard(ctx);
     SbViewer* v = nullptr;
     SbStatus s = viewer_new(ctx, sh_fmt, cov_fmt, target_format, n, &v);
     if (s != SB_OK) return s;
@@ -547,6 +584,7 @@ SbStatus sb_viewer_create_from_device(SbContext* ctx, int32_t sh_fmt, int32_t co
     if (stride == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
     if (d_bytes != n * stride) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians buffer size != n * size_of::<G>()");
     if (n && (!d_pods || (reinterpret_cast<uintptr_t>(d_pods) & 15u))) return fail(ctx, SB_ERR_INVALID_ARG, "device pods must be 16-byte aligned");
+    DeviceGuard device_guard(ctx);
     SbViewer* v = nullptr;
     SbStatus s = viewer_new(ctx, sh_fmt, cov_fmt, target_format, n, &v);
     if (s != SB_OK) return s;
@@ -557,6 +595,7 @@ SbStatus sb_viewer_create_from_device(SbContext* ctx, int32_t sh_fmt, int32_t co
 
 void sb_viewer_destroy(SbViewer* v) {
     if (!v) return;
+    DeviceGuard device_guard(v->ctx);
     if (v->twin) sb_viewer_destroy(v->twin);
     for (cudaStream_t s : v->bstream)
         if (s) cudaStreamDestroy(s);
@@ -627,6 +666,7 @@ SbStatus sb_viewer_selection_ptr(SbViewer* v, uint32_t** d_words, uint64_t* n_wo
 
 SbStatus sb_viewer_set_selection(SbViewer* v, void* stream, const uint32_t* words, uint64_t n_words) {
     if (!v || (!words && n_words)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (n_words != ((uint64_t)v->n + 31) / 32) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "selection must hold ceil(n/32) words");
     SB_CUDA(v->ctx, cudaMemcpyAsync(v->selection.p, words, n_words * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
     return SB_OK;
@@ -634,6 +674,7 @@ SbStatus sb_viewer_set_selection(SbViewer* v, void* stream, const uint32_t* word
 
 SbStatus sb_viewer_read_selection(SbViewer* v, void* stream, uint32_t* out, uint64_t n_words) {
     if (!v || (!out && n_words)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (n_words != ((uint64_t)v->n + 31) / 32) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "selection must hold ceil(n/32) words");
     SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     SB_CUDA(v->ctx, cudaMemcpy(out, v->selection.p, n_words * 4, cudaMemcpyDeviceToHost));
@@ -648,6 +689,7 @@ SbStatus sb_viewer_set_invert_selection(SbViewer* v, int32_t invert) {
 
 SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float y0, float x1, float y1) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
     SB_CUDA(v->ctx, sb::launch_select_rect(static_cast<const uint8_t*>(v->d_gaussians), v->n, v->stride, u, x0, y0, x1, y1,
                                            v->selection.as<uint32_t>(), static_cast<cudaStream_t>(stream)));
@@ -656,6 +698,7 @@ SbStatus sb_viewer_select_rect(SbViewer* v, void* stream, float x0, float y0, fl
 
 SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* points_xy, uint32_t n_points, float radius, int32_t accumulate) {
     if (!v || !points_xy) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (n_points == 0 || n_points > SB_BRUSH_MAX_POINTS || !(radius >= 0.0f))
         return fail(v->ctx, SB_ERR_INVALID_ARG, "brush stroke needs 1..SB_BRUSH_MAX_POINTS points and a non-negative radius");
     const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
@@ -666,6 +709,7 @@ SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* points_x
 
 SbStatus sb_viewer_apply_rgb_override(SbViewer* v, void* stream, const float rgb[3], float alpha) {
     if (!v || !rgb) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* pods = const_cast<uint8_t*>(static_cast<const uint8_t*>(v->d_gaussians));  // the reference edits viewer.gaussians_buffer in place
     if (!v->orig_colors.p) {
@@ -678,6 +722,7 @@ SbStatus sb_viewer_apply_rgb_override(SbViewer* v, void* stream, const float rgb
 
 SbStatus sb_viewer_restore_gaussians(SbViewer* v, void* stream) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (!v->orig_colors.p) return SB_OK;  // never edited
     uint8_t* pods = const_cast<uint8_t*>(static_cast<const uint8_t*>(v->d_gaussians));
     const float rgb[3] = {0.0f, 0.0f, 0.0f};
@@ -688,7 +733,12 @@ SbStatus sb_viewer_restore_gaussians(SbViewer* v, void* stream) {
 SbStatus sb_viewer_render_with_pass(SbViewer* v, void* stream, const SbTarget* target, const SbDepthAttachment* depth, int32_t load,
                                     int32_t run_stages) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        SbStatus os = report_overflow(v);
+        if (os != SB_OK) return os;
+    }
     if (run_stages) {
         SbStatus s = do_preprocess(v, v->camera, v->gaussian_transform, st);
         if (s == SB_OK) s = do_sort(v, st, true);
@@ -699,11 +749,13 @@ SbStatus sb_viewer_render_with_pass(SbViewer* v, void* stream, const SbTarget* t
 
 SbStatus sb_viewer_preprocess(SbViewer* v, void* stream) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     return do_preprocess(v, v->camera, v->gaussian_transform, static_cast<cudaStream_t>(stream));
 }
 
 SbStatus sb_viewer_sort(SbViewer* v, void* stream) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     SbStatus fs = flush_sorted(v, static_cast<cudaStream_t>(stream));  // a previous frame's result, if it was left in the alt buffers
     if (fs != SB_OK) return fs;
     return do_sort(v, static_cast<cudaStream_t>(stream));
@@ -711,15 +763,20 @@ SbStatus sb_viewer_sort(SbViewer* v, void* stream) {
 
 SbStatus sb_viewer_draw(SbViewer* v, void* stream, const SbTarget* target) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
+    SbStatus os = report_overflow(v);
+    if (os != SB_OK) return os;
     return do_draw(v, v->camera, v->gaussian_transform, target, 1, static_cast<cudaStream_t>(stream));
 }
 
 SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // validate before enqueuing anything
     sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
     SbStatus s = check_target(v, target, u);
+    if (s == SB_OK) s = report_overflow(v);
     if (s != SB_OK) return s;
     s = do_preprocess(v, v->camera, v->gaussian_transform, st);
     if (s != SB_OK) return s;
@@ -730,6 +787,7 @@ SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target) {
 
 SbStatus sb_viewer_render_to_host(SbViewer* v, void* stream, const SbCameraPod* cam, void* host_pixels, uint64_t host_bytes) {
     if (!v || !cam || !host_pixels) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     const uint32_t w = (uint32_t)cam->size[0], h = (uint32_t)cam->size[1];
     const uint64_t need = (uint64_t)w * h * bytes_per_pixel(v->target_format);
     if (host_bytes != need) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "host frame buffer size mismatch");
@@ -784,6 +842,7 @@ void sync_twin(SbViewer* v) {
 SbStatus sb_viewer_render_batch(SbViewer* v, void* stream, const SbCameraPod* cams, const SbTarget* targets, void* const* host_pixels,
                                 uint32_t count) {
     if (!v || (count && (!cams || (!targets && !host_pixels)))) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (count == 0) return SB_OK;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     SbStatus s = batch_setup(v);
@@ -792,8 +851,11 @@ SbStatus sb_viewer_render_batch(SbViewer* v, void* stream, const SbCameraPod* ca
     // validate every target before enqueuing anything
     const uint32_t bpp = bytes_per_pixel(v->target_format);
     std::vector<SbTarget> tg(count);
+    // slots alternate so that the LAST view always lands in the primary viewer: after the batch its buffers (records, indices,
+    // keys, indirect args) hold the view v->camera names, as the reference's would after its last update_camera + render
+    auto slot_of = [count](uint32_t i) { return (count - 1u - i) & 1u; };
     for (uint32_t i = 0; i < count; i++) {
-        SbViewer* slot = (i & 1u) ? v->twin : v;
+        SbViewer* slot = slot_of(i) ? v->twin : v;
         const uint32_t w = (uint32_t)cams[i].size[0], h = (uint32_t)cams[i].size[1];
         if (targets) {
             tg[i] = targets[i];
@@ -810,12 +872,15 @@ SbStatus sb_viewer_render_batch(SbViewer* v, void* stream, const SbCameraPod* ca
         s = check_target(v, &tg[i], u);
         if (s != SB_OK) return s;
     }
+    s = report_overflow(v);
+    if (s == SB_OK) s = report_overflow(v->twin);
+    if (s != SB_OK) return s;
     // fork: both internal streams start after everything already enqueued on the caller's stream
     SB_CUDA(v->ctx, cudaEventRecord(v->bevent[2], user));
     for (int k = 0; k < 2; k++) SB_CUDA(v->ctx, cudaStreamWaitEvent(v->bstream[k], v->bevent[2], 0));
     for (uint32_t i = 0; i < count; i++) {
-        SbViewer* slot = (i & 1u) ? v->twin : v;
-        cudaStream_t st = v->bstream[i & 1u];
+        SbViewer* slot = slot_of(i) ? v->twin : v;
+        cudaStream_t st = v->bstream[slot_of(i)];
         s = do_preprocess(slot, cams[i], v->gaussian_transform, st);
         if (s == SB_OK) s = do_sort(slot, st, true);
         if (s == SB_OK) s = do_draw(slot, cams[i], v->gaussian_transform, &tg[i], 1, st);
@@ -854,6 +919,7 @@ SbStatus sb_viewer_radix_sort_indirect_args_ptr(SbViewer* v, const SbDispatchInd
 }
 SbStatus sb_viewer_indirect_indices_ptr(SbViewer* v, const uint32_t** d_indices, uint64_t* count) {
     if (!v || !d_indices || !count) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     SbStatus fs = flush_sorted(v, v->last_stream);
     if (fs != SB_OK) return fs;
     *d_indices = v->indices.as<uint32_t>();
@@ -862,6 +928,7 @@ SbStatus sb_viewer_indirect_indices_ptr(SbViewer* v, const uint32_t** d_indices,
 }
 SbStatus sb_viewer_gaussians_depth_ptr(SbViewer* v, const float** d_keys, uint64_t* bytes) {
     if (!v || !d_keys || !bytes) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     SbStatus fs = flush_sorted(v, v->last_stream);
     if (fs != SB_OK) return fs;
     *d_keys = v->keys.as<float>();
@@ -871,6 +938,7 @@ SbStatus sb_viewer_gaussians_depth_ptr(SbViewer* v, const float** d_keys, uint64
 
 SbStatus sb_viewer_read_indirect_args(SbViewer* v, void* stream, SbDrawIndirectArgs* draw, SbDispatchIndirectArgs* dispatch) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     if (draw) SB_CUDA(v->ctx, cudaMemcpy(draw, v->d_draw(), sizeof *draw, cudaMemcpyDeviceToHost));
     if (dispatch) SB_CUDA(v->ctx, cudaMemcpy(dispatch, v->d_dispatch(), sizeof *dispatch, cudaMemcpyDeviceToHost));
@@ -878,6 +946,7 @@ SbStatus sb_viewer_read_indirect_args(SbViewer* v, void* stream, SbDrawIndirectA
 }
 SbStatus sb_viewer_read_indices(SbViewer* v, void* stream, uint32_t* out, uint64_t count) {
     if (!v || (!out && count)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (count > v->padded) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "count exceeds buffer");
     SbStatus fs = flush_sorted(v, static_cast<cudaStream_t>(stream));
     if (fs != SB_OK) return fs;
@@ -887,6 +956,7 @@ SbStatus sb_viewer_read_indices(SbViewer* v, void* stream, uint32_t* out, uint64
 }
 SbStatus sb_viewer_read_depth_keys(SbViewer* v, void* stream, float* out, uint64_t count) {
     if (!v || (!out && count)) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (count > v->padded) return fail(v->ctx, SB_ERR_BAD_BUFFER_SIZE, "count exceeds buffer");
     SbStatus fs = flush_sorted(v, static_cast<cudaStream_t>(stream));
     if (fs != SB_OK) return fs;
@@ -896,6 +966,7 @@ SbStatus sb_viewer_read_depth_keys(SbViewer* v, void* stream, float* out, uint64
 }
 SbStatus sb_viewer_read_frame_stats(SbViewer* v, void* stream, uint64_t* visible, uint64_t* duplicates, uint32_t* overflowed) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     uint32_t vis = 0, st[2] = {0, 0};
     SB_CUDA(v->ctx, cudaMemcpy(&vis, v->d_visible(), 4, cudaMemcpyDeviceToHost));
@@ -926,6 +997,7 @@ SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled) {
 
 SbStatus sb_viewer_set_raster_counting(SbViewer* v, int32_t enabled) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (enabled && !v->counters.p) SB_CUDA(v->ctx, v->counters.alloc(32));
     v->counting = enabled != 0;
     return SB_OK;
@@ -933,6 +1005,7 @@ SbStatus sb_viewer_set_raster_counting(SbViewer* v, int32_t enabled) {
 
 SbStatus sb_viewer_read_raster_counters(SbViewer* v, void* stream, uint64_t* alive, uint64_t* evaluated) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (!v->counters.p) return fail(v->ctx, SB_ERR_INVALID_ARG, "raster counting was never enabled");
     SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     unsigned long long c[2] = {0, 0};
@@ -944,6 +1017,7 @@ SbStatus sb_viewer_read_raster_counters(SbViewer* v, void* stream, uint64_t* ali
 
 SbStatus sb_viewer_read_raster_warp_counters(SbViewer* v, void* stream, uint64_t* warp_evals, uint64_t* warp_evals_alive) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (!v->counters.p) return fail(v->ctx, SB_ERR_INVALID_ARG, "raster counting was never enabled");
     SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     unsigned long long c[4] = {0, 0, 0, 0};
@@ -955,6 +1029,7 @@ SbStatus sb_viewer_read_raster_warp_counters(SbViewer* v, void* stream, uint64_t
 
 SbStatus sb_viewer_set_stage_timing(SbViewer* v, int32_t enabled) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (enabled && !v->ev[0])
         for (cudaEvent_t& e : v->ev) SB_CUDA(v->ctx, cudaEventCreate(&e));
     v->timing = enabled != 0;
@@ -963,6 +1038,7 @@ SbStatus sb_viewer_set_stage_timing(SbViewer* v, int32_t enabled) {
 
 SbStatus sb_viewer_read_stage_times(SbViewer* v, void* stream, float ms[6]) {
     if (!v || !ms) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     if (!v->timing) return fail(v->ctx, SB_ERR_INVALID_ARG, "stage timing is not enabled");
     SB_CUDA(v->ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     for (int i = 0; i < 6; i++) SB_CUDA(v->ctx, cudaEventElapsedTime(&ms[i], v->ev[i], v->ev[i + 1]));
@@ -971,9 +1047,11 @@ SbStatus sb_viewer_read_stage_times(SbViewer* v, void* stream, float ms[6]) {
 
 SbStatus sb_viewer_reserve_duplicates(SbViewer* v, uint64_t capacity) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(v->ctx);
     SB_CUDA(v->ctx, cudaDeviceSynchronize());
     SbStatus s = viewer_reserve(v, capacity);
     if (s == SB_OK) SB_CUDA(v->ctx, cudaMemset(v->bin_state.p, 0, 8));
+    *v->h_needed = 0;  // the caller's capacity stands until a frame reports that it needed more
     return s;
 }
 
@@ -987,6 +1065,7 @@ struct SbRadixSorter {
 
 SbStatus sb_sorter_create(SbContext* ctx, uint32_t capacity, SbRadixSorter** out) {
     if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(ctx);
     SbRadixSorter* s = new SbRadixSorter();
     s->ctx = ctx;
     s->capacity = capacity;
@@ -1003,6 +1082,7 @@ SbStatus sb_sorter_create(SbContext* ctx, uint32_t capacity, SbRadixSorter** out
 
 void sb_sorter_destroy(SbRadixSorter* s) {
     if (!s) return;
+    DeviceGuard device_guard(s->ctx);
     s->keys_alt.release();
     s->vals_alt.release();
     s->internal.release();
@@ -1012,6 +1092,7 @@ void sb_sorter_destroy(SbRadixSorter* s) {
 SbStatus sb_sorter_sort(SbRadixSorter* s, void* stream, uint32_t* d_keys, uint32_t* d_payload, const uint32_t* d_count,
                         uint32_t max_count, int32_t begin_bit, int32_t end_bit) {
     if (!s || !d_keys || !d_payload || !d_count) return fail(s ? s->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(s->ctx);
     if (max_count > s->capacity) return fail(s->ctx, SB_ERR_BAD_BUFFER_SIZE, "max_count exceeds sorter capacity");
     if (begin_bit < 0 || end_bit > 32 || begin_bit >= end_bit) return fail(s->ctx, SB_ERR_INVALID_ARG, "bad bit range");
     sb::SortScratch sc;
@@ -1040,7 +1121,7 @@ SbStatus sb_preprocessor_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt,
     if (stride == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
     if (n > 0x3fffffffull) return fail(ctx, SB_ERR_MODEL_TOO_LARGE, "more than 2^30 gaussians");
     if (n * stride > ctx->model_size_limit) return fail(ctx, SB_ERR_MODEL_TOO_LARGE, "model size exceeds the device limit");  // src/preprocessor.rs:381-388
-    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx);
     SbPreprocessor* p = new SbPreprocessor();
     p->ctx = ctx;
     p->sh_fmt = sh_fmt;
@@ -1059,6 +1140,7 @@ SbStatus sb_preprocessor_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt,
 
 void sb_preprocessor_destroy(SbPreprocessor* p) {
     if (!p) return;
+    DeviceGuard device_guard(p->ctx);
     p->scratch.release();
     p->visible.release();
     delete p;
@@ -1066,6 +1148,7 @@ void sb_preprocessor_destroy(SbPreprocessor* p) {
 
 SbStatus sb_preprocessor_preprocess(SbPreprocessor* pre, void* stream, const SbPreprocessorBindGroup* bg, uint32_t gaussian_count) {
     if (!pre || !bg) return fail(pre ? pre->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(pre->ctx);
     SbContext* ctx = pre->ctx;
     if (gaussian_count > pre->n) return fail(ctx, SB_ERR_INVALID_ARG, "gaussian_count exceeds the preprocessor's model size");
     if (bg->gaussians_bytes != (uint64_t)pre->n * pre->stride) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians buffer size != n * size_of::<G>()");
@@ -1104,6 +1187,7 @@ struct SbRenderer {
 
 SbStatus sb_renderer_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t target_format, uint64_t n, SbRenderer** out) {
     if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(ctx);
     SbViewer* v = nullptr;
     SbStatus s = viewer_new(ctx, sh_fmt, cov_fmt, target_format, n, &v);
     if (s != SB_OK) return s;
@@ -1132,12 +1216,14 @@ SbStatus sb_renderer_set_strict_exp(SbRenderer* r, int32_t strict) {
 SbStatus sb_renderer_render(SbRenderer* r, void* stream, const SbRendererBindGroup* bg, const SbTarget* target,
                             const SbDrawIndirectArgs* d_indirect_args, const SbDepthAttachment* depth, int32_t load) {
     if (!r || !bg || !d_indirect_args) return fail(r ? r->v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(r->v->ctx);
     SbViewer* v = r->v;
     SbContext* ctx = v->ctx;
     if (bg->gaussians_bytes != (uint64_t)v->n * v->stride) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "gaussians buffer size != n * size_of::<G>()");
     if (bg->indirect_indices_bytes < (uint64_t)v->n * 4) return fail(ctx, SB_ERR_BAD_BUFFER_SIZE, "indirect indices buffer smaller than 4 * n");
     if (v->n && (!bg->d_gaussians || !bg->d_indirect_indices)) return fail(ctx, SB_ERR_INVALID_ARG, "null buffer in bind group");
     if (reinterpret_cast<uintptr_t>(bg->d_gaussians) & 15u) return fail(ctx, SB_ERR_INVALID_ARG, "device pods must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(bg->d_indirect_indices) & 3u) return fail(ctx, SB_ERR_INVALID_ARG, "indirect indices must be 4-byte aligned");
     if (bg->gaussian_transform.display_mode > 2 || bg->gaussian_transform.sh_deg > 3) return fail(ctx, SB_ERR_INVALID_ARG, "bad gaussian transform pod");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     v->d_gaussians = bg->d_gaussians;
@@ -1150,6 +1236,7 @@ SbStatus sb_renderer_render(SbRenderer* r, void* stream, const SbRendererBindGro
     sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format, v->exact_cutoff && !depth_pass);
     v->recs_cut = u.cut_k > 0.0f;  // the vertex stage below already matches the pass (no cut with a depth attachment)
     SbStatus s = check_target(v, target, u);  // validate before enqueuing anything
+    if (s == SB_OK) s = report_overflow(v);
     if (s != SB_OK) return s;
     // vertex stage (render.wesl:76-130) for exactly the instances the draw names
     sb::PreParams p;
@@ -1199,6 +1286,7 @@ SbStatus sb_mm_create(SbContext* ctx, int32_t sh_fmt, int32_t cov_fmt, int32_t t
 
 void sb_mm_destroy(SbMultiModelViewer* mm) {
     if (!mm) return;
+    DeviceGuard device_guard(mm->ctx);
     for (auto& kv : mm->models) sb_viewer_destroy(kv.second);
     for (cudaStream_t st : mm->side)
         if (st) cudaStreamDestroy(st);
@@ -1209,6 +1297,7 @@ void sb_mm_destroy(SbMultiModelViewer* mm) {
 
 SbStatus sb_mm_insert_model(SbMultiModelViewer* mm, uint64_t key, const void* packed_pods, uint64_t n, int32_t* replaced) {
     if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(mm->ctx);
     SbViewer* v = nullptr;
     SbStatus s = sb_viewer_create(mm->ctx, mm->sh_fmt, mm->cov_fmt, mm->target_format, packed_pods, n, &v);
     if (s != SB_OK) return s;
@@ -1226,6 +1315,7 @@ SbStatus sb_mm_insert_model(SbMultiModelViewer* mm, uint64_t key, const void* pa
 
 SbStatus sb_mm_remove_model(SbMultiModelViewer* mm, uint64_t key, int32_t* removed) {
     if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(mm->ctx);
     auto it = mm->models.find(key);
     if (removed) *removed = it != mm->models.end();
     if (it != mm->models.end()) {
@@ -1257,6 +1347,98 @@ SbStatus sb_mm_update_gaussian_transform_with_pod(SbMultiModelViewer* mm, const 
     return SB_OK;
 }
 
+SbStatus sb_mm_update_camera(SbMultiModelViewer* mm, const float pos[3], float yaw, float pitch, float z_near, float z_far,
+                             float vertical_fov, uint32_t width, uint32_t height) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    return sb_camera_pod(pos, yaw, pitch, z_near, z_far, vertical_fov, width, height, &mm->camera);
+}
+
+SbStatus sb_mm_update_model_transform(SbMultiModelViewer* mm, uint64_t key, const float pos[3], const float rot[4], const float scale[3]) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    return sb_model_transform_pod(pos, rot, scale, &it->second->model_transform);
+}
+
+SbStatus sb_mm_update_gaussian_transform(SbMultiModelViewer* mm, float size, int32_t display_mode, int32_t sh_deg, int32_t no_sh0,
+                                         float max_std_dev) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SbGaussianTransformPod pod;
+    SbStatus s = sb_gaussian_transform_pod(size, display_mode, sh_deg, no_sh0, max_std_dev, &pod);
+    if (s != SB_OK) return fail(mm->ctx, s, "bad gaussian transform");
+    mm->gaussian_transform = pod;
+    return SB_OK;
+}
+
+namespace {
+SbStatus mm_adopt(SbMultiModelViewer* mm, uint64_t key, SbViewer* v, int32_t* replaced) {
+    auto it = mm->models.find(key);
+    if (replaced) *replaced = it != mm->models.end();
+    if (it != mm->models.end()) {
+        cudaDeviceSynchronize();
+        sb_viewer_destroy(it->second);
+        it->second = v;
+    } else {
+        mm->models[key] = v;
+    }
+    return SB_OK;
+}
+}  // namespace
+
+SbStatus sb_mm_insert_model_from_gaussians(SbMultiModelViewer* mm, uint64_t key, const SbGaussian* src, uint64_t n, int32_t* replaced) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(mm->ctx);
+    SbViewer* v = nullptr;
+    SbStatus s = sb_viewer_create_from_gaussians(mm->ctx, mm->sh_fmt, mm->cov_fmt, mm->target_format, src, n, &v);
+    if (s != SB_OK) return s;
+    return mm_adopt(mm, key, v, replaced);
+}
+
+SbStatus sb_mm_insert_model_from_device(SbMultiModelViewer* mm, uint64_t key, const void* d_pods, uint64_t d_bytes, uint64_t n,
+                                        int32_t* replaced) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(mm->ctx);
+    SbViewer* v = nullptr;
+    SbStatus s = sb_viewer_create_from_device(mm->ctx, mm->sh_fmt, mm->cov_fmt, mm->target_format, d_pods, d_bytes, n, &v);
+    if (s != SB_OK) return s;
+    return mm_adopt(mm, key, v, replaced);
+}
+
+SbStatus sb_mm_select_rect(SbMultiModelViewer* mm, uint64_t key, void* stream, float x0, float y0, float x1, float y1) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    SbViewer* v = it->second;
+    v->camera = mm->camera;  // the world camera buffer the selection pass binds (selection/viewport.rs)
+    return sb_viewer_select_rect(v, stream, x0, y0, x1, y1);
+}
+
+SbStatus sb_mm_select_brush(SbMultiModelViewer* mm, uint64_t key, void* stream, const float* points_xy, uint32_t n_points, float radius,
+                            int32_t accumulate) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    SbViewer* v = it->second;
+    v->camera = mm->camera;
+    return sb_viewer_select_brush(v, stream, points_xy, n_points, radius, accumulate);
+}
+
+SbStatus sb_mm_enable_selection(SbMultiModelViewer* mm, uint64_t key, int32_t enabled, int32_t invert) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    it->second->selection_enabled = enabled != 0;
+    it->second->invert_selection = invert ? 1u : 0u;
+    return SB_OK;
+}
+
+SbStatus sb_mm_read_selection(SbMultiModelViewer* mm, uint64_t key, void* stream, uint32_t* out, uint64_t n_words) {
+    if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    auto it = mm->models.find(key);
+    if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
+    return sb_viewer_read_selection(it->second, stream, out, n_words);
+}
+
 SbStatus sb_mm_set_selection(SbMultiModelViewer* mm, uint64_t key, void* stream, const uint32_t* words, uint64_t n_words, int32_t invert) {
     if (!mm) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     auto it = mm->models.find(key);
@@ -1273,14 +1455,21 @@ SbStatus sb_mm_set_selection(SbMultiModelViewer* mm, uint64_t key, void* stream,
     return SB_OK;
 }
 
-SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const uint64_t* keys, uint32_t n_keys) {
+namespace {
+SbStatus mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const uint64_t* keys, uint32_t n_keys,
+                   const SbDepthAttachment* depth, int load) {
     if (!mm || (!keys && n_keys)) return fail(mm ? mm->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(mm->ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<SbViewer*> models;
     for (uint32_t i = 0; i < n_keys; i++) {  // multi_model.rs:482-489: resolve every key first
         auto it = mm->models.find(keys[i]);
         if (it == mm->models.end()) return fail(mm->ctx, SB_ERR_MODEL_NOT_FOUND, "model not found");
         models.push_back(it->second);
+    }
+    for (SbViewer* v : models) {
+        SbStatus os = report_overflow(v);
+        if (os != SB_OK) return os;
     }
     // Several distinct models: their preprocess / sort / binning chains are independent (own buffers) and mostly latency-
     // bound, so they run concurrently on side streams; the rasters keep the key order on the caller's stream.
@@ -1308,9 +1497,9 @@ SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* targ
             if (s == SB_OK) s = do_sort(models[i], sd, true);
             if (s != SB_OK) return s;
         }
-        int clr = 1;
+        int clr = load ? 0 : 1;
         for (size_t i = 0; i < models.size(); i++) {  // multi_model.rs:505-527: one pass, models in key order
-            SbStatus s = do_draw(models[i], mm->camera, mm->gaussian_transform, target, clr, mm->side[i % SbMultiModelViewer::kSide], nullptr, st,
+            SbStatus s = do_draw(models[i], mm->camera, mm->gaussian_transform, target, clr, mm->side[i % SbMultiModelViewer::kSide], depth, st,
                                  mm->bin_done[i]);
             if (s != SB_OK) return s;
             models[i]->last_stream = st;  // ordered after this model's sort through bin_done
@@ -1327,16 +1516,27 @@ SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* targ
     if (models.empty()) {  // a render pass that only clears
         if (!target || !target->d_pixels) return fail(mm->ctx, SB_ERR_INVALID_ARG, "null target");
         if (target->format != mm->target_format) return fail(mm->ctx, SB_ERR_INVALID_ARG, "target format mismatch");
-        SB_CUDA(mm->ctx, sb::launch_clear(*target, st));
+        if (!load) SB_CUDA(mm->ctx, sb::launch_clear(*target, st));
         return SB_OK;
     }
-    int clear = 1;
+    int clear = load ? 0 : 1;
     for (SbViewer* v : models) {  // multi_model.rs:505-527: one pass, models in key order
-        SbStatus s = do_draw(v, mm->camera, mm->gaussian_transform, target, clear, st);
+        SbStatus s = do_draw(v, mm->camera, mm->gaussian_transform, target, clear, st, depth);
         if (s != SB_OK) return s;
         clear = 0;
     }
     return SB_OK;
+}
+
+}  // namespace
+
+SbStatus sb_mm_render(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const uint64_t* keys, uint32_t n_keys) {
+    return mm_render(mm, stream, target, keys, n_keys, nullptr, 0);
+}
+
+SbStatus sb_mm_render_with_pass(SbMultiModelViewer* mm, void* stream, const SbTarget* target, const SbDepthAttachment* depth, int32_t load,
+                                const uint64_t* keys, uint32_t n_keys) {
+    return mm_render(mm, stream, target, keys, n_keys, depth, load);
 }
 
 SbStatus sb_mm_read_model_indices(SbMultiModelViewer* mm, uint64_t key, void* stream, uint32_t* out, uint64_t count,

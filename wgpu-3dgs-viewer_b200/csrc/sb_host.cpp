@@ -272,17 +272,47 @@ SbStatus sb_read_ply(const char* path, SbGaussian** out, uint64_t* n_out) {
     };
     const int ix = find("x"), iy = find("y"), iz = find("z"), iop = find("opacity");
     int idc[3], isc[3], irot[4], irest[45];
-    for (int c = 0; c < 3; c++) idc[c] = find("f_dc_" + std::to_string(c));
-    for (int c = 0; c < 3; c++) isc[c] = find("scale_" + std::to_string(c));
-    for (int c = 0; c < 4; c++) irot[c] = find("rot_" + std::to_string(c));
-    for (int c = 0; c < 45; c++) irest[c] = find("f_rest_" + std::to_string(c));
-    if (ix < 0 || iy < 0 || iz < 0 || iop < 0 || idc[0] < 0 || isc[0] < 0 || irot[0] < 0) {
+    bool have_all = ix >= 0 && iy >= 0 && iz >= 0 && iop >= 0;
+    for (int c = 0; c < 3; c++) have_all = ((idc[c] = find("f_dc_" + std::to_string(c))) >= 0) && have_all;
+    for (int c = 0; c < 3; c++) have_all = ((isc[c] = find("scale_" + std::to_string(c))) >= 0) && have_all;
+    for (int c = 0; c < 4; c++) have_all = ((irot[c] = find("rot_" + std::to_string(c))) >= 0) && have_all;
+    // f_rest_*: channel-major, K = count / 3 coefficients per channel (K = 0, 3, 8 or 15 for SH degree 0..3).  The set must
+    // be contiguous from f_rest_0 and a whole number of coefficients per channel; anything else is rejected, not guessed at.
+    int n_rest = 0;
+    for (int c = 0; c < 45; c++) {
+        irest[c] = find("f_rest_" + std::to_string(c));
+        if (irest[c] >= 0) {
+            if (n_rest != c) have_all = false;  // a hole in the set
+            n_rest = c + 1;
+        }
+    }
+    if (find("f_rest_45") >= 0 || n_rest % 3 != 0) have_all = false;
+    const int rest_per_channel = n_rest / 3;
+    if (!have_all) {  // every one of x/y/z/opacity/f_dc_0..2/scale_0..2/rot_0..3 is required
         std::fclose(fp);
         return SB_ERR_IO;
     }
     const size_t np = props.size();
+    // the vertex count of the header must fit the file: never trust it for the allocation
+    {
+        const long data_start = std::ftell(fp);
+        if (data_start < 0 || std::fseek(fp, 0, SEEK_END) != 0) {
+            std::fclose(fp);
+            return SB_ERR_IO;
+        }
+        const long file_end = std::ftell(fp);
+        if (file_end < data_start || std::fseek(fp, data_start, SEEK_SET) != 0 ||
+            n > (uint64_t)(file_end - data_start) / (np * 4)) {
+            std::fclose(fp);
+            return SB_ERR_IO;
+        }
+    }
     std::vector<float> row(np);
     SbGaussian* g = static_cast<SbGaussian*>(std::calloc(n ? n : 1, sizeof(SbGaussian)));
+    if (!g) {
+        std::fclose(fp);
+        return SB_ERR_IO;
+    }
     const float SH_C0 = 0.2820948f;
     for (uint64_t i = 0; i < n; i++) {
         if (std::fread(row.data(), 4, np, fp) != np) {
@@ -300,8 +330,8 @@ SbStatus sb_read_ply(const char* path, SbGaussian** out, uint64_t* n_out) {
         float a = (1.0f / (1.0f + std::exp(-row[iop]))) * 255.0f;
         a = !(a > 0.0f) ? 0.0f : (a > 255.0f ? 255.0f : a);
         o.color[3] = (uint8_t)a;
-        for (int k = 0; k < 15; k++)
-            for (int c = 0; c < 3; c++) o.sh[k * 3 + c] = irest[c * 15 + k] >= 0 ? row[irest[c * 15 + k]] : 0.0f;
+        for (int k = 0; k < rest_per_channel; k++)  // coefficients past the file's SH degree stay 0
+            for (int c = 0; c < 3; c++) o.sh[k * 3 + c] = row[irest[c * rest_per_channel + k]];
         for (int c = 0; c < 3; c++) o.scale[c] = std::exp(row[isc[c]]);
         const float qx = row[irot[1]], qy = row[irot[2]], qz = row[irot[3]], qw = row[irot[0]];
         const float inv = 1.0f / std::sqrt(((qx * qx + qy * qy) + qz * qz) + qw * qw);

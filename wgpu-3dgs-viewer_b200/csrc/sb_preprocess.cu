@@ -696,11 +696,16 @@ cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
     constexpr int T = tile_records(STRIDE);
     constexpr int S = ring_stages(STRIDE);
     constexpr size_t smem = (size_t)S * T * STRIDE + 8 * (2 * S * (T / 32) + 16) + 4 * (S * (T / 32) + 8 + 8 * (T / 32) + 8);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<SH, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {   // per-device function attribute: set once per device, not once per process
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            e = cudaFuncSetAttribute(preprocess_kernel<SH, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
     }
     p.num_tiles = (p.n + T - 1) / T;
     const int grid = (int)min((uint32_t)num_sms, p.num_tiles);

@@ -47,6 +47,8 @@ struct BinParams {
     uint32_t dup_capacity;
     uint32_t tiles_x;
     uint32_t ty_lo, ty_hi;  // tile rows of the rendered strip (inclusive)
+    uint32_t max_visible;   // n: the device-side count is clamped to it, indices >= n name no Gaussian (robust-buffer behaviour)
+    uint32_t indices_vec4;  // the index list is 16-byte aligned (a caller's sub-buffer need not be)
 };
 
 // tiles of one splat, clipped to the strip's tile rows
@@ -66,12 +68,46 @@ __device__ __forceinline__ uint32_t splat_tiles(const TileBox* tboxes, uint32_t 
     return w * (y1 - y0 + 1);
 }
 
-// K4: chained scan (decoupled look-back) of tiles-per-splat in depth order.
+// Decoupled look-back over 62-bit aggregates (flag in the two top bits): the duplicate total of a frame can exceed 2^32 (millions
+// of close-up splats covering thousands of tiles each), and an overflowing frame must still be FLAGGED, never wrapped.
+constexpr unsigned long long kFlag62Aggregate = 1ull << 62;
+constexpr unsigned long long kFlag62Prefix = 2ull << 62;
+constexpr unsigned long long kValue62Mask = (1ull << 62) - 1;
+__device__ __forceinline__ unsigned long long lookback62(unsigned long long* status, uint32_t tile, unsigned long long aggregate, uint32_t lane) {
+    if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? kFlag62Prefix : kFlag62Aggregate) | aggregate);
+    unsigned long long excl = 0;
+    if (tile > 0) {
+        int base = (int)tile - 1;
+        while (true) {
+            const int idx = base - (int)lane;
+            unsigned long long v;
+            do {
+                v = idx >= 0 ? ld_relaxed_u64(&status[idx]) : kFlag62Prefix;
+            } while (__any_sync(0xffffffffu, (v >> 62) == 0));
+            const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+            const int first = pm ? (__ffs(pm) - 1) : 31;
+            unsigned long long contrib = ((int)lane <= first) ? (v & kValue62Mask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            excl += contrib;
+            if (pm) break;
+            base -= 32;
+        }
+        if (lane == 0) st_relaxed_u64(&status[tile], kFlag62Prefix | (excl + aggregate));
+    }
+    return excl;
+}
+
+__device__ __forceinline__ uint32_t sat32(unsigned long long v) { return v > 0xffffffffull ? 0xffffffffu : (uint32_t)v; }
+
+// K4: chained scan (decoupled look-back) of tiles-per-splat in depth order.  Sums are carried in 64 bits; the offsets it writes
+// saturate at 2^32 - 1 (>= any capacity), so the emit's `offset < capacity` guard drops exactly the duplicates that do not fit.
 __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams p) {
-    __shared__ uint32_t warp_sums[kScanThreads / 32];
-    __shared__ uint32_t s_tile, s_base;
+    __shared__ unsigned long long warp_sums[kScanThreads / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_tile;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t v = *p.visible_count;
+    const uint32_t v = min(*p.visible_count, p.max_visible);
     if (blockIdx.x * kScanTile >= v && blockIdx.x > 0) return;
     if (tid == 0) s_tile = atomicAdd(p.scan_counter, 1u);
     __syncthreads();
@@ -79,10 +115,10 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     const uint32_t base = tile * kScanTile + tid * kScanItems;
     const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
     uint32_t cnt[kScanItems];
-    uint32_t sum = 0;
+    unsigned long long sum = 0;
     static_assert(kScanItems % 4 == 0, "a thread's run of splats is read and written as 128-bit vectors");
     uint32_t gidx[kScanItems];
-    const bool whole = base + kScanItems <= v;  // the run starts at a multiple of kScanItems: 16-byte aligned
+    const bool whole = base + kScanItems <= v && p.indices_vec4;  // the run starts at a multiple of kScanItems: 16-byte aligned
     if (whole) {
 #pragma unroll
         for (int q = 0; q < kScanItems / 4; q++) {
@@ -97,58 +133,61 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
     for (int i = 0; i < kScanItems; i++) {
         const uint32_t r = base + i;
         uint32_t x0, y0, w;
-        cnt[i] = r < v ? splat_tiles(p.tboxes, gidx[i], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
+        cnt[i] = (r < v && gidx[i] < p.max_visible) ? splat_tiles(p.tboxes, gidx[i], p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
         sum += cnt[i];
     }
-    uint32_t inc = sum;
+    unsigned long long inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
         if ((int)lane >= o) inc += t;
     }
     if (lane == 31) warp_sums[warp] = inc;
     __syncthreads();
-    uint32_t wexcl = 0, total = 0;
+    unsigned long long wexcl = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < kScanThreads / 32; w++) {
-        const uint32_t t = warp_sums[w];
+        const unsigned long long t = warp_sums[w];
         if (w < (int)warp) wexcl += t;
         total += t;
     }
     if (warp == 0) {
-        const uint32_t excl = lookback(p.scan_status, tile, total, lane);
+        const unsigned long long excl = lookback62(p.scan_status, tile, total, lane);
         if (lane == 0) s_base = excl;
     }
     __syncthreads();
-    uint32_t off = s_base + wexcl + inc - sum;
+    unsigned long long off = s_base + wexcl + inc - sum;
     if (whole) {
 #pragma unroll
         for (int q = 0; q < kScanItems / 4; q++) {
             uint4 o;
-            o.x = off; off += cnt[4 * q];
-            o.y = off; off += cnt[4 * q + 1];
-            o.z = off; off += cnt[4 * q + 2];
-            o.w = off; off += cnt[4 * q + 3];
+            o.x = sat32(off); off += cnt[4 * q];
+            o.y = sat32(off); off += cnt[4 * q + 1];
+            o.z = sat32(off); off += cnt[4 * q + 2];
+            o.w = sat32(off); off += cnt[4 * q + 3];
             reinterpret_cast<uint4*>(p.dup_offsets + base)[q] = o;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < kScanItems; i++) {
             const uint32_t r = base + i;
-            if (r < v) p.dup_offsets[r] = off;
+            if (r < v) p.dup_offsets[r] = sat32(off);
             off += cnt[i];
         }
     }
     const uint32_t last_tile = v == 0 ? 0 : (v - 1) / kScanTile;
     if (tile == last_tile && tid == 0) {
-        const uint32_t d = s_base + total;
-        if (p.needed_host) *p.needed_host = d;
+        const unsigned long long d = s_base + total;
+        if (p.needed_host) {
+            p.needed_host[0] = sat32(d);                      // duplicates this frame needed (saturated)
+            if (d > p.dup_capacity) p.needed_host[1] += 1u;   // overflow events (the host compares with the count it has seen)
+        }
         if (d > p.dup_capacity) {
             *p.overflow = 1u;
             *p.dup_count = p.dup_capacity;
         } else {
             *p.overflow = 0u;
-            *p.dup_count = d;
+            *p.dup_count = (uint32_t)d;
         }
     }
 }
@@ -156,7 +195,7 @@ __global__ void __launch_bounds__(kScanThreads) dup_scan_kernel(const BinParams 
 // K5: emit (tile id, Gaussian index) in depth order.  One lane per splat; splats covering more
 // than 32 tiles are expanded by the whole warp.
 __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
-    const uint32_t v = *p.visible_count;
+    const uint32_t v = min(*p.visible_count, p.max_visible);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = gridDim.x * (blockDim.x / 32);
     const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
@@ -165,7 +204,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
         uint32_t g = 0, n = 0, x0 = 0, y0 = 0, w = 1, off = 0;
         if (r < v) {
             g = sorted[r];
-            n = splat_tiles(p.tboxes, g, p.ty_lo, p.ty_hi, x0, y0, w);
+            n = g < p.max_visible ? splat_tiles(p.tboxes, g, p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
             off = p.dup_offsets[r];
         }
         if (n > 0 && n <= 32) {
@@ -964,6 +1003,9 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     bp.tiles_x = u.tiles_x;
     bp.ty_lo = ty_lo;
     bp.ty_hi = ty_hi;
+    bp.max_visible = p.max_visible;
+    bp.indices_vec4 = (reinterpret_cast<uintptr_t>(p.sorted_indices) & 15u) == 0 &&
+                      (p.sorted_indices_alt == nullptr || (reinterpret_cast<uintptr_t>(p.sorted_indices_alt) & 15u) == 0);
 
     const unsigned scan_grid = (unsigned)(((size_t)p.max_visible + kScanTile - 1) / kScanTile);
     dup_scan_kernel<<<scan_grid > 0 ? scan_grid : 1, kScanThreads, 0, stream>>>(bp);

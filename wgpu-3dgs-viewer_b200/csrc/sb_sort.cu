@@ -750,11 +750,16 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
     const size_t need = (kLookbackOffset + (size_t)num_passes * tiles * kRadix) * sizeof(uint32_t);
     if (need > scratch.internal_bytes) return cudaErrorInvalidValue;
     cudaError_t e;
-    static bool configured = false;
-    if (!configured) {
-        e = set_smem_all();
+    {   // the opt-in shared-memory size is a per-device function attribute: set once per device, not once per process
+        static bool configured[64] = {};
+        int dev = 0;
+        e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            e = set_smem_all();
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
     }
     uint32_t* ghist = scratch.internal;
     uint32_t* tickets = scratch.internal + kTicketOffset;

@@ -45,6 +45,9 @@ EXPORTED_SYMBOLS = [
     "sb_mm_destroy", "sb_mm_insert_model", "sb_mm_remove_model", "sb_mm_update_camera_with_pod",
     "sb_mm_update_model_transform_with_pod", "sb_mm_update_gaussian_transform_with_pod", "sb_mm_set_selection",
     "sb_mm_render", "sb_mm_read_model_indices",
+    "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
+    "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
+    "sb_mm_render_with_pass",
 ]
 
 
@@ -213,6 +216,16 @@ def load() -> C.CDLL:
     sig("sb_mm_set_selection", i32, vp, u64, vp, vp, u64, i32)
     sig("sb_mm_render", i32, vp, vp, P(Target), vp, u32)
     sig("sb_mm_read_model_indices", i32, vp, u64, vp, vp, u64, P(DrawIndirectArgs))
+    sig("sb_mm_update_camera", i32, vp, vp, f32, f32, f32, f32, f32, u32, u32)
+    sig("sb_mm_update_model_transform", i32, vp, u64, vp, vp, vp)
+    sig("sb_mm_update_gaussian_transform", i32, vp, f32, i32, i32, i32, f32)
+    sig("sb_mm_insert_model_from_gaussians", i32, vp, u64, vp, u64, P(i32))
+    sig("sb_mm_insert_model_from_device", i32, vp, u64, vp, u64, u64, P(i32))
+    sig("sb_mm_select_rect", i32, vp, u64, vp, f32, f32, f32, f32)
+    sig("sb_mm_select_brush", i32, vp, u64, vp, P(f32), u32, f32, i32)
+    sig("sb_mm_enable_selection", i32, vp, u64, i32, i32)
+    sig("sb_mm_read_selection", i32, vp, u64, vp, vp, u64)
+    sig("sb_mm_render_with_pass", i32, vp, vp, P(Target), P(DepthAttachment), i32, vp, u32)
     _lib = l
     return l
 
@@ -657,6 +670,60 @@ class MultiModelViewer:
         d = DrawIndirectArgs()
         _check(load().sb_mm_read_model_indices(self._h, key, _stream_handle(stream), out.ctypes.data, count, C.byref(d)), self.ctx._h)
         return out, d.instance_count
+
+    # --- non-pod updates (src/multi_model.rs:398-464)
+    def update_camera(self, pos, yaw, pitch, width, height, z_near=0.1, z_far=1e4, fov_y=float(np.deg2rad(np.float32(60.0)))):
+        p = _f(pos)
+        _check(load().sb_mm_update_camera(self._h, p.ctypes.data, yaw, pitch, z_near, z_far, fov_y, width, height), self.ctx._h)
+
+    def update_model_transform(self, key: int, pos=(0, 0, 0), rot=(0, 0, 0, 1), scale=(1, 1, 1)):
+        a, b, c = _f(pos), _f(rot), _f(scale)
+        _check(load().sb_mm_update_model_transform(self._h, key, a.ctypes.data, b.ctypes.data, c.ctypes.data), self.ctx._h)
+
+    def update_gaussian_transform(self, size=1.0, display_mode=MODE_SPLAT, sh_deg=3, no_sh0=False, max_std_dev=3.0):
+        _check(load().sb_mm_update_gaussian_transform(self._h, size, display_mode, sh_deg, int(no_sh0), max_std_dev), self.ctx._h)
+
+    def insert_model_from_gaussians(self, key: int, gaussians: np.ndarray) -> bool:
+        g = np.ascontiguousarray(gaussians, dtype=GAUSSIAN_DTYPE)
+        rep = C.c_int32()
+        _check(load().sb_mm_insert_model_from_gaussians(self._h, key, g.ctypes.data, len(g), C.byref(rep)), self.ctx._h)
+        return bool(rep.value)
+
+    def insert_model_from_device(self, key: int, device_pods, n: int) -> bool:
+        rep = C.c_int32()
+        self._keepalive = getattr(self, "_keepalive", {})
+        self._keepalive[key] = device_pods
+        _check(load().sb_mm_insert_model_from_device(self._h, key, device_pods.data_ptr(), _nbytes(device_pods), n, C.byref(rep)), self.ctx._h)
+        return bool(rep.value)
+
+    # --- per-model selection buffers (src/multi_model.rs:81-84)
+    def select_rect(self, key: int, x0, y0, x1, y1, stream=None):
+        _check(load().sb_mm_select_rect(self._h, key, _stream_handle(stream), x0, y0, x1, y1), self.ctx._h)
+
+    def select_brush(self, key: int, points, radius, accumulate=False, stream=None):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        _check(load().sb_mm_select_brush(self._h, key, _stream_handle(stream), pts.ctypes.data_as(C.POINTER(C.c_float)), len(pts),
+                                         float(radius), int(accumulate)), self.ctx._h)
+
+    def enable_selection(self, key: int, enabled=True, invert=True):
+        _check(load().sb_mm_enable_selection(self._h, key, int(enabled), int(invert)), self.ctx._h)
+
+    def read_selection(self, key: int, n: int, stream=None) -> np.ndarray:
+        out = np.zeros((n + 31) // 32, dtype=np.uint32)
+        _check(load().sb_mm_read_selection(self._h, key, _stream_handle(stream), out.ctypes.data, len(out)), self.ctx._h)
+        return out
+
+    def render_with_pass(self, target, width, height, keys, depth=None, compare=COMPARE_ALWAYS, depth_write=False, load_target=True,
+                         stream=None):
+        """new_with_options(depth_stencil) + renderer.render_with_pass per model inside a caller's pass."""
+        t = make_target(target, width, height, self.target_format)
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        d = None
+        if depth is not None:
+            d = DepthAttachment()
+            d.d_depth, d.pitch_bytes, d.compare, d.write_enabled = depth.data_ptr(), width * 4, compare, int(depth_write)
+        _check(load().sb_mm_render_with_pass(self._h, _stream_handle(stream), C.byref(t), C.byref(d) if d is not None else None,
+                                             int(load_target), k.ctypes.data, len(k)), self.ctx._h)
 
     def close(self):
         if self._h:
