@@ -218,8 +218,10 @@ def test_config4_multi_model_8x1M_rect_mask(sb, ob, ctx):
         oimg, _ = ob.render(omodels(far, sel, invert), ocam, ogt, n_threads=threads)
         d = idiff(frames[invert], oimg)
         assert d <= 2, f"invert {invert}: max-abs {d}/255"
-    # invert = 0 shows only what projects into the rectangle: nothing is lit far outside it
-    assert frames[0][:200, :400, :3].max() == 0 and frames[1][:200, :400, :3].max() > 0
+    # invert = 0 shows only what projects into the rectangle [480,1440)x[270,810): the band left of it (80 px clear of the
+    # border, same rows) is empty, while invert = 1 hides exactly those Gaussians and leaves the band lit
+    assert frames[0][300:780, :400, :3].max() == 0 and frames[1][300:780, :400, :3].max() > 0
+    assert frames[0][300:780, 600:1300, :3].max() > 0
     mm.close()
 
 

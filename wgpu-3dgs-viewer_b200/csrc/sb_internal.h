@@ -25,6 +25,7 @@ struct PreParams {
     unsigned long long* tile_status;   // decoupled look-back state (zeroed before launch)
     uint32_t* visible_count;           // V for downstream kernels
     uint32_t* visible_host;            // nullable: device alias of a mapped pinned word that also receives V
+    uint32_t* sort_prep;               // nullable: [kSortPrepOr] |= key, [kSortPrepNand] |= ~key over the visible keys (zeroed before launch)
     Uniforms u;
 };
 
@@ -57,6 +58,16 @@ size_t sort_internal_bytes(uint32_t capacity);
 cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count,
                         int begin_bit, int end_bit, const SortScratch& scratch, int num_sms, cudaStream_t stream,
                         uint32_t* parity_out = nullptr, uint32_t expected_count = 0);
+// Key-adaptive sort (v4).  `prep` (kSortPrepWords u32, nullable): [kSortPrepOr] / [kSortPrepNand] hold the OR of the keys and the
+// OR of their complements (K1 accumulates them while it writes the keys); everything after them must be zero when prep_zeroed.
+// begin_bit >= 0: sort exactly bits [begin_bit, end_bit) and ignore or / nand.  The result is left where the last pass wrote it;
+// *parity_out (device) = 1: in scratch.keys_alt / payload_alt (launch_sort_finish brings it home).
+constexpr int kSortPrepOr = 0, kSortPrepNand = 1, kSortPrepPasses = 2, kSortPrepParity = 3, kSortPrepPlan = 4, kSortPrepTickets = 8,
+              kSortPrepHist = 16, kSortPrepWords = 16 + 4 * 512;
+size_t sort_prep_bytes();
+cudaError_t launch_sort_adaptive(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count, uint32_t* prep,
+                                 bool prep_zeroed, int begin_bit, int end_bit, const SortScratch& scratch, int num_sms,
+                                 cudaStream_t stream, uint32_t* parity_out);
 cudaError_t launch_sort_finish(uint32_t* keys, uint32_t* payload, const SortScratch& scratch, const uint32_t* d_count, uint32_t max_count,
                                const uint32_t* parity, int num_sms, cudaStream_t stream);
 

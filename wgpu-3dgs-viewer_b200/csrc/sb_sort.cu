@@ -10,6 +10,7 @@
 // The sort is STABLE (ties keep input order) like the reference's (radix_sort.wgsl:325-343),
 // which is what makes the final order canonical (ascending Gaussian index within equal keys).
 // The number of keys is read from device memory (the reference's indirect dispatch).
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 
@@ -599,6 +600,389 @@ __global__ void __launch_bounds__(kV3Threads, kV3CtasPerSm)
         onesweep3_tile<NBITS, false>(sm, kin, vin, kout, vout, count, shift, gcount, lookback, tile);
 }
 
+// ================================================================ K2'/K3' (v4): key-adaptive onesweep
+//
+// Depth keys of one frame are f32 values of 1 - ndc.z: most of their 32 bits never vary (sign, the exponent's high bits, and —
+// because 1 - ndc.z is a difference of numbers near 1 — the low mantissa bits).  K1 accumulates the OR and the OR-of-complements
+// of the visible keys while it writes them; the bits that differ between at least two keys are `or & nand`, and the sort only
+// has to cover bit range [lo, hi) of them: 17 bits for the 6 M bench scene from outside, 26 from inside.  One prologue kernel
+// turns that into a plan — ceil((hi - lo) / 9) passes of at most 9 bits, widths balanced — builds every pass's histogram in one
+// read of the keys and zeroes the look-back tables; the pass kernels read their shift and width from the plan.  Two passes
+// instead of four (one of them skipped) for the bench scene, and 3 launches of real work instead of 7.
+// Digits are at most 9 bits wide: 512 bins, two per thread (every per-digit quantity is a 64-bit vector: one ld/st each), 16 KB
+// of warp histograms in the 32 KB the staging buffer needs anyway, six 256-thread CTAs per SM as before.
+constexpr int kV4MaxBits = 9;
+constexpr int kV4Bins = 1 << kV4MaxBits;  // 512
+constexpr int kV4Threads = 256;
+constexpr int kV4Items = 16;
+constexpr int kV4Tile = kV4Threads * kV4Items;  // 4096
+constexpr int kV4Warps = kV4Threads / 32;
+constexpr int kV4CtasPerSm = 6;
+static_assert(kV4Bins == 2 * kV4Threads, "two digits per thread");
+
+// prep words (sb_internal.h kSortPrep*): [0] or, [1] nand, [2] passes, [3] parity, [4..8) plan, [8..12) tickets, [16..) hist[4][512]
+constexpr uint32_t kPlanValid = 1u << 17;
+constexpr uint32_t kPlanAltIn = 1u << 16;
+
+struct Sort4Smem {
+    union {
+        uint32_t warp_hist[kV4Warps][kV4Bins];  // 16 KB
+        struct {
+            uint32_t keys[kV4Tile];
+            uint32_t vals[kV4Tile];
+        } stage;                                 // 32 KB
+    };
+    uint32_t digit_off[kV4Bins];  // first the tile-local start of each digit, then (after the look-back) its global base
+    uint32_t scan_a[kV4Warps];
+    uint32_t scan_b[kV4Warps];
+    uint32_t tile;
+};
+
+__device__ __forceinline__ void st_relaxed_v2(uint32_t* p, uint32_t a, uint32_t b) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_v2(const uint32_t* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// lanes whose digit (< 2^nbits, nbits <= 9, warp-uniform) equals this lane's: one vote per significant digit bit
+__device__ __forceinline__ uint32_t match_digit9(uint32_t d, int nbits) {
+    uint32_t differ = 0u;
+#pragma unroll
+    for (int b = 0; b < kV4MaxBits; b++) {
+        if (b < nbits) {
+            uint32_t x;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                ".reg .b32 t, m, r;\n"
+                "and.b32 t, %1, %2;\n"
+                "setp.ne.u32 p, t, 0;\n"
+                "vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+                "selp.b32 r, -1, 0, p;\n"
+                "xor.b32 %0, m, r;\n"
+                "}\n"
+                : "=r"(x)
+                : "r"(d), "r"(1u << b));
+            differ |= x;
+        }
+    }
+    return ~differ;
+}
+
+// The sort plan from the varying-bit mask: passes, and for pass p its shift / width / input side.
+struct SortPlan4 {
+    int passes;
+    int shift[kMaxPasses], bits[kMaxPasses];
+};
+__device__ __forceinline__ SortPlan4 make_plan4(uint32_t varying) {
+    SortPlan4 pl;
+    pl.passes = 0;
+#pragma unroll
+    for (int p = 0; p < kMaxPasses; p++) pl.shift[p] = pl.bits[p] = 0;
+    if (varying == 0u) return pl;
+    const int lo = __ffs(varying) - 1, hi = 32 - __clz(varying);
+    const int nbits = hi - lo;
+    pl.passes = (nbits + kV4MaxBits - 1) / kV4MaxBits;
+    const int base = nbits / pl.passes, rem = nbits % pl.passes;
+    int sh = lo;
+#pragma unroll
+    for (int p = 0; p < kMaxPasses; p++) {
+        if (p < pl.passes) {
+            pl.shift[p] = sh;
+            pl.bits[p] = base + (p < rem ? 1 : 0);
+            sh += pl.bits[p];
+        }
+    }
+    return pl;
+}
+
+// K2': plan + all histograms in one read of the keys + look-back tables zeroed.  `prep` arrives zeroed apart from or / nand.
+// explicit_mask != 0: sort exactly those bits (the standalone sorter's begin/end range, the tile sort's tile-id bits).
+__global__ void __launch_bounds__(512) sort4_prologue_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count,
+                                                             uint32_t max_count, uint32_t* __restrict__ prep, uint32_t explicit_mask,
+                                                             uint32_t* __restrict__ lookback, uint32_t tiles_alloc,
+                                                             uint32_t* __restrict__ parity_out) {
+    __shared__ uint32_t hist[kMaxPasses][kV4Bins];
+    const uint32_t count = min(*d_count, max_count);
+    const uint32_t varying = count < 2u ? 0u : (explicit_mask ? explicit_mask : (prep[kSortPrepOr] & prep[kSortPrepNand]));
+    const SortPlan4 pl = make_plan4(varying);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t parity = 0;
+        for (int p = 0; p < kMaxPasses; p++) {
+            uint32_t w = 0;
+            if (p < pl.passes) {
+                w = (uint32_t)pl.shift[p] | ((uint32_t)pl.bits[p] << 8) | (parity ? kPlanAltIn : 0u) | kPlanValid;
+                parity ^= 1u;
+            }
+            prep[kSortPrepPlan + p] = w;
+        }
+        prep[kSortPrepPasses] = (uint32_t)pl.passes;
+        prep[kSortPrepParity] = parity;
+        if (parity_out) *parity_out = parity;
+    }
+    if (pl.passes == 0) return;
+    // zero the look-back tables of the tiles this sort will use
+    {
+        const uint32_t tiles = (count + kV4Tile - 1) / kV4Tile;
+        const uint32_t vec_per_pass = tiles * (kV4Bins / 4);
+        for (int p = 0; p < pl.passes; p++) {
+            uint4* lb = reinterpret_cast<uint4*>(lookback + (size_t)p * tiles_alloc * kV4Bins);
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_pass; i += gridDim.x * blockDim.x) lb[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    for (int i = threadIdx.x; i < kMaxPasses * kV4Bins; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t nvec = count / 4;
+    const uint4* kv = reinterpret_cast<const uint4*>(keys);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nvec; base += stride) {  // warp-uniform trip count (votes below)
+        const uint32_t i = base + threadIdx.x;
+        const bool ok = i < nvec;
+        uint4 k = make_uint4(0, 0, 0, 0);
+        if (ok) k = __ldg(&kv[i]);
+#pragma unroll
+        for (int p = 0; p < kMaxPasses; p++) {
+            if (p < pl.passes) {
+                const int sh = pl.shift[p];
+                const uint32_t mask = (1u << pl.bits[p]) - 1u;
+                const uint32_t d0 = (k.x >> sh) & mask, d1 = (k.y >> sh) & mask, d2 = (k.z >> sh) & mask, d3 = (k.w >> sh) & mask;
+                // a warp whose 128 keys share the digit (sorted or clustered input) adds once instead of serialising 128 atomics
+                const uint32_t ref = __shfl_sync(0xffffffffu, d0, 0);
+                if (__all_sync(0xffffffffu, ok && d0 == ref && d1 == ref && d2 == ref && d3 == ref)) {
+                    if ((threadIdx.x & 31u) == 0) atomicAdd(&hist[p][ref], 128u);
+                } else if (ok) {
+                    atomicAdd(&hist[p][d0], 1u);
+                    atomicAdd(&hist[p][d1], 1u);
+                    atomicAdd(&hist[p][d2], 1u);
+                    atomicAdd(&hist[p][d3], 1u);
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (uint32_t i = nvec * 4 + threadIdx.x; i < count; i += blockDim.x) {
+            const uint32_t key = keys[i];
+            for (int p = 0; p < pl.passes; p++) atomicAdd(&hist[p][(key >> pl.shift[p]) & ((1u << pl.bits[p]) - 1u)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pl.passes * kV4Bins; i += blockDim.x) {
+        const uint32_t v = (&hist[0][0])[i];
+        if (v) atomicAdd(&prep[kSortPrepHist + i], v);
+    }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void onesweep4_tile(Sort4Smem& sm, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t count,
+                                               int shift, int nbits, uint2 gcount, uint32_t* __restrict__ lookback, uint32_t tile) {
+    const uint32_t kMask = (1u << nbits) - 1u;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tile_base = tile * kV4Tile;
+    const uint32_t tile_count = FULL ? (uint32_t)kV4Tile : (count - tile_base);
+
+    uint32_t key[kV4Items];
+    const uint32_t woff = warp * (32 * kV4Items) + lane;
+    const uint32_t* kp = keys_in + tile_base + woff;
+#pragma unroll
+    for (int i = 0; i < kV4Items; i++) key[i] = (FULL || woff + i * 32 < tile_count) ? __ldg(kp + i * 32) : 0xffffffffu;
+
+    uint32_t* wh = sm.warp_hist[warp];
+    {
+        uint4* z = reinterpret_cast<uint4*>(wh);
+#pragma unroll
+        for (int q = 0; q < kV4Bins / 128; q++) z[lane + 32 * q] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+
+    // ---- warp-level multi-split: rank among the equal digits of the warp (stable), no shared-memory atomics
+    uint32_t rank2[kV4Items / 2];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < kV4Items; i++) {
+        const bool ok = FULL || (woff + i * 32) < tile_count;
+        const uint32_t d = (key[i] >> shift) & kMask;
+        uint32_t peers = match_digit9(d, nbits);
+        if (!FULL) {
+            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            peers &= ok ? okm : ~okm;
+        }
+        const uint32_t below = __popc(peers & lt);
+        uint32_t pre = 0;
+        if (below == 0 && ok) {
+            pre = wh[d];
+            wh[d] = pre + (uint32_t)__popc(peers);
+        }
+        __syncwarp();
+        pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
+        if (i & 1) rank2[i >> 1] |= (pre + below) << 16;
+        else rank2[i >> 1] = pre + below;
+    }
+    __syncthreads();
+
+    // ---- thread t owns digits 2t, 2t+1: scan over warps, publish the tile aggregates, scans over digits
+    uint2 digit_count, local_excl, global_excl, nearest = make_uint2(0, 0);
+    {
+        uint2 run = make_uint2(0, 0);
+#pragma unroll
+        for (int w = 0; w < kV4Warps; w++) {
+            uint2* slot = reinterpret_cast<uint2*>(&sm.warp_hist[w][2 * tid]);
+            const uint2 t = *slot;
+            *slot = run;
+            run.x += t.x;
+            run.y += t.y;
+        }
+        digit_count = run;
+        const uint32_t flag = tile == 0 ? kLbPrefix : kLbAggregate;
+        st_relaxed_v2(&lookback[(size_t)tile * kV4Bins + 2 * tid], flag | digit_count.x, flag | digit_count.y);
+        if (tile > 0) nearest = ld_relaxed_v2(&lookback[(size_t)(tile - 1) * kV4Bins + 2 * tid]);
+        uint32_t a = digit_count.x + digit_count.y, b = gcount.x + gcount.y;
+        const uint32_t a_own = a, b_own = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o);
+            const uint32_t tb = __shfl_up_sync(0xffffffffu, b, o);
+            if ((int)lane >= o) {
+                a += ta;
+                b += tb;
+            }
+        }
+        if (lane == 31) {
+            sm.scan_a[warp] = a;
+            sm.scan_b[warp] = b;
+        }
+        __syncthreads();
+        uint32_t wa = 0, wb = 0;
+#pragma unroll
+        for (int w = 0; w < kV4Warps; w++) {
+            if (w < (int)warp) {
+                wa += sm.scan_a[w];
+                wb += sm.scan_b[w];
+            }
+        }
+        local_excl.x = a - a_own + wa;
+        local_excl.y = local_excl.x + digit_count.x;
+        global_excl.x = b - b_own + wb;
+        global_excl.y = global_excl.x + gcount.x;
+        *reinterpret_cast<uint2*>(&sm.digit_off[2 * tid]) = local_excl;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < kV4Items; i++) {
+        const uint32_t d = (key[i] >> shift) & kMask;
+        rank2[i >> 1] += (wh[d] + sm.digit_off[d]) << (16 * (i & 1));
+    }
+    __syncthreads();  // histograms and local starts are dead: the storage becomes the staging buffer / the global bases
+    const uint32_t vals_smem = smem_u32(sm.stage.vals);
+    const uint32_t* vp = vals_in + tile_base + woff;
+#pragma unroll
+    for (int i = 0; i < kV4Items; i++) {
+        if (FULL || (woff + i * 32) < tile_count) {
+            const uint32_t pos = (rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            sm.stage.keys[pos] = key[i];
+            cp_async_4(vals_smem + pos * 4u, vp + i * 32);  // payload: global -> staging slot, no register
+        }
+    }
+
+    {
+        // decoupled look-back for both digits at once: the two words of a tile are written by one thread with one 64-bit
+        // store, but each carries its own flag and is handled on its own
+        uint32_t ex0 = 0, ex1 = 0;
+        bool done0 = false, done1 = false;
+        int t = (int)tile - 1;
+        bool have = true;
+        while (t >= 0 && !(done0 && done1)) {
+            const uint2 v = have ? nearest : ld_relaxed_v2(&lookback[(size_t)t * kV4Bins + 2 * tid]);
+            have = false;
+            if ((!done0 && (v.x >> 30) == 0) || (!done1 && (v.y >> 30) == 0)) {
+                __nanosleep(40);
+                continue;
+            }
+            if (!done0) {
+                ex0 += v.x & kLbValueMask;
+                done0 = (v.x >> 30) == 2;
+            }
+            if (!done1) {
+                ex1 += v.y & kLbValueMask;
+                done1 = (v.y >> 30) == 2;
+            }
+            --t;
+            if (done0 && done1) break;
+            // the next four predecessors in one round trip
+            uint2 u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                u[j] = (t - j) >= 0 ? ld_relaxed_v2(&lookback[(size_t)(t - j) * kV4Bins + 2 * tid]) : make_uint2(kLbPrefix, kLbPrefix);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (done0 && done1) break;
+                if ((!done0 && (u[j].x >> 30) == 0) || (!done1 && (u[j].y >> 30) == 0)) break;  // not published: poll it at the top
+                if (!done0) {
+                    ex0 += u[j].x & kLbValueMask;
+                    done0 = (u[j].x >> 30) == 2;
+                }
+                if (!done1) {
+                    ex1 += u[j].y & kLbValueMask;
+                    done1 = (u[j].y >> 30) == 2;
+                }
+                --t;
+            }
+        }
+        if (tile > 0)
+            st_relaxed_v2(&lookback[(size_t)tile * kV4Bins + 2 * tid], kLbPrefix | (ex0 + digit_count.x), kLbPrefix | (ex1 + digit_count.y));
+        *reinterpret_cast<uint2*>(&sm.digit_off[2 * tid]) =
+            make_uint2(global_excl.x + ex0 - local_excl.x, global_excl.y + ex1 - local_excl.y);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kV4Items; i++) {
+        const uint32_t j = i * kV4Threads + tid;
+        if (FULL || j < tile_count) {
+            const uint32_t k = sm.stage.keys[j];
+            const uint32_t dst = sm.digit_off[(k >> shift) & kMask] + j;
+            keys_out[dst] = k;
+            vals_out[dst] = sm.stage.vals[j];
+        }
+    }
+}
+
+// K3': one digit pass; shift, width and input side come from the plan the prologue wrote.
+__global__ void __launch_bounds__(kV4Threads, kV4CtasPerSm)
+    onesweep4_kernel(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
+                     uint32_t* __restrict__ vals_b, const uint32_t* __restrict__ d_count, uint32_t max_count,
+                     uint32_t* __restrict__ prep, uint32_t* __restrict__ lookback_base, uint32_t tiles_alloc, int pass) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Sort4Smem& sm = *reinterpret_cast<Sort4Smem*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t pl = prep[kSortPrepPlan + pass];
+    if (!(pl & kPlanValid)) return;  // fewer passes than launches: nothing to do
+    // one round trip: ticket, count and this thread's two digit totals are in flight together
+    uint32_t q = 0;
+    if (tid == 0) q = atomicAdd(&prep[kSortPrepTickets + pass], 1u);
+    const uint32_t count = min(*d_count, max_count);
+    const uint2 gcount = *reinterpret_cast<const uint2*>(&prep[kSortPrepHist + pass * kV4Bins + 2 * tid]);
+    if (tid == 0) sm.tile = q;
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile * kV4Tile >= count) return;  // surplus CTA
+    const int shift = (int)(pl & 0xffu), nbits = (int)((pl >> 8) & 0xffu);
+    const bool alt_in = (pl & kPlanAltIn) != 0;
+    const uint32_t* kin = alt_in ? keys_b : keys_a;
+    const uint32_t* vin = alt_in ? vals_b : vals_a;
+    uint32_t* kout = alt_in ? keys_a : keys_b;
+    uint32_t* vout = alt_in ? vals_a : vals_b;
+    uint32_t* lookback = lookback_base + (size_t)pass * tiles_alloc * kV4Bins;
+    if ((tile + 1) * kV4Tile <= count)
+        onesweep4_tile<true>(sm, kin, vin, kout, vout, count, shift, nbits, gcount, lookback, tile);
+    else
+        onesweep4_tile<false>(sm, kin, vin, kout, vout, count, shift, nbits, gcount, lookback, tile);
+}
+
 // One block after the histograms: which passes are the identity (one digit holds every key) and where each
 // remaining pass reads its input; state[0] = 1 when the result ends in the alt buffers.
 __global__ void sort_plan_kernel(uint32_t* __restrict__ internal, const uint32_t* __restrict__ d_count, uint32_t max_count, int num_passes,
@@ -723,8 +1107,59 @@ constexpr uint32_t kSmallSort = 1500000;
 }  // namespace
 
 size_t sort_internal_bytes(uint32_t capacity) {
-    const size_t tiles = ((size_t)capacity + kV3Tile - 1) / kV3Tile;  // the smaller of the two tile sizes
-    return (kLookbackOffset + (size_t)kMaxPasses * tiles * kRadix) * sizeof(uint32_t);
+    const size_t tiles = ((size_t)capacity + kV3Tile - 1) / kV3Tile;  // the smaller of the tile sizes
+    const size_t v3 = (kLookbackOffset + (size_t)kMaxPasses * tiles * kRadix) * sizeof(uint32_t);
+    const size_t v4 = ((size_t)kSortPrepWords + (size_t)kMaxPasses * tiles * kV4Bins) * sizeof(uint32_t);
+    return v3 > v4 ? v3 : v4;
+}
+
+size_t sort_prep_bytes() { return (size_t)kSortPrepWords * sizeof(uint32_t); }
+
+cudaError_t launch_sort_adaptive(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count, uint32_t* prep,
+                                 bool prep_zeroed, int begin_bit, int end_bit, const SortScratch& scratch, int num_sms,
+                                 cudaStream_t stream, uint32_t* parity_out) {
+    if (max_count == 0) return parity_out ? cudaMemsetAsync(parity_out, 0, 4, stream) : cudaSuccess;
+    const size_t tiles = ((size_t)max_count + kV4Tile - 1) / kV4Tile;
+    uint32_t explicit_mask = 0;
+    if (begin_bit >= 0) {
+        if (end_bit > 32 || begin_bit >= end_bit) return cudaErrorInvalidValue;
+        explicit_mask = (end_bit - begin_bit == 32) ? 0xffffffffu : (((1u << (end_bit - begin_bit)) - 1u) << begin_bit);
+    }
+    uint32_t* lookback = scratch.internal;
+    if (!prep) {  // no caller-owned prep words: they live in front of the look-back tables
+        prep = scratch.internal;
+        lookback = scratch.internal + kSortPrepWords;
+        prep_zeroed = false;
+    }
+    const size_t need = ((size_t)(lookback - scratch.internal) + (size_t)kMaxPasses * tiles * kV4Bins) * sizeof(uint32_t);
+    if (need > scratch.internal_bytes) return cudaErrorInvalidValue;
+    cudaError_t e;
+    {   // per-device function attribute
+        static bool configured[64] = {};
+        int dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            e = cudaFuncSetAttribute(onesweep4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sort4Smem));
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+    }
+    if (!prep_zeroed) {
+        // keep or / nand (K1 wrote them) when the caller owns the prep words; everything else starts from zero
+        uint32_t* from = (prep == scratch.internal) ? prep : prep + kSortPrepPasses;
+        e = cudaMemsetAsync(from, 0, (size_t)(prep + kSortPrepWords - from) * sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int pro_grid = (int)std::min<size_t>((size_t)num_sms * 2, (tiles * kV4Tile / 4 + 511) / 512);
+    sort4_prologue_kernel<<<pro_grid > 0 ? pro_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, prep, explicit_mask, lookback,
+                                                                          (uint32_t)tiles, parity_out);
+    // the number of passes is decided on the device; launches beyond it exit at once
+    const int max_passes = begin_bit >= 0 ? (end_bit - begin_bit + kV4MaxBits - 1) / kV4MaxBits : kMaxPasses;
+    for (int p = 0; p < max_passes; p++)
+        onesweep4_kernel<<<(unsigned)tiles, kV4Threads, sizeof(Sort4Smem), stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt,
+                                                                                     d_count, max_count, prep, lookback, (uint32_t)tiles, p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_sort_finish(uint32_t* keys, uint32_t* payload, const SortScratch& scratch, const uint32_t* d_count, uint32_t max_count,
