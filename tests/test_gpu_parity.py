@@ -439,7 +439,7 @@ def test_standalone_radix_sorter(sb, ctx):
         s.close()
 
 
-@pytest.mark.parametrize("impl", ["v1", "v3"])
+@pytest.mark.parametrize("impl", ["v1", "v3", "v4"])
 def test_radix_sorter_both_pass_kernels(sb, impl):
     """Both digit-pass kernels (SB_SORT_IMPL=v1: 8192-pair tiles, shared-memory peer masks; v3: 4096-pair tiles, vote ranking,
     cp.async payload) forced on every shape: odd bit ranges, begin_bit > 0, a device count below the capacity, an empty

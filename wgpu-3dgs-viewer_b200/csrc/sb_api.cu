@@ -199,6 +199,7 @@ struct SbViewer {
     // the alt buffers) and binning reads them there; they are copied home to indices/keys only when somebody asks for
     // them (read_*, *_ptr, the stage-wise sort call) — 48 MB less traffic per 6 M-Gaussian frame.
     bool sorted_pending = false;
+    bool sort_prep_fresh = false;  // the depth sort's prep words were zeroed (with K1's scratch) and not consumed yet
     cudaStream_t last_stream = nullptr;
     CUtensorMap recs_map;        // 2-D view of recs[] (12 x n floats, 48-byte rows) for TMA gather4
     bool use_gather4 = false;
@@ -246,7 +247,8 @@ SbStatus viewer_alloc(SbViewer* v) {
         const bool want_bulk = path && std::string(path) == "bulk";
         v->use_gather4 = !want_bulk && encode_recs_map(v->recs.p, n, &v->recs_map);
     }
-    SB_CUDA(ctx, v->pre_scratch.alloc(sb::preprocess_scratch_bytes(n, v->sh_fmt, v->cov_fmt)));
+    // [depth sort prep words | K1 ticket + look-back]: zeroed together by the one memset in front of K1
+    SB_CUDA(ctx, v->pre_scratch.alloc(sb::preprocess_scratch_prefix_bytes() + sb::preprocess_scratch_bytes(n, v->sh_fmt, v->cov_fmt)));
     SB_CUDA(ctx, v->selection.alloc(((size_t)n + 31) / 32 * 4 + 4));
     SB_CUDA(ctx, cudaMemset(v->selection.p, 0, v->selection.bytes));
     const SbDrawIndirectArgs d = {6, 0, 0, 0};          // IndirectArgsBuffer::new
@@ -362,6 +364,8 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.tboxes = v->tboxes.as<sb::TileBox>();
     p.visible_count = v->d_visible();
     p.visible_host = v->d_needed + 4;  // mapped pinned: the next frame's sort reads it (no synchronisation) as a size hint
+    p.sort_prep = v->pre_scratch.as<uint32_t>();
+    v->sort_prep_fresh = true;         // zeroed by K1's memset, or / nand accumulated by K1: the next depth sort needs no clearing
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format, v->exact_cutoff);
     v->recs_cut = p.u.cut_k > 0.0f;
     v->sorted_pending = false;  // a new visible set replaces whatever a previous frame left behind
@@ -388,10 +392,22 @@ sb::SortScratch depth_sort_scratch(SbViewer* v) {
 }
 
 SbStatus do_sort(SbViewer* v, cudaStream_t stream, bool defer_copy_home = false) {
-    // keys = f32 depth bit patterns in [0, 0x3F800000]; pads (2.0) beyond V are left in place
-    // size hint = the visible count the previous preprocess of this viewer reported (0 = none yet): a heuristic only
-    SB_CUDA(v->ctx, sb::launch_sort(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), v->d_visible(), v->n, 0, 32, depth_sort_scratch(v),
-                                    v->ctx->num_sms, stream, defer_copy_home ? v->d_sort_parity() : nullptr, v->h_needed[4]));
+    // keys = f32 depth bit patterns in [0, 0x3F800000]; pads (2.0) beyond V are left in place.  The digit plan comes from the
+    // bits K1 saw varying among the visible keys (SB_DEPTH_SORT=v3 selects the fixed 4 x 8-bit round-1 sort for A/B runs).
+    static const bool legacy = [] { const char* c = std::getenv("SB_DEPTH_SORT"); return c && std::string(c) == "v3"; }();
+    if (legacy) {
+        // size hint = the visible count the previous preprocess of this viewer reported (0 = none yet): a heuristic only
+        SB_CUDA(v->ctx, sb::launch_sort(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), v->d_visible(), v->n, 0, 32, depth_sort_scratch(v),
+                                        v->ctx->num_sms, stream, defer_copy_home ? v->d_sort_parity() : nullptr, v->h_needed[4]));
+    } else {
+        SB_CUDA(v->ctx, sb::launch_sort_adaptive(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), v->d_visible(), v->n,
+                                                 v->pre_scratch.as<uint32_t>(), v->sort_prep_fresh, -1, 0, depth_sort_scratch(v),
+                                                 v->ctx->num_sms, stream, v->d_sort_parity()));
+        v->sort_prep_fresh = false;
+        if (!defer_copy_home)
+            SB_CUDA(v->ctx, sb::launch_sort_finish(v->keys.as<uint32_t>(), v->indices.as<uint32_t>(), depth_sort_scratch(v), v->d_visible(),
+                                                   v->n, v->d_sort_parity(), v->ctx->num_sms, stream));
+    }
     v->sorted_pending = defer_copy_home;
     v->last_stream = stream;
     if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[2], stream));

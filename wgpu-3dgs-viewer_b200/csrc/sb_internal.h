@@ -32,6 +32,9 @@ struct PreParams {
 int preprocess_records_per_tile(int sh_fmt, int cov_fmt);
 // scratch bytes needed for tile_counter + tile_status
 size_t preprocess_scratch_bytes(uint32_t n, int sh_fmt, int cov_fmt);
+// When PreParams.sort_prep is set it must point at the START of `scratch`, whose first preprocess_scratch_prefix_bytes() bytes
+// are the depth sort's prep words; K1's own words follow (scratch_bytes = prefix + preprocess_scratch_bytes).
+size_t preprocess_scratch_prefix_bytes();
 cudaError_t launch_preprocess(int sh_fmt, int cov_fmt, PreParams& p, void* scratch, size_t scratch_bytes,
                               int num_sms, cudaStream_t stream);
 
@@ -63,7 +66,7 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
 // begin_bit >= 0: sort exactly bits [begin_bit, end_bit) and ignore or / nand.  The result is left where the last pass wrote it;
 // *parity_out (device) = 1: in scratch.keys_alt / payload_alt (launch_sort_finish brings it home).
 constexpr int kSortPrepOr = 0, kSortPrepNand = 1, kSortPrepPasses = 2, kSortPrepParity = 3, kSortPrepPlan = 4, kSortPrepTickets = 8,
-              kSortPrepHist = 16, kSortPrepWords = 16 + 4 * 512;
+              kSortPrepDone = 12, kSortPrepHist = 16, kSortPrepWords = 16 + 4 * 512;
 size_t sort_prep_bytes();
 cudaError_t launch_sort_adaptive(uint32_t* keys, uint32_t* payload, const uint32_t* d_count, uint32_t max_count, uint32_t* prep,
                                  bool prep_zeroed, int begin_bit, int end_bit, const SortScratch& scratch, int num_sms,

@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         float key = 0.0f;
     };
     Deferred d1, d2, d3;  // outputs of the previous three tiles, oldest = d3
+    uint32_t key_or = 0u, key_nand = 0u;  // which key bits are 1 / 0 in at least one visible key: the depth sort's digit plan
 
     // Writes a tile's (index, key) pairs.  Everything that depends on other warps (the warp prefix inside
     // the tile) or other CTAs (the tile base from the look-back) is read here, three tiles late.
@@ -655,6 +656,8 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         d1.g = g;
         d1.lane_rank = __popc(bal & lanemask_lt());
         d1.key = ssub(1.0f, nz);  // preprocess.wesl:105
+        key_or |= vis ? __float_as_uint(d1.key) : 0u;
+        key_nand |= vis ? ~__float_as_uint(d1.key) : 0u;
         d1.tile = tile;
         d1.ring = ring;
         d1.par = rpar;
@@ -662,6 +665,14 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
     flush(d3);
     flush(d2);
     flush(d1);
+    if (p.sort_prep != nullptr) {
+        key_or = __reduce_or_sync(0xffffffffu, key_or);
+        key_nand = __reduce_or_sync(0xffffffffu, key_nand);
+        if (lane == 0) {
+            if (key_or) atomicOr(&p.sort_prep[kSortPrepOr], key_or);
+            if (key_nand) atomicOr(&p.sort_prep[kSortPrepNand], key_nand);
+        }
+    }
 }
 
 // ================================================================ vertex stage of a standalone Renderer
@@ -745,6 +756,8 @@ cudaError_t launch_vertex_stage(int sh_fmt, int cov_fmt, PreParams& p, const uin
 
 int preprocess_records_per_tile(int sh_fmt, int cov_fmt) { return tile_records(pod_stride(sh_fmt, cov_fmt)); }
 
+size_t preprocess_scratch_prefix_bytes() { return (sort_prep_bytes() + 255) & ~(size_t)255; }
+
 size_t preprocess_scratch_bytes(uint32_t n, int sh_fmt, int cov_fmt) {
     const int t = preprocess_records_per_tile(sh_fmt, cov_fmt);
     const size_t tiles = (n + t - 1) / t;
@@ -762,10 +775,13 @@ cudaError_t launch_preprocess(int sh_fmt, int cov_fmt, PreParams& p, void* scrat
         if (e != cudaSuccess) return e;
         return cudaMemsetAsync(p.visible_count, 0, 4, stream);
     }
+    // one memset zeroes K1's ticket + look-back words AND, in front of them, the depth sort's prep words (p.sort_prep, when the
+    // caller placed them there): the sort then needs no clearing launch of its own
     cudaError_t e = cudaMemsetAsync(scratch, 0, scratch_bytes, stream);
     if (e != cudaSuccess) return e;
-    p.tile_counter = reinterpret_cast<uint32_t*>(scratch);
-    p.tile_status = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(scratch) + 16);
+    uint8_t* k1 = reinterpret_cast<uint8_t*>(scratch) + (p.sort_prep ? preprocess_scratch_prefix_bytes() : 0);
+    p.tile_counter = reinterpret_cast<uint32_t*>(k1);
+    p.tile_status = reinterpret_cast<unsigned long long*>(k1 + 16);
 #define SB_CASE(SHV, COVV) \
     if (sh_fmt == SHV && cov_fmt == COVV) return launch_one<SHV, COVV>(p, num_sms, stream);
     SB_CASE(SB_SH_SINGLE, SB_COV_SINGLE)

@@ -613,20 +613,27 @@ __global__ void __launch_bounds__(kV3Threads, kV3CtasPerSm)
 // of warp histograms in the 32 KB the staging buffer needs anyway, six 256-thread CTAs per SM as before.
 constexpr int kV4MaxBits = 9;
 constexpr int kV4Bins = 1 << kV4MaxBits;  // 512
-constexpr int kV4Threads = 256;
-constexpr int kV4Items = 16;
+constexpr int kV4Threads = 512;
+#ifndef SB_V4_ITEMS
+#define SB_V4_ITEMS 8
+#endif
+constexpr int kV4Items = SB_V4_ITEMS;
 constexpr int kV4Tile = kV4Threads * kV4Items;  // 4096
 constexpr int kV4Warps = kV4Threads / 32;
-constexpr int kV4CtasPerSm = 6;
-static_assert(kV4Bins == 2 * kV4Threads, "two digits per thread");
+#ifndef SB_V4_CTAS
+#define SB_V4_CTAS 4
+#endif
+constexpr int kV4CtasPerSm = SB_V4_CTAS;
 
-// prep words (sb_internal.h kSortPrep*): [0] or, [1] nand, [2] passes, [3] parity, [4..8) plan, [8..12) tickets, [16..) hist[4][512]
+static_assert(kV4Bins == kV4Threads, "one digit per thread");
+
+// prep words (sb_internal.h kSortPrep*): [0] or, [1] nand, [2] passes, [3] parity, [4..8) plan, [8..12) tickets, [12] prologue CTAs done, [16..) hist[4][512]
 constexpr uint32_t kPlanValid = 1u << 17;
 constexpr uint32_t kPlanAltIn = 1u << 16;
 
 struct Sort4Smem {
     union {
-        uint32_t warp_hist[kV4Warps][kV4Bins];  // 16 KB
+        uint32_t warp_hist[kV4Warps][kV4Bins];  // 32 KB
         struct {
             uint32_t keys[kV4Tile];
             uint32_t vals[kV4Tile];
@@ -634,7 +641,6 @@ struct Sort4Smem {
     };
     uint32_t digit_off[kV4Bins];  // first the tile-local start of each digit, then (after the look-back) its global base
     uint32_t scan_a[kV4Warps];
-    uint32_t scan_b[kV4Warps];
     uint32_t tile;
 };
 
@@ -652,7 +658,7 @@ __device__ __forceinline__ uint32_t match_digit9(uint32_t d, int nbits) {
     uint32_t differ = 0u;
 #pragma unroll
     for (int b = 0; b < kV4MaxBits; b++) {
-        if (b < nbits) {
+        if (b < kV4MaxBits - 1 || nbits == kV4MaxBits) {  // a bit above the digit's width is 0 in every lane: its vote changes nothing
             uint32_t x;
             asm volatile(
                 "{\n"
@@ -727,10 +733,9 @@ __global__ void __launch_bounds__(512) sort4_prologue_kernel(const uint32_t* __r
     // zero the look-back tables of the tiles this sort will use
     {
         const uint32_t tiles = (count + kV4Tile - 1) / kV4Tile;
-        const uint32_t vec_per_pass = tiles * (kV4Bins / 4);
         for (int p = 0; p < pl.passes; p++) {
-            uint4* lb = reinterpret_cast<uint4*>(lookback + (size_t)p * tiles_alloc * kV4Bins);
-            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_pass; i += gridDim.x * blockDim.x) lb[i] = make_uint4(0, 0, 0, 0);
+            uint4* ts = reinterpret_cast<uint4*>(lookback + (size_t)p * tiles_alloc * kV4Bins);
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tiles * (kV4Bins / 4); i += gridDim.x * blockDim.x) ts[i] = make_uint4(0, 0, 0, 0);
         }
     }
     for (int i = threadIdx.x; i < kMaxPasses * kV4Bins; i += blockDim.x) (&hist[0][0])[i] = 0;
@@ -738,26 +743,34 @@ __global__ void __launch_bounds__(512) sort4_prologue_kernel(const uint32_t* __r
     const uint32_t nvec = count / 4;
     const uint4* kv = reinterpret_cast<const uint4*>(keys);
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < nvec; base += stride) {  // warp-uniform trip count (votes below)
-        const uint32_t i = base + threadIdx.x;
-        const bool ok = i < nvec;
-        uint4 k = make_uint4(0, 0, 0, 0);
-        if (ok) k = __ldg(&kv[i]);
+    constexpr int kU = 2;  // 128-bit loads in flight per thread: the kernel is bound by the latency of its one read of the keys
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nvec; base += kU * stride) {  // warp-uniform trip count (votes below)
+        uint4 k[kU];
+        bool ok[kU];
 #pragma unroll
-        for (int p = 0; p < kMaxPasses; p++) {
-            if (p < pl.passes) {
-                const int sh = pl.shift[p];
-                const uint32_t mask = (1u << pl.bits[p]) - 1u;
-                const uint32_t d0 = (k.x >> sh) & mask, d1 = (k.y >> sh) & mask, d2 = (k.z >> sh) & mask, d3 = (k.w >> sh) & mask;
-                // a warp whose 128 keys share the digit (sorted or clustered input) adds once instead of serialising 128 atomics
-                const uint32_t ref = __shfl_sync(0xffffffffu, d0, 0);
-                if (__all_sync(0xffffffffu, ok && d0 == ref && d1 == ref && d2 == ref && d3 == ref)) {
-                    if ((threadIdx.x & 31u) == 0) atomicAdd(&hist[p][ref], 128u);
-                } else if (ok) {
-                    atomicAdd(&hist[p][d0], 1u);
-                    atomicAdd(&hist[p][d1], 1u);
-                    atomicAdd(&hist[p][d2], 1u);
-                    atomicAdd(&hist[p][d3], 1u);
+        for (int u = 0; u < kU; u++) {
+            const uint32_t i = base + u * stride + threadIdx.x;
+            ok[u] = i < nvec;
+            k[u] = ok[u] ? __ldg(&kv[i]) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+#pragma unroll
+            for (int p = 0; p < kMaxPasses; p++) {
+                if (p < pl.passes) {
+                    const int sh = pl.shift[p];
+                    const uint32_t mask = (1u << pl.bits[p]) - 1u;
+                    const uint32_t d0 = (k[u].x >> sh) & mask, d1 = (k[u].y >> sh) & mask, d2 = (k[u].z >> sh) & mask, d3 = (k[u].w >> sh) & mask;
+                    // a warp whose 128 keys share the digit (sorted or clustered input) adds once instead of serialising 128 atomics
+                    const uint32_t ref = __shfl_sync(0xffffffffu, d0, 0);
+                    if (__all_sync(0xffffffffu, ok[u] && d0 == ref && d1 == ref && d2 == ref && d3 == ref)) {
+                        if ((threadIdx.x & 31u) == 0) atomicAdd(&hist[p][ref], 128u);
+                    } else if (ok[u]) {
+                        atomicAdd(&hist[p][d0], 1u);
+                        atomicAdd(&hist[p][d1], 1u);
+                        atomicAdd(&hist[p][d2], 1u);
+                        atomicAdd(&hist[p][d3], 1u);
+                    }
                 }
             }
         }
@@ -773,12 +786,40 @@ __global__ void __launch_bounds__(512) sort4_prologue_kernel(const uint32_t* __r
         const uint32_t v = (&hist[0][0])[i];
         if (v) atomicAdd(&prep[kSortPrepHist + i], v);
     }
+    // The last CTA to get here turns every pass's digit totals into exclusive prefixes (the global base of each digit), in place:
+    // the pass kernels then need no scan of their own over the totals.
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&prep[kSortPrepDone], 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    static_assert(kV4Bins == 512, "one bin per thread of the 512-thread prologue CTA");
+    __shared__ uint32_t wsum[16];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int p = 0; p < pl.passes; p++) {
+        const uint32_t c = __ldcg(&prep[kSortPrepHist + p * kV4Bins + threadIdx.x]);
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (uint32_t w = 0; w < warp; w++) base += wsum[w];
+        prep[kSortPrepHist + p * kV4Bins + threadIdx.x] = base + inc - c;
+        __syncthreads();
+    }
 }
 
 template <bool FULL>
 __device__ __forceinline__ void onesweep4_tile(Sort4Smem& sm, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t count,
-                                               int shift, int nbits, uint2 gcount, uint32_t* __restrict__ lookback, uint32_t tile) {
+                                               const int shift, const int nbits, const uint32_t* __restrict__ gbase,
+                                               uint32_t* __restrict__ lookback, uint32_t tile) {
     const uint32_t kMask = (1u << nbits) - 1u;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t tile_base = tile * kV4Tile;
@@ -823,51 +864,31 @@ __device__ __forceinline__ void onesweep4_tile(Sort4Smem& sm, const uint32_t* __
     }
     __syncthreads();
 
-    // ---- thread t owns digits 2t, 2t+1: scan over warps, publish the tile aggregates, scans over digits
-    uint2 digit_count, local_excl, global_excl, nearest = make_uint2(0, 0);
+    // ---- thread d owns digit d: scan over the warps, publish the tile aggregate, scan over the digits
+    uint32_t digit_count, local_excl, nearest = 0;
     {
-        uint2 run = make_uint2(0, 0);
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kV4Warps; w++) {
-            uint2* slot = reinterpret_cast<uint2*>(&sm.warp_hist[w][2 * tid]);
-            const uint2 t = *slot;
-            *slot = run;
-            run.x += t.x;
-            run.y += t.y;
+            const uint32_t t = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = run;
+            run += t;
         }
         digit_count = run;
-        const uint32_t flag = tile == 0 ? kLbPrefix : kLbAggregate;
-        st_relaxed_v2(&lookback[(size_t)tile * kV4Bins + 2 * tid], flag | digit_count.x, flag | digit_count.y);
-        if (tile > 0) nearest = ld_relaxed_v2(&lookback[(size_t)(tile - 1) * kV4Bins + 2 * tid]);
-        uint32_t a = digit_count.x + digit_count.y, b = gcount.x + gcount.y;
-        const uint32_t a_own = a, b_own = b;
+        st_relaxed_u32(&lookback[(size_t)tile * kV4Bins + tid], (tile == 0 ? kLbPrefix : kLbAggregate) | digit_count);
+        if (tile > 0) nearest = ld_relaxed_u32(&lookback[(size_t)(tile - 1) * kV4Bins + tid]);
+        uint32_t a = digit_count;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o);
-            const uint32_t tb = __shfl_up_sync(0xffffffffu, b, o);
-            if ((int)lane >= o) {
-                a += ta;
-                b += tb;
-            }
+            if ((int)lane >= o) a += ta;
         }
-        if (lane == 31) {
-            sm.scan_a[warp] = a;
-            sm.scan_b[warp] = b;
-        }
+        if (lane == 31) sm.scan_a[warp] = a;
         __syncthreads();
-        uint32_t wa = 0, wb = 0;
-#pragma unroll
-        for (int w = 0; w < kV4Warps; w++) {
-            if (w < (int)warp) {
-                wa += sm.scan_a[w];
-                wb += sm.scan_b[w];
-            }
-        }
-        local_excl.x = a - a_own + wa;
-        local_excl.y = local_excl.x + digit_count.x;
-        global_excl.x = b - b_own + wb;
-        global_excl.y = global_excl.x + gcount.x;
-        *reinterpret_cast<uint2*>(&sm.digit_off[2 * tid]) = local_excl;
+        // totals of the warps before mine: lanes 0..15 fetch one each, one REDUX adds them
+        const uint32_t part = (lane < warp && lane < (uint32_t)kV4Warps) ? sm.scan_a[lane] : 0u;
+        local_excl = a - digit_count + __reduce_add_sync(0xffffffffu, part);
+        sm.digit_off[tid] = local_excl;
     }
     __syncthreads();
 
@@ -889,53 +910,41 @@ __device__ __forceinline__ void onesweep4_tile(Sort4Smem& sm, const uint32_t* __
     }
 
     {
-        // decoupled look-back for both digits at once: the two words of a tile are written by one thread with one 64-bit
-        // store, but each carries its own flag and is handled on its own
-        uint32_t ex0 = 0, ex1 = 0;
-        bool done0 = false, done1 = false;
+        // decoupled look-back (thread per digit): the nearest predecessor was prefetched before the staging writes; then
+        // seven per round trip.  (A two-level variant — groups of 16 tiles with group aggregates / prefixes — was built and
+        // measured slower at 6 M and at 64 M keys: profiles/r02_sort_variants.txt.)
+        const uint32_t global_excl = gbase[tid];  // exclusive digit prefix (prologue); the L2 round trip overlaps the look-back
+        uint32_t tile_excl = 0;
         int t = (int)tile - 1;
         bool have = true;
-        while (t >= 0 && !(done0 && done1)) {
-            const uint2 v = have ? nearest : ld_relaxed_v2(&lookback[(size_t)t * kV4Bins + 2 * tid]);
+        while (t >= 0) {
+            const uint32_t v0 = have ? nearest : ld_relaxed_u32(&lookback[(size_t)t * kV4Bins + tid]);
             have = false;
-            if ((!done0 && (v.x >> 30) == 0) || (!done1 && (v.y >> 30) == 0)) {
+            if ((v0 >> 30) == 0) {
                 __nanosleep(40);
                 continue;
             }
-            if (!done0) {
-                ex0 += v.x & kLbValueMask;
-                done0 = (v.x >> 30) == 2;
-            }
-            if (!done1) {
-                ex1 += v.y & kLbValueMask;
-                done1 = (v.y >> 30) == 2;
-            }
+            tile_excl += v0 & kLbValueMask;
             --t;
-            if (done0 && done1) break;
-            // the next four predecessors in one round trip
-            uint2 u[4];
+            if ((v0 >> 30) == 2) break;
+            uint32_t v[7];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                u[j] = (t - j) >= 0 ? ld_relaxed_v2(&lookback[(size_t)(t - j) * kV4Bins + 2 * tid]) : make_uint2(kLbPrefix, kLbPrefix);
+            for (int j = 0; j < 7; j++) v[j] = (t - j) >= 0 ? ld_relaxed_u32(&lookback[(size_t)(t - j) * kV4Bins + tid]) : kLbPrefix;
+            bool done = false;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (done0 && done1) break;
-                if ((!done0 && (u[j].x >> 30) == 0) || (!done1 && (u[j].y >> 30) == 0)) break;  // not published: poll it at the top
-                if (!done0) {
-                    ex0 += u[j].x & kLbValueMask;
-                    done0 = (u[j].x >> 30) == 2;
-                }
-                if (!done1) {
-                    ex1 += u[j].y & kLbValueMask;
-                    done1 = (u[j].y >> 30) == 2;
-                }
+            for (int j = 0; j < 7; j++) {
+                if (done) break;
+                if ((v[j] >> 30) == 0) break;
+                tile_excl += v[j] & kLbValueMask;
                 --t;
+                if ((v[j] >> 30) == 2) {
+                    done = true;
+                    t = -1;
+                }
             }
         }
-        if (tile > 0)
-            st_relaxed_v2(&lookback[(size_t)tile * kV4Bins + 2 * tid], kLbPrefix | (ex0 + digit_count.x), kLbPrefix | (ex1 + digit_count.y));
-        *reinterpret_cast<uint2*>(&sm.digit_off[2 * tid]) =
-            make_uint2(global_excl.x + ex0 - local_excl.x, global_excl.y + ex1 - local_excl.y);
+        if (tile > 0) st_relaxed_u32(&lookback[(size_t)tile * kV4Bins + tid], kLbPrefix | (tile_excl + digit_count));
+        sm.digit_off[tid] = global_excl + tile_excl - local_excl;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -959,13 +968,15 @@ __global__ void __launch_bounds__(kV4Threads, kV4CtasPerSm)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Sort4Smem& sm = *reinterpret_cast<Sort4Smem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
+    // launched with programmatic stream serialization: the launch itself overlaps the previous kernel's tail; nothing the
+    // previous kernel wrote is read before this returns (a no-op for an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t pl = prep[kSortPrepPlan + pass];
     if (!(pl & kPlanValid)) return;  // fewer passes than launches: nothing to do
-    // one round trip: ticket, count and this thread's two digit totals are in flight together
+    // one round trip: ticket and count are in flight together
     uint32_t q = 0;
     if (tid == 0) q = atomicAdd(&prep[kSortPrepTickets + pass], 1u);
     const uint32_t count = min(*d_count, max_count);
-    const uint2 gcount = *reinterpret_cast<const uint2*>(&prep[kSortPrepHist + pass * kV4Bins + 2 * tid]);
     if (tid == 0) sm.tile = q;
     __syncthreads();
     const uint32_t tile = sm.tile;
@@ -977,10 +988,11 @@ __global__ void __launch_bounds__(kV4Threads, kV4CtasPerSm)
     uint32_t* kout = alt_in ? keys_a : keys_b;
     uint32_t* vout = alt_in ? vals_a : vals_b;
     uint32_t* lookback = lookback_base + (size_t)pass * tiles_alloc * kV4Bins;
+    const uint32_t* gbase = prep + kSortPrepHist + pass * kV4Bins;
     if ((tile + 1) * kV4Tile <= count)
-        onesweep4_tile<true>(sm, kin, vin, kout, vout, count, shift, nbits, gcount, lookback, tile);
+        onesweep4_tile<true>(sm, kin, vin, kout, vout, count, shift, nbits, gbase, lookback, tile);
     else
-        onesweep4_tile<false>(sm, kin, vin, kout, vout, count, shift, nbits, gcount, lookback, tile);
+        onesweep4_tile<false>(sm, kin, vin, kout, vout, count, shift, nbits, gbase, lookback, tile);
 }
 
 // One block after the histograms: which passes are the identity (one digit holds every key) and where each
@@ -1097,6 +1109,7 @@ int sort_impl_forced() {
         const char* c = std::getenv("SB_SORT_IMPL");
         if (c && std::string(c) == "v1") return 1;
         if (c && std::string(c) == "v3") return 3;
+        if (c && std::string(c) == "v4") return 4;
         return 0;
     }();
     return forced;
@@ -1151,14 +1164,27 @@ cudaError_t launch_sort_adaptive(uint32_t* keys, uint32_t* payload, const uint32
         e = cudaMemsetAsync(from, 0, (size_t)(prep + kSortPrepWords - from) * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;
     }
-    const int pro_grid = (int)std::min<size_t>((size_t)num_sms * 2, (tiles * kV4Tile / 4 + 511) / 512);
+    const int pro_grid = (int)std::min<size_t>((size_t)num_sms * 4, (tiles * kV4Tile / 4 + 511) / 512);
     sort4_prologue_kernel<<<pro_grid > 0 ? pro_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, prep, explicit_mask, lookback,
                                                                           (uint32_t)tiles, parity_out);
     // the number of passes is decided on the device; launches beyond it exit at once
     const int max_passes = begin_bit >= 0 ? (end_bit - begin_bit + kV4MaxBits - 1) / kV4MaxBits : kMaxPasses;
-    for (int p = 0; p < max_passes; p++)
-        onesweep4_kernel<<<(unsigned)tiles, kV4Threads, sizeof(Sort4Smem), stream>>>(keys, payload, scratch.keys_alt, scratch.payload_alt,
-                                                                                     d_count, max_count, prep, lookback, (uint32_t)tiles, p);
+    static const bool pdl = [] { const char* c = std::getenv("SB_SORT_PDL"); return !(c && std::string(c) == "0"); }();
+    for (int p = 0; p < max_passes; p++) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)tiles);
+        cfg.blockDim = dim3(kV4Threads);
+        cfg.dynamicSmemBytes = sizeof(Sort4Smem);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        e = cudaLaunchKernelEx(&cfg, onesweep4_kernel, keys, payload, scratch.keys_alt, scratch.payload_alt, d_count, max_count, prep,
+                               lookback, (uint32_t)tiles, p);
+        if (e != cudaSuccess) return e;
+    }
     return cudaGetLastError();
 }
 
@@ -1175,6 +1201,12 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
     if (max_count == 0) return cudaSuccess;
     const int num_passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
     if (num_passes < 1 || num_passes > kMaxPasses) return cudaErrorInvalidValue;
+    if (sort_impl_forced() == 4) {  // the key-adaptive kernels on an explicit bit range (<= 9-bit digits)
+        uint32_t* parity = parity_out ? parity_out : scratch.internal + kSortPrepParity;
+        cudaError_t e4 = launch_sort_adaptive(keys, payload, d_count, max_count, nullptr, false, begin_bit, end_bit, scratch, num_sms, stream, parity_out);
+        if (e4 != cudaSuccess || parity_out) return e4;
+        return launch_sort_finish(keys, payload, scratch, d_count, max_count, parity, num_sms, stream);
+    }
     int impl = sort_impl(num_passes);
     // Few keys: a pass is bound by the look-back chain (one hop per tile), so the 8192-pair kernel wins (measured: 0.63 M depth
     // keys 0.106 ms with the 4096-pair kernel, 0.076 ms with this one; 6 M keys 0.173 against 0.203 ms).
