@@ -270,6 +270,8 @@ def run_cuda(args):
     frame = target.cpu().numpy()
     assert frame[..., 3].min() == 255 and frame[..., :3].max() > 0
 
+    strips = None if args.no_strips else run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,11 +340,95 @@ def run_cuda(args):
         "roofline_stages": roofs,
         "stages": {"ms": stage, "sum_ms": frame_stage_ms, "dominant": dominant, "visible": V, "tile_duplicates": D},
     }
+    if strips is not None:
+        out["strips"] = strips
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(pods, n)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+STRIP_W, STRIP_H = 7680, 4320
+STRIP_STEPS, STRIP_WARMUP = 20, 4
+
+
+def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
+    """BASELINE config 5b: ONE 7680x4320 frame of the bench scene split into `world` horizontal screen strips (strong scaling).
+    Every rank runs the full-frame cull, keeps the splats whose tile box meets its strip (sb_viewer_set_strip_cull), sorts,
+    bins and rasterises that subset, and its rasterizer stores the pixels straight into the frame on rank 0 (peer-mapped over
+    NVLink; batched NCCL send/recv when peer mapping is unavailable).  Timed like the main loop: barrier + synchronize on
+    both sides, CUDA events on the launching stream, max over ranks, median of REPEATS regions."""
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    viewer.update_camera_with_pod(sb.camera_pod(pos, yaw, pitch, STRIP_W, STRIP_H))
+    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0)
+    for _ in range(STRIP_WARMUP):
+        sf.render(stream)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    regions = []
+    for _ in range(REPEATS):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(STRIP_STEPS):
+            sf.render(stream)
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / STRIP_STEPS
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        regions.append(ms)
+    ms = float(np.median(regions))
+    # this rank's share of the work, and its stage times
+    viewer.set_stage_timing(True)
+    sf.render(stream)
+    stage = viewer.read_stage_times(stream)
+    st = viewer.read_frame_stats(stream)
+    viewer.set_stage_timing(False)
+    barrier()
+    share = torch.tensor([float(st["visible"]), float(st["duplicates"])], device="cuda", dtype=torch.float64)
+    shares = [torch.zeros_like(share) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(shares, share)
+    else:
+        shares = [share]
+    out = None
+    if rank == 0:
+        got = sf.frame.clone()
+        viewer.set_strip_cull(False)
+        ref = torch.zeros((STRIP_H, STRIP_W, 4), dtype=torch.uint8, device="cuda")
+        for attempt in range(3):
+            try:
+                viewer.render(ref, STRIP_W, STRIP_H, stream=stream)
+                break
+            except sb.SplatError as e:
+                if "render again" not in str(e):
+                    raise
+        stream.synchronize()
+        full = viewer.read_frame_stats(stream)
+        out = {"workload": f"one {STRIP_W}x{STRIP_H} RGBA8 frame of the bench scene, outside camera, {world} horizontal strip(s) "
+                           "of whole 16-pixel tile rows (BASELINE.json config 5b)",
+               "n_gpus": world, "scaling": "strong", "ms_per_frame": ms, "frames_per_s": 1000.0 / ms, "steps": STRIP_STEPS,
+               "warmup": STRIP_WARMUP, "transport": {"peer": "rasterizer stores into rank 0's frame through a CUDA-IPC peer mapping "
+                                                            "(NVLink) + one 4-byte all-reduce as the fence",
+                                                    "sendrecv": "one batched NCCL send/recv group straight into the frame's rows",
+                                                    "local": "single GPU"}[sf.mode],
+               "partitioning": "full-frame cull on every rank, then each rank keeps / sorts / bins / rasterises only the splats "
+                               "whose tile box meets its strip",
+               "identical_to_single_gpu_frame": bool(torch.equal(got, ref)),
+               "full_frame": {"visible": full["visible"], "tile_duplicates": full["duplicates"]},
+               "per_rank": [{"rows": sb.sharding.strip_rows(STRIP_H, world, r)[1], "visible": int(shares[r][0].item()),
+                             "tile_duplicates": int(shares[r][1].item())} for r in range(world)],
+               "rank0_stage_ms": {k: float(v) for k, v in stage.items()}}
+    barrier()
+    sf.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -427,6 +513,7 @@ def parse_args():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--n", type=int, default=N_GAUSSIANS, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strips", action="store_true", help="skip the 8K screen-strip frame (config 5b)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

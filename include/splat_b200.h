@@ -274,6 +274,23 @@ SB_API SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict);
  * fewer (splat, tile) duplicates and fragments, bit-identical frames.  Never applied to float targets, ellipse/point modes
  * or depth-tested passes.  0 switches it off (the instrumented fragment counts then equal the reference's). */
 SB_API SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled);
+/* One frame split into screen strips over several GPUs (BASELINE config 5b; the reference has no multi-GPU code —
+ * the unit being sharded is Viewer::render, src/lib.rs:266-275).  With strip culling on, a sb_viewer_render whose target is a
+ * strip (SbTarget.rows != 0) runs the reference's full-frame cull as always, then keeps only the visible splats whose tile box
+ * meets the strip: the indirect args, indices and keys of that frame describe the strip's own visible set (a subset of the
+ * full frame's, in the same order), and the depth sort, binning and colour evaluation run on that subset only.  The strips of
+ * all ranks reassemble the single-GPU frame bit for bit.  Default off (a strip render then keeps the full-frame artefacts). */
+SB_API SbStatus sb_viewer_set_strip_cull(SbViewer* v, int32_t enabled);
+/* Strip gather without a gather: the rank that owns the final frame allocates it with sb_shared_frame_create and publishes the
+ * 64-byte handle (any transport: the tests and bench.py use torch.distributed); every other process of the node opens it and
+ * gets a device pointer, valid on ITS GPU, that aliases the owner's memory over NVLink (CUDA IPC, peer access enabled on
+ * open).  Each rank then renders its strip straight into `frame + row0 * pitch` — the rasterizer's final pixel stores are the
+ * transfer — and one barrier (NCCL) after the raster kernels orders them before the owner reads the frame. */
+#define SB_SHARED_HANDLE_BYTES 64
+SB_API SbStatus sb_shared_frame_create(SbContext* ctx, uint64_t bytes, void** d_frame, uint8_t handle[SB_SHARED_HANDLE_BYTES]);
+SB_API SbStatus sb_shared_frame_open(SbContext* ctx, const uint8_t handle[SB_SHARED_HANDLE_BYTES], void** d_frame);
+SB_API SbStatus sb_shared_frame_close(SbContext* ctx, void* d_frame);    /* a pointer obtained from _open */
+SB_API SbStatus sb_shared_frame_destroy(SbContext* ctx, void* d_frame);  /* a pointer obtained from _create */
 /* Tracing (the reference has none: every pass has timestamp_writes: None, src/radix_sorter.rs:504-507).
  * When enabled, cudaEvents are recorded on the launching stream between the stages of a frame;
  * ms[0..5] = preprocess, depth sort, tile count+emit, tile sort, gather, raster. */

@@ -1,7 +1,7 @@
 """Config 5b: ONE 7680x4320 frame split into horizontal screen strips, one per GPU, gathered with
 NCCL (torch.distributed) to rank 0.  Launch: torchrun --nproc-per-node G scripts/strips_8k.py
-(G = 1 runs the single-GPU frame).  Every rank culls and depth-sorts the full frame identically,
-then bins and rasterises only its strip."""
+(G = 1 runs the single-GPU frame).  Every rank runs the full-frame cull, then keeps, depth-sorts, bins and
+rasterises only the splats of its own strip (splat_b200/sharding.py: StripFrame)."""
 import argparse
 import json
 import os
@@ -21,6 +21,7 @@ ap.add_argument("--n", type=int, default=6_000_000)
 ap.add_argument("--size", type=int, nargs=2, default=[7680, 4320])
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--mode", default="peer", choices=["peer", "sendrecv"])
 ap.add_argument("--check", action="store_true", help="rank 0 also renders the full frame alone and compares")
 args = ap.parse_args()
 
@@ -36,14 +37,12 @@ pods = sb.pack_gaussians(sb.scenes.synthetic_gaussians(args.n, sb.scenes.BASE_SE
 v = sb.Viewer(ctx, pods, args.n)
 pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
 v.update_camera(pos, yaw, pitch, w, h)
-r0, rows = sharding.strip_rows(h, world, rank)
-strip = torch.zeros((rows, w, 4), dtype=torch.uint8, device="cuda")
+sf = sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=args.mode)
 stream = torch.cuda.current_stream()
 
 
 def step():
-    v.render(strip, w, h, stream=stream, row0=r0, rows=rows)
-    return sharding.gather_strips(strip, h, world, rank, dst=0)
+    return sf.render()
 
 
 for _ in range(args.warmup):
@@ -62,8 +61,11 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     out = dict(config="8K strips", gaussians=args.n, size=[w, h], n_gpus=world, ms_per_frame=float(ms.item()),
-               frames_per_s=1000.0 / float(ms.item()), strip_rows=[sharding.strip_rows(h, world, r)[1] for r in range(world)])
+               frames_per_s=1000.0 / float(ms.item()), strip_rows=[sharding.strip_rows(h, world, r)[1] for r in range(world)],
+               transport=sf.mode)
     if args.check:
+        full = full.clone()
+        v.set_strip_cull(False)
         ref = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
         v.render(ref, w, h, stream=stream)
         torch.cuda.synchronize()

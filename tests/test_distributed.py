@@ -29,7 +29,8 @@ def _worker(rank, world, port, height, width, out):
     # the "frame": row index in every channel, so a mis-placed strip is detected
     r0, rows = sharding.strip_rows(height, world, rank)
     strip = torch.arange(r0, r0 + rows, dtype=torch.int32).view(-1, 1, 1).expand(rows, width, 4).contiguous()
-    full = sharding.gather_strips(strip, height, world, rank, dst=0)
+    frame = torch.full((height, width, 4), -1, dtype=torch.int32) if rank == 0 else None
+    full = sharding.gather_strips(strip, frame, height, world, rank, dst=0)
     # view sharding: every view rendered exactly once; "render" = view id; max-over-ranks timing
     mine = sharding.views_for_rank(64, world, rank)
     counts = torch.zeros(64, dtype=torch.int32)
@@ -58,7 +59,15 @@ def test_strip_partition_properties():
 
 
 def test_gather_strips_and_view_sharding_gloo_ws2():
-    world, height, width = 2, 200, 8
+    _run_gather(2, 200, 8)
+
+
+def test_gather_strips_ragged_and_empty_strips_gloo_ws3():
+    """17 rows = 2 tile rows over 3 ranks: one rank has no strip at all, one a ragged 1-row strip."""
+    _run_gather(3, 17, 4)
+
+
+def _run_gather(world, height, width):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -71,4 +80,4 @@ def test_gather_strips_and_view_sharding_gloo_ws2():
         assert p.exitcode == 0
     assert ok, "gathered strips do not reassemble the frame"
     assert counts == [1] * 64, "every view must be rendered by exactly one rank"
-    assert tmax == 2.0
+    assert tmax == float(world)

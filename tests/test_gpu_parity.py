@@ -262,6 +262,122 @@ def test_screen_strips_match_full_frame(sb, ob, ctx):
     v.close()
 
 
+@pytest.mark.parametrize("cam_name,mode", [("outside", 0), ("inside", 0), ("inside", 1), ("outside", 2)])
+def test_strip_cull_subsets_reassemble_the_frame(sb, ob, ctx, cam_name, mode):
+    """Config 5b as the north star states it: every strip culls to and sorts its OWN visible set.  The strips still reassemble
+    the full frame bit for bit; a strip's sorted list is a subsequence of the full frame's (same relative order, same keys);
+    together the strips cover every splat that has a tile at all, and a strip's list is a fraction of the full one."""
+    torch = _torch()
+    n, w, h = 60000, 640, 368
+    g, pods = make_scene(sb, ob, n, 77)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE if cam_name == "outside" else sb.scenes.CAMERA_INSIDE
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera_with_pod(sb.camera_pod(pos, yaw, pitch, w, h))
+    v.update_gaussian_transform(1.0, mode, 3, False, 3.0)
+    full = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    v.render(full, w, h)
+    torch.cuda.synchronize()
+    V = int(v.read_indirect_args()[0][1])
+    fidx, fkeys = v.read_indices(V), v.read_depth_keys(V).view(np.uint32)
+    pos_of = np.full(n, -1, dtype=np.int64)
+    pos_of[fidx] = np.arange(V)
+    dup_full = v.read_frame_stats()["duplicates"]
+    v.set_strip_cull(True)
+    for parts in (2, 5):
+        out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        covered = np.zeros(n, dtype=bool)
+        total, dups = 0, 0
+        for i in range(parts):
+            r0, rows = sb.sharding.strip_rows(h, parts, i)
+            v.render(out[r0:r0 + rows], w, h, row0=r0, rows=rows)
+            torch.cuda.synchronize()
+            draw, disp = v.read_indirect_args()
+            Vs = int(draw[1])
+            assert list(draw) == [6, Vs, 0, 0] and list(disp) == [(Vs + 3839) // 3840, 1, 1]
+            sidx, skeys = v.read_indices(Vs), v.read_depth_keys(Vs).view(np.uint32)
+            where = pos_of[sidx]
+            assert np.all(where >= 0), "a strip's splat is not in the full frame's visible set"
+            assert np.all(np.diff(where) > 0), "a strip's order is not the full frame's order"
+            assert np.array_equal(skeys, fkeys[where])
+            covered[sidx] = True
+            total += Vs
+            dups += v.read_frame_stats()["duplicates"]
+        assert torch.equal(out, full), f"{parts} culled strips differ from the full frame"
+        assert dups == dup_full, "the strips' (splat, tile) duplicates must partition the full frame's"
+        assert total < V * (1.0 + 0.9 * (parts - 1) / parts) or V < 1000, "strip lists are not smaller than the full list"
+    v.set_strip_cull(False)
+    v.render(full, w, h)  # the option is per render: full-frame artefacts again
+    torch.cuda.synchronize()
+    assert int(v.read_indirect_args()[0][1]) == V
+    v.close()
+
+
+def _strip_worker(rank, world, port, n, w, h, q):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "wgpu-3dgs-viewer_b200"))
+    import splat_b200 as sb
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ctx = sb.Context(rank)
+    pods = sb.pack_gaussians(sb.scenes.synthetic_gaussians(n, 91))
+    v = sb.Viewer(ctx, pods, n)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v.update_camera_with_pod(sb.camera_pod(pos, yaw, pitch, w, h))
+    res = {}
+    for mode in ("peer", "sendrecv"):
+        sf = sb.sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=mode)
+        for _ in range(3):
+            frame = sf.render()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            got = frame.clone()
+            v.set_strip_cull(False)
+            ref = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+            v.render(ref, w, h)
+            torch.cuda.synchronize()
+            res[mode] = (sf.mode, bool(torch.equal(got, ref)))
+        dist.barrier()
+        sf.close()
+    if rank == 0:
+        q.put(res)
+    v.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_strips_over_two_gpus_land_in_one_frame(sb):
+    """Two processes, two GPUs, NCCL: each rank renders its own strip (own cull, own sort) into the owner's frame — once through
+    the peer-mapped frame (the rasterizer's stores cross NVLink), once through the batched send/recv — and the result equals the
+    single-GPU frame.  Skipped on a one-GPU box."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_strip_worker, args=(r, 2, port, 200_000, 1920, 1080, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res["sendrecv"] == ("sendrecv", True)
+    assert res["peer"][1], "strips written through the peer-mapped frame differ from the single-GPU frame"
+
+
 @pytest.mark.parametrize("explicit_stream", [False, True])
 def test_multi_model_draw_order_and_selection(sb, ob, ctx, explicit_stream):
     """Config 4: models composited in caller key order (multi_model.rs:505-527), per-model

@@ -193,6 +193,7 @@ struct SbViewer {
     bool selection_enabled = false;
     uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
     int strict_exp = 0;
+    bool strip_cull = false;     // a strip render keeps only the splats whose tile box meets the strip (sb_viewer_set_strip_cull)
     bool exact_cutoff = true;    // shrink splats to the radius beyond which a unorm8 blend is exactly the identity
     bool recs_cut = false;       // recs/tboxes currently hold cut extents (a depth-tested pass needs the full ones)
     // Viewer::render leaves the depth-sorted (key, index) pairs where the last sort pass wrote them (*d_sort_parity() = 1:
@@ -348,7 +349,8 @@ SbStatus check_target(SbViewer* v, const SbTarget* t, const sb::Uniforms& u) {
     return SB_OK;
 }
 
-SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, cudaStream_t stream) {
+SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, cudaStream_t stream,
+                       const SbTarget* strip = nullptr) {
     sb::PreParams p;
     std::memset(&p, 0, sizeof p);
     p.gaussians = static_cast<const uint8_t*>(v->d_gaussians);
@@ -367,6 +369,11 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.sort_prep = v->pre_scratch.as<uint32_t>();
     v->sort_prep_fresh = true;         // zeroed by K1's memset, or / nand accumulated by K1: the next depth sort needs no clearing
     p.u = make_uniforms(cam, v->model_transform, gt, v->target_format, v->exact_cutoff);
+    if (strip && strip->rows != 0) {  // strip render with strip culling: this rank's visible set is its strip's subset
+        p.strip_on = 1;
+        p.strip_ty_lo = strip->row0 / sb::kTile;
+        p.strip_ty_hi = (strip->row0 + strip->rows - 1) / sb::kTile;
+    }
     v->recs_cut = p.u.cut_k > 0.0f;
     v->sorted_pending = false;  // a new visible set replaces whatever a previous frame left behind
     if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[0], stream));
@@ -559,6 +566,48 @@ SbStatus sb_ctx_create(int32_t device_ordinal, SbContext** out) {
 }
 
 void sb_ctx_destroy(SbContext* ctx) { delete ctx; }
+
+SbStatus sb_shared_frame_create(SbContext* ctx, uint64_t bytes, void** d_frame, uint8_t handle[SB_SHARED_HANDLE_BYTES]) {
+    if (!ctx || !d_frame || !handle || bytes == 0) return fail(ctx, SB_ERR_INVALID_ARG, "null / empty shared frame");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SB_SHARED_HANDLE_BYTES, "CUDA IPC handle size");
+    DeviceGuard device_guard(ctx);
+    void* p = nullptr;
+    SB_CUDA(ctx, cudaMalloc(&p, bytes));  // its own allocation: an IPC handle names a whole cudaMalloc block
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail_cuda(ctx, e, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(handle, &h, sizeof h);
+    *d_frame = p;
+    return SB_OK;
+}
+
+SbStatus sb_shared_frame_open(SbContext* ctx, const uint8_t handle[SB_SHARED_HANDLE_BYTES], void** d_frame) {
+    if (!ctx || !d_frame || !handle) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(ctx);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    SB_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_frame = p;
+    return SB_OK;
+}
+
+SbStatus sb_shared_frame_close(SbContext* ctx, void* d_frame) {
+    if (!ctx || !d_frame) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(ctx);
+    SB_CUDA(ctx, cudaIpcCloseMemHandle(d_frame));
+    return SB_OK;
+}
+
+SbStatus sb_shared_frame_destroy(SbContext* ctx, void* d_frame) {
+    if (!ctx || !d_frame) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(ctx);
+    SB_CUDA(ctx, cudaFree(d_frame));
+    return SB_OK;
+}
 
 SbStatus sb_ctx_set_model_size_limit(SbContext* ctx, uint64_t bytes) {
     if (!ctx) return fail(nullptr, SB_ERR_INVALID_ARG, "null context");
@@ -794,7 +843,7 @@ SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target) {
     SbStatus s = check_target(v, target, u);
     if (s == SB_OK) s = report_overflow(v);
     if (s != SB_OK) return s;
-    s = do_preprocess(v, v->camera, v->gaussian_transform, st);
+    s = do_preprocess(v, v->camera, v->gaussian_transform, st, v->strip_cull ? target : nullptr);
     if (s != SB_OK) return s;
     s = do_sort(v, st, true);
     if (s != SB_OK) return s;
@@ -1008,6 +1057,12 @@ SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
 SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     v->exact_cutoff = enabled != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_set_strip_cull(SbViewer* v, int32_t enabled) {
+    if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    v->strip_cull = enabled != 0;
     return SB_OK;
 }
 

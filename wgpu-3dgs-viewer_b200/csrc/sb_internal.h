@@ -25,6 +25,8 @@ struct PreParams {
     unsigned long long* tile_status;   // decoupled look-back state (zeroed before launch)
     uint32_t* visible_count;           // V for downstream kernels
     uint32_t* visible_host;            // nullable: device alias of a mapped pinned word that also receives V
+    uint32_t strip_on;                 // 1: keep only the visible splats whose tile box meets tile rows [strip_ty_lo, strip_ty_hi]
+    uint32_t strip_ty_lo, strip_ty_hi; //    (one frame split into screen strips over several GPUs; needs recs)
     uint32_t* sort_prep;               // nullable: [kSortPrepOr] |= key, [kSortPrepNand] |= ~key over the visible keys (zeroed before launch)
     Uniforms u;
 };

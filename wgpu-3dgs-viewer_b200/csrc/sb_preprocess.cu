@@ -332,85 +332,91 @@ __device__ __forceinline__ bool cull_gaussian(const PreParams& p, const Uniforms
     return vis;
 }
 
-// Phase 2 (render.wesl:76-130): the vertex-stage work of a splat, written once per splat.
-template <int SH, int COV>
-__device__ __forceinline__ void emit_splat(const PreParams& p, const Uniforms& u, uint32_t g, const uint8_t* rec, const CullOut& o) {
+// Phase 2 (render.wesl:76-130): the vertex-stage work of a splat, written once per splat.  Split in two so that a strip
+// render ("drops splats whose quad bbox misses its strip") can decide on the tile box BEFORE the compaction and
+// evaluate the colour only for the strip's own splats.
+// 2a: geometry — pixel centre, inverse axes, cull extents (with the exact alpha cut-off), tile box.
+struct SplatGeom {
+    float cx, cy, ax, ay, bx, by, ex, ey, a;
+    uint32_t tmin, tmax;
+};
+__device__ __forceinline__ void splat_geometry(const Uniforms& u, const CullOut& o, SplatGeom& out) {
     const float4 head = o.head;
-    const float nx = o.nx, ny = o.ny;
-    const float* world = o.world;
     const float* axes = o.axes;
-    {
-        SplatRec out;
-        out.cx = smul(smul(sadd(nx, 1.0f), 0.5f), u.size[0]);
-        out.cy = smul(smul(ssub(1.0f, ny), 0.5f), u.size[1]);
-        // color(): render.wesl:58-73; -normalize(v) = -(v * (1/|v|))
-        const float vdx = ssub(u.cam_pos[0], world[0]), vdy = ssub(u.cam_pos[1], world[1]), vdz = ssub(u.cam_pos[2], world[2]);
-        float md[3];
+    out.cx = smul(smul(sadd(o.nx, 1.0f), 0.5f), u.size[0]);
+    out.cy = smul(smul(ssub(1.0f, o.ny), 0.5f), u.size[1]);
+    out.a = unorm8(__float_as_uint(head.w) >> 24);
+    bool valid;
+    if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
+        float vp[3];
 #pragma unroll
         for (int i = 0; i < 3; i++)
-            md[i] = sadd(sadd(smul(u.inv_sr[i], vdx), smul(u.inv_sr[3 + i], vdy)), smul(u.inv_sr[6 + i], vdz));
-        const float inv_ml = sdiv(1.0f, ssqrt(sadd(sadd(smul(md[0], md[0]), smul(md[1], md[1])), smul(md[2], md[2]))));
-        float rgb[3];
-        const uint32_t packed = __float_as_uint(head.w);
-        view_color<SH>(u, rec, packed, -smul(md[0], inv_ml), -smul(md[1], inv_ml), -smul(md[2], inv_ml), rgb);
-        // Fixed-point colour attachments clamp the SOURCE colour to [0,1] before the blend equation
-        // (Vulkan 1.3 spec 29.1 "Blending"; the reference renders to Rgba8Unorm, src/renderer.rs:296-300):
-        // done here once per splat, which also makes the post-blend clamp redundant (d, c <= 255, alpha <= 1).
-        const float cmax = u.color_scale == 255.0f ? 255.0f : __int_as_float(0x7f800000);
-        out.r = fminf(smul(rgb[0], u.color_scale), cmax);
-        out.g = fminf(smul(rgb[1], u.color_scale), cmax);
-        out.b = fminf(smul(rgb[2], u.color_scale), cmax);
-        out.a = unorm8(packed >> 24);
-        bool valid;
-        if (u.mode == SB_MODE_POINT) {  // render.wesl:92-104
-            float vp[3];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-                vp[i] = sadd(sadd(sadd(smul(u.vm[i], head.x), smul(u.vm[4 + i], head.y)), smul(u.vm[8 + i], head.z)),
-                             u.vm[12 + i]);
-            const float len = ssqrt(sadd(sadd(smul(vp[0], vp[0]), smul(vp[1], vp[1])), smul(vp[2], vp[2])));
-            const float half = sdiv(smul(smul(smul(0.01f, u.gsize), 0.5f), u.size[1]), len);
-            const float inv = sdiv(1.0f, half);
-            out.ax = inv; out.ay = 0.0f; out.bx = 0.0f; out.by = inv;
-            out.ex = half; out.ey = half;
-            valid = (half > 0.0f) && isfinite(inv) && isfinite(out.cx) && isfinite(out.cy);
-        } else {
-            const float mm = sadd(smul(axes[0], axes[0]), smul(axes[1], axes[1]));
-            const float nn = sadd(smul(axes[2], axes[2]), smul(axes[3], axes[3]));
-            out.ax = sdiv(smul(2.0f, axes[0]), mm);
-            out.ay = -sdiv(smul(2.0f, axes[1]), mm);
-            out.bx = sdiv(smul(2.0f, axes[2]), nn);
-            out.by = -sdiv(smul(2.0f, axes[3]), nn);
-            const float hs = smul(0.5f, u.std_dev);
-            out.ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
-            out.ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
-            valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, out.ex, out.ey);
-            if (u.cut_k > 0.0f) {  // exact alpha cut-off (sb_common.cuh): splat mode on a unorm8 target
-                const float rc2 = logf(out.a * u.cut_k) + kAlphaCutMargin;  // a = 0 -> -inf
-                if (!(rc2 > 0.0f)) {
-                    valid = false;  // a < kAlphaCut: every blend of this splat is the identity
-                } else if (rc2 < u.std_dev * u.std_dev) {
-                    const float s = sqrtf(rc2) / u.std_dev * 1.0001f;
-                    out.ex *= s;
-                    out.ey *= s;
-                }
+            vp[i] = sadd(sadd(sadd(smul(u.vm[i], head.x), smul(u.vm[4 + i], head.y)), smul(u.vm[8 + i], head.z)),
+                         u.vm[12 + i]);
+        const float len = ssqrt(sadd(sadd(smul(vp[0], vp[0]), smul(vp[1], vp[1])), smul(vp[2], vp[2])));
+        const float half = sdiv(smul(smul(smul(0.01f, u.gsize), 0.5f), u.size[1]), len);
+        const float inv = sdiv(1.0f, half);
+        out.ax = inv; out.ay = 0.0f; out.bx = 0.0f; out.by = inv;
+        out.ex = half; out.ey = half;
+        valid = (half > 0.0f) && isfinite(inv) && isfinite(out.cx) && isfinite(out.cy);
+    } else {
+        const float mm = sadd(smul(axes[0], axes[0]), smul(axes[1], axes[1]));
+        const float nn = sadd(smul(axes[2], axes[2]), smul(axes[3], axes[3]));
+        out.ax = sdiv(smul(2.0f, axes[0]), mm);
+        out.ay = -sdiv(smul(2.0f, axes[1]), mm);
+        out.bx = sdiv(smul(2.0f, axes[2]), nn);
+        out.by = -sdiv(smul(2.0f, axes[3]), nn);
+        const float hs = smul(0.5f, u.std_dev);
+        out.ex = smul(hs, ssqrt(sadd(smul(axes[0], axes[0]), smul(axes[2], axes[2]))));
+        out.ey = smul(hs, ssqrt(sadd(smul(axes[1], axes[1]), smul(axes[3], axes[3]))));
+        valid = finite4(out.ax, out.ay, out.bx, out.by) && finite4(out.cx, out.cy, out.ex, out.ey);
+        if (u.cut_k > 0.0f) {  // exact alpha cut-off (sb_common.cuh): splat mode on a unorm8 target
+            const float rc2 = logf(out.a * u.cut_k) + kAlphaCutMargin;  // a = 0 -> -inf
+            if (!(rc2 > 0.0f)) {
+                valid = false;  // a < kAlphaCut: every blend of this splat is the identity
+            } else if (rc2 < u.std_dev * u.std_dev) {
+                const float s = sqrtf(rc2) / u.std_dev * 1.0001f;
+                out.ex *= s;
+                out.ey *= s;
             }
         }
-        TileBox tb;
-        if (valid) {
-            tile_bbox(u, out.cx, out.cy, out.ex, out.ey, tb.tmin, tb.tmax);
-        } else {
-            tb.tmin = 1u | (1u << 16);
-            tb.tmax = 0u;
-            out.ex = out.ey = 0.0f;
-        }
-        float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
-        dst[0] = make_float4(out.cx, out.cy, out.ax, out.bx);
-        dst[1] = make_float4(out.ay, out.by, out.ex, out.ey);
-        dst[2] = make_float4(out.r, out.g, out.b, out.a);
-        *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(tb.tmin, tb.tmax);
     }
+    if (valid) {
+        tile_bbox(u, out.cx, out.cy, out.ex, out.ey, out.tmin, out.tmax);
+    } else {
+        out.tmin = 1u | (1u << 16);
+        out.tmax = 0u;
+        out.ex = out.ey = 0.0f;
+    }
+}
 
+// 2b: colour (render.wesl:58-73) + the record / tile-box stores.
+template <int SH, int COV>
+__device__ __forceinline__ void emit_splat(const PreParams& p, const Uniforms& u, uint32_t g, const uint8_t* rec, const CullOut& o,
+                                           const SplatGeom& geo) {
+    const float* world = o.world;
+    // color(): -normalize(v) = -(v * (1/|v|))
+    const float vdx = ssub(u.cam_pos[0], world[0]), vdy = ssub(u.cam_pos[1], world[1]), vdz = ssub(u.cam_pos[2], world[2]);
+    float md[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        md[i] = sadd(sadd(smul(u.inv_sr[i], vdx), smul(u.inv_sr[3 + i], vdy)), smul(u.inv_sr[6 + i], vdz));
+    const float inv_ml = sdiv(1.0f, ssqrt(sadd(sadd(smul(md[0], md[0]), smul(md[1], md[1])), smul(md[2], md[2]))));
+    float rgb[3];
+    const uint32_t packed = __float_as_uint(o.head.w);
+    view_color<SH>(u, rec, packed, -smul(md[0], inv_ml), -smul(md[1], inv_ml), -smul(md[2], inv_ml), rgb);
+    // Fixed-point colour attachments clamp the SOURCE colour to [0,1] before the blend equation
+    // (Vulkan 1.3 spec 29.1 "Blending"; the reference renders to Rgba8Unorm, src/renderer.rs:296-300):
+    // done here once per splat, which also makes the post-blend clamp redundant (d, c <= 255, alpha <= 1).
+    const float cmax = u.color_scale == 255.0f ? 255.0f : __int_as_float(0x7f800000);
+    const float cr = fminf(smul(rgb[0], u.color_scale), cmax);
+    const float cg = fminf(smul(rgb[1], u.color_scale), cmax);
+    const float cb = fminf(smul(rgb[2], u.color_scale), cmax);
+    float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
+    dst[0] = make_float4(geo.cx, geo.cy, geo.ax, geo.bx);
+    dst[1] = make_float4(geo.ay, geo.by, geo.ex, geo.ey);
+    dst[2] = make_float4(cr, cg, cb, geo.a);
+    *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(geo.tmin, geo.tmax);
 }
 
 template <int SH, int COV>
@@ -633,6 +639,18 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         CullOut co;
         vis = cull_gaussian<SH, COV>(p, u, g, rec, sd_size, vis, co);
         const float nz = co.nz;
+        // Strip render (one frame split into screen strips over several GPUs): the full-frame cull above is what every rank
+        // agrees on; a rank then keeps only the splats whose tile box meets its own tile rows, so its visible list — and the
+        // sort, binning and colour work behind it — is its strip's subset.  A subset of an order-preserving compaction keeps
+        // the order, so the strips reassemble the single-GPU frame bit for bit.
+        SplatGeom geo;
+        if (p.strip_on) {
+            if (vis) {
+                splat_geometry(u, co, geo);
+                const uint32_t y0 = geo.tmin >> 16, y1 = geo.tmax >> 16;
+                vis = (geo.tmin & 0xffffu) <= (geo.tmax & 0xffffu) && y0 <= y1 && y1 >= p.strip_ty_lo && y0 <= p.strip_ty_hi;
+            }
+        }
 
         // ---- order-preserving compaction, phase 1: publish this warp's count (non-blocking)
         const uint32_t bal = __ballot_sync(0xffffffffu, vis);
@@ -646,7 +664,10 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         d2 = d1;
 
         // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
-        if (vis && p.recs != nullptr) emit_splat<SH, COV>(p, u, g, rec, co);  // a standalone Preprocessor has no record buffer
+        if (vis && p.recs != nullptr) {  // a standalone Preprocessor has no record buffer
+            if (!p.strip_on) splat_geometry(u, co, geo);
+            emit_splat<SH, COV>(p, u, g, rec, co, geo);
+        }
 
         // the pods of this chunk are no longer needed: let the producer refill the slot
         __syncwarp();
@@ -694,7 +715,9 @@ __global__ void __launch_bounds__(256) vertex_kernel(const __grid_constant__ Pre
         CullOut co;
         cull_gaussian<SH, COV>(p, u, g, rec, sd_size, true, co);
         if (co.cw > 0.0f && co.nz >= 0.0f && co.nz <= 1.0f) {
-            emit_splat<SH, COV>(p, u, g, rec, co);
+            SplatGeom geo;
+            splat_geometry(u, co, geo);
+            emit_splat<SH, COV>(p, u, g, rec, co, geo);
         } else {
             *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(1u | (1u << 16), 0u);  // no tiles
         }

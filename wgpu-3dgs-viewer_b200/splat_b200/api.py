@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = [
     "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
     "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
     "sb_mm_render_with_pass",
+    "sb_viewer_set_strip_cull", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
 ]
 
 
@@ -190,6 +191,11 @@ def load() -> C.CDLL:
     sig("sb_viewer_raster_path", i32, vp, P(i32))
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
     sig("sb_viewer_set_exact_cutoff", i32, vp, i32)
+    sig("sb_viewer_set_strip_cull", i32, vp, i32)
+    sig("sb_shared_frame_create", i32, vp, u64, P(vp), C.c_char_p)
+    sig("sb_shared_frame_open", i32, vp, C.c_char_p, P(vp))
+    sig("sb_shared_frame_close", i32, vp, vp)
+    sig("sb_shared_frame_destroy", i32, vp, vp)
     sig("sb_viewer_set_raster_counting", i32, vp, i32)
     sig("sb_viewer_read_raster_counters", i32, vp, vp, P(u64), P(u64))
     sig("sb_viewer_read_raster_warp_counters", i32, vp, vp, P(u64), P(u64))
@@ -331,6 +337,30 @@ class Context:
         if self._h:
             load().sb_ctx_destroy(self._h)
             self._h = C.c_void_p()
+
+
+class SharedFrame:
+    """A device frame buffer the other GPUs of the node render their strips into (sb_shared_frame_*, CUDA IPC over NVLink).
+    The owner creates it and publishes `handle` (64 bytes); peers construct it from that handle.  `ptr` is a device pointer
+    valid on the calling process's GPU."""
+
+    def __init__(self, ctx: Context, nbytes: int = 0, handle: bytes | None = None):
+        self.ctx, self.nbytes, self.owner = ctx, nbytes, handle is None
+        p = C.c_void_p()
+        if handle is None:
+            buf = C.create_string_buffer(64)
+            _check(load().sb_shared_frame_create(ctx._h, nbytes, C.byref(p), buf), ctx._h)
+            self.handle = buf.raw
+        else:
+            self.handle = bytes(handle)
+            _check(load().sb_shared_frame_open(ctx._h, self.handle, C.byref(p)), ctx._h)
+        self.ptr = int(p.value)
+
+    def close(self):
+        if self.ptr:
+            fn = load().sb_shared_frame_destroy if self.owner else load().sb_shared_frame_close
+            _check(fn(self.ctx._h, self.ptr), self.ctx._h)
+            self.ptr = 0
 
 
 class Viewer:
@@ -507,6 +537,10 @@ class Viewer:
 
     def set_exact_cutoff(self, enabled: bool):
         _check(load().sb_viewer_set_exact_cutoff(self._h, int(enabled)), self.ctx._h)
+
+    def set_strip_cull(self, enabled: bool):
+        """Strip renders keep only the visible splats whose tile box meets the strip (one frame sharded over GPUs)."""
+        _check(load().sb_viewer_set_strip_cull(self._h, int(enabled)), self.ctx._h)
 
     STAGES = ("preprocess", "depth_sort", "tile_emit", "tile_sort", "gather", "raster")
 

@@ -2,10 +2,16 @@
 
 * view batches (BASELINE config 5a): independent frames, scene replicated, view k -> rank k mod G;
   no data-path collective.
-* one very large frame (config 5b): horizontal screen strips, tile-row aligned; every rank runs the
-  full-frame cull + depth sort (identical artefacts on every rank), bins and rasterises only its
-  strip, then ONE gather of the strips over torch.distributed (NCCL over NVLink on GPUs, gloo in
-  the CPU tests).
+* one very large frame (config 5b): horizontal screen strips, tile-row aligned.  Every rank runs the
+  reference's full-frame cull (identical decisions on every rank), keeps only the splats whose tile
+  box meets ITS strip (`sb_viewer_set_strip_cull`), depth-sorts, bins and rasterises that subset.
+  The strips land in ONE frame on the owner rank:
+    - `StripFrame(mode="peer")`: the owner's frame is mapped into every process (CUDA IPC over
+      NVLink, `sb_shared_frame_*`) and each rank's rasterizer stores its pixels straight into
+      `frame + row0 * pitch` — the kernel's final stores are the transfer; one tiny all-reduce
+      orders them before the owner reads.
+    - `gather_strips` (mode="sendrecv", also the gloo CPU path): one batched send/recv group that
+      receives every strip directly into its rows of the final frame (no padding, no concatenation).
 """
 from __future__ import annotations
 
@@ -17,7 +23,8 @@ def views_for_rank(n_views: int, world: int, rank: int) -> list[int]:
 
 
 def strip_rows(height: int, world: int, rank: int) -> tuple[int, int]:
-    """(row0, rows) of rank's strip; boundaries fall on 16-pixel tile rows so no tile is shared."""
+    """(row0, rows) of rank's strip; boundaries fall on 16-pixel tile rows so no tile is shared.  rows == 0: the rank has no
+    strip (more ranks than tile rows) and must not render (SbTarget.rows == 0 would mean the full frame)."""
     tile_rows = (height + TILE - 1) // TILE
     t0 = tile_rows * rank // world
     t1 = tile_rows * (rank + 1) // world
@@ -29,21 +36,136 @@ def max_strip_rows(height: int, world: int) -> int:
     return max(strip_rows(height, world, r)[1] for r in range(world))
 
 
-def gather_strips(strip, height: int, world: int, rank: int, dst: int = 0):
-    """Gathers per-rank strips (torch tensors [rows_r, W, C]) into the full frame on `dst`.
-    Strips are padded to a common row count so a single fixed-size gather is used."""
-    import torch
+def gather_strips(strip, frame, height: int, world: int, rank: int, dst: int = 0):
+    """Brings every rank's strip (tensor [rows_r, W, C]; may be empty) into `frame` ([H, W, C], on `dst` only) with one
+    batched group of point-to-point transfers: the owner receives each strip straight into its rows of the final frame.
+    Returns `frame` on dst, None elsewhere.  Works over NCCL (device tensors) and gloo (CPU tensors)."""
     import torch.distributed as dist
 
+    r0, rows = strip_rows(height, world, rank)
     if world == 1:
-        return strip
-    pad_rows = max_strip_rows(height, world)
-    buf = torch.zeros((pad_rows,) + tuple(strip.shape[1:]), dtype=strip.dtype, device=strip.device)
-    buf[: strip.shape[0]] = strip
+        if strip.data_ptr() != frame[r0:r0 + rows].data_ptr():
+            frame[r0:r0 + rows].copy_(strip)
+        return frame
+    ops = []
     if rank == dst:
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.gather(buf, parts, dst=dst)
-        rows = [strip_rows(height, world, r)[1] for r in range(world)]
-        return torch.cat([p[:n] for p, n in zip(parts, rows)], dim=0)
-    dist.gather(buf, None, dst=dst)
-    return None
+        if rows and strip.data_ptr() != frame[r0:r0 + rows].data_ptr():
+            frame[r0:r0 + rows].copy_(strip)
+        for r in range(world):
+            if r == dst:
+                continue
+            q0, qn = strip_rows(height, world, r)
+            if qn:
+                ops.append(dist.P2POp(dist.irecv, frame[q0:q0 + qn], r))
+    elif rows:
+        ops.append(dist.P2POp(dist.isend, strip, dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return frame if rank == dst else None
+
+
+class StripFrame:
+    """One frame rendered as `world` screen strips into a single buffer on rank `dst` (config 5b)."""
+
+    def __init__(self, ctx, viewer, width: int, height: int, bytes_per_pixel: int, world: int, rank: int, dst: int = 0,
+                 mode: str = "peer"):
+        import torch
+        import torch.distributed as dist
+        from . import api
+
+        self.viewer, self.width, self.height, self.world, self.rank, self.dst = viewer, width, height, world, rank, dst
+        self.pitch = width * bytes_per_pixel
+        self.bpp = bytes_per_pixel
+        self.row0, self.rows = strip_rows(height, world, rank)
+        self.mode = mode if world > 1 else "local"
+        self.shared = None
+        self.strip = None
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nbytes = height * self.pitch
+        if self.mode == "peer":
+            try:
+                if rank == dst:
+                    self.shared = api.SharedFrame(ctx, nbytes)
+                    box = [self.shared.handle]
+                else:
+                    box = [None]
+                dist.broadcast_object_list(box, src=dst)
+                ok = 1
+                if rank != dst:
+                    try:
+                        self.shared = api.SharedFrame(ctx, handle=box[0])
+                    except api.SplatError:
+                        ok = 0
+                t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 0:
+                    raise api.SplatError("peer mapping unavailable on some rank")
+            except api.SplatError:
+                if self.shared is not None:
+                    self.shared.close()
+                    self.shared = None
+                self.mode = "sendrecv"
+        if self.mode == "peer":
+            self.frame_ptr = self.shared.ptr
+            self.frame = _wrap(self.shared.ptr, (height, width, bytes_per_pixel)) if rank == dst else None
+        else:
+            self.frame = torch.zeros((height, width, bytes_per_pixel), dtype=torch.uint8, device="cuda") if rank == dst else None
+            if self.mode == "sendrecv" and rank != dst:
+                self.strip = torch.zeros((self.rows, width, bytes_per_pixel), dtype=torch.uint8, device="cuda")
+        viewer.set_strip_cull(True)
+
+    def render(self, stream=None):
+        """Enqueue this rank's strip and whatever completes the frame on the owner; stream-ordered, no host sync."""
+        import torch
+        import torch.distributed as dist
+        from . import api
+
+        v, w, h = self.viewer, self.width, self.height
+        if self.rows:
+            if self.mode == "sendrecv" and self.rank != self.dst:
+                ptr = self.strip.data_ptr()
+            else:
+                base = self.frame_ptr if self.mode == "peer" else self.frame.data_ptr()
+                ptr = base + self.row0 * self.pitch
+            for attempt in range(3):
+                try:
+                    v.render(ptr, w, h, stream=stream, row0=self.row0, rows=self.rows, pitch=self.pitch)
+                    break
+                except api.SplatError as e:  # an earlier frame overflowed its duplicate buffers: they were grown, render again
+                    if "render again" not in str(e) or attempt == 2:
+                        raise
+        if self.world == 1:
+            return self.frame
+        ctxm = torch.cuda.stream(stream) if stream is not None else _null()
+        with ctxm:
+            if self.mode == "peer":
+                dist.all_reduce(self._flag)  # stream-ordered fence: every rank's raster stores precede the owner's next read
+            else:
+                strip = self.strip if self.rank != self.dst else self.frame[self.row0:self.row0 + self.rows]
+                gather_strips(strip, self.frame, h, self.world, self.rank, self.dst)
+        return self.frame
+
+    def close(self):
+        self.viewer.set_strip_cull(False)
+        if self.shared is not None:
+            self.shared.close()
+            self.shared = None
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _wrap(ptr: int, shape):
+    """torch uint8 view over a raw device pointer (the shared frame is cudaMalloc'ed by the library, not by torch)."""
+    import torch
+
+    class _Cai:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+    return torch.as_tensor(_Cai(), device="cuda")
