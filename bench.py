@@ -361,30 +361,40 @@ def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
     both sides, CUDA events on the launching stream, max over ranks, median of REPEATS regions."""
     pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
     viewer.update_camera_with_pod(sb.camera_pod(pos, yaw, pitch, STRIP_W, STRIP_H))
-    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0)
-    for _ in range(STRIP_WARMUP):
-        sf.render(stream)
-    stream.synchronize()
-    torch.cuda.synchronize()
-    regions = []
-    for _ in range(REPEATS):
-        barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(STRIP_STEPS):
+
+    def time_strips(sf):
+        for _ in range(STRIP_WARMUP):
             sf.render(stream)
-        e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / STRIP_STEPS
+        regions = []
+        for _ in range(REPEATS):
+            barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(STRIP_STEPS):
+                sf.render(stream)
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            t_ms = e0.elapsed_time(e1) / STRIP_STEPS
+            barrier()
+            if world > 1:
+                t = torch.tensor([t_ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_ms = float(t.item())
+            regions.append(t_ms)
+        return float(np.median(regions))
+
+    ms_equal = None
+    if world > 1:  # strips of equal height, for the record (the scene is not centred: the lower strips carry more splats)
+        sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0)
+        ms_equal = time_strips(sf)
         barrier()
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        regions.append(ms)
-    ms = float(np.median(regions))
+        sf.close()
+    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream)
+    ms = time_strips(sf)
     # this rank's share of the work, and its stage times
     viewer.set_stage_timing(True)
     sf.render(stream)
@@ -420,10 +430,12 @@ def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
                                                     "sendrecv": "one batched NCCL send/recv group straight into the frame's rows",
                                                     "local": "single GPU"}[sf.mode],
                "partitioning": "full-frame cull on every rank, then each rank keeps / sorts / bins / rasterises only the splats "
-                               "whose tile box meets its strip",
+                               "whose tile box meets its strip; strip boundaries balance the (splat, tile) duplicates per tile row "
+                               "of one calibration frame rendered at set-up (a viewer would use its previous frame)",
+               "ms_per_frame_equal_height_strips": ms_equal,
                "identical_to_single_gpu_frame": bool(torch.equal(got, ref)),
                "full_frame": {"visible": full["visible"], "tile_duplicates": full["duplicates"]},
-               "per_rank": [{"rows": sb.sharding.strip_rows(STRIP_H, world, r)[1], "visible": int(shares[r][0].item()),
+               "per_rank": [{"row0": sf.bounds[r][0], "rows": sf.bounds[r][1], "visible": int(shares[r][0].item()),
                              "tile_duplicates": int(shares[r][1].item())} for r in range(world)],
                "rank0_stage_ms": {k: float(v) for k, v in stage.items()}}
     barrier()

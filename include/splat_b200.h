@@ -281,6 +281,10 @@ SB_API SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled);
  * full frame's, in the same order), and the depth sort, binning and colour evaluation run on that subset only.  The strips of
  * all ranks reassemble the single-GPU frame bit for bit.  Default off (a strip render then keeps the full-frame artefacts). */
 SB_API SbStatus sb_viewer_set_strip_cull(SbViewer* v, int32_t enabled);
+/* Work per 16-pixel tile row of the last binned frame: out[y] = number of (splat, tile) duplicates in tile row y (synchronises).
+ * After a full-frame render it is what a strip partition balances on (rasterizer and binning time follow the duplicates,
+ * not the rows): splat_b200/sharding.py: balanced_strips. */
+SB_API SbStatus sb_viewer_read_tile_row_work(SbViewer* v, void* stream, uint64_t* out, uint32_t n_rows);
 /* Strip gather without a gather: the rank that owns the final frame allocates it with sb_shared_frame_create and publishes the
  * 64-byte handle (any transport: the tests and bench.py use torch.distributed); every other process of the node opens it and
  * gets a device pointer, valid on ITS GPU, that aliases the owner's memory over NVLink (CUDA IPC, peer access enabled on

@@ -58,6 +58,25 @@ def test_strip_partition_properties():
                 assert r0 % 16 == 0 or n == 0
 
 
+def test_balanced_strips_properties():
+    from splat_b200 import sharding
+    rng = np.random.default_rng(5)
+    for height in (16, 17, 368, 1080, 4320):
+        tile_rows = (height + 15) // 16
+        for world in (1, 2, 3, 8):
+            work = rng.integers(0, 5000, tile_rows) * (rng.random(tile_rows) < 0.7)
+            b = sharding.balanced_strips(work, height, world, per_row_cost=3.0)
+            assert len(b) == world and b[0][0] == 0 and sum(n for _, n in b) == height
+            for (a0, an), (b0, _) in zip(b, b[1:]):
+                assert a0 + an == b0 and (b0 % 16 == 0 or b0 == height)
+
+            def load(bounds):
+                return max(sum(float(work[y]) + 3.0 for y in range(r0 // 16, (r0 + n + 15) // 16)) if n else 0.0 for r0, n in bounds)
+
+            equal = [sharding.strip_rows(height, world, r) for r in range(world)]
+            assert load(b) <= load(equal) + 1e-9, "balanced strips must not be heavier than equal-height strips"
+
+
 def test_gather_strips_and_view_sharding_gloo_ws2():
     _run_gather(2, 200, 8)
 

@@ -193,6 +193,7 @@ struct SbViewer {
     bool selection_enabled = false;
     uint32_t invert_selection = 1;  // src/selection/buffer.rs:157-165
     int strict_exp = 0;
+    uint32_t last_tiles_x = 0, last_tiles_y = 0;  // tile grid of the last binned frame (tile_ranges is indexed by it)
     bool strip_cull = false;     // a strip render keeps only the splats whose tile box meets the strip (sb_viewer_set_strip_cull)
     bool exact_cutoff = true;    // shrink splats to the radius beyond which a unorm8 blend is exactly the identity
     bool recs_cut = false;       // recs/tboxes currently hold cut extents (a depth-tested pass needs the full ones)
@@ -536,6 +537,8 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.counters = v->counting ? v->counters.as<unsigned long long>() : nullptr;
     if (v->counting && clear) SB_CUDA(v->ctx, cudaMemsetAsync(v->counters.p, 0, 32, stream));
     SB_CUDA(v->ctx, sb::launch_bin_and_raster(p, v->ctx->num_sms, stream));
+    v->last_tiles_x = p.u.tiles_x;
+    v->last_tiles_y = p.u.tiles_y;
     return SB_OK;
 }
 
@@ -1057,6 +1060,26 @@ SbStatus sb_viewer_set_strict_exp(SbViewer* v, int32_t strict) {
 SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     v->exact_cutoff = enabled != 0;
+    return SB_OK;
+}
+
+SbStatus sb_viewer_read_tile_row_work(SbViewer* v, void* stream, uint64_t* out, uint32_t n_rows) {
+    if (!v || !out) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (n_rows != v->last_tiles_y || v->last_tiles_x == 0) return fail(v->ctx, SB_ERR_INVALID_ARG, "n_rows differs from the last frame's tile rows");
+    DeviceGuard device_guard(v->ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t tiles = (size_t)v->last_tiles_x * v->last_tiles_y;
+    std::vector<uint32_t> ranges(tiles * 2);
+    SB_CUDA(v->ctx, cudaMemcpyAsync(ranges.data(), v->tile_ranges.p, tiles * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(v->ctx, cudaStreamSynchronize(st));
+    for (uint32_t y = 0; y < n_rows; y++) {
+        uint64_t sum = 0;
+        for (uint32_t x = 0; x < v->last_tiles_x; x++) {
+            const size_t t = (size_t)y * v->last_tiles_x + x;
+            sum += ranges[2 * t + 1] - ranges[2 * t];
+        }
+        out[y] = sum;
+    }
     return SB_OK;
 }
 

@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
     "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
     "sb_mm_render_with_pass",
-    "sb_viewer_set_strip_cull", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
+    "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
 ]
 
 
@@ -192,6 +192,7 @@ def load() -> C.CDLL:
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
     sig("sb_viewer_set_exact_cutoff", i32, vp, i32)
     sig("sb_viewer_set_strip_cull", i32, vp, i32)
+    sig("sb_viewer_read_tile_row_work", i32, vp, vp, P(u64), u32)
     sig("sb_shared_frame_create", i32, vp, u64, P(vp), C.c_char_p)
     sig("sb_shared_frame_open", i32, vp, C.c_char_p, P(vp))
     sig("sb_shared_frame_close", i32, vp, vp)
@@ -537,6 +538,12 @@ class Viewer:
 
     def set_exact_cutoff(self, enabled: bool):
         _check(load().sb_viewer_set_exact_cutoff(self._h, int(enabled)), self.ctx._h)
+
+    def read_tile_row_work(self, n_rows: int, stream=None) -> np.ndarray:
+        """(splat, tile) duplicates per 16-pixel tile row of the last binned (full) frame."""
+        out = np.zeros(n_rows, dtype=np.uint64)
+        _check(load().sb_viewer_read_tile_row_work(self._h, _stream_handle(stream), out.ctypes.data_as(C.POINTER(C.c_uint64)), n_rows), self.ctx._h)
+        return out
 
     def set_strip_cull(self, enabled: bool):
         """Strip renders keep only the visible splats whose tile box meets the strip (one frame sharded over GPUs)."""

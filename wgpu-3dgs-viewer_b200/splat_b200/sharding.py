@@ -32,17 +32,58 @@ def strip_rows(height: int, world: int, rank: int) -> tuple[int, int]:
     return r0, r1 - r0
 
 
+def balanced_strips(row_work, height: int, world: int, per_row_cost: float = 0.0) -> list[tuple[int, int]]:
+    """Strip boundaries (whole tile rows, contiguous, one strip per rank) that minimise the heaviest strip's work, where a tile
+    row costs row_work[y] + per_row_cost (row_work = (splat, tile) duplicates per tile row of a calibration / previous frame:
+    binning and rasterizer time follow the duplicates, not the rows).  Exact min-max contiguous partition by bisection on the
+    bottleneck; deterministic, so every rank that holds the same row_work computes the same strips."""
+    tile_rows = (height + TILE - 1) // TILE
+    cost = [float(row_work[y]) + per_row_cost for y in range(tile_rows)]
+    assert len(cost) == tile_rows
+
+    def parts_needed(limit):
+        parts, acc = 1, 0.0
+        for c in cost:
+            if acc + c > limit and acc > 0.0:
+                parts, acc = parts + 1, 0.0
+            acc += c
+        return parts
+
+    lo, hi = max(cost) if cost else 0.0, sum(cost)
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if parts_needed(mid) <= world:
+            hi = mid
+        else:
+            lo = mid
+    cuts, acc = [0], 0.0  # greedy fill under the bottleneck `hi`
+    for y, c in enumerate(cost):
+        if acc + c > hi and acc > 0.0 and len(cuts) < world:
+            cuts.append(y)
+            acc = 0.0
+        acc += c
+    while len(cuts) < world:  # fewer strips than ranks: the remaining ranks get empty strips at the end
+        cuts.append(tile_rows)
+    cuts.append(tile_rows)
+    out = []
+    for r in range(world):
+        r0, r1 = min(cuts[r] * TILE, height), min(cuts[r + 1] * TILE, height)
+        out.append((r0, r1 - r0))
+    return out
+
+
 def max_strip_rows(height: int, world: int) -> int:
     return max(strip_rows(height, world, r)[1] for r in range(world))
 
 
-def gather_strips(strip, frame, height: int, world: int, rank: int, dst: int = 0):
+def gather_strips(strip, frame, height: int, world: int, rank: int, dst: int = 0, bounds=None):
     """Brings every rank's strip (tensor [rows_r, W, C]; may be empty) into `frame` ([H, W, C], on `dst` only) with one
     batched group of point-to-point transfers: the owner receives each strip straight into its rows of the final frame.
     Returns `frame` on dst, None elsewhere.  Works over NCCL (device tensors) and gloo (CPU tensors)."""
     import torch.distributed as dist
 
-    r0, rows = strip_rows(height, world, rank)
+    bounds = bounds or [strip_rows(height, world, r) for r in range(world)]
+    r0, rows = bounds[rank]
     if world == 1:
         if strip.data_ptr() != frame[r0:r0 + rows].data_ptr():
             frame[r0:r0 + rows].copy_(strip)
@@ -54,7 +95,7 @@ def gather_strips(strip, frame, height: int, world: int, rank: int, dst: int = 0
         for r in range(world):
             if r == dst:
                 continue
-            q0, qn = strip_rows(height, world, r)
+            q0, qn = bounds[r]
             if qn:
                 ops.append(dist.P2POp(dist.irecv, frame[q0:q0 + qn], r))
     elif rows:
@@ -69,7 +110,9 @@ class StripFrame:
     """One frame rendered as `world` screen strips into a single buffer on rank `dst` (config 5b)."""
 
     def __init__(self, ctx, viewer, width: int, height: int, bytes_per_pixel: int, world: int, rank: int, dst: int = 0,
-                 mode: str = "peer"):
+                 mode: str = "peer", balance: bool = False, stream=None):
+        """balance: rank `dst` renders the full frame once (a calibration frame; a viewer would use its previous frame), reads the
+        (splat, tile) duplicates per tile row and broadcasts strips of equal work instead of equal height."""
         import torch
         import torch.distributed as dist
         from . import api
@@ -77,7 +120,28 @@ class StripFrame:
         self.viewer, self.width, self.height, self.world, self.rank, self.dst = viewer, width, height, world, rank, dst
         self.pitch = width * bytes_per_pixel
         self.bpp = bytes_per_pixel
-        self.row0, self.rows = strip_rows(height, world, rank)
+        self.bounds = [strip_rows(height, world, r) for r in range(world)]
+        if balance and world > 1:
+            box = [None]
+            if rank == dst:
+                viewer.set_strip_cull(False)
+                scratch = torch.zeros((height, width, bytes_per_pixel), dtype=torch.uint8, device="cuda")
+                for attempt in range(3):
+                    try:
+                        viewer.render(scratch, width, height, stream=stream)
+                        break
+                    except api.SplatError as e:
+                        if "render again" not in str(e) or attempt == 2:
+                            raise
+                tile_rows = (height + TILE - 1) // TILE
+                work = viewer.read_tile_row_work(tile_rows, stream)
+                del scratch
+                # a tile costs its list plus a fixed part (CTA start, clear, store): ~16 list entries per tile
+                box = [balanced_strips(work, height, world, per_row_cost=16.0 * ((width + TILE - 1) // TILE))]
+            dist.broadcast_object_list(box, src=dst)
+            self.bounds = [tuple(b) for b in box[0]]
+        self.balanced = bool(balance and world > 1)
+        self.row0, self.rows = self.bounds[rank]
         self.mode = mode if world > 1 else "local"
         self.shared = None
         self.strip = None
@@ -143,7 +207,7 @@ class StripFrame:
                 dist.all_reduce(self._flag)  # stream-ordered fence: every rank's raster stores precede the owner's next read
             else:
                 strip = self.strip if self.rank != self.dst else self.frame[self.row0:self.row0 + self.rows]
-                gather_strips(strip, self.frame, h, self.world, self.rank, self.dst)
+                gather_strips(strip, self.frame, h, self.world, self.rank, self.dst, self.bounds)
         return self.frame
 
     def close(self):
