@@ -281,6 +281,10 @@ SB_API SbStatus sb_viewer_set_exact_cutoff(SbViewer* v, int32_t enabled);
  * full frame's, in the same order), and the depth sort, binning and colour evaluation run on that subset only.  The strips of
  * all ranks reassemble the single-GPU frame bit for bit.  Default off (a strip render then keeps the full-frame artefacts). */
 SB_API SbStatus sb_viewer_set_strip_cull(SbViewer* v, int32_t enabled);
+/* Measured denominators for the rasterizer's roofline (no reference counterpart; SURVEY 8d asks for "achieved FP32 and
+ * shared-memory throughput vs peak"): two microbenchmarks run on the context's device — FP32 issue in lane-ops/s with an FMA
+ * counted once, and conflict-free shared-memory read bandwidth in bytes/s.  Synchronises. */
+SB_API SbStatus sb_probe_peaks(SbContext* ctx, void* stream, double* fp32_lane_ops_per_s, double* smem_bytes_per_s);
 /* Work per 16-pixel tile row of the last binned frame: out[y] = number of (splat, tile) duplicates in tile row y (synchronises).
  * After a full-frame render it is what a strip partition balances on (rasterizer and binning time follow the duplicates,
  * not the rows): splat_b200/sharding.py: balanced_strips. */

@@ -612,6 +612,14 @@ SbStatus sb_shared_frame_destroy(SbContext* ctx, void* d_frame) {
     return SB_OK;
 }
 
+SbStatus sb_probe_peaks(SbContext* ctx, void* stream, double* fp32_lane_ops_per_s, double* smem_bytes_per_s) {
+    if (!ctx || !fp32_lane_ops_per_s || !smem_bytes_per_s) return fail(ctx, SB_ERR_INVALID_ARG, "null");
+    DeviceGuard device_guard(ctx);
+    SB_CUDA(ctx, sb::probe_fp32_peak(ctx->num_sms, static_cast<cudaStream_t>(stream), fp32_lane_ops_per_s));
+    SB_CUDA(ctx, sb::probe_smem_peak(ctx->num_sms, static_cast<cudaStream_t>(stream), smem_bytes_per_s));
+    return SB_OK;
+}
+
 SbStatus sb_ctx_set_model_size_limit(SbContext* ctx, uint64_t bytes) {
     if (!ctx) return fail(nullptr, SB_ERR_INVALID_ARG, "null context");
     ctx->model_size_limit = bytes;

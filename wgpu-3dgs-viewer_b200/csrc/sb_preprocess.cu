@@ -419,7 +419,7 @@ __device__ __forceinline__ void emit_splat(const PreParams& p, const Uniforms& u
     *reinterpret_cast<uint2*>(&p.tboxes[g]) = make_uint2(geo.tmin, geo.tmax);
 }
 
-template <int SH, int COV>
+template <int SH, int COV, bool STRIP>
 __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
     preprocess_kernel(const __grid_constant__ PreParams p) {
     constexpr int STRIDE = pod_stride(SH, COV);
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         // sort, binning and colour work behind it — is its strip's subset.  A subset of an order-preserving compaction keeps
         // the order, so the strips reassemble the single-GPU frame bit for bit.
         SplatGeom geo;
-        if (p.strip_on) {
+        if constexpr (STRIP) {  // its own instantiation: the full-frame kernel keeps its register allocation and schedule
             if (vis) {
                 splat_geometry(u, co, geo);
                 const uint32_t y0 = geo.tmin >> 16, y1 = geo.tmax >> 16;
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
 
         // ---- vertex-stage work for survivors (render.wesl:76-130), written once per splat
         if (vis && p.recs != nullptr) {  // a standalone Preprocessor has no record buffer
-            if (!p.strip_on) splat_geometry(u, co, geo);
+            if constexpr (!STRIP) splat_geometry(u, co, geo);
             emit_splat<SH, COV>(p, u, g, rec, co, geo);
         }
 
@@ -736,14 +736,19 @@ cudaError_t launch_one(PreParams& p, int num_sms, cudaStream_t stream) {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 0 || dev >= 64 || !configured[dev]) {
-            e = cudaFuncSetAttribute(preprocess_kernel<SH, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(preprocess_kernel<SH, COV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(preprocess_kernel<SH, COV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
     p.num_tiles = (p.n + T - 1) / T;
     const int grid = (int)min((uint32_t)num_sms, p.num_tiles);
-    preprocess_kernel<SH, COV><<<grid, T + 64, smem, stream>>>(p);
+    if (p.strip_on && p.recs != nullptr)
+        preprocess_kernel<SH, COV, true><<<grid, T + 64, smem, stream>>>(p);
+    else
+        preprocess_kernel<SH, COV, false><<<grid, T + 64, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
             uint32_t key = y0 * p.tiles_x + x0, col = 0;
             for (uint32_t j = 0; j < n; j++) {
                 const uint32_t o = off + j;
-                if (o < p.dup_capacity) {
+                if (o < p.dup_capacity && o >= off) {  // (off saturates at 2^32 - 1: off + j must not wrap back into range)
                     p.dup_keys[o] = key;
                     p.dup_vals[o] = g;
                 }
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
             const uint32_t inv = mul_ok ? 0xffffffffu / bw + 1u : 0u;
             for (uint32_t j = lane; j < bn; j += 32) {
                 const uint32_t o = boff + j;
-                if (o < p.dup_capacity) {
+                if (o < p.dup_capacity && o >= boff) {
                     const uint32_t q = mul_ok ? __umulhi(j, inv) : j / bw;
                     p.dup_keys[o] = (by0 + q) * p.tiles_x + (bx0 + (j - q * bw));
                     p.dup_vals[o] = bg;

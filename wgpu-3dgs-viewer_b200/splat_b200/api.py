@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
     "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
     "sb_mm_render_with_pass",
-    "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
+    "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
 ]
 
 
@@ -192,6 +192,7 @@ def load() -> C.CDLL:
     sig("sb_viewer_set_strict_exp", i32, vp, i32)
     sig("sb_viewer_set_exact_cutoff", i32, vp, i32)
     sig("sb_viewer_set_strip_cull", i32, vp, i32)
+    sig("sb_probe_peaks", i32, vp, vp, P(C.c_double), P(C.c_double))
     sig("sb_viewer_read_tile_row_work", i32, vp, vp, P(u64), u32)
     sig("sb_shared_frame_create", i32, vp, u64, P(vp), C.c_char_p)
     sig("sb_shared_frame_open", i32, vp, C.c_char_p, P(vp))
@@ -330,6 +331,12 @@ class Context:
         self._h = C.c_void_p()
         _check(load().sb_ctx_create(device, C.byref(self._h)))
         self.device = device
+
+    def probe_peaks(self, stream=None):
+        """(FP32 lane-ops/s with FMA = 1, shared-memory bytes/s) measured on this device by two microbenchmarks."""
+        a, b = C.c_double(), C.c_double()
+        _check(load().sb_probe_peaks(self._h, _stream_handle(stream), C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
 
     def set_model_size_limit(self, nbytes: int):
         _check(load().sb_ctx_set_model_size_limit(self._h, nbytes), self._h)
