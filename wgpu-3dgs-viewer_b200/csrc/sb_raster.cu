@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
         }
         if (n > 0 && n <= 32) {
             // row-major walk of the box without a division per tile
-            uint32_t key = y0 * p.tiles_x + x0, col = 0;
+            uint32_t key = (y0 - p.ty_lo) * p.tiles_x + x0, col = 0;  // strip-relative tile id: fewer key bits for the tile sort
             for (uint32_t j = 0; j < n; j++) {
                 const uint32_t o = off + j;
                 if (o < p.dup_capacity && o >= off) {  // (off saturates at 2^32 - 1: off + j must not wrap back into range)
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
                 const uint32_t o = boff + j;
                 if (o < p.dup_capacity && o >= boff) {
                     const uint32_t q = mul_ok ? __umulhi(j, inv) : j / bw;
-                    p.dup_keys[o] = (by0 + q) * p.tiles_x + (bx0 + (j - q * bw));
+                    p.dup_keys[o] = (by0 - p.ty_lo + q) * p.tiles_x + (bx0 + (j - q * bw));
                     p.dup_vals[o] = bg;
                 }
             }
@@ -982,8 +982,12 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(p.buf.tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
+    // tile ids are relative to the strip's first tile row: a strip of a huge frame sorts fewer key bits (an 8K frame has 17,
+    // an eighth of it 14: two 8-bit passes instead of three); the ranges land in the frame-wide table through an offset pointer
+    const uint32_t strip_tiles = (ty_hi - ty_lo + 1) * u.tiles_x;
+    uint32_t* const ranges_rel = p.buf.tile_ranges + 2 * (size_t)ty_lo * u.tiles_x;
     int bits = 1;
-    while ((1u << bits) < num_tiles) bits++;
+    while ((1u << bits) < strip_tiles) bits++;
 
     BinParams bp;
     bp.tboxes = p.tboxes;
@@ -1017,10 +1021,10 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     if (p.events) cudaEventRecord(p.events[1], stream);
 
     if (p.recs_map)
-        tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_count, p.buf.tile_ranges);
+        tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_count, ranges_rel);
     else
         gather_kernel<<<num_sms * 8, 256, 0, stream>>>(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, p.recs, p.buf.tile_recs,
-                                                      p.buf.tile_ranges);
+                                                      ranges_rel);
     if (p.buf.tile_order)
         tile_order_kernel<<<1, 1024, 0, stream>>>(p.buf.tile_ranges, ty_lo * u.tiles_x, (ty_hi - ty_lo + 1) * u.tiles_x, p.buf.tile_order);
     if (p.events) cudaEventRecord(p.events[2], stream);

