@@ -5,7 +5,8 @@
 //! `&wgpu::TextureView`, this crate takes a [`Context`], nothing, a CUDA stream and a [`Target`]
 //! (caller-owned device memory).  `render` only enqueues work, like recording into an encoder.
 //!
-//! SOURCE ONLY — never compiled in the build container (no Rust toolchain there).
+//! SOURCE ONLY — never compiled in the build container (no Rust toolchain there).  The `extern "C"` block is generated from
+//! the header (all exports); the safe layer below wraps every one of them under the reference's names.
 #![allow(non_camel_case_types)]
 
 use std::ffi::{c_char, c_void, CStr};
@@ -59,52 +60,8 @@ pub mod ffi {
         pub d_indirect_indices: *const u32, pub indirect_indices_bytes: u64,
     }
 
-    #[link(name = "splat_b200")]
-    extern "C" {
-        pub fn sb_preprocessor_create(ctx: *mut SbContext, sh: i32, cov: i32, n: u64, out: *mut *mut SbPreprocessor) -> i32;
-        pub fn sb_preprocessor_destroy(p: *mut SbPreprocessor);
-        pub fn sb_preprocessor_preprocess(p: *mut SbPreprocessor, stream: *mut c_void, bind_group: *const PreprocessorBindGroup, gaussian_count: u32) -> i32;
-        pub fn sb_sorter_create(ctx: *mut SbContext, capacity: u32, out: *mut *mut SbRadixSorter) -> i32;
-        pub fn sb_sorter_destroy(s: *mut SbRadixSorter);
-        pub fn sb_sorter_sort(s: *mut SbRadixSorter, stream: *mut c_void, d_keys: *mut u32, d_payload: *mut u32, d_count: *const u32, max_count: u32, begin_bit: i32, end_bit: i32) -> i32;
-        pub fn sb_renderer_create(ctx: *mut SbContext, sh: i32, cov: i32, target_format: i32, n: u64, out: *mut *mut SbRenderer) -> i32;
-        pub fn sb_renderer_destroy(r: *mut SbRenderer);
-        pub fn sb_renderer_render(r: *mut SbRenderer, stream: *mut c_void, bind_group: *const RendererBindGroup, target: *const Target, d_indirect_args: *const DrawIndirectArgs, depth: *const DepthAttachment, load: i32) -> i32;
-        pub fn sb_last_error_string(ctx: *const SbContext) -> *const c_char;
-        pub fn sb_pod_stride(sh_fmt: i32, cov_fmt: i32) -> u32;
-        pub fn sb_pack_gaussians(src: *const Gaussian, n: u64, sh_fmt: i32, cov_fmt: i32, out: *mut c_void) -> i32;
-        pub fn sb_camera_pod(pos: *const f32, yaw: f32, pitch: f32, z_near: f32, z_far: f32, fov: f32, w: u32, h: u32, out: *mut CameraPod) -> i32;
-        pub fn sb_ctx_create(device: i32, out: *mut *mut SbContext) -> i32;
-        pub fn sb_ctx_destroy(ctx: *mut SbContext);
-        pub fn sb_viewer_create_from_gaussians(ctx: *mut SbContext, sh: i32, cov: i32, target_format: i32, src: *const Gaussian, n: u64, out: *mut *mut SbViewer) -> i32;
-        pub fn sb_viewer_create(ctx: *mut SbContext, sh: i32, cov: i32, target_format: i32, pods: *const c_void, n: u64, out: *mut *mut SbViewer) -> i32;
-        pub fn sb_viewer_destroy(v: *mut SbViewer);
-        pub fn sb_viewer_update_camera_with_pod(v: *mut SbViewer, pod: *const CameraPod) -> i32;
-        pub fn sb_viewer_update_model_transform_with_pod(v: *mut SbViewer, pod: *const ModelTransformPod) -> i32;
-        pub fn sb_viewer_update_gaussian_transform_with_pod(v: *mut SbViewer, pod: *const GaussianTransformPod) -> i32;
-        pub fn sb_viewer_enable_selection(v: *mut SbViewer, enabled: i32) -> i32;
-        pub fn sb_viewer_set_selection(v: *mut SbViewer, stream: *mut c_void, words: *const u32, n_words: u64) -> i32;
-        pub fn sb_viewer_set_invert_selection(v: *mut SbViewer, invert: i32) -> i32;
-        pub fn sb_viewer_select_rect(v: *mut SbViewer, stream: *mut c_void, x0: f32, y0: f32, x1: f32, y1: f32) -> i32;
-        pub fn sb_viewer_select_brush(v: *mut SbViewer, stream: *mut c_void, points_xy: *const f32, n_points: u32, radius: f32, accumulate: i32) -> i32;
-        pub fn sb_viewer_apply_rgb_override(v: *mut SbViewer, stream: *mut c_void, rgb: *const f32, alpha: f32) -> i32;
-        pub fn sb_viewer_restore_gaussians(v: *mut SbViewer, stream: *mut c_void) -> i32;
-        pub fn sb_viewer_set_exact_cutoff(v: *mut SbViewer, enabled: i32) -> i32;
-        pub fn sb_viewer_render(v: *mut SbViewer, stream: *mut c_void, target: *const Target) -> i32;
-        pub fn sb_viewer_render_with_pass(v: *mut SbViewer, stream: *mut c_void, target: *const Target, depth: *const DepthAttachment, load: i32, run_stages: i32) -> i32;
-        pub fn sb_viewer_preprocess(v: *mut SbViewer, stream: *mut c_void) -> i32;
-        pub fn sb_viewer_sort(v: *mut SbViewer, stream: *mut c_void) -> i32;
-        pub fn sb_viewer_draw(v: *mut SbViewer, stream: *mut c_void, target: *const Target) -> i32;
-        pub fn sb_viewer_read_indirect_args(v: *mut SbViewer, stream: *mut c_void, draw: *mut DrawIndirectArgs, dispatch: *mut DispatchIndirectArgs) -> i32;
-        pub fn sb_mm_create(ctx: *mut SbContext, sh: i32, cov: i32, target_format: i32, out: *mut *mut SbMultiModelViewer) -> i32;
-        pub fn sb_mm_destroy(mm: *mut SbMultiModelViewer);
-        pub fn sb_mm_insert_model(mm: *mut SbMultiModelViewer, key: u64, pods: *const c_void, n: u64, replaced: *mut i32) -> i32;
-        pub fn sb_mm_remove_model(mm: *mut SbMultiModelViewer, key: u64, removed: *mut i32) -> i32;
-        pub fn sb_mm_update_camera_with_pod(mm: *mut SbMultiModelViewer, pod: *const CameraPod) -> i32;
-        pub fn sb_mm_update_model_transform_with_pod(mm: *mut SbMultiModelViewer, key: u64, pod: *const ModelTransformPod) -> i32;
-        pub fn sb_mm_update_gaussian_transform_with_pod(mm: *mut SbMultiModelViewer, pod: *const GaussianTransformPod) -> i32;
-        pub fn sb_mm_render(mm: *mut SbMultiModelViewer, stream: *mut c_void, target: *const Target, keys: *const u64, n_keys: u32) -> i32;
-    }
+    // every export of include/splat_b200.h (generated: scripts/gen_rust_ffi.py; tests/test_abi.py keeps it in step with the header)
+    include!("ffi_gen.rs");
 }
 
 pub use ffi::{CameraPod, Gaussian, GaussianTransformPod, ModelTransformPod, Target};
@@ -190,7 +147,139 @@ impl<'c, G: GaussianPod> Viewer<'c, G> {
         check(unsafe { ffi::sb_viewer_select_brush(self.raw, stream.0, stroke.as_ptr().cast(), stroke.len() as u32, radius, accumulate as i32) }, self.ctx.0)
     }
 }
+/// A device buffer of a [`Viewer`], as the reference's public buffer fields expose it (`viewer.gaussians_buffer`,
+/// `.indirect_args_buffer`, `.radix_sort_indirect_args_buffer`, `.indirect_indices_buffer`, `.gaussians_depth_buffer`,
+/// `.selection_buffer`: src/lib.rs:65-82): a raw device pointer + size, valid while the viewer lives.
+#[derive(Clone, Copy, Debug)] pub struct DeviceBuffer<T> { pub ptr: *const T, pub len: u64 }
+
+/// `ViewerCreateOptions` (src/lib.rs:279-293).
+#[derive(Clone, Copy, Debug, Default)] pub struct ViewerCreateOptions { pub depth_stencil: Option<(i32 /* compare */, bool /* depth write */)> }
+
+impl<'c, G: GaussianPod> Viewer<'c, G> {
+    /// `Viewer::new_with_options` — the depth-stencil state is passed per pass here (`render_with_pass`), so the options only record it.
+    pub fn new_with_options(ctx: &'c Context, texture_format: i32, gaussians: &[Gaussian], _options: ViewerCreateOptions) -> Result<Self, Error> { Self::new(ctx, texture_format, gaussians) }
+    /// From pods already packed by `wgpu-3dgs-core` (`GaussiansBuffer::<G>` contents), host or device resident.
+    pub fn from_pods(ctx: &'c Context, texture_format: i32, pods: &[u8]) -> Result<Self, Error> {
+        let n = pods.len() as u64 / unsafe { ffi::sb_pod_stride(G::SH, G::COV) } as u64;
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { ffi::sb_viewer_create(ctx.0, G::SH, G::COV, texture_format, pods.as_ptr().cast(), n, &mut raw) }, ctx.0)?;
+        Ok(Self { raw, ctx, _g: PhantomData })
+    }
+    /// `TryFrom<wgpu::Buffer>`: adopt a caller-owned device buffer after the size check (src/buffer/camera.rs:42-58 pattern).
+    pub unsafe fn from_device(ctx: &'c Context, texture_format: i32, d_pods: *const c_void, bytes: u64, n: u64) -> Result<Self, Error> {
+        let mut raw = std::ptr::null_mut();
+        check(ffi::sb_viewer_create_from_device(ctx.0, G::SH, G::COV, texture_format, d_pods, bytes, n, &mut raw), ctx.0)?;
+        Ok(Self { raw, ctx, _g: PhantomData })
+    }
+    pub fn update_camera_pose(&mut self, pos: glam::Vec3, yaw: f32, pitch: f32, z: std::ops::Range<f32>, vertical_fov: f32, size: glam::UVec2) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_update_camera(self.raw, pos.to_array().as_ptr(), yaw, pitch, z.start, z.end, vertical_fov, size.x, size.y) }, self.ctx.0)
+    }
+    pub fn update_model_transform_raw(&mut self, pos: glam::Vec3, rot: glam::Quat, scale: glam::Vec3) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_update_model_transform(self.raw, pos.to_array().as_ptr(), rot.to_array().as_ptr(), scale.to_array().as_ptr()) }, self.ctx.0)
+    }
+    /// `update_gaussian_transform(queue, size, display_mode, sh_deg, no_sh0, max_std_dev)` (src/lib.rs:237-254).
+    pub fn update_gaussian_transform(&mut self, size: f32, display_mode: i32, sh_deg: i32, no_sh0: bool, max_std_dev: f32) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_update_gaussian_transform(self.raw, size, display_mode, sh_deg, no_sh0 as i32, max_std_dev) }, self.ctx.0)
+    }
+    // ---- the public buffer fields of the reference Viewer
+    pub fn gaussians_buffer(&self) -> Result<DeviceBuffer<c_void>, Error> { let (mut p, mut b) = (std::ptr::null(), 0u64); check(unsafe { ffi::sb_viewer_gaussians_ptr(self.raw, &mut p, &mut b) }, self.ctx.0)?; Ok(DeviceBuffer { ptr: p, len: b }) }
+    pub fn indirect_args_buffer(&self) -> Result<DeviceBuffer<ffi::DrawIndirectArgs>, Error> { let mut p = std::ptr::null(); check(unsafe { ffi::sb_viewer_indirect_args_ptr(self.raw, &mut p) }, self.ctx.0)?; Ok(DeviceBuffer { ptr: p, len: 16 }) }
+    pub fn radix_sort_indirect_args_buffer(&self) -> Result<DeviceBuffer<ffi::DispatchIndirectArgs>, Error> { let mut p = std::ptr::null(); check(unsafe { ffi::sb_viewer_radix_sort_indirect_args_ptr(self.raw, &mut p) }, self.ctx.0)?; Ok(DeviceBuffer { ptr: p, len: 12 }) }
+    pub fn indirect_indices_buffer(&self) -> Result<DeviceBuffer<u32>, Error> { let (mut p, mut c) = (std::ptr::null(), 0u64); check(unsafe { ffi::sb_viewer_indirect_indices_ptr(self.raw, &mut p, &mut c) }, self.ctx.0)?; Ok(DeviceBuffer { ptr: p, len: c }) }
+    pub fn gaussians_depth_buffer(&self) -> Result<DeviceBuffer<f32>, Error> { let (mut p, mut b) = (std::ptr::null(), 0u64); check(unsafe { ffi::sb_viewer_gaussians_depth_ptr(self.raw, &mut p, &mut b) }, self.ctx.0)?; Ok(DeviceBuffer { ptr: p, len: b }) }
+    /// `viewer.selection_buffer` (editor `SelectionBuffer`: bit i%32 of word i/32) — enable the feature first.
+    pub fn selection_buffer(&self) -> Result<DeviceBuffer<u32>, Error> { let (mut p, mut n) = (std::ptr::null_mut(), 0u64); check(unsafe { ffi::sb_viewer_selection_ptr(self.raw, &mut p, &mut n) }, self.ctx.0)?; Ok(DeviceBuffer { ptr: p as *const u32, len: n }) }
+    pub fn enable_selection(&mut self, enabled: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_enable_selection(self.raw, enabled as i32) }, self.ctx.0) }
+    pub fn set_selection(&mut self, stream: Stream, words: &[u32]) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_selection(self.raw, stream.0, words.as_ptr(), words.len() as u64) }, self.ctx.0) }
+    pub fn read_selection(&self, stream: Stream, out: &mut [u32]) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_read_selection(self.raw, stream.0, out.as_mut_ptr(), out.len() as u64) }, self.ctx.0) }
+    /// `invert_selection_buffer.update(queue, invert)` (src/selection/buffer.rs:167-171); default = inverted.
+    pub fn set_invert_selection(&mut self, invert: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_invert_selection(self.raw, invert as i32) }, self.ctx.0) }
+    /// editor `NonDestructiveModifier<BasicSelectionModifier>` with an rgb override (tests/e2e/selection.rs:54-116).
+    pub fn apply_rgb_override(&mut self, stream: Stream, rgb: glam::Vec3, alpha: f32) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_apply_rgb_override(self.raw, stream.0, rgb.to_array().as_ptr(), alpha) }, self.ctx.0) }
+    pub fn restore_gaussians(&mut self, stream: Stream) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_restore_gaussians(self.raw, stream.0) }, self.ctx.0) }
+    // ---- frames beyond `render`
+    /// One frame straight to (pinned) host memory: camera pod in, pixels out.
+    pub fn render_to_host(&mut self, stream: Stream, camera: &CameraPod, pixels: &mut [u8]) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_render_to_host(self.raw, stream.0, camera, pixels.as_mut_ptr().cast(), pixels.len() as u64) }, self.ctx.0) }
+    /// A batch of camera views of the same scene (two in flight); `targets` are device frames.
+    pub fn render_batch(&mut self, stream: Stream, cameras: &[CameraPod], targets: &[Target]) -> Result<(), Error> {
+        assert_eq!(cameras.len(), targets.len());
+        check(unsafe { ffi::sb_viewer_render_batch(self.raw, stream.0, cameras.as_ptr(), targets.as_ptr(), std::ptr::null(), cameras.len() as u32) }, self.ctx.0)
+    }
+    pub fn render_batch_to_host(&mut self, stream: Stream, cameras: &[CameraPod], host_frames: &[*mut c_void]) -> Result<(), Error> {
+        assert_eq!(cameras.len(), host_frames.len());
+        check(unsafe { ffi::sb_viewer_render_batch(self.raw, stream.0, cameras.as_ptr(), std::ptr::null(), host_frames.as_ptr(), cameras.len() as u32) }, self.ctx.0)
+    }
+    /// `render_with_pass` after running the stages too (one call per frame inside a caller's pass).
+    pub fn render_in_pass(&self, stream: Stream, target: &Target, depth: Option<&ffi::DepthAttachment>, load: bool) -> Result<(), Error> {
+        check(unsafe { ffi::sb_viewer_render_with_pass(self.raw, stream.0, target, depth.map_or(std::ptr::null(), |d| d as *const _), load as i32, 1) }, self.ctx.0)
+    }
+    // ---- artefact read-back (synchronising; the reference's tests download the buffers the same way)
+    pub fn read_indirect_args(&self, stream: Stream) -> Result<(ffi::DrawIndirectArgs, ffi::DispatchIndirectArgs), Error> {
+        let (mut d, mut s) = (ffi::DrawIndirectArgs::default(), ffi::DispatchIndirectArgs::default());
+        check(unsafe { ffi::sb_viewer_read_indirect_args(self.raw, stream.0, &mut d, &mut s) }, self.ctx.0)?; Ok((d, s))
+    }
+    pub fn read_indices(&self, stream: Stream, out: &mut [u32]) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_read_indices(self.raw, stream.0, out.as_mut_ptr(), out.len() as u64) }, self.ctx.0) }
+    pub fn read_depth_keys(&self, stream: Stream, out: &mut [f32]) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_read_depth_keys(self.raw, stream.0, out.as_mut_ptr(), out.len() as u64) }, self.ctx.0) }
+    /// (visible, tile duplicates, overflowed) of the last frame.
+    pub fn read_frame_stats(&self, stream: Stream) -> Result<(u64, u64, bool), Error> { let (mut v, mut d, mut o) = (0u64, 0u64, 0u32); check(unsafe { ffi::sb_viewer_read_frame_stats(self.raw, stream.0, &mut v, &mut d, &mut o) }, self.ctx.0)?; Ok((v, d, o != 0)) }
+    pub fn read_tile_row_work(&self, stream: Stream, out: &mut [u64]) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_read_tile_row_work(self.raw, stream.0, out.as_mut_ptr(), out.len() as u32) }, self.ctx.0) }
+    // ---- knobs without a reference counterpart
+    pub fn raster_path_is_gather4(&self) -> Result<bool, Error> { let mut g = 0; check(unsafe { ffi::sb_viewer_raster_path(self.raw, &mut g) }, self.ctx.0)?; Ok(g != 0) }
+    pub fn set_strict_exp(&mut self, strict: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_strict_exp(self.raw, strict as i32) }, self.ctx.0) }
+    pub fn set_exact_cutoff(&mut self, enabled: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_exact_cutoff(self.raw, enabled as i32) }, self.ctx.0) }
+    /// Strip renders keep only the splats of their own strip (one frame sharded over GPUs).
+    pub fn set_strip_cull(&mut self, enabled: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_strip_cull(self.raw, enabled as i32) }, self.ctx.0) }
+    pub fn reserve_duplicates(&mut self, capacity: u64) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_reserve_duplicates(self.raw, capacity) }, self.ctx.0) }
+    pub fn set_stage_timing(&mut self, enabled: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_stage_timing(self.raw, enabled as i32) }, self.ctx.0) }
+    /// ms of preprocess, depth sort, tile count+emit, tile sort, gather, raster of the last frame.
+    pub fn read_stage_times(&self, stream: Stream) -> Result<[f32; 6], Error> { let mut ms = [0f32; 6]; check(unsafe { ffi::sb_viewer_read_stage_times(self.raw, stream.0, ms.as_mut_ptr()) }, self.ctx.0)?; Ok(ms) }
+    pub fn set_raster_counting(&mut self, enabled: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_raster_counting(self.raw, enabled as i32) }, self.ctx.0) }
+    pub fn read_raster_counters(&self, stream: Stream) -> Result<(u64, u64), Error> { let (mut a, mut e) = (0u64, 0u64); check(unsafe { ffi::sb_viewer_read_raster_counters(self.raw, stream.0, &mut a, &mut e) }, self.ctx.0)?; Ok((a, e)) }
+    pub fn read_raster_warp_counters(&self, stream: Stream) -> Result<(u64, u64), Error> { let (mut a, mut e) = (0u64, 0u64); check(unsafe { ffi::sb_viewer_read_raster_warp_counters(self.raw, stream.0, &mut a, &mut e) }, self.ctx.0)?; Ok((a, e)) }
+}
 impl<G: GaussianPod> Drop for Viewer<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_viewer_destroy(self.raw) } } }
+
+// ---- free functions of the boundary
+pub fn version() -> String { unsafe { CStr::from_ptr(ffi::sb_version()) }.to_string_lossy().into_owned() }
+pub fn status_string(status: i32) -> String { unsafe { CStr::from_ptr(ffi::sb_status_string(status)) }.to_string_lossy().into_owned() }
+/// `size_of::<G>()` of the pod format (tests/e2e/multi_model.rs:43-53 pins buffer size = count * size_of::<G>()).
+pub fn pod_stride<G: GaussianPod>() -> u32 { unsafe { ffi::sb_pod_stride(G::SH, G::COV) } }
+/// `GaussiansDepthBuffer` size for n Gaussians (src/buffer/depth.rs:5-21) and the padded key count (src/radix_sorter.rs:922-939).
+pub fn keys_buffer_size_bytes(n: u32) -> u64 { unsafe { ffi::sb_keys_buffer_size_bytes(n) } }
+pub fn padded_key_count(n: u32) -> u32 { unsafe { ffi::sb_padded_key_count(n) } }
+/// `Gaussians::read_from_file(path, GaussiansSource::Ply)` (examples/simple.rs:157-160).
+pub fn read_ply(path: &std::path::Path) -> Result<Vec<Gaussian>, Error> {
+    let c = std::ffi::CString::new(path.to_string_lossy().as_bytes()).map_err(|e| Error::InvalidArg(e.to_string()))?;
+    let (mut p, mut n) = (std::ptr::null_mut::<Gaussian>(), 0u64);
+    check(unsafe { ffi::sb_read_ply(c.as_ptr(), &mut p, &mut n) }, std::ptr::null())?;
+    let v = unsafe { std::slice::from_raw_parts(p, n as usize) }.to_vec();
+    unsafe { ffi::sb_free(p.cast()) };
+    Ok(v)
+}
+impl ModelTransformPod {
+    pub fn new(pos: glam::Vec3, rot: glam::Quat, scale: glam::Vec3) -> Self { let mut o = std::mem::MaybeUninit::<Self>::uninit(); unsafe { ffi::sb_model_transform_pod(pos.to_array().as_ptr(), rot.to_array().as_ptr(), scale.to_array().as_ptr(), o.as_mut_ptr()); o.assume_init() } }
+}
+impl GaussianTransformPod {
+    pub fn new(size: f32, display_mode: i32, sh_deg: i32, no_sh0: bool, max_std_dev: f32) -> Self { let mut o = std::mem::MaybeUninit::<Self>::uninit(); unsafe { ffi::sb_gaussian_transform_pod(size, display_mode, sh_deg, no_sh0 as i32, max_std_dev, o.as_mut_ptr()); o.assume_init() } }
+}
+impl CameraPod {
+    /// The reference `Camera` (pos, yaw, pitch, z range, vertical fov) straight to a pod (src/camera.rs:71-93 + src/buffer/camera.rs:72-80).
+    pub fn from_pose(pos: glam::Vec3, yaw: f32, pitch: f32, z: std::ops::Range<f32>, vertical_fov: f32, size: glam::UVec2) -> Self { let mut o = std::mem::MaybeUninit::<Self>::uninit(); unsafe { ffi::sb_camera_pod(pos.to_array().as_ptr(), yaw, pitch, z.start, z.end, vertical_fov, size.x, size.y, o.as_mut_ptr()); o.assume_init() } }
+}
+impl Context {
+    /// `device.limits().max_storage_buffer_binding_size` of the reference's size check (src/preprocessor.rs:239-246).
+    pub fn set_model_size_limit(&mut self, bytes: u64) -> Result<(), Error> { check(unsafe { ffi::sb_ctx_set_model_size_limit(self.0, bytes) }, self.0) }
+    /// Measured FP32-issue (lane-ops/s, FMA = 1) and shared-memory (bytes/s) peaks of this device.
+    pub fn probe_peaks(&self, stream: Stream) -> Result<(f64, f64), Error> { let (mut a, mut b) = (0f64, 0f64); check(unsafe { ffi::sb_probe_peaks(self.0, stream.0, &mut a, &mut b) }, self.0)?; Ok((a, b)) }
+}
+
+/// A frame other GPUs of the node render their strips into (CUDA IPC over NVLink): the owner creates and publishes `handle`.
+pub struct SharedFrame<'c> { pub ptr: *mut c_void, pub handle: [u8; 64], owner: bool, ctx: &'c Context }
+impl<'c> SharedFrame<'c> {
+    pub fn create(ctx: &'c Context, bytes: u64) -> Result<Self, Error> { let (mut p, mut h) = (std::ptr::null_mut(), [0u8; 64]); check(unsafe { ffi::sb_shared_frame_create(ctx.0, bytes, &mut p, h.as_mut_ptr()) }, ctx.0)?; Ok(Self { ptr: p, handle: h, owner: true, ctx }) }
+    pub fn open(ctx: &'c Context, handle: [u8; 64]) -> Result<Self, Error> { let mut p = std::ptr::null_mut(); check(unsafe { ffi::sb_shared_frame_open(ctx.0, handle.as_ptr(), &mut p) }, ctx.0)?; Ok(Self { ptr: p, handle, owner: false, ctx }) }
+}
+impl Drop for SharedFrame<'_> { fn drop(&mut self) { unsafe { if self.owner { ffi::sb_shared_frame_destroy(self.ctx.0, self.ptr) } else { ffi::sb_shared_frame_close(self.ctx.0, self.ptr) } }; } }
 
 /// `MultiModelViewer<G, K>` (src/multi_model.rs:291-531); keys are hashed to u64 by the caller.
 pub struct MultiModelViewer<'c, G: GaussianPod = DefaultGaussianPod> { raw: *mut ffi::SbMultiModelViewer, ctx: &'c Context, _g: PhantomData<G> }
@@ -210,6 +299,27 @@ impl<'c, G: GaussianPod> MultiModelViewer<'c, G> {
     pub fn update_gaussian_transform_with_pod(&mut self, pod: &GaussianTransformPod) -> Result<(), Error> { check(unsafe { ffi::sb_mm_update_gaussian_transform_with_pod(self.raw, pod) }, self.ctx.0) }
     /// `render(encoder, view, keys)` → `Err(ModelNotFound)` like the reference.
     pub fn render(&self, stream: Stream, target: &Target, keys: &[u64]) -> Result<(), Error> { check(unsafe { ffi::sb_mm_render(self.raw, stream.0, target, keys.as_ptr(), keys.len() as u32) }, self.ctx.0) }
+}
+impl<'c, G: GaussianPod> MultiModelViewer<'c, G> {
+    /// `new_with_options(depth_stencil)` (src/multi_model.rs:319-337): the state is supplied per pass (`render_with_pass`).
+    pub fn new_with_options(ctx: &'c Context, texture_format: i32, _options: ViewerCreateOptions) -> Result<Self, Error> { Self::new(ctx, texture_format) }
+    /// `insert_model_with(device, key, gaussians_buffer)` (src/multi_model.rs:366): adopt device-resident pods.
+    pub unsafe fn insert_model_with(&mut self, key: u64, d_pods: *const c_void, bytes: u64, n: u64) -> Result<bool, Error> { let mut r = 0; check(ffi::sb_mm_insert_model_from_device(self.raw, key, d_pods, bytes, n, &mut r), self.ctx.0)?; Ok(r != 0) }
+    pub fn insert_model_from_gaussians(&mut self, key: u64, gaussians: &[Gaussian]) -> Result<bool, Error> { let mut r = 0; check(unsafe { ffi::sb_mm_insert_model_from_gaussians(self.raw, key, gaussians.as_ptr(), gaussians.len() as u64, &mut r) }, self.ctx.0)?; Ok(r != 0) }
+    /// Non-pod updates (src/multi_model.rs:398-466).
+    pub fn update_camera(&mut self, pos: glam::Vec3, yaw: f32, pitch: f32, z: std::ops::Range<f32>, vertical_fov: f32, size: glam::UVec2) -> Result<(), Error> { check(unsafe { ffi::sb_mm_update_camera(self.raw, pos.to_array().as_ptr(), yaw, pitch, z.start, z.end, vertical_fov, size.x, size.y) }, self.ctx.0) }
+    pub fn update_model_transform(&mut self, key: u64, pos: glam::Vec3, rot: glam::Quat, scale: glam::Vec3) -> Result<(), Error> { check(unsafe { ffi::sb_mm_update_model_transform(self.raw, key, pos.to_array().as_ptr(), rot.to_array().as_ptr(), scale.to_array().as_ptr()) }, self.ctx.0) }
+    pub fn update_gaussian_transform(&mut self, size: f32, display_mode: i32, sh_deg: i32, no_sh0: bool, max_std_dev: f32) -> Result<(), Error> { check(unsafe { ffi::sb_mm_update_gaussian_transform(self.raw, size, display_mode, sh_deg, no_sh0 as i32, max_std_dev) }, self.ctx.0) }
+    // per-model selection (each model has its own SelectionBuffer in the reference's multi-model example)
+    pub fn enable_selection(&mut self, key: u64, enabled: bool, invert: bool) -> Result<(), Error> { check(unsafe { ffi::sb_mm_enable_selection(self.raw, key, enabled as i32, invert as i32) }, self.ctx.0) }
+    pub fn set_selection(&mut self, key: u64, stream: Stream, words: &[u32], invert: bool) -> Result<(), Error> { check(unsafe { ffi::sb_mm_set_selection(self.raw, key, stream.0, words.as_ptr(), words.len() as u64, invert as i32) }, self.ctx.0) }
+    pub fn select_rect(&mut self, key: u64, stream: Stream, min: glam::Vec2, max: glam::Vec2) -> Result<(), Error> { check(unsafe { ffi::sb_mm_select_rect(self.raw, key, stream.0, min.x, min.y, max.x, max.y) }, self.ctx.0) }
+    pub fn select_brush(&mut self, key: u64, stream: Stream, stroke: &[glam::Vec2], radius: f32, accumulate: bool) -> Result<(), Error> { check(unsafe { ffi::sb_mm_select_brush(self.raw, key, stream.0, stroke.as_ptr().cast(), stroke.len() as u32, radius, accumulate as i32) }, self.ctx.0) }
+    pub fn read_selection(&self, key: u64, stream: Stream, out: &mut [u32]) -> Result<(), Error> { check(unsafe { ffi::sb_mm_read_selection(self.raw, key, stream.0, out.as_mut_ptr(), out.len() as u64) }, self.ctx.0) }
+    /// `render_with_pass`-style multi-model frame: composite over the target, depth-tested against the pass's attachment.
+    pub fn render_with_pass(&self, stream: Stream, target: &Target, depth: Option<&ffi::DepthAttachment>, load: bool, keys: &[u64]) -> Result<(), Error> { check(unsafe { ffi::sb_mm_render_with_pass(self.raw, stream.0, target, depth.map_or(std::ptr::null(), |d| d as *const _), load as i32, keys.as_ptr(), keys.len() as u32) }, self.ctx.0) }
+    /// Sorted indices of one model after a frame, with its `IndirectArgsBuffer` contents ({6, V, 0, 0}).
+    pub fn read_model_indices(&self, key: u64, stream: Stream, out: &mut [u32]) -> Result<ffi::DrawIndirectArgs, Error> { let mut d = ffi::DrawIndirectArgs::default(); check(unsafe { ffi::sb_mm_read_model_indices(self.raw, key, stream.0, out.as_mut_ptr(), out.len() as u64, &mut d) }, self.ctx.0)?; Ok(d) }
 }
 impl<G: GaussianPod> Drop for MultiModelViewer<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_mm_destroy(self.raw) } } }
 
@@ -240,4 +350,5 @@ impl<'c, G: GaussianPod> Renderer<'c, G> {
     pub fn render(&self, stream: Stream, target: &Target, bind_group: &ffi::RendererBindGroup, d_indirect_args: *const ffi::DrawIndirectArgs) -> Result<(), Error> { check(unsafe { ffi::sb_renderer_render(self.raw, stream.0, bind_group, target, d_indirect_args, std::ptr::null(), 0) }, self.ctx.0) }
     pub fn render_with_pass(&self, stream: Stream, target: &Target, depth: Option<&ffi::DepthAttachment>, bind_group: &ffi::RendererBindGroup, d_indirect_args: *const ffi::DrawIndirectArgs) -> Result<(), Error> { check(unsafe { ffi::sb_renderer_render(self.raw, stream.0, bind_group, target, d_indirect_args, depth.map_or(std::ptr::null(), |d| d as *const _), 1) }, self.ctx.0) }
 }
+impl<G: GaussianPod> Renderer<'_, G> { pub fn set_strict_exp(&mut self, strict: bool) -> Result<(), Error> { check(unsafe { ffi::sb_renderer_set_strict_exp(self.raw, strict as i32) }, self.ctx.0) } }
 impl<G: GaussianPod> Drop for Renderer<'_, G> { fn drop(&mut self) { unsafe { ffi::sb_renderer_destroy(self.raw) } } }
