@@ -49,7 +49,11 @@ enum { SB_COV_SINGLE = 0, SB_COV_HALF = 1, SB_COV_ROT_SCALE = 2 };
 /* core::GaussianDisplayMode */
 enum { SB_MODE_SPLAT = 0, SB_MODE_ELLIPSE = 1, SB_MODE_POINT = 2 };
 /* wgpu::TextureFormat subset accepted as render target (src/renderer.rs:120-155) */
-enum { SB_TARGET_RGBA8_UNORM = 0, SB_TARGET_BGRA8_UNORM = 1, SB_TARGET_RGBA16_FLOAT = 2, SB_TARGET_RGBA32_FLOAT = 3 };
+/* The reference renders into any wgpu::TextureFormat (src/renderer.rs:120-155).  The two *_SRGB formats store sRGB codes:
+ * every blend decodes the destination to linear, blends, and encodes the result (as fixed-function blending does on an sRGB
+ * attachment); Rgba8UnormSrgb is what the reference's own doctests create (src/selection/mod.rs:46). */
+enum { SB_TARGET_RGBA8_UNORM = 0, SB_TARGET_BGRA8_UNORM = 1, SB_TARGET_RGBA16_FLOAT = 2, SB_TARGET_RGBA32_FLOAT = 3,
+       SB_TARGET_RGBA8_UNORM_SRGB = 4, SB_TARGET_BGRA8_UNORM_SRGB = 5 };
 
 /* core::Gaussian (tests/e2e/viewer.rs:42-48) — the un-packed source splat. */
 typedef struct {

@@ -22,7 +22,7 @@ assert GAUSSIAN_DTYPE.itemsize == 224
 SH_SINGLE, SH_HALF, SH_NORM8, SH_NONE = 0, 1, 2, 3
 COV_SINGLE, COV_HALF, COV_ROT_SCALE = 0, 1, 2
 MODE_SPLAT, MODE_ELLIPSE, MODE_POINT = 0, 1, 2
-TARGET_RGBA8, TARGET_BGRA8, TARGET_RGBA16F, TARGET_RGBA32F = 0, 1, 2, 3
+TARGET_RGBA8, TARGET_BGRA8, TARGET_RGBA16F, TARGET_RGBA32F, TARGET_RGBA8_SRGB, TARGET_BGRA8_SRGB = 0, 1, 2, 3, 4, 5
 
 
 class CameraPod(C.Structure):
@@ -60,7 +60,8 @@ def build(force: bool = False) -> str:
     """Compile the C restatement (gcc) into oracle/_build/."""
     src = os.path.join(_HERE, "splat_oracle.c")
     hdr = os.path.join(_HERE, "splat_oracle.h")
-    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    tab = os.path.join(_HERE, "srgb_tables.h")
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(tab)):
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     subprocess.check_call(
@@ -204,7 +205,8 @@ def render(models, cam: CameraPod, gt: GaussianTransformPod, target_format=TARGE
     w, h = int(cam.size[0]), int(cam.size[1])
     rows = h - row0 if rows is None else rows
     arr = (Model * len(models))(*[m.c for m in models])
-    dt = {TARGET_RGBA8: np.uint8, TARGET_BGRA8: np.uint8, TARGET_RGBA16F: np.uint16, TARGET_RGBA32F: np.float32}[target_format]
+    dt = {TARGET_RGBA8: np.uint8, TARGET_BGRA8: np.uint8, TARGET_RGBA16F: np.uint16, TARGET_RGBA32F: np.float32,
+          TARGET_RGBA8_SRGB: np.uint8, TARGET_BGRA8_SRGB: np.uint8}[target_format]
     out = np.zeros((rows, w, 4), dtype=dt)
     st = Stats()
     lib().so_render(arr, len(models), C.byref(cam), C.byref(gt), target_format, int(strict_exp), row0, rows,

@@ -619,6 +619,24 @@ float so_exp_neg_poly(float x) {
     return p;
 }
 
+/* `*Srgb` targets (the reference accepts any TextureFormat: src/renderer.rs:120-155; its doctests use Rgba8UnormSrgb,
+ * src/selection/mod.rs:46): the attachment stores sRGB codes; ALPHA_BLENDING decodes the destination to linear, blends, and
+ * encodes the result back (Vulkan 1.3 §29.1 / §16 "sRGB"), once per blend.  Tables: oracle/srgb_tables.h (generated). */
+#include "srgb_tables.h"
+static float srgb_decode(int code) { float f; memcpy(&f, &SO_SRGB_DECODE_BITS[code], 4); return f; }
+static int srgb_encode(float x) { /* number of thresholds 1..255 that are <= x */
+    int lo = 0, hi = 255;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) / 2;
+        float t; memcpy(&t, &SO_SRGB_THRESHOLD_BITS[mid], 4);
+        if (x >= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+static int fmt_is_srgb(int f) { return f == SO_TARGET_RGBA8_SRGB || f == SO_TARGET_BGRA8_SRGB; }
+static int fmt_is_unorm(int f) { return f == SO_TARGET_RGBA8 || f == SO_TARGET_BGRA8 || fmt_is_srgb(f); } /* 8-bit codes in memory */
+static int fmt_is_bgra(int f) { return f == SO_TARGET_BGRA8 || f == SO_TARGET_BGRA8_SRGB; }
+
 static int depth_passes(int compare, float z, float d) {
     switch (compare) {
         case 1: return 0;
@@ -688,7 +706,11 @@ static void raster_band(const SoSplat* sp, uint32_t count, const Uniforms* u, in
                 }
                 float om = 1.0f - alpha;
                 float* d = row + (size_t)px * 4;
-                if (is_unorm) {
+                if (is_unorm == 2) {
+                    /* sRGB attachment: state = the stored code; decode, blend in linear with the source clamped to [0,1], encode */
+                    for (int c = 0; c < 3; c++)
+                        d[c] = (float)srgb_encode(fmaf(srgb_decode((int)d[c]), om, fminf(cf[c], 1.0f) * alpha));
+                } else if (is_unorm) {
                     /* ALPHA_BLENDING into unorm8 (renderer.rs:296-300): the target is
                        re-quantised after every blend; state kept in 0..255 units. */
                     for (int c = 0; c < 3; c++)
@@ -726,7 +748,7 @@ void so_render(const SoModel* models, uint32_t n_models, const SoCameraPod* cam,
     uint32_t width = (uint32_t)cam->size[0], height = (uint32_t)cam->size[1];
     if (row0 > height) row0 = height;
     if (rows > height - row0) rows = height - row0;
-    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_unorm = fmt_is_unorm(target_format) ? (fmt_is_srgb(target_format) ? 2 : 1) : 0;
     int is_f16 = target_format == SO_TARGET_RGBA16F;
     if (n_threads <= 0) n_threads = so_max_threads();
     /* clear to BLACK = (0,0,0,1): renderer.rs:171-177 */
@@ -761,7 +783,7 @@ void so_render(const SoModel* models, uint32_t n_models, const SoCameraPod* cam,
     size_t npx = (size_t)rows * width;
     if (is_unorm) {
         uint8_t* out = (uint8_t*)target;
-        int ri = target_format == SO_TARGET_BGRA8 ? 2 : 0, bi = 2 - ri;
+        int ri = fmt_is_bgra(target_format) ? 2 : 0, bi = 2 - ri;
         for (size_t i = 0; i < npx; i++) {
             out[i * 4 + ri] = (uint8_t)acc[i * 4 + 0];
             out[i * 4 + 1] = (uint8_t)acc[i * 4 + 1];
@@ -825,9 +847,9 @@ void so_select_brush(const SoModel* model, const SoCameraPod* cam, const float* 
 
 /* target <-> the f32 accumulator the blend runs in (unorm8: 0..255 units) */
 static float* acc_load(int target_format, int load, const void* target, size_t npx) {
-    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_unorm = fmt_is_unorm(target_format) ? (fmt_is_srgb(target_format) ? 2 : 1) : 0;
     int is_f16 = target_format == SO_TARGET_RGBA16F;
-    int ri = target_format == SO_TARGET_BGRA8 ? 2 : 0, bi = 2 - ri;
+    int ri = fmt_is_bgra(target_format) ? 2 : 0, bi = 2 - ri;
     float* acc = (float*)malloc((npx ? npx : 1) * 4 * sizeof(float));
     for (size_t i = 0; i < npx; i++) {
         if (!load) {
@@ -846,9 +868,9 @@ static float* acc_load(int target_format, int load, const void* target, size_t n
 }
 
 static void acc_store(int target_format, const float* acc, void* target, size_t npx) {
-    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_unorm = fmt_is_unorm(target_format) ? (fmt_is_srgb(target_format) ? 2 : 1) : 0;
     int is_f16 = target_format == SO_TARGET_RGBA16F;
-    int ri = target_format == SO_TARGET_BGRA8 ? 2 : 0, bi = 2 - ri;
+    int ri = fmt_is_bgra(target_format) ? 2 : 0, bi = 2 - ri;
     if (is_unorm) {
         uint8_t* out = (uint8_t*)target;
         for (size_t i = 0; i < npx; i++) {
@@ -870,7 +892,7 @@ static void draw_instances(const SoModel* model, const SoCameraPod* cam, const S
                            const uint32_t* indices, uint32_t count, int clip_quads, int target_format, int strict_exp,
                            float* acc, float* depth, int depth_compare, int depth_write, int n_threads) {
     uint32_t width = (uint32_t)cam->size[0], height = (uint32_t)cam->size[1];
-    int is_unorm = target_format == SO_TARGET_RGBA8 || target_format == SO_TARGET_BGRA8;
+    int is_unorm = fmt_is_unorm(target_format) ? (fmt_is_srgb(target_format) ? 2 : 1) : 0;
     int is_f16 = target_format == SO_TARGET_RGBA16F;
     if (n_threads <= 0) n_threads = so_max_threads();
     SoSplat* sp = (SoSplat*)malloc((size_t)(count ? count : 1) * sizeof(SoSplat));

@@ -50,7 +50,8 @@ typedef struct {
 enum { SO_SH_SINGLE = 0, SO_SH_HALF = 1, SO_SH_NORM8 = 2, SO_SH_NONE = 3 };
 enum { SO_COV_SINGLE = 0, SO_COV_HALF = 1, SO_COV_ROT_SCALE = 2 };
 enum { SO_MODE_SPLAT = 0, SO_MODE_ELLIPSE = 1, SO_MODE_POINT = 2 };
-enum { SO_TARGET_RGBA8 = 0, SO_TARGET_BGRA8 = 1, SO_TARGET_RGBA16F = 2, SO_TARGET_RGBA32F = 3 };
+enum { SO_TARGET_RGBA8 = 0, SO_TARGET_BGRA8 = 1, SO_TARGET_RGBA16F = 2, SO_TARGET_RGBA32F = 3, SO_TARGET_RGBA8_SRGB = 4,
+       SO_TARGET_BGRA8_SRGB = 5 };
 
 /* CameraPod: /root/reference/src/buffer/camera.rs:63-80 — 144 bytes */
 typedef struct {

@@ -36,7 +36,7 @@ def run_frame(sb, ob, ctx, pods, n, cam_args, w, h, sh_fmt=0, cov_fmt=0, mode=0,
         v.enable_selection(True)
         v.set_selection(selection)
         v.set_invert_selection(bool(invert))
-    bpp = {0: (torch.uint8, 4), 1: (torch.uint8, 4), 2: (torch.float16, 4), 3: (torch.float32, 4)}[target_format]
+    bpp = {0: (torch.uint8, 4), 1: (torch.uint8, 4), 2: (torch.float16, 4), 3: (torch.float32, 4), 4: (torch.uint8, 4), 5: (torch.uint8, 4)}[target_format]
     target = torch.zeros((h, w, 4), dtype=bpp[0], device="cuda")
     v.render(target, w, h)
     torch.cuda.synchronize()
@@ -118,7 +118,7 @@ def test_pod_formats(sb, ob, ctx, sh_fmt, cov_fmt):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("target_format", [0, 1, 2, 3])
+@pytest.mark.parametrize("target_format", [0, 1, 2, 3, 4, 5])
 def test_modes_and_targets(sb, ob, ctx, mode, target_format):
     n = 8000
     g, pods = make_scene(sb, ob, n, 40 + mode)
@@ -128,8 +128,47 @@ def test_modes_and_targets(sb, ob, ctx, mode, target_format):
     if target_format in (0, 1):
         assert d <= 1, f"unorm8 max-abs {d}/255"       # tolerance 2/255 (north star); strict exp => expect 0-1
         assert np.all(r["img"][..., 3] == 255)
+    elif target_format in (4, 5):
+        # *Srgb attachments: decode - blend - encode per blend through the shared exact tables: strict exp => identical codes
+        assert d == 0, f"sRGB max-abs {d}/255"
+        assert np.all(r["img"][..., 3] == 255) and r["img"][..., :3].max() > 0
     else:
         assert d <= 1e-3, f"float target max-abs {d}"  # north-star tolerance for float targets
+
+
+def test_srgb_target_semantics(sb, ob, ctx):
+    """An sRGB attachment is not a relabelled unorm8 one: the same scene rendered to Rgba8UnormSrgb holds the sRGB ENCODING of
+    (roughly) what the linear target holds, fast-exp frames stay within tolerance of the oracle, bgra swizzles, and compositing
+    over existing content (LoadOp::Load) decodes what it finds."""
+    torch = _torch()
+    n, w, h = 12000, 512, 288
+    g, pods = make_scene(sb, ob, n, 83)
+    lin = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, w, h, target_format=0, strict=False)
+    srgb = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, w, h, target_format=4, strict=False)
+    bgra = run_frame(sb, ob, ctx, pods, n, sb.scenes.CAMERA_OUTSIDE, w, h, target_format=5, strict=False)
+    assert img_diff(srgb) <= 2 and img_diff(bgra) <= 2
+    assert np.array_equal(srgb["img"][..., [2, 1, 0, 3]], bgra["img"])
+    x = lin["img"][..., :3].astype(np.float64) / 255.0
+    enc = np.where(x <= 0.0031308, 12.92 * x, 1.055 * np.power(x, 1 / 2.4) - 0.055) * 255.0
+    lit = lin["img"][..., :3] > 24  # away from black, where one linear code spans many sRGB codes
+    assert np.abs(enc - srgb["img"][..., :3].astype(np.float64))[lit].mean() < 6.0
+    assert srgb["img"][..., :3].astype(np.int64).sum() > 1.5 * lin["img"][..., :3].astype(np.int64).sum()
+    # LoadOp::Load over a mid-grey sRGB background
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v = sb.Viewer(ctx, pods, n, target_format=4)
+    v.set_strict_exp(True)
+    v.update_camera_with_pod(sb.camera_pod(pos, yaw, pitch, w, h))
+    bg = np.zeros((h, w, 4), dtype=np.uint8)
+    bg[..., 0], bg[..., 1], bg[..., 2], bg[..., 3] = 188, 128, 64, 255
+    target = torch.from_numpy(bg.copy()).cuda()
+    v.render_with_pass(target, w, h, load_target=True)
+    torch.cuda.synchronize()
+    got = target.cpu().numpy()
+    v.close()
+    om = ob.OracleModel(pods, n)
+    exp = ob.render_pass(om, ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(), bg.copy(), True, target_format=4, strict_exp=True)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(got[0, 0], bg[0, 0]) or got[..., :3].max() > 0  # untouched pixels keep their codes
 
 
 @pytest.mark.parametrize("sh_deg,no_sh0,std_dev,size", [(0, False, 3.0, 1.0), (1, False, 2.0, 1.0), (2, True, 3.0, 0.5),

@@ -264,3 +264,58 @@ def test_alpha_cutoff_identity_bound():
     a_big = f32(0.0021)
     x2 = (d[:, 0, 0] * float(f32(1.0) - a_big) + float(f32(255.0) * a_big)).astype(f32)
     assert (np.rint(x2) != d[:, 0, 0]).any()
+
+
+def test_srgb_tables_and_oracle_srgb_target(ob, sb):
+    """The shared sRGB tables: every code decodes inside its own encode interval (a blend with alpha = 0 is the identity), both
+    generated copies are identical and up to date, thresholds increase; and the oracle's Rgba8UnormSrgb frame agrees with a
+    float64 decode-blend-encode restatement of the same composite."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    a = open(os.path.join(root, "oracle", "srgb_tables.h")).read()
+    b = open(os.path.join(root, "wgpu-3dgs-viewer_b200", "csrc", "sb_srgb_tables.h")).read()
+    bits = lambda txt: [int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", txt)]
+    assert bits(a) == bits(b) and len(bits(a)) == 512
+    dec = np.array(bits(a)[:256], dtype=np.uint32).view(np.float32)
+    thr = np.array(bits(a)[256:], dtype=np.uint32).view(np.float32)
+    assert np.all(np.diff(thr.astype(np.float64)) > 0) and dec[0] == 0.0 and dec[255] == 1.0
+    assert np.all(thr <= dec) and np.all(dec[:-1] < thr[1:])
+    x = np.arange(256) / 255.0
+    ref = np.where(x <= 0.04045, x / 12.92, ((x + 0.055) / 1.055) ** 2.4)
+    assert np.allclose(dec, ref, rtol=1e-6, atol=1e-9)
+
+    n, w, h = 4000, 320, 180
+    g = sb.scenes.synthetic_gaussians(n, 5)
+    pods = ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE))
+    m = ob.OracleModel(pods, n)
+    cam = ob.camera_pod(*sb.scenes.CAMERA_OUTSIDE, w, h)
+    gt = ob.gaussian_transform_pod()
+    img, _ = ob.render(m, cam, gt, ob.TARGET_RGBA8_SRGB)
+    imgb, _ = ob.render(m, cam, gt, ob.TARGET_BGRA8_SRGB)
+    assert np.array_equal(img[..., [2, 1, 0, 3]], imgb)
+    # float64 restatement: the oracle's splat records composited with decode -> blend -> encode per blend
+    p = ob.preprocess(m, cam, gt)
+    _, idx = ob.radix_sort(p["keys"][: p["count"]].view(np.uint32), p["indices"][: p["count"]])
+    sp = ob.project(m, cam, gt, idx)
+    acc = np.zeros((h, w, 3))
+    eotf = lambda c: np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    oetf = lambda l: np.where(l <= 0.0031308, 12.92 * l, 1.055 * np.power(np.maximum(l, 0), 1 / 2.4) - 0.055)
+    for s_ in sp:
+        if not s_["valid"]:
+            continue
+        x0, x1 = int(max(np.floor(s_["cx"] - s_["ext_x"] - 1), 0)), int(min(np.ceil(s_["cx"] + s_["ext_x"] + 1), w - 1))
+        y0, y1 = int(max(np.floor(s_["cy"] - s_["ext_y"] - 1), 0)), int(min(np.ceil(s_["cy"] + s_["ext_y"] + 1), h - 1))
+        if x1 < x0 or y1 < y0:
+            continue
+        dx = (np.arange(x0, x1 + 1) + 0.5) - float(s_["cx"])
+        dy = ((np.arange(y0, y1 + 1) + 0.5) - float(s_["cy"]))[:, None]
+        qx, qy = dx * float(s_["ax"]) + dy * float(s_["ay"]), dx * float(s_["bx"]) + dy * float(s_["by"])
+        r2 = qx * qx + qy * qy
+        alpha = np.where(r2 <= 9.0, float(s_["a"]) * np.exp(-r2), 0.0)[..., None]
+        src = np.minimum(np.array([s_["r"], s_["g"], s_["b"]], dtype=np.float64), 1.0)
+        win = acc[y0:y1 + 1, x0:x1 + 1]
+        win[...] = np.rint(np.clip(oetf(eotf(win / 255.0) * (1 - alpha) + src * alpha), 0, 1) * 255.0)
+    d = np.abs(acc - img[..., :3].astype(np.float64))
+    assert d.max() <= 2 and np.count_nonzero(d) < 0.01 * d.size

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <string>
@@ -56,8 +57,9 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
-bool is_unorm(int fmt) { return fmt == SB_TARGET_RGBA8_UNORM || fmt == SB_TARGET_BGRA8_UNORM; }
-uint32_t bytes_per_pixel(int fmt) { return is_unorm(fmt) ? 4u : fmt == SB_TARGET_RGBA16_FLOAT ? 8u : 16u; }
+bool is_unorm(int fmt) { return fmt == SB_TARGET_RGBA8_UNORM || fmt == SB_TARGET_BGRA8_UNORM; }  // linear 8-bit
+bool is_srgb(int fmt) { return fmt == SB_TARGET_RGBA8_UNORM_SRGB || fmt == SB_TARGET_BGRA8_UNORM_SRGB; }
+uint32_t bytes_per_pixel(int fmt) { return (is_unorm(fmt) || is_srgb(fmt)) ? 4u : fmt == SB_TARGET_RGBA16_FLOAT ? 8u : 16u; }
 
 // ---- strict host maths for the per-frame uniforms (this file is compiled with
 // -Xcompiler -ffp-contract=off): the same individually rounded operations, in the same order,
@@ -104,6 +106,7 @@ sb::Uniforms make_uniforms(const SbCameraPod& cam, const SbModelTransformPod& mt
     u.std_dev = (float)gt.max_std_dev / 255.0f * 3.0f;
     u.gsize = gt.size;
     u.color_scale = is_unorm(target_format) ? 255.0f : 1.0f;
+    u.color_max = is_unorm(target_format) ? 255.0f : is_srgb(target_format) ? 1.0f : std::numeric_limits<float>::infinity();
     // exact alpha cut-off: only where a blend below the threshold is provably the identity (sb_common.cuh)
     u.cut_k = (alpha_cut && is_unorm(target_format) && gt.display_mode == SB_MODE_SPLAT) ? 1.0f / sb::kAlphaCut : 0.0f;
     u.mode = gt.display_mode;
@@ -291,7 +294,7 @@ SbStatus viewer_reserve(SbViewer* v, uint64_t cap) {
 SbStatus viewer_new(SbContext* ctx, int sh_fmt, int cov_fmt, int target_format, uint64_t n, SbViewer** out) {
     if (!ctx || !out) return fail(ctx, SB_ERR_INVALID_ARG, "null context/out");
     if (sb_pod_stride(sh_fmt, cov_fmt) == 0) return fail(ctx, SB_ERR_INVALID_ARG, "unknown pod format");
-    if (target_format < 0 || target_format > SB_TARGET_RGBA32_FLOAT) return fail(ctx, SB_ERR_INVALID_ARG, "unknown target format");
+    if (target_format < 0 || target_format > SB_TARGET_BGRA8_UNORM_SRGB) return fail(ctx, SB_ERR_INVALID_ARG, "unknown target format");
     if (n > 0x3fffffffull) return fail(ctx, SB_ERR_MODEL_TOO_LARGE, "more than 2^30 gaussians");
     const uint64_t model_size = n * sb_pod_stride(sh_fmt, cov_fmt);
     if (model_size > ctx->model_size_limit) {  // src/preprocessor.rs:239-246

@@ -27,7 +27,8 @@ struct Uniforms {
     float cam_pos[3];
     float std_dev;     // gaussian_transform_max_std_dev
     float gsize;       // gaussian_transform.size
-    float color_scale; // 255 for unorm8 targets, 1 for float targets
+    float color_scale; // 255 for unorm8 targets, 1 for float and sRGB targets
+    float color_max;   // source-colour clamp after scaling: 255 (unorm8), 1 (sRGB: fixed-point attachment), +inf (float)
     float cut_k;       // exact alpha cut-off (splat mode on unorm8 targets): 1 / kAlphaCut, 0 = off
     uint32_t mode, sh_deg, no_sh0;
     uint32_t width, height;

@@ -408,10 +408,9 @@ __device__ __forceinline__ void emit_splat(const PreParams& p, const Uniforms& u
     // Fixed-point colour attachments clamp the SOURCE colour to [0,1] before the blend equation
     // (Vulkan 1.3 spec 29.1 "Blending"; the reference renders to Rgba8Unorm, src/renderer.rs:296-300):
     // done here once per splat, which also makes the post-blend clamp redundant (d, c <= 255, alpha <= 1).
-    const float cmax = u.color_scale == 255.0f ? 255.0f : __int_as_float(0x7f800000);
-    const float cr = fminf(smul(rgb[0], u.color_scale), cmax);
-    const float cg = fminf(smul(rgb[1], u.color_scale), cmax);
-    const float cb = fminf(smul(rgb[2], u.color_scale), cmax);
+    const float cr = fminf(smul(rgb[0], u.color_scale), u.color_max);
+    const float cg = fminf(smul(rgb[1], u.color_scale), u.color_max);
+    const float cb = fminf(smul(rgb[2], u.color_scale), u.color_max);
     float4* dst = reinterpret_cast<float4*>(&p.recs[g]);
     dst[0] = make_float4(geo.cx, geo.cy, geo.ax, geo.bx);
     dst[1] = make_float4(geo.ay, geo.by, geo.ex, geo.ey);

@@ -281,7 +281,22 @@ constexpr int kG4Stages = SB_G4_STAGES;
 constexpr int kG4PerLane = kBatchG4 / 128;
 constexpr int kG4StageF4 = (kBatchG4 / 4) * 16;
 
-enum { FMT_UNORM8 = 0, FMT_F16 = 1, FMT_F32 = 2 };
+enum { FMT_UNORM8 = 0, FMT_F16 = 1, FMT_F32 = 2, FMT_SRGB8 = 3 };  // FMT_SRGB8: same bytes as FMT_UNORM8, the blend works on decoded values
+
+// sRGB attachments: the pixel state is the stored 8-bit code; a blend decodes it, blends in linear and encodes the result.
+// Tables and the exact definition of encode(): scripts/gen_srgb_tables.py (the oracle holds its own generated copy).
+#include "sb_srgb_tables.h"
+__device__ __forceinline__ float srgb_blend(float code, float om, float src_alpha) {
+    const float dl = __uint_as_float(__ldg(&SB_SRGB_DECODE_BITS[(int)code]));
+    const float o = __fmaf_rn(dl, om, src_alpha);
+    // encode(o) = number of thresholds 1..255 that are <= o.  A fast-math guess, then exact comparisons walk to the answer:
+    // the result does not depend on how good the guess is.
+    const float s = o <= 0.0031308f ? 12.92f * o : 1.055f * __powf(o, 0.41666667f) - 0.055f;
+    int g = min(max(__float2int_rn(s * 255.0f), 0), 255);
+    while (g < 255 && o >= __uint_as_float(__ldg(&SB_SRGB_THRESHOLD_BITS[g + 1]))) ++g;
+    while (g > 0 && o < __uint_as_float(__ldg(&SB_SRGB_THRESHOLD_BITS[g]))) --g;
+    return (float)g;
+}
 
 // exp(-x) from exactly rounded steps; mirrors so_exp_neg_poly in oracle/splat_oracle.c
 __device__ __forceinline__ float exp_neg_poly(float x) {
@@ -385,7 +400,7 @@ struct PixelState {
 
 template <int FMT>
 __device__ __forceinline__ void load_dst(PixelState& st, const uint8_t* row, uint32_t x, int bgra) {
-    if constexpr (FMT == FMT_UNORM8) {
+    if constexpr (FMT == FMT_UNORM8 || FMT == FMT_SRGB8) {
         const uchar4 c = reinterpret_cast<const uchar4*>(row)[x];
         st.d01 = pk2(bgra ? c.z : c.x, c.y);
         st.d23 = pk2(bgra ? c.x : c.z, 1.0f);
@@ -405,7 +420,7 @@ __device__ __forceinline__ void store_dst(const PixelState& st, uint8_t* row, ui
     float d0, d1, d2, d3;
     upk2(st.d01, d0, d1);
     upk2(st.d23, d2, d3);
-    if constexpr (FMT == FMT_UNORM8) {
+    if constexpr (FMT == FMT_UNORM8 || FMT == FMT_SRGB8) {
         uchar4 c;
         c.x = (unsigned char)(bgra ? d2 : d0);
         c.y = (unsigned char)d1;
@@ -499,6 +514,15 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
         float d2, d3;
         upk2(st.d23, d2, d3);
         d2 = rint_small(__fmaf_rn(d2, om, __fmul_rn(q2.z, alpha)));
+        st.d23 = pk2(d2, d3);
+    } else if constexpr (FMT == FMT_SRGB8) {
+        float d0, d1, d2, d3;
+        upk2(st.d01, d0, d1);
+        upk2(st.d23, d2, d3);
+        d0 = srgb_blend(d0, om, __fmul_rn(q2.x, alpha));  // the source colour was clamped to [0,1] per splat (K1: color_max)
+        d1 = srgb_blend(d1, om, __fmul_rn(q2.y, alpha));
+        d2 = srgb_blend(d2, om, __fmul_rn(q2.z, alpha));
+        st.d01 = pk2(d0, d1);
         st.d23 = pk2(d2, d3);
     } else {
         // (b*alpha, 1*alpha): 1*alpha is exact, so d3 = fma(d3, 1-alpha, alpha) as in the oracle
@@ -958,9 +982,10 @@ void launch_raster(const RasterKernelParams& kp, const CUtensorMap* recs_map, di
 cudaError_t launch_clear(const SbTarget& t, cudaStream_t stream) {
     const uint32_t rows = t.rows == 0 ? t.height : t.rows;
     if (rows == 0 || t.width == 0) return cudaSuccess;
-    const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
-                    : t.format == SB_TARGET_RGBA16_FLOAT                                       ? FMT_F16
-                                                                                               : FMT_F32;
+    const bool srgb = t.format == SB_TARGET_RGBA8_UNORM_SRGB || t.format == SB_TARGET_BGRA8_UNORM_SRGB;
+    const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM || srgb) ? FMT_UNORM8  // BLACK is code 0 either way
+                    : t.format == SB_TARGET_RGBA16_FLOAT                                               ? FMT_F16
+                                                                                                       : FMT_F32;
     clear_kernel<<<dim3((t.width + 255) / 256, rows), 256, 0, stream>>>(reinterpret_cast<uint8_t*>(t.d_pixels), t.pitch_bytes, t.width,
                                                                       rows, fmt);
     return cudaGetLastError();
@@ -1054,7 +1079,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     kp.sd = u.std_dev;
     kp.sd2 = u.std_dev * u.std_dev;
     kp.outline = (u.std_dev - 0.1f) * (u.std_dev - 0.1f);
-    kp.bgra = t.format == SB_TARGET_BGRA8_UNORM;
+    kp.bgra = t.format == SB_TARGET_BGRA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM_SRGB;
     kp.clear = p.clear;
     kp.obb_cull = p.obb_cull;
     kp.cut_k = p.cut_k;
@@ -1075,7 +1100,9 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     // point where the other view's kernels get SM slots, instead of queueing behind one 8160-CTA grid.
     const uint32_t rows_total = ty_hi - ty_lo + 1;
     const uint32_t bands = (uint32_t)std::min<int>(std::max(p.raster_bands, 1), (int)rows_total);
-    const int fmt = (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
+    const bool srgb = t.format == SB_TARGET_RGBA8_UNORM_SRGB || t.format == SB_TARGET_BGRA8_UNORM_SRGB;
+    const int fmt = srgb ? FMT_SRGB8
+                    : (t.format == SB_TARGET_RGBA8_UNORM || t.format == SB_TARGET_BGRA8_UNORM) ? FMT_UNORM8
                     : t.format == SB_TARGET_RGBA16_FLOAT                                       ? FMT_F16
                                                                                                : FMT_F32;
     for (uint32_t band = 0; band < bands; band++) {
@@ -1097,6 +1124,9 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     SB_RASTER(SB_MODE_POINT, FMT_UNORM8)
     SB_RASTER(SB_MODE_POINT, FMT_F16)
     SB_RASTER(SB_MODE_POINT, FMT_F32)
+    SB_RASTER(SB_MODE_SPLAT, FMT_SRGB8)
+    SB_RASTER(SB_MODE_ELLIPSE, FMT_SRGB8)
+    SB_RASTER(SB_MODE_POINT, FMT_SRGB8)
 #undef SB_RASTER
     }
     if (p.events) cudaEventRecord(p.events[3], stream);

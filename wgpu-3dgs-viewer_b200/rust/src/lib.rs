@@ -64,6 +64,15 @@ pub mod ffi {
     include!("ffi_gen.rs");
 }
 
+/// `wgpu::TextureFormat`s the renderer can target (`SB_TARGET_*`): the reference takes any format (src/renderer.rs:120-155).
+pub mod texture_format {
+    pub const RGBA8_UNORM: i32 = 0; pub const BGRA8_UNORM: i32 = 1; pub const RGBA16_FLOAT: i32 = 2; pub const RGBA32_FLOAT: i32 = 3;
+    pub const RGBA8_UNORM_SRGB: i32 = 4; pub const BGRA8_UNORM_SRGB: i32 = 5;
+}
+/// `GaussianDisplayMode` and `wgpu::CompareFunction` as the C ABI numbers them.
+pub mod display_mode { pub const SPLAT: i32 = 0; pub const ELLIPSE: i32 = 1; pub const POINT: i32 = 2; }
+pub mod compare { pub const NEVER: i32 = 1; pub const LESS: i32 = 2; pub const EQUAL: i32 = 3; pub const LESS_EQUAL: i32 = 4; pub const GREATER: i32 = 5; pub const NOT_EQUAL: i32 = 6; pub const GREATER_EQUAL: i32 = 7; pub const ALWAYS: i32 = 8; }
+
 pub use ffi::{CameraPod, Gaussian, GaussianTransformPod, ModelTransformPod, Target};
 
 /// Mirrors `ViewerCreateError` / `MultiModelViewerAccessError` (reference src/error.rs:7-50).

@@ -8,7 +8,7 @@ tests/ and bench.py drive.  There is NO CPU fallback: if the library is missing,
 """
 from .api import (  # noqa: F401
     COV_HALF, COV_ROT_SCALE, COV_SINGLE, MODE_ELLIPSE, MODE_POINT, MODE_SPLAT, SH_HALF, SH_NONE, SH_NORM8,
-    SH_SINGLE, TARGET_BGRA8, TARGET_RGBA8, TARGET_RGBA16F, TARGET_RGBA32F, GAUSSIAN_DTYPE, CameraPod,
+    SH_SINGLE, TARGET_BGRA8, TARGET_RGBA8, TARGET_RGBA16F, TARGET_RGBA32F, TARGET_RGBA8_SRGB, TARGET_BGRA8_SRGB, GAUSSIAN_DTYPE, CameraPod,
     Context, GaussianTransformPod, ModelTransformPod, MultiModelViewer, RadixSorter, SplatError, Viewer,
     build, camera_pod, gaussian_transform_pod, lib_path, load, model_transform_pod, pack_gaussians,
     pod_stride, read_ply, padded_key_count, keys_buffer_size_bytes, EXPORTED_SYMBOLS, DepthAttachment,

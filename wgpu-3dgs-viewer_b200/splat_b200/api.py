@@ -14,7 +14,7 @@ _LIB = os.environ.get("SB_LIB") or os.path.join(_PKG, "lib", "libsplat_b200.so")
 SH_SINGLE, SH_HALF, SH_NORM8, SH_NONE = 0, 1, 2, 3
 COV_SINGLE, COV_HALF, COV_ROT_SCALE = 0, 1, 2
 MODE_SPLAT, MODE_ELLIPSE, MODE_POINT = 0, 1, 2
-TARGET_RGBA8, TARGET_BGRA8, TARGET_RGBA16F, TARGET_RGBA32F = 0, 1, 2, 3
+TARGET_RGBA8, TARGET_BGRA8, TARGET_RGBA16F, TARGET_RGBA32F, TARGET_RGBA8_SRGB, TARGET_BGRA8_SRGB = 0, 1, 2, 3, 4, 5
 
 GAUSSIAN_DTYPE = np.dtype(
     [("pos", "<f4", 3), ("color", "u1", 4), ("sh", "<f4", 45), ("scale", "<f4", 3), ("rot", "<f4", 4)]
@@ -301,7 +301,7 @@ def read_ply(path: str) -> np.ndarray:
 
 # ---------------------------------------------------------------- device objects
 
-_BPP = {TARGET_RGBA8: 4, TARGET_BGRA8: 4, TARGET_RGBA16F: 8, TARGET_RGBA32F: 16}
+_BPP = {TARGET_RGBA8: 4, TARGET_BGRA8: 4, TARGET_RGBA16F: 8, TARGET_RGBA32F: 16, TARGET_RGBA8_SRGB: 4, TARGET_BGRA8_SRGB: 4}
 
 
 def _stream_handle(stream) -> int:
