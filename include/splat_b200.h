@@ -149,6 +149,9 @@ SB_API SbStatus sb_gaussian_transform_pod(float size, int32_t display_mode, int3
 /* Gaussians::read_from_file(path, GaussiansSource::Ply) (core; examples/simple.rs:157-160).
  * *out is malloc'ed; release with sb_free. */
 SB_API SbStatus sb_read_ply(const char* path, SbGaussian** out, uint64_t* n);
+/* Gaussians::read_from_file(path, GaussiansSource::Spz) (examples/simple.rs:157-160): Niantic .spz, versions 2 and 3 (gzip).
+ * The decoder is in the external wgpu-3dgs-core; the container layout is restated from the published format (recalled). */
+SB_API SbStatus sb_read_spz(const char* path, SbGaussian** out, uint64_t* n);
 SB_API void sb_free(void* p);
 
 /* ---------------------------------------------------------------- context */

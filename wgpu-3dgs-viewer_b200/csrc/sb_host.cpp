@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <zlib.h>
+
 #include "../../include/splat_b200.h"
 
 namespace {
@@ -338,6 +340,103 @@ SbStatus sb_read_ply(const char* path, SbGaussian** out, uint64_t* n_out) {
         o.rot[0] = qx * inv; o.rot[1] = qy * inv; o.rot[2] = qz * inv; o.rot[3] = qw * inv;
     }
     std::fclose(fp);
+    *out = g;
+    *n_out = n;
+    return SB_OK;
+}
+
+// Niantic .spz (gzip stream; versions 2 and 3), the second source `Gaussians::read_from_file` tries (examples/simple.rs:157-160:
+// `[GaussiansSource::Ply, GaussiansSource::Spz]`).  The decoder lives in the un-vendored wgpu-3dgs-core; this restates the
+// published container: a 16-byte header {magic 'NGSP', version, numPoints, shDegree, fractionalBits, flags, reserved} followed by
+// positions (3 x 24-bit fixed point), alphas (u8), colours (3 x u8), scales (3 x u8), rotations (3 x u8 in v2, 4 bytes
+// "smallest three" in v3) and SH (shDim x 3 x u8), each as one array over all points.  Mapped onto `Gaussian` like the PLY path:
+// colour = (0.5 + SH_C0 * dc) * 255 truncated to u8, alpha = the stored byte, scale = exp(log-scale), rotation normalised xyzw.
+// File coordinates are kept as they are (no axis convention change): RECALLED layout, unverifiable here.
+SbStatus sb_read_spz(const char* path, SbGaussian** out, uint64_t* n_out) {
+    if (!path || !out || !n_out) return SB_ERR_INVALID_ARG;
+    gzFile gz = gzopen(path, "rb");
+    if (!gz) return SB_ERR_IO;
+    std::vector<uint8_t> data;
+    {
+        uint8_t buf[1 << 16];
+        int got;
+        while ((got = gzread(gz, buf, sizeof buf)) > 0) {
+            data.insert(data.end(), buf, buf + got);
+            if (data.size() > (size_t)16 << 30) break;  // refuse absurd streams
+        }
+        const bool bad = got < 0;
+        gzclose(gz);
+        if (bad) return SB_ERR_IO;
+    }
+    if (data.size() < 16) return SB_ERR_IO;
+    uint32_t magic, version, n;
+    std::memcpy(&magic, &data[0], 4);
+    std::memcpy(&version, &data[4], 4);
+    std::memcpy(&n, &data[8], 4);
+    const uint32_t sh_degree = data[12], frac_bits = data[13];
+    if (magic != 0x5053474eu || (version != 2u && version != 3u) || sh_degree > 3u || frac_bits > 30u) return SB_ERR_IO;
+    static const uint32_t kShDim[4] = {0, 3, 8, 15};
+    const uint32_t sh_dim = kShDim[sh_degree];
+    const uint32_t rot_bytes = version == 3u ? 4u : 3u;
+    const uint64_t per_point = 9u + 1u + 3u + 3u + rot_bytes + (uint64_t)sh_dim * 3u;
+    if (data.size() - 16 < per_point * n) return SB_ERR_IO;  // the header's count must fit the stream
+    const uint8_t* pos = &data[16];
+    const uint8_t* alpha = pos + (size_t)n * 9;
+    const uint8_t* col = alpha + (size_t)n;
+    const uint8_t* scl = col + (size_t)n * 3;
+    const uint8_t* rot = scl + (size_t)n * 3;
+    const uint8_t* sh = rot + (size_t)n * rot_bytes;
+    SbGaussian* g = static_cast<SbGaussian*>(std::calloc(n ? n : 1, sizeof(SbGaussian)));
+    if (!g) return SB_ERR_IO;
+    const float pos_scale = 1.0f / (float)(1u << frac_bits);
+    const float SH_C0 = 0.2820948f, kColorScale = 0.15f;
+    for (uint32_t i = 0; i < n; i++) {
+        SbGaussian& o = g[i];
+        for (int c = 0; c < 3; c++) {
+            const uint8_t* b = pos + (size_t)i * 9 + c * 3;
+            int32_t v = (int32_t)b[0] | ((int32_t)b[1] << 8) | ((int32_t)b[2] << 16);
+            if (v & 0x800000) v |= ~0xffffff;  // sign-extend 24 bits
+            o.pos[c] = (float)v * pos_scale;
+        }
+        for (int c = 0; c < 3; c++) {
+            const float dc = ((float)col[(size_t)i * 3 + c] / 255.0f - 0.5f) / kColorScale;
+            float v = (0.5f + SH_C0 * dc) * 255.0f;
+            v = !(v > 0.0f) ? 0.0f : (v > 255.0f ? 255.0f : v);
+            o.color[c] = (uint8_t)v;
+        }
+        o.color[3] = alpha[i];
+        for (int c = 0; c < 3; c++) o.scale[c] = std::exp((float)scl[(size_t)i * 3 + c] / 16.0f - 10.0f);
+        float q[4];
+        if (version == 2u) {
+            const uint8_t* r = rot + (size_t)i * 3;
+            float sum = 0.0f;
+            for (int c = 0; c < 3; c++) {
+                q[c] = (float)r[c] / 127.5f - 1.0f;
+                sum += q[c] * q[c];
+            }
+            q[3] = std::sqrt(std::fmax(0.0f, 1.0f - sum));
+        } else {
+            uint32_t comp;
+            std::memcpy(&comp, rot + (size_t)i * 4, 4);
+            const uint32_t largest = comp >> 30;
+            float sum = 0.0f;
+            for (int k = 3; k >= 0; k--) {
+                if ((uint32_t)k == largest) continue;
+                const uint32_t mag = comp & 0x1ffu, neg = (comp >> 9) & 1u;
+                comp >>= 10;
+                q[k] = 0.70710678f * (float)mag / 511.0f;
+                if (neg) q[k] = -q[k];
+                sum += q[k] * q[k];
+            }
+            q[largest] = std::sqrt(std::fmax(0.0f, 1.0f - sum));
+        }
+        const float len = std::sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+        const float inv = len > 0.0f ? 1.0f / len : 0.0f;
+        for (int c = 0; c < 4; c++) o.rot[c] = q[c] * inv;
+        if (!(len > 0.0f)) o.rot[3] = 1.0f;
+        for (uint32_t k = 0; k < sh_dim; k++)
+            for (int c = 0; c < 3; c++) o.sh[k * 3 + c] = ((float)sh[((size_t)i * sh_dim + k) * 3 + c] - 128.0f) / 128.0f;
+    }
     *out = g;
     *n_out = n;
     return SB_OK;

@@ -265,6 +265,17 @@ pub fn read_ply(path: &std::path::Path) -> Result<Vec<Gaussian>, Error> {
     unsafe { ffi::sb_free(p.cast()) };
     Ok(v)
 }
+/// `Gaussians::read_from_file(path, GaussiansSource::Spz)`: Niantic .spz v2 / v3.
+pub fn read_spz(path: &std::path::Path) -> Result<Vec<Gaussian>, Error> {
+    let c = std::ffi::CString::new(path.to_string_lossy().as_bytes()).map_err(|e| Error::InvalidArg(e.to_string()))?;
+    let (mut p, mut n) = (std::ptr::null_mut::<Gaussian>(), 0u64);
+    check(unsafe { ffi::sb_read_spz(c.as_ptr(), &mut p, &mut n) }, std::ptr::null())?;
+    let v = unsafe { std::slice::from_raw_parts(p, n as usize) }.to_vec();
+    unsafe { ffi::sb_free(p.cast()) };
+    Ok(v)
+}
+/// `Gaussians::read_from_file`: PLY first, then SPZ, as the reference's examples try them (examples/simple.rs:157-160).
+pub fn read_from_file(path: &std::path::Path) -> Result<Vec<Gaussian>, Error> { read_ply(path).or_else(|_| read_spz(path)) }
 impl ModelTransformPod {
     pub fn new(pos: glam::Vec3, rot: glam::Quat, scale: glam::Vec3) -> Self { let mut o = std::mem::MaybeUninit::<Self>::uninit(); unsafe { ffi::sb_model_transform_pod(pos.to_array().as_ptr(), rot.to_array().as_ptr(), scale.to_array().as_ptr(), o.as_mut_ptr()); o.assume_init() } }
 }

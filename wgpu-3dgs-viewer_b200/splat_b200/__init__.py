@@ -11,7 +11,7 @@ from .api import (  # noqa: F401
     SH_SINGLE, TARGET_BGRA8, TARGET_RGBA8, TARGET_RGBA16F, TARGET_RGBA32F, TARGET_RGBA8_SRGB, TARGET_BGRA8_SRGB, GAUSSIAN_DTYPE, CameraPod,
     Context, GaussianTransformPod, ModelTransformPod, MultiModelViewer, RadixSorter, SplatError, Viewer,
     build, camera_pod, gaussian_transform_pod, lib_path, load, model_transform_pod, pack_gaussians,
-    pod_stride, read_ply, padded_key_count, keys_buffer_size_bytes, EXPORTED_SYMBOLS, DepthAttachment,
+    pod_stride, read_ply, read_spz, padded_key_count, keys_buffer_size_bytes, EXPORTED_SYMBOLS, DepthAttachment,
     COMPARE_NEVER, COMPARE_LESS, COMPARE_EQUAL, COMPARE_LESS_EQUAL, COMPARE_GREATER, COMPARE_NOT_EQUAL, COMPARE_GREATER_EQUAL,
     COMPARE_ALWAYS, Preprocessor, Renderer, PreprocessorBindGroup, RendererBindGroup, DrawIndirectArgs, DispatchIndirectArgs,
 )

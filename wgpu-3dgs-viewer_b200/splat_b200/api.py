@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
     "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
     "sb_mm_render_with_pass",
-    "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
+    "sb_read_spz", "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
 ]
 
 
@@ -148,6 +148,7 @@ def load() -> C.CDLL:
     sig("sb_model_transform_pod", i32, vp, vp, vp, P(ModelTransformPod))
     sig("sb_gaussian_transform_pod", i32, f32, i32, i32, i32, f32, P(GaussianTransformPod))
     sig("sb_read_ply", i32, C.c_char_p, P(vp), P(u64))
+    sig("sb_read_spz", i32, C.c_char_p, P(vp), P(u64))
     sig("sb_free", None, vp)
     sig("sb_ctx_create", i32, i32, P(vp))
     sig("sb_ctx_destroy", None, vp)
@@ -292,6 +293,17 @@ def gaussian_transform_pod(size=1.0, display_mode=MODE_SPLAT, sh_deg=3, no_sh0=F
 def read_ply(path: str) -> np.ndarray:
     ptr, n = C.c_void_p(), C.c_uint64()
     _check(load().sb_read_ply(path.encode(), C.byref(ptr), C.byref(n)))
+    try:
+        buf = (C.c_uint8 * (n.value * GAUSSIAN_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=GAUSSIAN_DTYPE).copy()
+    finally:
+        load().sb_free(ptr)
+
+
+def read_spz(path: str) -> np.ndarray:
+    """`Gaussians::read_from_file(path, GaussiansSource::Spz)`: Niantic .spz v2 / v3 -> Gaussian records."""
+    ptr, n = C.c_void_p(), C.c_uint64()
+    _check(load().sb_read_spz(path.encode(), C.byref(ptr), C.byref(n)))
     try:
         buf = (C.c_uint8 * (n.value * GAUSSIAN_DTYPE.itemsize)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=GAUSSIAN_DTYPE).copy()
