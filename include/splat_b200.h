@@ -223,6 +223,16 @@ SB_API SbStatus sb_viewer_select_brush(SbViewer* v, void* stream, const float* p
  * (the HSV / contrast / exposure / gamma edits of the external crate are not built).  restore drops the edit. */
 SB_API SbStatus sb_viewer_apply_rgb_override(SbViewer* v, void* stream, const float rgb[3], float alpha);
 SB_API SbStatus sb_viewer_restore_gaussians(SbViewer* v, void* stream);
+/* The editor's full BasicColorModifiers (`basic_color_modifiers_buffer.update(queue, rgb_or_hsv, alpha, contrast, exposure, gamma)`,
+ * tests/e2e/selection.rs:80-92; examples/selection.rs:218-229) on the selected Gaussians, non-destructively like the override:
+ * rgb override or HSV (hue shift in turns, saturation scale, value scale), then contrast, exposure (stops), gamma, alpha scale.
+ * Neutral: {0, {0,1,1}, 1, 0, 0, 1}.  The arithmetic is the external wgpu-3dgs-editor's, restated from its documented meaning. */
+typedef struct SbBasicColorModifiers {
+    int32_t rgb_override;   /* 1: rgb_or_hsv is the override colour; 0: it is (hue shift, saturation scale, value scale) */
+    float rgb_or_hsv[3];
+    float alpha, contrast, exposure, gamma;
+} SbBasicColorModifiers;
+SB_API SbStatus sb_viewer_apply_basic_color_modifiers(SbViewer* v, void* stream, const SbBasicColorModifiers* m);
 
 /* Viewer::render(encoder, texture_view): src/lib.rs:266-275 — enqueue the whole frame */
 SB_API SbStatus sb_viewer_render(SbViewer* v, void* stream, const SbTarget* target);

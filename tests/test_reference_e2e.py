@@ -200,6 +200,99 @@ def test_rgb_override_matches_oracle_on_edited_pods(sb, ob, ctx):
     v.close()
 
 
+def _basic_color_np(c_u8, rgb=None, hsv=(0.0, 1.0, 1.0), alpha=1.0, contrast=0.0, exposure=0.0, gamma=1.0):
+    """numpy restatement of the BasicColorModifiers contract (include/splat_b200.h): every step an individually rounded f32 op."""
+    f = np.float32
+    c = c_u8.astype(f) / f(255.0)
+    r, g, b = c[:, 0], c[:, 1], c[:, 2]
+    a = c[:, 3] * f(alpha)
+    if rgb is not None:
+        r, g, b = (np.full_like(r, f(x)) for x in rgb)
+    else:
+        mx, mn = np.maximum(r, np.maximum(g, b)), np.minimum(r, np.minimum(g, b))
+        d = mx - mn
+        with np.errstate(all="ignore"):
+            h6 = np.where(mx == r, (g - b) / d, np.where(mx == g, (b - r) / d + f(2.0), (r - g) / d + f(4.0)))
+            h6 = np.where(d > 0, h6, f(0.0)).astype(f)
+            h = (h6 / f(6.0) + f(hsv[0])).astype(f)
+            h = (h - np.floor(h)).astype(f)
+            sat = np.clip(np.where(mx > 0, d / mx, f(0.0)).astype(f) * f(hsv[1]), 0, 1).astype(f)
+        val = np.clip(mx * f(hsv[2]), 0, 1).astype(f)
+        hh, vs = h * f(6.0), val * sat
+        out = []
+        for nn in (5.0, 3.0, 1.0):
+            k = f(nn) + hh
+            k = np.where(k >= 6, k - f(6.0), k).astype(f)
+            t = np.maximum(f(0.0), np.minimum(np.minimum(k, f(4.0) - k), f(1.0)))
+            out.append((val - vs * t).astype(f))
+        r, g, b = out
+    res = []
+    for x in (r, g, b):
+        x = ((x - f(0.5)) * (f(1.0) + f(contrast)) + f(0.5)).astype(f)
+        x = (x * f(np.exp2(np.float64(exposure)))).astype(f)
+        if gamma != 1.0:
+            x = np.power(np.maximum(x, 0).astype(np.float64), gamma).astype(f)
+        res.append(x)
+    res.append(a)
+    return np.stack([np.rint(np.clip(x, 0, 1) * f(255.0)).astype(np.uint8) for x in res], axis=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,exact", [
+    (dict(hsv=(0.0, 1.0, 1.0)), True),                                   # neutral: nothing changes
+    (dict(hsv=(0.35, 0.6, 1.2), alpha=0.8), True),                       # hue rotation, desaturate, brighten
+    (dict(hsv=(-0.2, 1.5, 0.7), contrast=0.5), True),                    # negative hue shift wraps; contrast
+    (dict(rgb=(0.25, 1.0, 0.5), alpha=0.5, contrast=-0.3), True),        # override then contrast
+    (dict(hsv=(0.1, 1.0, 1.0), exposure=0.75, gamma=2.2), False),        # exposure and gamma: powers, +-1 code
+])
+def test_basic_color_modifiers(sb, ob, ctx, kw, exact):
+    """f4: the editor's BasicColorModifiers (HSV / contrast / exposure / gamma / alpha, or rgb override) on the selected
+    Gaussians rewrite exactly the colour words the numpy statement predicts, leave the others alone, compose non-destructively
+    (a second edit starts from the source again), restore brings the source back — and the frame is the oracle's frame of
+    pods edited the same way."""
+    import torch
+    n, w, h = 20000, 640, 360
+    g = sb.scenes.synthetic_gaussians(n, 37)
+    pods = sb.pack_gaussians(g)
+    stride = sb.pod_stride(0, 0)
+    pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
+    v = sb.Viewer(ctx, pods, n)
+    v.update_camera(pos, yaw, pitch, w, h)
+    v.set_strict_exp(True)
+    v.select_rect(150.0, 60.0, 500.0, 320.0)
+    sel = v.read_selection()
+    bits = ((sel[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+    assert 0 < bits.sum() < n
+    v.apply_basic_color_modifiers(hsv=(0.5, 0.0, 0.3))  # an earlier edit that must leave no trace
+    v.apply_basic_color_modifiers(**kw)
+    t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    v.render(t, w, h)
+    torch.cuda.synchronize()
+    ptr, nbytes = v.device_pointers()["gaussians"]
+    got = np.empty(nbytes, dtype=np.uint8)
+    import ctypes
+    torch.cuda.synchronize()
+    cudart = ctypes.CDLL("libcudart.so.12")
+    assert cudart.cudaMemcpy(ctypes.c_void_p(got.ctypes.data), ctypes.c_void_p(ptr), ctypes.c_size_t(nbytes), 2) == 0
+    got = got.reshape(n, stride)
+    src = pods.reshape(n, stride)
+    exp_words = src[:, 12:16].copy()
+    exp_words[bits] = _basic_color_np(src[bits, 12:16], **kw)
+    if exact:
+        assert np.array_equal(got[:, 12:16], exp_words)
+    else:
+        assert np.abs(got[:, 12:16].astype(np.int32) - exp_words.astype(np.int32)).max() <= 1
+    assert np.array_equal(got[~bits], src[~bits]) and np.array_equal(np.delete(got, [12, 13, 14, 15], axis=1), np.delete(src, [12, 13, 14, 15], axis=1))
+    oimg, _ = ob.render(ob.OracleModel(got.reshape(-1).copy(), n), ob.camera_pod(pos, yaw, pitch, w, h), ob.gaussian_transform_pod(), strict_exp=True)
+    assert np.array_equal(t.cpu().numpy(), oimg)
+    v.restore_gaussians()
+    torch.cuda.synchronize()
+    back = np.empty(nbytes, dtype=np.uint8)
+    assert cudart.cudaMemcpy(ctypes.c_void_p(back.ctypes.data), ctypes.c_void_p(ptr), ctypes.c_size_t(nbytes), 2) == 0
+    assert np.array_equal(back, pods.reshape(-1).view(np.uint8))
+    v.close()
+
+
 def test_cpp_host_mirror_e2e(sb):
     """The typed C++ host mirror (host/splat_b200.hpp) runs the reference's viewer e2e test."""
     import os

@@ -799,6 +799,21 @@ SbStatus sb_viewer_apply_rgb_override(SbViewer* v, void* stream, const float rgb
     return SB_OK;
 }
 
+SbStatus sb_viewer_apply_basic_color_modifiers(SbViewer* v, void* stream, const SbBasicColorModifiers* m) {
+    if (!v || !m) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (!(m->gamma > 0.0f)) return fail(v->ctx, SB_ERR_INVALID_ARG, "gamma must be positive");
+    DeviceGuard device_guard(v->ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* pods = const_cast<uint8_t*>(static_cast<const uint8_t*>(v->d_gaussians));
+    if (!v->orig_colors.p) {  // NonDestructiveModifier: every edit starts from the source colours
+        SB_CUDA(v->ctx, v->orig_colors.alloc((size_t)(v->n ? v->n : 1) * 4));
+        SB_CUDA(v->ctx, sb::launch_snapshot_colors(pods, v->n, v->stride, v->orig_colors.as<uint32_t>(), st));
+    }
+    SB_CUDA(v->ctx, sb::launch_basic_color_modifiers(pods, v->n, v->stride, v->orig_colors.as<uint32_t>(), v->selection.as<uint32_t>(),
+                                                     m->rgb_override, m->rgb_or_hsv, m->alpha, m->contrast, m->exposure, m->gamma, st));
+    return SB_OK;
+}
+
 SbStatus sb_viewer_restore_gaussians(SbViewer* v, void* stream) {
     if (!v) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
     DeviceGuard device_guard(v->ctx);

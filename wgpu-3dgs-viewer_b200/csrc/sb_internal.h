@@ -143,6 +143,11 @@ cudaError_t launch_snapshot_colors(const uint8_t* gaussians, uint32_t n, uint32_
 cudaError_t launch_rgb_override(uint8_t* gaussians, uint32_t n, uint32_t stride, const uint32_t* orig, const uint32_t* selection,
                                 const float rgb[3], float alpha, cudaStream_t stream);
 
+// editor BasicColorModifiers on the selected Gaussians (rgb override or HSV, then contrast / exposure / gamma, alpha scale)
+cudaError_t launch_basic_color_modifiers(uint8_t* gaussians, uint32_t n, uint32_t stride, const uint32_t* orig, const uint32_t* selection,
+                                         int rgb_override, const float rgb_or_hsv[3], float alpha, float contrast, float exposure,
+                                         float gamma, cudaStream_t stream);
+
 // ---------------------------------------------------------------- measured peaks (sb_probe.cu)
 cudaError_t probe_fp32_peak(int num_sms, cudaStream_t stream, double* lane_ops_per_s);
 cudaError_t probe_smem_peak(int num_sms, cudaStream_t stream, double* bytes_per_s);

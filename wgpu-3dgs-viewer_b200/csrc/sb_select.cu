@@ -129,7 +129,86 @@ __global__ void __launch_bounds__(256) rgb_override_kernel(uint8_t* __restrict__
     *reinterpret_cast<uint32_t*>(gaussians + (size_t)g * stride + 12) = c;
 }
 
+// The editor's BasicColorModifiers on the selected Gaussians (`basic_color_modifiers_buffer.update(queue, rgb_or_hsv, alpha, contrast,
+// exposure, gamma)`, tests/e2e/selection.rs:80-92; the arithmetic itself lives in the un-vendored wgpu-3dgs-editor and is RESTATED
+// here from its documented meaning, not from its source): on the source colour of a selected Gaussian, in this order —
+//   rgb override, or HSV: hue += dh (turns, wraps), saturation *= ks, value *= kv (each clamped to [0,1]);
+//   contrast:  c = (c - 0.5) * (1 + contrast) + 0.5;   exposure:  c *= 2^exposure;   gamma:  c = max(c, 0)^gamma;
+//   alpha *= alpha scale;  then pack4x8unorm.  Neutral values (0, 1, 1 / 1 / 0 / 0 / 1) leave the colour word unchanged.
+// Every step but 2^exposure (done once on the host) and the power is an individually rounded f32 operation.
+struct ColorMods {
+    int rgb_override;
+    float p0, p1, p2;  // override rgb, or (dh, ks, kv)
+    float alpha, contrast1, gain, gamma;  // contrast1 = 1 + contrast, gain = 2^exposure
+};
+
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+__global__ void __launch_bounds__(256) basic_color_kernel(uint8_t* __restrict__ gaussians, uint32_t n, uint32_t stride,
+                                                          const uint32_t* __restrict__ orig, const uint32_t* __restrict__ selection,
+                                                          const ColorMods m) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t c = orig[g];
+    if (selection && ((selection[g >> 5] >> (g & 31u)) & 1u)) {
+        float r = __fdiv_rn((float)(c & 255u), 255.0f), gg = __fdiv_rn((float)((c >> 8) & 255u), 255.0f),
+              b = __fdiv_rn((float)((c >> 16) & 255u), 255.0f);
+        const float a = __fmul_rn(__fdiv_rn((float)(c >> 24), 255.0f), m.alpha);
+        if (m.rgb_override) {
+            r = m.p0; gg = m.p1; b = m.p2;
+        } else {
+            const float mx = fmaxf(r, fmaxf(gg, b)), mn = fminf(r, fminf(gg, b)), d = __fsub_rn(mx, mn);
+            float h6 = 0.0f;
+            if (d > 0.0f) {
+                if (mx == r) h6 = __fdiv_rn(__fsub_rn(gg, b), d);
+                else if (mx == gg) h6 = __fadd_rn(__fdiv_rn(__fsub_rn(b, r), d), 2.0f);
+                else h6 = __fadd_rn(__fdiv_rn(__fsub_rn(r, gg), d), 4.0f);
+            }
+            float h = __fadd_rn(__fdiv_rn(h6, 6.0f), m.p0);
+            h = __fsub_rn(h, floorf(h));
+            const float sat = clamp01(__fmul_rn(mx > 0.0f ? __fdiv_rn(d, mx) : 0.0f, m.p1));
+            const float val = clamp01(__fmul_rn(mx, m.p2));
+            const float hh = __fmul_rn(h, 6.0f), vs = __fmul_rn(val, sat);
+            float out[3];
+            const float ns[3] = {5.0f, 3.0f, 1.0f};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                float k = __fadd_rn(ns[i], hh);
+                if (k >= 6.0f) k = __fsub_rn(k, 6.0f);
+                const float t = fmaxf(0.0f, fminf(fminf(k, __fsub_rn(4.0f, k)), 1.0f));
+                out[i] = __fsub_rn(val, __fmul_rn(vs, t));
+            }
+            r = out[0]; gg = out[1]; b = out[2];
+        }
+        float ch[3] = {r, gg, b};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            float x = __fadd_rn(__fmul_rn(__fsub_rn(ch[i], 0.5f), m.contrast1), 0.5f);
+            x = __fmul_rn(x, m.gain);
+            if (m.gamma != 1.0f) x = powf(fmaxf(x, 0.0f), m.gamma);
+            ch[i] = x;
+        }
+        c = unorm8_pack(ch[0]) | (unorm8_pack(ch[1]) << 8) | (unorm8_pack(ch[2]) << 16) | (unorm8_pack(a) << 24);
+    }
+    *reinterpret_cast<uint32_t*>(gaussians + (size_t)g * stride + 12) = c;
+}
+
 }  // namespace
+
+cudaError_t launch_basic_color_modifiers(uint8_t* gaussians, uint32_t n, uint32_t stride, const uint32_t* orig, const uint32_t* selection,
+                                         int rgb_override, const float rgb_or_hsv[3], float alpha, float contrast, float exposure,
+                                         float gamma, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    ColorMods m;
+    m.rgb_override = rgb_override;
+    m.p0 = rgb_or_hsv[0]; m.p1 = rgb_or_hsv[1]; m.p2 = rgb_or_hsv[2];
+    m.alpha = alpha;
+    m.contrast1 = 1.0f + contrast;
+    m.gain = exp2f(exposure);
+    m.gamma = gamma;
+    basic_color_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gaussians, n, stride, orig, selection, m);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_select_rect(const uint8_t* gaussians, uint32_t n, uint32_t stride, const Uniforms& u, float x0, float y0, float x1,
                                float y1, uint32_t* words, cudaStream_t stream) {

@@ -42,6 +42,11 @@ pub mod ffi {
     #[repr(C)] #[derive(Clone, Copy, Debug)]
     pub struct DepthAttachment { pub d_depth: *mut c_void, pub pitch_bytes: u32, pub compare: i32, pub write_enabled: i32 }
 
+    /// editor `BasicColorModifiersPod` (tests/e2e/selection.rs:80-92): rgb override or HSV, then alpha / contrast / exposure / gamma.
+    #[repr(C)] #[derive(Clone, Copy, Debug)]
+    pub struct BasicColorModifiers { pub rgb_override: i32, pub rgb_or_hsv: [f32; 3], pub alpha: f32, pub contrast: f32, pub exposure: f32, pub gamma: f32 }
+    impl Default for BasicColorModifiers { fn default() -> Self { Self { rgb_override: 0, rgb_or_hsv: [0.0, 1.0, 1.0], alpha: 1.0, contrast: 0.0, exposure: 0.0, gamma: 1.0 } } }
+
     /// The `Preprocessor` bind group (reference src/preprocessor.rs:104-221): bindings 0-9 on caller-owned device buffers.
     #[repr(C)] #[derive(Clone, Copy)]
     pub struct PreprocessorBindGroup {
@@ -205,6 +210,8 @@ impl<'c, G: GaussianPod> Viewer<'c, G> {
     pub fn set_invert_selection(&mut self, invert: bool) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_set_invert_selection(self.raw, invert as i32) }, self.ctx.0) }
     /// editor `NonDestructiveModifier<BasicSelectionModifier>` with an rgb override (tests/e2e/selection.rs:54-116).
     pub fn apply_rgb_override(&mut self, stream: Stream, rgb: glam::Vec3, alpha: f32) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_apply_rgb_override(self.raw, stream.0, rgb.to_array().as_ptr(), alpha) }, self.ctx.0) }
+    /// `basic_color_modifiers_buffer.update_with_pod(queue, &BasicColorModifiersPod { .. })` + `modifier.apply(..)` (examples/selection.rs:218-229).
+    pub fn apply_basic_color_modifiers(&mut self, stream: Stream, m: &ffi::BasicColorModifiers) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_apply_basic_color_modifiers(self.raw, stream.0, m) }, self.ctx.0) }
     pub fn restore_gaussians(&mut self, stream: Stream) -> Result<(), Error> { check(unsafe { ffi::sb_viewer_restore_gaussians(self.raw, stream.0) }, self.ctx.0) }
     // ---- frames beyond `render`
     /// One frame straight to (pinned) host memory: camera pod in, pixels out.

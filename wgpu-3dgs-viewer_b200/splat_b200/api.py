@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
     "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
     "sb_mm_render_with_pass",
-    "sb_read_spz", "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
+    "sb_read_spz", "sb_viewer_apply_basic_color_modifiers", "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
 ]
 
 
@@ -62,6 +62,11 @@ class ModelTransformPod(C.Structure):
 
 class GaussianTransformPod(C.Structure):
     _fields_ = [("size", C.c_float), ("display_mode", C.c_uint8), ("sh_deg", C.c_uint8), ("no_sh0", C.c_uint8), ("max_std_dev", C.c_uint8)]
+
+
+class BasicColorModifiers(C.Structure):
+    _fields_ = [("rgb_override", C.c_int32), ("rgb_or_hsv", C.c_float * 3), ("alpha", C.c_float), ("contrast", C.c_float),
+                ("exposure", C.c_float), ("gamma", C.c_float)]
 
 
 class DrawIndirectArgs(C.Structure):
@@ -149,6 +154,7 @@ def load() -> C.CDLL:
     sig("sb_gaussian_transform_pod", i32, f32, i32, i32, i32, f32, P(GaussianTransformPod))
     sig("sb_read_ply", i32, C.c_char_p, P(vp), P(u64))
     sig("sb_read_spz", i32, C.c_char_p, P(vp), P(u64))
+    sig("sb_viewer_apply_basic_color_modifiers", i32, vp, vp, P(BasicColorModifiers))
     sig("sb_free", None, vp)
     sig("sb_ctx_create", i32, i32, P(vp))
     sig("sb_ctx_destroy", None, vp)
@@ -456,6 +462,16 @@ class Viewer:
         """editor NonDestructiveModifier + rgb override on the selected Gaussians (tests/e2e/selection.rs:54-116)."""
         c = _f(rgb)
         _check(load().sb_viewer_apply_rgb_override(self._h, _stream_handle(stream), c.ctypes.data_as(C.POINTER(C.c_float)), float(alpha)), self.ctx._h)
+
+    def apply_basic_color_modifiers(self, rgb=None, hsv=(0.0, 1.0, 1.0), alpha=1.0, contrast=0.0, exposure=0.0, gamma=1.0, stream=None):
+        """editor BasicColorModifiers on the selected Gaussians: rgb override (rgb=...) or HSV (hue shift in turns, saturation
+        scale, value scale), then contrast, exposure (stops), gamma and the alpha scale."""
+        m = BasicColorModifiers()
+        m.rgb_override = int(rgb is not None)
+        for i, x in enumerate(rgb if rgb is not None else hsv):
+            m.rgb_or_hsv[i] = float(x)
+        m.alpha, m.contrast, m.exposure, m.gamma = float(alpha), float(contrast), float(exposure), float(gamma)
+        _check(load().sb_viewer_apply_basic_color_modifiers(self._h, _stream_handle(stream), C.byref(m)), self.ctx._h)
 
     def restore_gaussians(self, stream=None):
         _check(load().sb_viewer_restore_gaussians(self._h, _stream_handle(stream)), self.ctx._h)
