@@ -35,8 +35,9 @@ SH_FMT, COV_FMT = 0, 0           # pod single/single, 224 B
 N_VIEWS = 64                     # orbit cameras (config 5a)
 METRIC = "frames_per_sec_1080p_6M_gaussians"
 REPEATS = 5                      # timed regions per measurement (the median is reported)
-KERNELS_PER_FRAME = 17           # preprocess 1, depth sort 1+1+1+4 (init, hist, plan, passes; the result stays where the last pass
-                                 # wrote it), scan 1, emit 1, tile sort 1+1+2+1, tile ranges 1, raster 1
+KERNELS_PER_FRAME = 16           # preprocess 1, depth sort 1 + 4 (prologue, pass launches: the plan decides on the device how many do
+                                 # work; the result stays where the last pass wrote it), scan 1, emit 1, tile sort 1+1+2+1 (init,
+                                 # histogram, passes, finish), tile ranges 1, tile schedule 1, raster 1
 
 
 def peaks():
@@ -106,7 +107,7 @@ def ncu_traffic():
         val, unit = txt.split()[:2]
         return float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
-    for key, stage in (("preprocess_kernel", "preprocess"), ("raster_gather4_kernel", "raster"), ("onesweep3_kernel", "depth_sort_pass")):
+    for key, stage in (("preprocess_kernel", "preprocess"), ("raster_gather4_kernel", "raster"), ("onesweep4_kernel", "depth_sort_pass")):
         rows = summ.get(key) or []
         vals = [to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"]) for r in rows
                 if "dram__bytes_read.sum" in r and "dram__bytes_write.sum" in r]
@@ -287,7 +288,11 @@ def run_cuda(args):
     # rasterizer: irreducible FP32 work = every blended fragment is tested (9 lane-ops) and blended
     # (15 lane-ops on unorm8: exp scale, alpha, 1-alpha, 3 x (mul, fma, 2 add)); FMA counts once (24 + 1 MUFU)
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    fp32_peak = 148 * 128 * sm_clock * 1e6 / 1e9           # G lane-ops/s at the clock sampled under load
+    # measured denominators (sb_probe_peaks: FFMA-chain and LDS.128 microbenchmarks run on this device just now); the nominal
+    # figures — 148 SMs x 128 lanes (x 128 B) x the SM clock sampled under load — are kept beside them
+    fp32_meas, smem_meas = ctx.probe_peaks(stream)
+    fp32_nominal = 148 * 128 * sm_clock * 1e6 / 1e9
+    fp32_peak = fp32_meas / 1e9                            # G lane-ops/s (FMA = 1)
     raster_ops = alive * 24.0
     raster_gops = raster_ops / stage["raster"] / 1e6
     # shared memory: the datapath moves one 128-byte wavefront per clock and SM.  A (warp, splat) evaluation broadcasts the
@@ -295,21 +300,23 @@ def run_cuda(args):
     # 128-bit loads = 8 wavefronts, and every one of a tile's 8 warps runs ceil(list / 32) rounds (>= D / 32 in total).
     smem_wavefronts = 3.0 * warp_evals + 8.0 * 8.0 * D / 32.0
     smem_gbs = smem_wavefronts * 128.0 / stage["raster"] / 1e6
-    smem_peak = 148 * 128 * sm_clock * 1e6 / 1e9              # GB/s
+    smem_peak = smem_meas / 1e9                               # GB/s
     roofs = {
         "raster": {"bound": "fp32", "kernel": "raster_gather4_kernel<splat,unorm8> (K6)", "achieved": raster_gops, "peak": fp32_peak,
                    "unit": "Gop/s (FP32 lane-ops, FMA = 1)", "frac": raster_gops / fp32_peak, "traffic": None,
-                   "peak_source": f"nominal 148 SMs x 128 lanes x {sm_clock:.0f} MHz sampled under load (no measured FP32 peak in MEASURED_PEAKS.json)",
+                   "peak_source": "measured: sb_probe_peaks FFMA-chain microbenchmark on this device (csrc/sb_probe.cu)",
+                   "peak_nominal": fp32_nominal,
                    "algorithmic_ops": raster_ops, "alive_fragments": alive, "evaluated_lane_pairs": evaluated,
                    "lane_efficiency": alive / evaluated if evaluated else None, "ms": stage["raster"],
                    "warp_splat_evaluations": warp_evals,
                    "smem": {"achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s (128-byte wavefronts)", "frac": smem_gbs / smem_peak,
                             "wavefronts": smem_wavefronts,
-                            "peak_source": f"nominal 148 SMs x 128 B/clk x {sm_clock:.0f} MHz sampled under load"}},
+                            "peak_source": "measured: sb_probe_peaks conflict-free LDS.128 microbenchmark on this device",
+                            "peak_nominal": fp32_nominal}},
         "preprocess": {"bound": "hbm", "kernel": "preprocess_kernel<single,single> (K1)", "achieved": pre_gbs, "peak": hbm_peak,
                        "unit": "GB/s", "frac": pre_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                        "algorithmic_bytes": pre_bytes, "ms": stage["preprocess"]},
-        "depth_sort": {"bound": "hbm", "kernel": "histogram_kernel + onesweep3_kernel x4 (K2/K3)", "achieved": sort_gbs, "peak": hbm_peak,
+        "depth_sort": {"bound": "hbm", "kernel": "sort4_prologue_kernel + onesweep4_kernel (key-adaptive: 2 passes of <= 9 bits on this scene) (K2'/K3')", "achieved": sort_gbs, "peak": hbm_peak,
                        "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                        "algorithmic_bytes": sort_bytes, "gkeys_per_s": V / stage["depth_sort"] / 1e6, "ms": stage["depth_sort"]},
     }
@@ -393,7 +400,14 @@ def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
         ms_equal = time_strips(sf)
         barrier()
         sf.close()
-    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream)
+    ms_replicated = None
+    if world > 1:  # balanced strips, every rank culling the whole scene for its strip (sb_viewer_set_strip_cull)
+        sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream)
+        ms_replicated = time_strips(sf)
+        barrier()
+        sf.close()
+    # the headline arrangement: balanced strips + the Preprocessor partitioned over the ranks (sb_strips_*)
+    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream, partition_cull=True)
     ms = time_strips(sf)
     # this rank's share of the work, and its stage times
     viewer.set_stage_timing(True)
@@ -433,6 +447,10 @@ def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
                                "whose tile box meets its strip; strip boundaries balance the (splat, tile) duplicates per tile row "
                                "of one calibration frame rendered at set-up (a viewer would use its previous frame)",
                "ms_per_frame_equal_height_strips": ms_equal,
+               "ms_per_frame_replicated_cull": ms_replicated,
+               "preprocessor": ("partitioned: rank r culls Gaussians [n r/G, n (r+1)/G) and stores each strip's (index, key) pairs, "
+                                "records and tile boxes into the owning rank over NVLink (sb_strips_*), one all-reduce in between"
+                                if sf.strips is not None else "replicated full-frame cull with the strip filter in K1"),
                "identical_to_single_gpu_frame": bool(torch.equal(got, ref)),
                "full_frame": {"visible": full["visible"], "tile_duplicates": full["duplicates"]},
                "per_rank": [{"row0": sf.bounds[r][0], "rows": sf.bounds[r][1], "visible": int(shares[r][0].item()),

@@ -316,6 +316,26 @@ SB_API SbStatus sb_shared_frame_create(SbContext* ctx, uint64_t bytes, void** d_
 SB_API SbStatus sb_shared_frame_open(SbContext* ctx, const uint8_t handle[SB_SHARED_HANDLE_BYTES], void** d_frame);
 SB_API SbStatus sb_shared_frame_close(SbContext* ctx, void* d_frame);    /* a pointer obtained from _open */
 SB_API SbStatus sb_shared_frame_destroy(SbContext* ctx, void* d_frame);  /* a pointer obtained from _create */
+/* Strips with the Preprocessor's work partitioned as well (the scalable form of the strip case; same frames bit for bit): rank r
+ * preprocesses Gaussians [n r / G, n (r + 1) / G) only and stores, over NVLink, the (index, key) pairs, splat records and tile
+ * boxes each strip needs straight into the owning rank's buffers; after ONE barrier across the ranks (the caller's: any
+ * stream-ordered collective) each rank strings its inbox together — ascending source rank = ascending Gaussian index, i.e. the
+ * strip's visible list exactly as a single-GPU cull compacts it — and runs the unchanged sort / binning / rasterizer on it.
+ *   create   (every rank) viewer = the replicated scene; row0s/rows = every rank's strip (whole tile rows; rows 0 = no strip);
+ *            `exported` = this rank's three IPC handles, to be given to every other rank
+ *   connect  (every rank) all ranks' exports, in rank order
+ *   scatter  enqueue: K1 on the slice + the scatter into the peers      -> barrier across ranks ->
+ *   render   enqueue: concat + depth sort + binning + rasterizer of this rank's strip into `target` (SbTarget.row0/rows = its strip)
+ * After `render` the viewer's artefacts (args, indices, keys) describe the strip's visible set, as with sb_viewer_set_strip_cull.
+ * A second barrier must separate a frame's `render` from the next frame's `scatter` (the strip fence of the shared frame does). */
+typedef struct SbStrips SbStrips;
+typedef struct SbStripsExport { uint8_t handles[3][SB_SHARED_HANDLE_BYTES]; } SbStripsExport;
+SB_API SbStatus sb_strips_create(SbViewer* v, uint32_t world, uint32_t rank, const uint32_t* row0s, const uint32_t* rows, SbStrips** out,
+                                 SbStripsExport* exported);
+SB_API SbStatus sb_strips_connect(SbStrips* s, const SbStripsExport* all_ranks);
+SB_API SbStatus sb_strips_scatter(SbStrips* s, void* stream);
+SB_API SbStatus sb_strips_render(SbStrips* s, void* stream, const SbTarget* target);
+SB_API void sb_strips_destroy(SbStrips* s);
 /* Tracing (the reference has none: every pass has timestamp_writes: None, src/radix_sorter.rs:504-507).
  * When enabled, cudaEvents are recorded on the launching stream between the stages of a frame;
  * ms[0..5] = preprocess, depth sort, tile count+emit, tile sort, gather, raster. */

@@ -10,7 +10,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-kernels = sys.argv[2:] or ["preprocess_kernel", "onesweep3_kernel", "raster_gather4_kernel"]
+kernels = sys.argv[2:] or ["preprocess_kernel", "onesweep4_kernel", "raster_gather4_kernel"]
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 

@@ -354,6 +354,7 @@ def test_strip_cull_subsets_reassemble_the_frame(sb, ob, ctx, cam_name, mode):
 def _strip_worker(rank, world, port, n, w, h, q):
     import os
     import sys
+    import numpy as np
     import torch
     import torch.distributed as dist
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -369,19 +370,39 @@ def _strip_worker(rank, world, port, n, w, h, q):
     pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
     v.update_camera_with_pod(sb.camera_pod(pos, yaw, pitch, w, h))
     res = {}
-    for mode in ("peer", "sendrecv"):
-        sf = sb.sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=mode)
+    sel = np.random.default_rng(4).integers(0, 2**32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32)
+    for mode in ("peer", "sendrecv", "exchange", "exchange+selection"):
+        if mode == "exchange+selection":  # the selection mask is indexed by the Gaussian's index in the WHOLE model on every slice
+            v.enable_selection(True)
+            v.set_selection(sel)
+        sf = sb.sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode="peer" if mode.startswith("exchange") else mode,
+                                    balance=mode.startswith("exchange"), partition_cull=mode.startswith("exchange"))
         for _ in range(3):
             frame = sf.render()
         torch.cuda.synchronize()
         dist.barrier()
+        lists = None
+        if mode.startswith("exchange"):
+            # this rank's artefacts describe its strip's visible set exactly as the strip-culling K1 leaves them
+            Vx = int(v.read_indirect_args()[0][1])
+            ix, kx = v.read_indices(Vx), v.read_depth_keys(Vx).view(np.uint32)
+            r0, rows = sf.bounds[rank]
+            chk = torch.zeros((max(rows, 1), w, 4), dtype=torch.uint8, device="cuda")
+            v.set_strip_cull(True)
+            v.render(chk, w, h, row0=r0, rows=rows)
+            torch.cuda.synchronize()
+            Vs = int(v.read_indirect_args()[0][1])
+            lists = bool(Vx == Vs and np.array_equal(ix, v.read_indices(Vs)) and np.array_equal(kx, v.read_depth_keys(Vs).view(np.uint32)))
+            agree = torch.tensor([int(lists)], device="cuda")
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            lists = bool(agree.item())
         if rank == 0:
             got = frame.clone()
             v.set_strip_cull(False)
             ref = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
             v.render(ref, w, h)
             torch.cuda.synchronize()
-            res[mode] = (sf.mode, bool(torch.equal(got, ref)))
+            res[mode] = (sf.mode, bool(torch.equal(got, ref)), lists)
         dist.barrier()
         sf.close()
     if rank == 0:
@@ -413,8 +434,11 @@ def test_strips_over_two_gpus_land_in_one_frame(sb):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert res["sendrecv"] == ("sendrecv", True)
+    assert res["sendrecv"][:2] == ("sendrecv", True)
     assert res["peer"][1], "strips written through the peer-mapped frame differ from the single-GPU frame"
+    for mode in ("exchange", "exchange+selection"):
+        assert res[mode][1], f"{mode}: partitioned-cull strips differ from the single-GPU frame"
+        assert res[mode][2], f"{mode}: a rank's exchanged visible list differs from the strip-culling Preprocessor's"
 
 
 @pytest.mark.parametrize("explicit_stream", [False, True])

@@ -354,11 +354,13 @@ SbStatus check_target(SbViewer* v, const SbTarget* t, const sb::Uniforms& u) {
 }
 
 SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformPod& gt, cudaStream_t stream,
-                       const SbTarget* strip = nullptr) {
+                       const SbTarget* strip = nullptr, uint32_t slice_lo = 0, uint32_t slice_n = 0xffffffffu) {
     sb::PreParams p;
     std::memset(&p, 0, sizeof p);
-    p.gaussians = static_cast<const uint8_t*>(v->d_gaussians);
-    p.n = v->n;
+    if (slice_n == 0xffffffffu) slice_n = v->n;  // the whole model (a slice: the partitioned strips, sb_strips_scatter)
+    p.gaussians = static_cast<const uint8_t*>(v->d_gaussians) + (size_t)slice_lo * v->stride;
+    p.n = slice_n;
+    p.index_base = slice_lo;
     p.selection = v->selection_enabled ? (v->selection_override ? v->selection_override : v->selection.as<uint32_t>()) : nullptr;
     p.invert_selection = v->invert_selection;
     p.indices = v->indices.as<uint32_t>();
@@ -366,8 +368,8 @@ SbStatus do_preprocess(SbViewer* v, const SbCameraPod& cam, const SbGaussianTran
     p.keys_capacity = v->padded;
     p.draw_args = v->d_draw();
     p.sort_args = v->d_dispatch();
-    p.recs = v->recs.as<sb::SplatRec>();
-    p.tboxes = v->tboxes.as<sb::TileBox>();
+    p.recs = v->recs.as<sb::SplatRec>() + slice_lo;
+    p.tboxes = v->tboxes.as<sb::TileBox>() + slice_lo;
     p.visible_count = v->d_visible();
     p.visible_host = v->d_needed + 4;  // mapped pinned: the next frame's sort reads it (no synchronisation) as a size hint
     p.sort_prep = v->pre_scratch.as<uint32_t>();
@@ -1107,6 +1109,170 @@ SbStatus sb_viewer_read_tile_row_work(SbViewer* v, void* stream, uint64_t* out, 
         out[y] = sum;
     }
     return SB_OK;
+}
+
+struct SbStrips {
+    SbViewer* v = nullptr;
+    uint32_t world = 0, rank = 0;
+    uint32_t row0s[sb::kMaxStripRanks] = {}, rows[sb::kMaxStripRanks] = {};
+    uint32_t slice_lo = 0, slice_n = 0, segment_capacity = 0;
+    DeviceBuf inbox;    // [world][segment_capacity] uint2 pairs, then [world] counts (64-byte aligned)
+    DeviceBuf scratch;  // scatter tickets + look-back status
+    size_t counts_offset = 0;
+    void* peer_inbox[sb::kMaxStripRanks] = {};   // peer-mapped (own pointers at [rank])
+    void* peer_recs[sb::kMaxStripRanks] = {};
+    void* peer_tboxes[sb::kMaxStripRanks] = {};
+    bool connected = false;
+};
+
+SbStatus sb_strips_create(SbViewer* v, uint32_t world, uint32_t rank, const uint32_t* row0s, const uint32_t* rows, SbStrips** out,
+                          SbStripsExport* exported) {
+    if (!v || !row0s || !rows || !out || !exported) return fail(v ? v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (world == 0 || world > (uint32_t)sb::kMaxStripRanks || rank >= world) return fail(v->ctx, SB_ERR_INVALID_ARG, "bad world / rank (at most 16 ranks)");
+    DeviceGuard device_guard(v->ctx);
+    SbStrips* s = new SbStrips();
+    s->v = v;
+    s->world = world;
+    s->rank = rank;
+    for (uint32_t r = 0; r < world; r++) {
+        s->row0s[r] = row0s[r];
+        s->rows[r] = rows[r];
+    }
+    // slices: ascending index ranges, boundaries at multiples of 32 so a selection word never straddles two ranks' K1
+    auto cut = [&](uint32_t r) { return r >= world ? v->n : (uint32_t)(((uint64_t)v->n * r / world) & ~31ull); };
+    s->slice_lo = cut(rank);
+    s->slice_n = cut(rank + 1) - s->slice_lo;
+    uint32_t cap = 0;
+    for (uint32_t r = 0; r < world; r++) cap = std::max(cap, cut(r + 1) - cut(r));
+    s->segment_capacity = (cap + 31u) & ~31u;
+    s->counts_offset = ((size_t)world * s->segment_capacity * sizeof(uint2) + 63) & ~(size_t)63;
+    cudaError_t e = s->inbox.alloc(s->counts_offset + 64);
+    if (e == cudaSuccess) e = cudaMemset(s->inbox.p, 0, s->inbox.bytes);
+    if (e == cudaSuccess) e = s->scratch.alloc(sb::strip_scatter_scratch_bytes(s->segment_capacity, world));
+    cudaIpcMemHandle_t h[3];
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[0], v->recs.p);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[1], v->tboxes.p);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[2], s->inbox.p);
+    if (e != cudaSuccess) {
+        s->inbox.release();
+        s->scratch.release();
+        delete s;
+        return fail_cuda(v->ctx, e, "strip exchange buffers");
+    }
+    for (int i = 0; i < 3; i++) std::memcpy(exported->handles[i], &h[i], sizeof h[i]);
+    *out = s;
+    return SB_OK;
+}
+
+SbStatus sb_strips_connect(SbStrips* s, const SbStripsExport* all) {
+    if (!s || !all) return fail(s ? s->v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    if (s->connected) return fail(s->v->ctx, SB_ERR_INVALID_ARG, "already connected");
+    DeviceGuard device_guard(s->v->ctx);
+    for (uint32_t r = 0; r < s->world; r++) {
+        if (r == s->rank) {
+            s->peer_recs[r] = s->v->recs.p;
+            s->peer_tboxes[r] = s->v->tboxes.p;
+            s->peer_inbox[r] = s->inbox.p;
+            continue;
+        }
+        void** dst[3] = {&s->peer_recs[r], &s->peer_tboxes[r], &s->peer_inbox[r]};
+        for (int i = 0; i < 3; i++) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, all[r].handles[i], sizeof h);
+            SB_CUDA(s->v->ctx, cudaIpcOpenMemHandle(dst[i], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    s->connected = true;
+    return SB_OK;
+}
+
+SbStatus sb_strips_scatter(SbStrips* s, void* stream) {
+    if (!s) return fail(nullptr, SB_ERR_INVALID_ARG, "null");
+    SbViewer* v = s->v;
+    if (!s->connected) return fail(v->ctx, SB_ERR_INVALID_ARG, "sb_strips_connect first");
+    DeviceGuard device_guard(v->ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    // the reference's full-frame cull, on this rank's slice of the model
+    SbStatus ps = do_preprocess(v, v->camera, v->gaussian_transform, st, nullptr, s->slice_lo, s->slice_n);
+    if (ps != SB_OK) return ps;
+    sb::StripScatterParams p;
+    std::memset(&p, 0, sizeof p);
+    p.indices = v->indices.as<uint32_t>();
+    p.keys = v->keys.as<float>();
+    p.visible_count = v->d_visible();
+    p.max_visible = s->slice_n;
+    p.recs = v->recs.as<sb::SplatRec>();
+    p.tboxes = v->tboxes.as<sb::TileBox>();
+    p.world = s->world;
+    p.rank = s->rank;
+    p.segment_capacity = s->segment_capacity;
+    for (uint32_t r = 0; r < s->world; r++) {
+        if (s->rows[r] == 0 || s->row0s[r] >= u.height) {
+            p.ty_lo[r] = 1;
+            p.ty_hi[r] = 0;
+        } else {
+            p.ty_lo[r] = s->row0s[r] / sb::kTile;
+            p.ty_hi[r] = (std::min(s->row0s[r] + s->rows[r], u.height) - 1) / sb::kTile;
+        }
+        p.inbox_pairs[r] = static_cast<uint2*>(s->peer_inbox[r]);
+        p.inbox_counts[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(s->peer_inbox[r]) + s->counts_offset);
+        p.peer_recs[r] = static_cast<sb::SplatRec*>(s->peer_recs[r]);
+        p.peer_tboxes[r] = static_cast<sb::TileBox*>(s->peer_tboxes[r]);
+    }
+    SB_CUDA(v->ctx, sb::launch_strip_scatter(p, s->scratch.p, s->scratch.bytes, st));
+    return SB_OK;
+}
+
+SbStatus sb_strips_render(SbStrips* s, void* stream, const SbTarget* target) {
+    if (!s || !target) return fail(s ? s->v->ctx : nullptr, SB_ERR_INVALID_ARG, "null");
+    SbViewer* v = s->v;
+    DeviceGuard device_guard(v->ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sb::Uniforms u = make_uniforms(v->camera, v->model_transform, v->gaussian_transform, v->target_format);
+    SbStatus cs = check_target(v, target, u);
+    if (cs == SB_OK) cs = report_overflow(v);
+    if (cs != SB_OK) return cs;
+    // the depth sort's prep words start from zero again: or / nand must describe the strip's list, not the slice's
+    SB_CUDA(v->ctx, cudaMemsetAsync(v->pre_scratch.p, 0, sb::preprocess_scratch_prefix_bytes(), st));
+    sb::StripConcatParams c;
+    std::memset(&c, 0, sizeof c);
+    c.inbox_pairs = s->inbox.as<uint2>();
+    c.inbox_counts = reinterpret_cast<const uint32_t*>(s->inbox.as<uint8_t>() + s->counts_offset);
+    c.world = s->world;
+    c.segment_capacity = s->segment_capacity;
+    c.max_visible = v->n;
+    c.indices = v->indices.as<uint32_t>();
+    c.keys = v->keys.as<float>();
+    c.keys_capacity = v->padded;
+    c.draw_args = v->d_draw();
+    c.sort_args = v->d_dispatch();
+    c.visible_count = v->d_visible();
+    c.visible_host = v->d_needed + 4;
+    c.sort_prep = v->pre_scratch.as<uint32_t>();
+    SB_CUDA(v->ctx, sb::launch_strip_concat(c, v->ctx->num_sms, st));
+    v->sort_prep_fresh = true;
+    v->sorted_pending = false;
+    if (v->timing) SB_CUDA(v->ctx, cudaEventRecord(v->ev[1], st));  // "preprocess" of the stage times ends after the concat
+    SbStatus rs = do_sort(v, st, true);
+    if (rs != SB_OK) return rs;
+    return do_draw(v, v->camera, v->gaussian_transform, target, 1, st);
+}
+
+void sb_strips_destroy(SbStrips* s) {
+    if (!s) return;
+    DeviceGuard device_guard(s->v->ctx);
+    cudaDeviceSynchronize();
+    if (s->connected)
+        for (uint32_t r = 0; r < s->world; r++) {
+            if (r == s->rank) continue;
+            cudaIpcCloseMemHandle(s->peer_recs[r]);
+            cudaIpcCloseMemHandle(s->peer_tboxes[r]);
+            cudaIpcCloseMemHandle(s->peer_inbox[r]);
+        }
+    s->inbox.release();
+    s->scratch.release();
+    delete s;
 }
 
 SbStatus sb_viewer_set_strip_cull(SbViewer* v, int32_t enabled) {

@@ -25,6 +25,8 @@ struct PreParams {
     unsigned long long* tile_status;   // decoupled look-back state (zeroed before launch)
     uint32_t* visible_count;           // V for downstream kernels
     uint32_t* visible_host;            // nullable: device alias of a mapped pinned word that also receives V
+    uint32_t index_base;               // gaussians / recs / tboxes point at Gaussian `index_base` of the model (a slice is preprocessed):
+                                       // indices written and selection bits looked up are index_base + the slice-local index
     uint32_t strip_on;                 // 1: keep only the visible splats whose tile box meets tile rows [strip_ty_lo, strip_ty_hi]
     uint32_t strip_ty_lo, strip_ty_hi; //    (one frame split into screen strips over several GPUs; needs recs)
     uint32_t* sort_prep;               // nullable: [kSortPrepOr] |= key, [kSortPrepNand] |= ~key over the visible keys (zeroed before launch)
@@ -127,6 +129,43 @@ struct RasterParams {
 };
 cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_clear(const SbTarget& target, cudaStream_t stream);
+
+// ---------------------------------------------------------------- partitioned strips (sb_strips.cu)
+constexpr int kMaxStripRanks = 16;
+struct StripScatterParams {
+    const uint32_t* indices;        // this rank's visible list (global Gaussian indices, ascending) and keys
+    const float* keys;
+    const uint32_t* visible_count;
+    uint32_t max_visible;           // slice size
+    const SplatRec* recs;           // this rank's arrays, indexed by global Gaussian index
+    const TileBox* tboxes;
+    uint32_t world, rank;
+    uint32_t segment_capacity;      // entries per (destination, source) inbox segment
+    uint32_t ty_lo[kMaxStripRanks], ty_hi[kMaxStripRanks];  // tile rows of every rank's strip (lo > hi: no strip)
+    uint2* inbox_pairs[kMaxStripRanks];      // destination d's inbox: [world][segment_capacity] (index, key bits); peer-mapped
+    uint32_t* inbox_counts[kMaxStripRanks];  // destination d's [world] segment counts; peer-mapped
+    SplatRec* peer_recs[kMaxStripRanks];     // destination d's recs / tboxes; peer-mapped (own arrays for d == rank)
+    TileBox* peer_tboxes[kMaxStripRanks];
+    uint32_t* tickets;              // set by the launcher
+    unsigned long long* status;
+    uint32_t status_stride;
+};
+struct StripConcatParams {
+    const uint2* inbox_pairs;       // this rank's inbox
+    const uint32_t* inbox_counts;
+    uint32_t world, segment_capacity, max_visible;
+    uint32_t* indices;
+    float* keys;
+    uint32_t keys_capacity;
+    SbDrawIndirectArgs* draw_args;
+    SbDispatchIndirectArgs* sort_args;
+    uint32_t* visible_count;
+    uint32_t* visible_host;
+    uint32_t* sort_prep;            // zeroed by the caller; receives or / nand of the strip's keys
+};
+size_t strip_scatter_scratch_bytes(uint32_t max_visible, uint32_t world);
+cudaError_t launch_strip_scatter(StripScatterParams& p, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+cudaError_t launch_strip_concat(const StripConcatParams& p, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- viewport selection (sb_select.cu)
 // selection::viewport::main with an analytic rectangle mask; writes ceil(n/32) words.

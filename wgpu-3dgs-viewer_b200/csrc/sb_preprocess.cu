@@ -282,8 +282,9 @@ __device__ __forceinline__ bool cull_gaussian(const PreParams& p, const Uniforms
     if (vis) head = *reinterpret_cast<const float4*>(rec);
     // selection: preprocess.wesl:68-78
     if (p.selection != nullptr && vis) {
-        const uint32_t word = __ldg(&p.selection[g >> 5]);
-        const bool bit = (word >> (g & 31u)) & 1u;
+        const uint32_t gi = g + p.index_base;  // (a slice of the model: the mask is indexed by the Gaussian's index in the whole model)
+        const uint32_t word = __ldg(&p.selection[gi >> 5]);
+        const bool bit = (word >> (gi & 31u)) & 1u;
         const bool inverted = p.invert_selection != 0u;
         if (inverted == bit) vis = false;
     }
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(tile_records(pod_stride(SH, COV)) + 64, 1)
         const uint32_t warp_excl = __shfl_sync(0xffffffffu, inc - c, warp);
         if (d.vis) {
             const uint32_t slot = base + warp_excl + d.lane_rank;
-            p.indices[slot] = d.g;
+            p.indices[slot] = d.g + p.index_base;
             p.keys[slot] = d.key;
         }
         if (d.tile == p.num_tiles - 1) {

@@ -20,6 +20,9 @@ pub mod ffi {
     #[repr(C)] pub struct SbPreprocessor { _p: [u8; 0] }
     #[repr(C)] pub struct SbRadixSorter { _p: [u8; 0] }
     #[repr(C)] pub struct SbRenderer { _p: [u8; 0] }
+    #[repr(C)] pub struct SbStrips { _p: [u8; 0] }
+    /// The three CUDA-IPC handles a rank publishes for the partitioned strips (records, tile boxes, inbox).
+    #[repr(C)] #[derive(Clone, Copy)] pub struct StripsExport { pub handles: [[u8; 64]; 3] }
 
     /// `CameraPod` — byte-identical to the reference (src/buffer/camera.rs:63-80).
     #[repr(C)] #[derive(Clone, Copy, Debug, PartialEq, bytemuck::Pod, bytemuck::Zeroable)]
@@ -299,6 +302,23 @@ impl Context {
     /// Measured FP32-issue (lane-ops/s, FMA = 1) and shared-memory (bytes/s) peaks of this device.
     pub fn probe_peaks(&self, stream: Stream) -> Result<(f64, f64), Error> { let (mut a, mut b) = (0f64, 0f64); check(unsafe { ffi::sb_probe_peaks(self.0, stream.0, &mut a, &mut b) }, self.0)?; Ok((a, b)) }
 }
+
+/// One frame as screen strips with the Preprocessor's work partitioned over the ranks (`sb_strips_*`): `scatter`, a barrier across
+/// the ranks, `render`, a second barrier before the next frame.
+pub struct Strips<'v, 'c, G: GaussianPod> { raw: *mut ffi::SbStrips, viewer: &'v Viewer<'c, G>, pub exported: ffi::StripsExport }
+impl<'v, 'c, G: GaussianPod> Strips<'v, 'c, G> {
+    /// `bounds[r] = (row0, rows)` of every rank's strip (whole 16-pixel tile rows).
+    pub fn new(viewer: &'v Viewer<'c, G>, rank: u32, bounds: &[(u32, u32)]) -> Result<Self, Error> {
+        let (r0, rn): (Vec<u32>, Vec<u32>) = bounds.iter().cloned().unzip();
+        let (mut raw, mut ex) = (std::ptr::null_mut(), ffi::StripsExport { handles: [[0u8; 64]; 3] });
+        check(unsafe { ffi::sb_strips_create(viewer.raw, bounds.len() as u32, rank, r0.as_ptr(), rn.as_ptr(), &mut raw, &mut ex) }, viewer.ctx.0)?;
+        Ok(Self { raw, viewer, exported: ex })
+    }
+    pub fn connect(&mut self, all_ranks: &[ffi::StripsExport]) -> Result<(), Error> { check(unsafe { ffi::sb_strips_connect(self.raw, all_ranks.as_ptr()) }, self.viewer.ctx.0) }
+    pub fn scatter(&self, stream: Stream) -> Result<(), Error> { check(unsafe { ffi::sb_strips_scatter(self.raw, stream.0) }, self.viewer.ctx.0) }
+    pub fn render(&self, stream: Stream, target: &Target) -> Result<(), Error> { check(unsafe { ffi::sb_strips_render(self.raw, stream.0, target) }, self.viewer.ctx.0) }
+}
+impl<G: GaussianPod> Drop for Strips<'_, '_, G> { fn drop(&mut self) { unsafe { ffi::sb_strips_destroy(self.raw) } } }
 
 /// A frame other GPUs of the node render their strips into (CUDA IPC over NVLink): the owner creates and publishes `handle`.
 pub struct SharedFrame<'c> { pub ptr: *mut c_void, pub handle: [u8; 64], owner: bool, ctx: &'c Context }

@@ -48,7 +48,8 @@ EXPORTED_SYMBOLS = [
     "sb_mm_update_camera", "sb_mm_update_model_transform", "sb_mm_update_gaussian_transform", "sb_mm_insert_model_from_gaussians",
     "sb_mm_insert_model_from_device", "sb_mm_select_rect", "sb_mm_select_brush", "sb_mm_enable_selection", "sb_mm_read_selection",
     "sb_mm_render_with_pass",
-    "sb_read_spz", "sb_viewer_apply_basic_color_modifiers", "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
+    "sb_read_spz", "sb_viewer_apply_basic_color_modifiers", "sb_strips_create", "sb_strips_connect", "sb_strips_scatter", "sb_strips_render",
+    "sb_strips_destroy", "sb_probe_peaks", "sb_viewer_set_strip_cull", "sb_viewer_read_tile_row_work", "sb_shared_frame_create", "sb_shared_frame_open", "sb_shared_frame_close", "sb_shared_frame_destroy",
 ]
 
 
@@ -205,6 +206,11 @@ def load() -> C.CDLL:
     sig("sb_shared_frame_open", i32, vp, C.c_char_p, P(vp))
     sig("sb_shared_frame_close", i32, vp, vp)
     sig("sb_shared_frame_destroy", i32, vp, vp)
+    sig("sb_strips_create", i32, vp, u32, u32, P(u32), P(u32), P(vp), C.c_char_p)
+    sig("sb_strips_connect", i32, vp, C.c_char_p)
+    sig("sb_strips_scatter", i32, vp, vp)
+    sig("sb_strips_render", i32, vp, vp, P(Target))
+    sig("sb_strips_destroy", None, vp)
     sig("sb_viewer_set_raster_counting", i32, vp, i32)
     sig("sb_viewer_read_raster_counters", i32, vp, vp, P(u64), P(u64))
     sig("sb_viewer_read_raster_warp_counters", i32, vp, vp, P(u64), P(u64))
@@ -387,6 +393,40 @@ class SharedFrame:
             fn = load().sb_shared_frame_destroy if self.owner else load().sb_shared_frame_close
             _check(fn(self.ctx._h, self.ptr), self.ctx._h)
             self.ptr = 0
+
+
+class Strips:
+    """sb_strips_*: one frame as screen strips with the Preprocessor's work partitioned over the ranks as well.  Construct on every
+    rank, exchange `exported` (192 bytes) between all ranks, `connect(all_exports_in_rank_order)`; per frame `scatter(stream)`,
+    a barrier across the ranks, `render(stream, target...)`, and a second barrier before the next frame's scatter."""
+
+    EXPORT_BYTES = 192
+
+    def __init__(self, viewer: "Viewer", world: int, rank: int, bounds):
+        self.viewer, self.world, self.rank = viewer, world, rank
+        r0 = (C.c_uint32 * world)(*[int(b[0]) for b in bounds])
+        rn = (C.c_uint32 * world)(*[int(b[1]) for b in bounds])
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(self.EXPORT_BYTES)
+        _check(load().sb_strips_create(viewer._h, world, rank, r0, rn, C.byref(self._h), buf), viewer.ctx._h)
+        self.exported = buf.raw
+
+    def connect(self, all_exports):
+        blob = b"".join(bytes(e) for e in all_exports)
+        assert len(blob) == self.EXPORT_BYTES * self.world
+        _check(load().sb_strips_connect(self._h, blob), self.viewer.ctx._h)
+
+    def scatter(self, stream=None):
+        _check(load().sb_strips_scatter(self._h, _stream_handle(stream)), self.viewer.ctx._h)
+
+    def render(self, target, width, height, row0, rows, pitch=None, stream=None):
+        t = make_target(target, width, height, self.viewer.target_format, pitch, row0, rows)
+        _check(load().sb_strips_render(self._h, _stream_handle(stream), C.byref(t)), self.viewer.ctx._h)
+
+    def close(self):
+        if self._h:
+            load().sb_strips_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 class Viewer:

@@ -12,6 +12,10 @@
       orders them before the owner reads.
     - `gather_strips` (mode="sendrecv", also the gloo CPU path): one batched send/recv group that
       receives every strip directly into its rows of the final frame (no padding, no concatenation).
+  `StripFrame(partition_cull=True)` (needs the peer mode) also partitions the Preprocessor: rank r culls
+  Gaussians [n r / G, n (r + 1) / G) only and stores every strip's splats into the owning rank's
+  buffers over NVLink (`sb_strips_*`); one all-reduce separates that scatter from the strips' own
+  sort / binning / rasterizer.  Same frames bit for bit.
 """
 from __future__ import annotations
 
@@ -110,7 +114,7 @@ class StripFrame:
     """One frame rendered as `world` screen strips into a single buffer on rank `dst` (config 5b)."""
 
     def __init__(self, ctx, viewer, width: int, height: int, bytes_per_pixel: int, world: int, rank: int, dst: int = 0,
-                 mode: str = "peer", balance: bool = False, stream=None):
+                 mode: str = "peer", balance: bool = False, stream=None, partition_cull: bool = False):
         """balance: rank `dst` renders the full frame once (a calibration frame; a viewer would use its previous frame), reads the
         (splat, tile) duplicates per tile row and broadcasts strips of equal work instead of equal height."""
         import torch
@@ -178,6 +182,13 @@ class StripFrame:
             if self.mode == "sendrecv" and rank != dst:
                 self.strip = torch.zeros((self.rows, width, bytes_per_pixel), dtype=torch.uint8, device="cuda")
         viewer.set_strip_cull(True)
+        self.strips = None
+        if partition_cull and self.mode == "peer":
+            self.strips = api.Strips(viewer, world, rank, self.bounds)
+            exports = [None] * world
+            dist.all_gather_object(exports, self.strips.exported)
+            self.strips.connect(exports)
+            dist.barrier()
 
     def render(self, stream=None):
         """Enqueue this rank's strip and whatever completes the frame on the owner; stream-ordered, no host sync."""
@@ -186,6 +197,28 @@ class StripFrame:
         from . import api
 
         v, w, h = self.viewer, self.width, self.height
+        if self.strips is not None:
+            ctxm = torch.cuda.stream(stream) if stream is not None else _null()
+            for attempt in range(3):
+                try:
+                    self.strips.scatter(stream)           # K1 on this rank's slice of the model + stores into the peers
+                    break
+                except api.SplatError as e:
+                    if "render again" not in str(e) or attempt == 2:
+                        raise
+            with ctxm:
+                dist.all_reduce(self._flag)               # every rank's scatter has landed
+            if self.rows:
+                for attempt in range(3):
+                    try:
+                        self.strips.render(self.frame_ptr + self.row0 * self.pitch, w, h, self.row0, self.rows, self.pitch, stream)
+                        break
+                    except api.SplatError as e:
+                        if "render again" not in str(e) or attempt == 2:
+                            raise
+            with ctxm:
+                dist.all_reduce(self._flag)               # frame complete on the owner; inboxes free for the next scatter
+            return self.frame
         if self.rows:
             if self.mode == "sendrecv" and self.rank != self.dst:
                 ptr = self.strip.data_ptr()
@@ -211,6 +244,9 @@ class StripFrame:
         return self.frame
 
     def close(self):
+        if self.strips is not None:
+            self.strips.close()
+            self.strips = None
         self.viewer.set_strip_cull(False)
         if self.shared is not None:
             self.shared.close()
