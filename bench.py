@@ -400,14 +400,18 @@ def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
         ms_equal = time_strips(sf)
         barrier()
         sf.close()
-    ms_replicated = None
-    if world > 1:  # balanced strips, every rank culling the whole scene for its strip (sb_viewer_set_strip_cull)
-        sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream)
-        ms_replicated = time_strips(sf)
+    ms_partitioned = None
+    if world > 1:
+        # measured alternative: the Preprocessor partitioned over the ranks as well (sb_strips_*: rank r culls a slice of the model and
+        # ships each strip's splats to its owner over NVLink).  Same frames; not faster on this hardware — moving a 64-byte parcel
+        # over NVLink costs more than recomputing the splat from its 224-byte pod in HBM — so it is reported, not headlined.
+        sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream, partition_cull=True)
+        if sf.strips is not None:
+            ms_partitioned = time_strips(sf)
         barrier()
         sf.close()
-    # the headline arrangement: balanced strips + the Preprocessor partitioned over the ranks (sb_strips_*)
-    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream, partition_cull=True)
+    # the headline arrangement: balanced strips, every rank running the full-frame cull with the strip filter inside K1
+    sf = sb.sharding.StripFrame(ctx, viewer, STRIP_W, STRIP_H, 4, world, rank, dst=0, balance=True, stream=stream)
     ms = time_strips(sf)
     # this rank's share of the work, and its stage times
     viewer.set_stage_timing(True)
@@ -447,10 +451,10 @@ def run_strips(sb, torch, dist, ctx, viewer, world, rank, stream, barrier):
                                "whose tile box meets its strip; strip boundaries balance the (splat, tile) duplicates per tile row "
                                "of one calibration frame rendered at set-up (a viewer would use its previous frame)",
                "ms_per_frame_equal_height_strips": ms_equal,
-               "ms_per_frame_replicated_cull": ms_replicated,
-               "preprocessor": ("partitioned: rank r culls Gaussians [n r/G, n (r+1)/G) and stores each strip's (index, key) pairs, "
-                                "records and tile boxes into the owning rank over NVLink (sb_strips_*), one all-reduce in between"
-                                if sf.strips is not None else "replicated full-frame cull with the strip filter in K1"),
+               "ms_per_frame_partitioned_preprocessor": ms_partitioned,
+               "preprocessor": "full-frame cull on every rank with the strip filter inside K1 (ms_per_frame); "
+                               "ms_per_frame_partitioned_preprocessor = sb_strips_*: rank r culls Gaussians [n r/G, n (r+1)/G) and ships each "
+                               "strip's splats as 64-byte parcels into the owning rank over NVLink, one extra all-reduce",
                "identical_to_single_gpu_frame": bool(torch.equal(got, ref)),
                "full_frame": {"visible": full["visible"], "tile_duplicates": full["duplicates"]},
                "per_rank": [{"row0": sf.bounds[r][0], "rows": sf.bounds[r][1], "visible": int(shares[r][0].item()),

@@ -22,6 +22,7 @@ ap.add_argument("--size", type=int, nargs=2, default=[7680, 4320])
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--mode", default="peer", choices=["peer", "sendrecv"])
+ap.add_argument("--partition-cull", type=int, default=1, help="1: sb_strips_* (each rank preprocesses a slice of the model), 0: replicated cull")
 ap.add_argument("--check", action="store_true", help="rank 0 also renders the full frame alone and compares")
 args = ap.parse_args()
 
@@ -37,7 +38,7 @@ pods = sb.pack_gaussians(sb.scenes.synthetic_gaussians(args.n, sb.scenes.BASE_SE
 v = sb.Viewer(ctx, pods, args.n)
 pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
 v.update_camera(pos, yaw, pitch, w, h)
-sf = sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=args.mode)
+sf = sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=args.mode, balance=True, partition_cull=bool(args.partition_cull))
 stream = torch.cuda.current_stream()
 
 
@@ -62,7 +63,7 @@ if world > 1:
 if rank == 0:
     out = dict(config="8K strips", gaussians=args.n, size=[w, h], n_gpus=world, ms_per_frame=float(ms.item()),
                frames_per_s=1000.0 / float(ms.item()), strip_rows=[sharding.strip_rows(h, world, r)[1] for r in range(world)],
-               transport=sf.mode)
+               transport=sf.mode, partitioned_cull=sf.strips is not None)
     if args.check:
         full = full.clone()
         v.set_strip_cull(False)

@@ -1116,12 +1116,11 @@ struct SbStrips {
     uint32_t world = 0, rank = 0;
     uint32_t row0s[sb::kMaxStripRanks] = {}, rows[sb::kMaxStripRanks] = {};
     uint32_t slice_lo = 0, slice_n = 0, segment_capacity = 0;
-    DeviceBuf inbox;    // [world][segment_capacity] uint2 pairs, then [world] counts (64-byte aligned)
+    DeviceBuf inbox;    // [world][segment_capacity] 64-byte parcels, then [world] counts (64-byte aligned)
+    DeviceBuf outbox;   // the same shape, local: parcels packed for each destination before they are shipped in bulk
     DeviceBuf scratch;  // scatter tickets + look-back status
     size_t counts_offset = 0;
-    void* peer_inbox[sb::kMaxStripRanks] = {};   // peer-mapped (own pointers at [rank])
-    void* peer_recs[sb::kMaxStripRanks] = {};
-    void* peer_tboxes[sb::kMaxStripRanks] = {};
+    void* peer_inbox[sb::kMaxStripRanks] = {};   // peer-mapped (own pointer at [rank])
     bool connected = false;
 };
 
@@ -1145,16 +1144,18 @@ SbStatus sb_strips_create(SbViewer* v, uint32_t world, uint32_t rank, const uint
     uint32_t cap = 0;
     for (uint32_t r = 0; r < world; r++) cap = std::max(cap, cut(r + 1) - cut(r));
     s->segment_capacity = (cap + 31u) & ~31u;
-    s->counts_offset = ((size_t)world * s->segment_capacity * sizeof(uint2) + 63) & ~(size_t)63;
+    s->counts_offset = ((size_t)world * s->segment_capacity * 64 + 63) & ~(size_t)63;
     cudaError_t e = s->inbox.alloc(s->counts_offset + 64);
     if (e == cudaSuccess) e = cudaMemset(s->inbox.p, 0, s->inbox.bytes);
+    if (e == cudaSuccess) e = s->outbox.alloc(s->counts_offset + 64);
+    if (e == cudaSuccess) e = cudaMemset(s->outbox.p, 0, s->outbox.bytes);
     if (e == cudaSuccess) e = s->scratch.alloc(sb::strip_scatter_scratch_bytes(s->segment_capacity, world));
     cudaIpcMemHandle_t h[3];
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[0], v->recs.p);
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[1], v->tboxes.p);
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[2], s->inbox.p);
+    std::memset(h, 0, sizeof h);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[0], s->inbox.p);  // (handles 1 and 2 are reserved)
     if (e != cudaSuccess) {
         s->inbox.release();
+        s->outbox.release();
         s->scratch.release();
         delete s;
         return fail_cuda(v->ctx, e, "strip exchange buffers");
@@ -1170,17 +1171,12 @@ SbStatus sb_strips_connect(SbStrips* s, const SbStripsExport* all) {
     DeviceGuard device_guard(s->v->ctx);
     for (uint32_t r = 0; r < s->world; r++) {
         if (r == s->rank) {
-            s->peer_recs[r] = s->v->recs.p;
-            s->peer_tboxes[r] = s->v->tboxes.p;
             s->peer_inbox[r] = s->inbox.p;
             continue;
         }
-        void** dst[3] = {&s->peer_recs[r], &s->peer_tboxes[r], &s->peer_inbox[r]};
-        for (int i = 0; i < 3; i++) {
-            cudaIpcMemHandle_t h;
-            std::memcpy(&h, all[r].handles[i], sizeof h);
-            SB_CUDA(s->v->ctx, cudaIpcOpenMemHandle(dst[i], h, cudaIpcMemLazyEnablePeerAccess));
-        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all[r].handles[0], sizeof h);
+        SB_CUDA(s->v->ctx, cudaIpcOpenMemHandle(&s->peer_inbox[r], h, cudaIpcMemLazyEnablePeerAccess));
     }
     s->connected = true;
     return SB_OK;
@@ -1215,11 +1211,13 @@ SbStatus sb_strips_scatter(SbStrips* s, void* stream) {
             p.ty_lo[r] = s->row0s[r] / sb::kTile;
             p.ty_hi[r] = (std::min(s->row0s[r] + s->rows[r], u.height) - 1) / sb::kTile;
         }
-        p.inbox_pairs[r] = static_cast<uint2*>(s->peer_inbox[r]);
-        p.inbox_counts[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(s->peer_inbox[r]) + s->counts_offset);
-        p.peer_recs[r] = static_cast<sb::SplatRec*>(s->peer_recs[r]);
-        p.peer_tboxes[r] = static_cast<sb::TileBox*>(s->peer_tboxes[r]);
+        p.peer_inbox[r] = static_cast<uint4*>(s->peer_inbox[r]);
+        p.peer_inbox_counts[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(s->peer_inbox[r]) + s->counts_offset);
     }
+    p.inbox = s->inbox.as<uint4>();
+    p.inbox_counts = reinterpret_cast<uint32_t*>(s->inbox.as<uint8_t>() + s->counts_offset);
+    p.outbox = s->outbox.as<uint4>();
+    p.outbox_counts = reinterpret_cast<uint32_t*>(s->outbox.as<uint8_t>() + s->counts_offset);
     SB_CUDA(v->ctx, sb::launch_strip_scatter(p, s->scratch.p, s->scratch.bytes, st));
     return SB_OK;
 }
@@ -1237,8 +1235,11 @@ SbStatus sb_strips_render(SbStrips* s, void* stream, const SbTarget* target) {
     SB_CUDA(v->ctx, cudaMemsetAsync(v->pre_scratch.p, 0, sb::preprocess_scratch_prefix_bytes(), st));
     sb::StripConcatParams c;
     std::memset(&c, 0, sizeof c);
-    c.inbox_pairs = s->inbox.as<uint2>();
+    c.inbox = s->inbox.as<uint4>();
     c.inbox_counts = reinterpret_cast<const uint32_t*>(s->inbox.as<uint8_t>() + s->counts_offset);
+    c.rank = s->rank;
+    c.recs = v->recs.as<sb::SplatRec>();
+    c.tboxes = v->tboxes.as<sb::TileBox>();
     c.world = s->world;
     c.segment_capacity = s->segment_capacity;
     c.max_visible = v->n;
@@ -1266,11 +1267,10 @@ void sb_strips_destroy(SbStrips* s) {
     if (s->connected)
         for (uint32_t r = 0; r < s->world; r++) {
             if (r == s->rank) continue;
-            cudaIpcCloseMemHandle(s->peer_recs[r]);
-            cudaIpcCloseMemHandle(s->peer_tboxes[r]);
             cudaIpcCloseMemHandle(s->peer_inbox[r]);
         }
     s->inbox.release();
+    s->outbox.release();
     s->scratch.release();
     delete s;
 }

@@ -142,17 +142,23 @@ struct StripScatterParams {
     uint32_t world, rank;
     uint32_t segment_capacity;      // entries per (destination, source) inbox segment
     uint32_t ty_lo[kMaxStripRanks], ty_hi[kMaxStripRanks];  // tile rows of every rank's strip (lo > hi: no strip)
-    uint2* inbox_pairs[kMaxStripRanks];      // destination d's inbox: [world][segment_capacity] (index, key bits); peer-mapped
-    uint32_t* inbox_counts[kMaxStripRanks];  // destination d's [world] segment counts; peer-mapped
-    SplatRec* peer_recs[kMaxStripRanks];     // destination d's recs / tboxes; peer-mapped (own arrays for d == rank)
-    TileBox* peer_tboxes[kMaxStripRanks];
+    // A parcel is 64 bytes: {index, key bits, tile box min, max} + the 48-byte record.  Segments hold segment_capacity parcels.
+    uint4* inbox;                            // this rank's inbox: [world] segments (segment r = from rank r)
+    uint32_t* inbox_counts;                  //   and their [world] counts
+    uint4* outbox;                           // this rank's outbox: [world] segments (segment d = for rank d), local
+    uint32_t* outbox_counts;
+    uint4* peer_inbox[kMaxStripRanks];       // destination d's inbox and counts, peer-mapped
+    uint32_t* peer_inbox_counts[kMaxStripRanks];
     uint32_t* tickets;              // set by the launcher
     unsigned long long* status;
     uint32_t status_stride;
 };
 struct StripConcatParams {
-    const uint2* inbox_pairs;       // this rank's inbox
+    const uint4* inbox;             // this rank's inbox (64-byte parcels) and segment counts
     const uint32_t* inbox_counts;
+    uint32_t rank;
+    SplatRec* recs;                 // this rank's arrays: records / tile boxes of splats other ranks preprocessed are unpacked here
+    TileBox* tboxes;
     uint32_t world, segment_capacity, max_visible;
     uint32_t* indices;
     float* keys;

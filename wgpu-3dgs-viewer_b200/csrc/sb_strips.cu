@@ -7,13 +7,17 @@
 //
 //   strip_scatter_kernel   grid (tiles of the slice's visible list, G destinations).  Block (t, d) keeps the entries whose tile box
 //                          meets strip d — order-preserving compaction: ballots, block scan, decoupled look-back per destination —
-//                          and stores (index, key) into segment r of rank d's inbox, the 48-byte record and the tile box into rank
-//                          d's recs[index] / tboxes[index].  The last tile leaves the segment's count.
+//                          and PACKS them as 64-byte parcels {index, key, tile box, 48-byte record} into a local outbox segment
+//                          (its own strip's parcels go straight into its own inbox).  The last tile leaves the segment's count.
+//   strip_send_kernel      one coalesced 128-bit copy of every outbox segment into segment r of the destination's inbox: NVLink
+//                          sees full-line stores (scattering 16-byte pieces straight into the peers' arrays measured 0.5 ms at
+//                          two ranks — small remote writes waste the link).
 //   [one barrier across the ranks: every peer store above has landed]
-//   strip_concat_kernel    rank d strings its G inbox segments together in source order.  Slices are ascending index ranges and each
-//                          segment is in ascending index order, so the result is exactly the strip's visible list as a single-GPU
-//                          cull would have compacted it; it also rebuilds what K1 leaves for the stages behind it (indirect args,
-//                          visible count, pad keys, the depth sort's varying-bit masks).
+//   strip_concat_kernel    rank d strings its G inbox segments together in source order and unpacks the records / tile boxes into
+//                          its own recs[index] / tboxes[index].  Slices are ascending index ranges and each segment is in
+//                          ascending index order, so the result is exactly the strip's visible list as a single-GPU cull would
+//                          have compacted it; it also rebuilds what K1 leaves for the stages behind it (indirect args, visible
+//                          count, pad keys, the depth sort's varying-bit masks).
 //
 // From there the rank runs the unchanged depth sort, binning and rasterizer on its own list.  The reference has no multi-GPU
 // code; the unit being sharded is Viewer::render (src/lib.rs:266-275).
@@ -81,29 +85,42 @@ __global__ void __launch_bounds__(kXThreads) strip_scatter_kernel(const __grid_c
     }
     __syncthreads();
     const uint32_t base = s_base;
-    uint2* __restrict__ inbox = p.inbox_pairs[d] + (size_t)p.rank * p.segment_capacity;  // segment `rank` of destination d's inbox
-    const bool remote = d != p.rank;
-    float4* __restrict__ drecs = reinterpret_cast<float4*>(p.peer_recs[d]);
-    uint2* __restrict__ dboxes = reinterpret_cast<uint2*>(p.peer_tboxes[d]);
+    // parcels for a remote strip are packed locally and shipped in bulk; this rank's own strip goes straight into its own inbox
+    uint4* __restrict__ out = (d == p.rank ? p.inbox : p.outbox) + ((size_t)(d == p.rank ? p.rank : d) * p.segment_capacity) * 4;
 #pragma unroll
     for (int i = 0; i < kXItems; i++) {
         if ((hit_bits >> i) & 1u) {
             const uint32_t g = gs[i];
             const uint32_t slot = base + counts[i * NW + warp] + ((ranks >> (8 * i)) & 0xffu);
-            if (slot < p.segment_capacity) inbox[slot] = make_uint2(g, __float_as_uint(ks[i]));
-            if (remote) {  // the splat's record and tile box, by Gaussian index, into the destination's own arrays
-                const float4* src = reinterpret_cast<const float4*>(&p.recs[g]);
-                const float4 r0 = src[0], r1 = src[1], r2 = src[2];
-                float4* dst = drecs + (size_t)g * 3;
-                dst[0] = r0;
-                dst[1] = r1;
-                dst[2] = r2;
-                dboxes[g] = *reinterpret_cast<const uint2*>(&p.tboxes[g]);
+            if (slot < p.segment_capacity) {
+                const uint2 tb = *reinterpret_cast<const uint2*>(&p.tboxes[g]);
+                const uint4* src = reinterpret_cast<const uint4*>(&p.recs[g]);
+                uint4* dst = out + (size_t)slot * 4;
+                dst[0] = make_uint4(g, __float_as_uint(ks[i]), tb.x, tb.y);
+                dst[1] = src[0];
+                dst[2] = src[1];
+                dst[3] = src[2];
             }
         }
     }
     const uint32_t last_tile = v == 0 ? 0 : (v - 1) / kXTile;
-    if (tile == last_tile && tid == 0) p.inbox_counts[d][p.rank] = min(base + s_total, p.segment_capacity);
+    if (tile == last_tile && tid == 0) {
+        const uint32_t c = min(base + s_total, p.segment_capacity);
+        if (d == p.rank) p.inbox_counts[p.rank] = c;
+        else p.outbox_counts[d] = c;
+    }
+}
+
+// outbox segment d -> segment `rank` of destination d's inbox, 128-bit coalesced; block (x, d)
+__global__ void __launch_bounds__(256) strip_send_kernel(const __grid_constant__ StripScatterParams p) {
+    const uint32_t d = blockIdx.y;
+    if (d == p.rank) return;
+    const uint32_t c = p.outbox_counts[d];
+    const uint4* __restrict__ src = p.outbox + ((size_t)d * p.segment_capacity) * 4;
+    uint4* __restrict__ dst = p.peer_inbox[d] + ((size_t)p.rank * p.segment_capacity) * 4;
+    const size_t nvec = (size_t)c * 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.peer_inbox_counts[d][p.rank] = c;
 }
 
 __global__ void __launch_bounds__(512) strip_concat_kernel(const __grid_constant__ StripConcatParams p) {
@@ -125,11 +142,19 @@ __global__ void __launch_bounds__(512) strip_concat_kernel(const __grid_constant
     for (uint32_t i = blockIdx.x * blockDim.x + tid; i < v; i += gridDim.x * blockDim.x) {
         uint32_t r = 0;
         while (r + 1 < p.world && i >= s_prefix[r + 1]) ++r;
-        const uint2 q = p.inbox_pairs[(size_t)r * p.segment_capacity + (i - s_prefix[r])];
-        p.indices[i] = q.x;
-        p.keys[i] = __uint_as_float(q.y);
-        key_or |= q.y;
-        key_nand |= ~q.y;
+        const uint4* parcel = p.inbox + ((size_t)r * p.segment_capacity + (i - s_prefix[r])) * 4;
+        const uint4 h = parcel[0];  // index, key bits, tile box
+        p.indices[i] = h.x;
+        p.keys[i] = __uint_as_float(h.y);
+        key_or |= h.y;
+        key_nand |= ~h.y;
+        if (r != p.rank) {  // a splat another rank preprocessed: its record and tile box, by Gaussian index
+            uint4* rec = reinterpret_cast<uint4*>(&p.recs[h.x]);
+            rec[0] = parcel[1];
+            rec[1] = parcel[2];
+            rec[2] = parcel[3];
+            *reinterpret_cast<uint2*>(&p.tboxes[h.x]) = make_uint2(h.z, h.w);
+        }
     }
     if (p.sort_prep != nullptr) {
         key_or = __reduce_or_sync(0xffffffffu, key_or);
@@ -180,6 +205,7 @@ cudaError_t launch_strip_scatter(StripScatterParams& p, void* scratch, size_t sc
     p.status_stride = (uint32_t)tiles;
     const dim3 grid((unsigned)(tiles - 1 > 0 ? tiles - 1 : 1), p.world);
     strip_scatter_kernel<<<grid, kXThreads, 0, stream>>>(p);
+    if (p.world > 1) strip_send_kernel<<<dim3(64, p.world), 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
