@@ -93,6 +93,87 @@ def test_multi_model_red_and_green(sb, ctx):  # tests/e2e/multi_model.rs:100-154
     mm.close()
 
 
+def _mm_reference_scene(sb, ctx):
+    """tests/e2e/multi_model.rs: "red" = one unit Gaussian at (0,0,1), "green" = one at (1,0,1), given::camera_pod()."""
+    red = sb.scenes.single_red_gaussian()
+    green = red.copy()
+    green["color"][0] = (0, 255, 0, 255)
+    green["pos"][0] = (1, 0, 1)
+    mm = sb.MultiModelViewer(ctx)
+    mm.insert_model_from_gaussians(1, red)      # viewer.insert_model(&device, "red", &red_gaussians)
+    mm.insert_model_from_gaussians(2, green)
+    return mm
+
+
+def _mm_pixel_sums(mm, keys):
+    import torch
+    t = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    mm.render(t, W, H, keys)
+    torch.cuda.synchronize()
+    img = t.cpu().numpy()
+    return img, [int(img[..., c].astype(np.int64).sum()) for c in range(4)]
+
+
+def test_multi_model_update_camera_with_or_without_pod_equal(sb, ctx):  # tests/e2e/multi_model.rs:56-112
+    a = _mm_reference_scene(sb, ctx)
+    a.update_camera((0, 0, 0), 0.1, 0.1, W, H)                  # update_camera(&queue, &given::camera(), size)
+    b = _mm_reference_scene(sb, ctx)
+    b.update_camera_with_pod(given_camera(sb))                  # update_camera_with_pod(&queue, &given::camera_pod())
+    img1, _ = _mm_pixel_sums(a, [1, 2])
+    img2, _ = _mm_pixel_sums(b, [1, 2])
+    assert np.array_equal(img1, img2)
+    a.close()
+    b.close()
+
+
+def test_multi_model_render_should_render_correctly(sb, ctx):  # tests/e2e/multi_model.rs:114-155
+    mm = _mm_reference_scene(sb, ctx)
+    mm.update_camera_with_pod(given_camera(sb))
+    _, (r, g, b, a) = _mm_pixel_sums(mm, [1, 2])
+    assert r > 1 and g > 1 and b < 1 and a > 1
+    mm.close()
+
+
+@pytest.mark.parametrize("with_pod", [False, True])
+def test_multi_model_no_sh0_renders_grey(sb, ctx, with_pod):  # tests/e2e/multi_model.rs:157-232
+    mm = _mm_reference_scene(sb, ctx)
+    mm.update_camera_with_pod(given_camera(sb))
+    if with_pod:
+        mm.update_gaussian_transform_with_pod(sb.gaussian_transform_pod(1.0, sb.MODE_SPLAT, 3, True, 3.0))
+    else:
+        mm.update_gaussian_transform(1.0, sb.MODE_SPLAT, 3, True, 3.0)
+    _, (r, g, b, a) = _mm_pixel_sums(mm, [1, 2])
+    assert r > 1 and g > 1 and b > 1 and a > 1
+    mm.close()
+
+
+@pytest.mark.parametrize("with_pod", [False, True])
+def test_multi_model_behind_camera_draws_nothing(sb, ctx, with_pod):  # tests/e2e/multi_model.rs:234-328
+    mm = _mm_reference_scene(sb, ctx)
+    mm.update_camera_with_pod(given_camera(sb))
+    for key in (1, 2):
+        if with_pod:
+            mm.update_model_transform_with_pod(key, sb.model_transform_pod((0, 0, -1), (0, 0, 0, 1), (1, 1, 1)))
+        else:
+            mm.update_model_transform(key, (0, 0, -1), (0, 0, 0, 1), (1, 1, 1))
+    _, (r, g, b, a) = _mm_pixel_sums(mm, [1, 2])
+    assert r == 0 and g == 0 and b == 0
+    with pytest.raises(sb.SplatError):                           # MultiModelViewerAccessError::ModelNotFound
+        mm.update_model_transform(3, (0, 0, 0), (0, 0, 0, 1), (1, 1, 1))
+    mm.close()
+
+
+def test_multi_model_remove_model_should_not_render_removed_model(sb, ctx):  # tests/e2e/multi_model.rs:330-373
+    mm = _mm_reference_scene(sb, ctx)
+    mm.update_camera_with_pod(given_camera(sb))
+    assert mm.remove_model(2)
+    _, (r, g, b, a) = _mm_pixel_sums(mm, [1])
+    assert r > 1 and g < 1 and b < 1 and a > 1
+    with pytest.raises(sb.SplatError):
+        mm.render(__import__("torch").zeros((H, W, 4), dtype=__import__("torch").uint8, device="cuda"), W, H, [1, 2])
+    mm.close()
+
+
 def test_selection_default_invert_hides_nothing(sb, ctx):  # src/selection/buffer.rs:157-165
     import torch
     v = sb.Viewer(ctx, gaussians=sb.scenes.single_red_gaussian())
