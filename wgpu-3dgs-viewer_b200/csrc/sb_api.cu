@@ -180,7 +180,7 @@ struct SbViewer {
     DeviceBuf indices, keys, args, recs, tboxes, pre_scratch;
     DeviceBuf sort_keys_alt, sort_vals_alt, sort_internal;
     DeviceBuf depth_keys_alt, depth_vals_alt;  // the depth sort's own ping-pong buffers: its result may stay there (sorted_pending)
-    DeviceBuf dup_offsets, dup_keys, dup_vals, tile_recs, tile_ranges, tile_order, bin_state;
+    DeviceBuf dup_offsets, tboxes_sorted, win_first, dup_keys, dup_vals, tile_recs, tile_ranges, tile_order, bin_state;
     DeviceBuf selection;
     DeviceBuf orig_colors;  // NonDestructiveModifier's source copy (colour words), taken at the first edit
     DeviceBuf internal_target;
@@ -263,6 +263,7 @@ SbStatus viewer_alloc(SbViewer* v) {
     std::memcpy(init + 16, &s, sizeof s);
     SB_CUDA(ctx, cudaMemcpy(v->args.p, init, sizeof init, cudaMemcpyHostToDevice));
     SB_CUDA(ctx, v->dup_offsets.alloc(((size_t)n + 1) * 4));
+    SB_CUDA(ctx, v->tboxes_sorted.alloc((size_t)(n ? n : 1) * sizeof(sb::TileBox)));
     const size_t scan_tiles = ((size_t)n + 1023) / 1024 + 2;
     SB_CUDA(ctx, v->bin_state.alloc(32 + scan_tiles * sizeof(unsigned long long)));
     SB_CUDA(ctx, cudaMemset(v->bin_state.p, 0, v->bin_state.bytes));
@@ -283,6 +284,7 @@ SbStatus viewer_reserve(SbViewer* v, uint64_t cap) {
     v->dup_capacity = cap;
     SB_CUDA(ctx, v->dup_keys.alloc(cap * 4 + 16));  // tile_ranges_kernel reads whole uint4s
     SB_CUDA(ctx, v->dup_vals.alloc(cap * 4));
+    SB_CUDA(ctx, v->win_first.alloc((cap / 4096 + 2) * 4));  // one entry per 4096-duplicate emit window
     if (!v->use_gather4) SB_CUDA(ctx, v->tile_recs.alloc(cap * sizeof(sb::SplatRec)));
     const uint64_t sort_cap = cap > v->padded ? cap : v->padded;
     SB_CUDA(ctx, v->sort_keys_alt.alloc(sort_cap * 4));
@@ -483,6 +485,9 @@ SbStatus do_draw(SbViewer* v, const SbCameraPod& cam, const SbGaussianTransformP
     p.visible_count = v->ext_count ? v->ext_count : v->d_visible();
     p.max_visible = v->n;
     p.buf.dup_offsets = v->dup_offsets.as<uint32_t>();
+    p.buf.tboxes_sorted = v->tboxes_sorted.as<sb::TileBox>();
+    p.buf.win_first = v->win_first.as<uint32_t>();
+    p.buf.win_capacity = (uint32_t)(v->win_first.bytes / 4);
     p.buf.dup_keys = v->dup_keys.as<uint32_t>();
     p.buf.dup_vals = v->dup_vals.as<uint32_t>();
     p.buf.tile_ranges = v->tile_ranges.as<uint32_t>();
@@ -683,7 +688,7 @@ void sb_viewer_destroy(SbViewer* v) {
     for (cudaEvent_t e : v->bevent)
         if (e) cudaEventDestroy(e);
     for (DeviceBuf* b : {&v->gaussians_owned, &v->indices, &v->keys, &v->args, &v->recs, &v->tboxes, &v->pre_scratch, &v->sort_keys_alt,
-                         &v->sort_vals_alt, &v->sort_internal, &v->depth_keys_alt, &v->depth_vals_alt, &v->dup_offsets, &v->dup_keys, &v->dup_vals, &v->tile_recs,
+                         &v->sort_vals_alt, &v->sort_internal, &v->depth_keys_alt, &v->depth_vals_alt, &v->dup_offsets, &v->tboxes_sorted, &v->win_first, &v->dup_keys, &v->dup_vals, &v->tile_recs,
                          &v->tile_ranges, &v->tile_order, &v->bin_state, &v->selection, &v->orig_colors, &v->internal_target, &v->counters})
         b->release();
     if (v->h_needed) cudaFreeHost(const_cast<uint32_t*>(v->h_needed));

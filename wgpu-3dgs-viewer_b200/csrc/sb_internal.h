@@ -81,6 +81,9 @@ cudaError_t launch_sort_finish(uint32_t* keys, uint32_t* payload, const SortScra
 // ---------------------------------------------------------------- binning + raster (sb_raster.cu)
 struct RasterBuffers {
     uint32_t* dup_offsets;    // [n+1] exclusive scan of tiles-per-splat in sorted order
+    TileBox* tboxes_sorted;   // [n] tile boxes in depth order (nullable: the v1 scan / emit pair gathers them twice instead)
+    uint32_t* win_first;      // [win_capacity] first splat (depth rank) of every 4096-duplicate emit window
+    uint32_t win_capacity;
     uint32_t* dup_keys;       // [dup_capacity] tile id
     uint32_t* dup_vals;       // [dup_capacity] Gaussian index (in depth order within a tile)
     uint32_t* tile_ranges;    // [tiles*2] begin,end into dup arrays

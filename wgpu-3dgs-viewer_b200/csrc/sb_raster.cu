@@ -37,6 +37,10 @@ struct BinParams {
     const uint32_t* sort_parity;         // nullable: result is in sorted_indices
     const uint32_t* visible_count;
     uint32_t* dup_offsets;
+    TileBox* tboxes_sorted;  // v2 binning: the tile boxes in depth order (written by the scan, streamed by the emit)
+    uint32_t tiles_prefixed; // v2 binning: 1 = dup_tiles_kernel turned the tile sums into prefixes; 0 = dup_offsets sums them itself
+    uint32_t* win_first;     // v2 binning: [w] = the splat (depth rank) whose run of duplicates covers duplicate 4096 w
+    uint32_t win_capacity;   //   entries of win_first
     uint32_t* dup_keys;
     uint32_t* dup_vals;
     uint32_t* dup_count;
@@ -52,9 +56,7 @@ struct BinParams {
 };
 
 // tiles of one splat, clipped to the strip's tile rows
-__device__ __forceinline__ uint32_t splat_tiles(const TileBox* tboxes, uint32_t g, uint32_t ty_lo, uint32_t ty_hi, uint32_t& x0,
-                                                uint32_t& y0, uint32_t& w) {
-    const uint2 q = __ldg(reinterpret_cast<const uint2*>(&tboxes[g]));
+__device__ __forceinline__ uint32_t box_tiles(uint2 q, uint32_t ty_lo, uint32_t ty_hi, uint32_t& x0, uint32_t& y0, uint32_t& w) {
     const uint32_t tmin = q.x, tmax = q.y;
     x0 = tmin & 0xffffu;
     y0 = tmin >> 16;
@@ -66,6 +68,10 @@ __device__ __forceinline__ uint32_t splat_tiles(const TileBox* tboxes, uint32_t 
     if (y0 > y1) return 0;
     w = x1 - x0 + 1;
     return w * (y1 - y0 + 1);
+}
+__device__ __forceinline__ uint32_t splat_tiles(const TileBox* tboxes, uint32_t g, uint32_t ty_lo, uint32_t ty_hi, uint32_t& x0,
+                                                uint32_t& y0, uint32_t& w) {
+    return box_tiles(__ldg(reinterpret_cast<const uint2*>(&tboxes[g])), ty_lo, ty_hi, x0, y0, w);
 }
 
 // Decoupled look-back over 62-bit aggregates (flag in the two top bits): the duplicate total of a frame can exceed 2^32 (millions
@@ -243,6 +249,333 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
                 }
             }
         }
+    }
+}
+
+
+// ---------------------------------------------------------------- binning v2
+// K4' — reduce, then scan: three small kernels WITHOUT a look-back chain.  ncu of the chained scan (v1): 31 % of the stall samples
+// are the CTA barrier behind warp 0's look-back and the kernel takes ~65 us for 6 M splats whatever its memory traffic — with several
+// hundred tiles in flight almost every predecessor a tile inspects holds an aggregate, not a prefix, so every tile walks back ~14
+// windows of 32 at one L2 round trip each while its other warps wait.  Here:
+//   dup_count   one CTA per 4096 splats, STRIPED (thread t takes splats t, t + 512, ...): the index loads and the stores of the
+//               boxes in depth order are coalesced, a thread's eight tile-box gathers are independent and all in flight together;
+//               block sum -> tile_sums[tile].  No ordering between CTAs, no ticket.
+//   dup_tiles   one CTA: exclusive scan of the tile sums (64-bit), the frame's duplicate total, overflow flag, host words.
+//   dup_offsets one CTA per 4096 splats: streams the sorted boxes, block scan + its tile's base -> per-splat offsets (saturated)
+//               and the first splat of every 4096-duplicate emit window.
+constexpr int kEmitWinLog2 = 12;
+constexpr int kEmitWin = 1 << kEmitWinLog2;  // duplicates per emit window
+constexpr int kScan2Threads = 512;
+constexpr int kScan2Items = 8;
+constexpr int kScan2Tile = kScan2Threads * kScan2Items;
+static_assert(kScan2Tile == kScanTile, "both scans use the same tile (scan_status sizing, launch grid)");
+
+__global__ void __launch_bounds__(kScan2Threads) dup_count_kernel(const BinParams p) {
+    __shared__ unsigned long long warp_sums[kScan2Threads / 32];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t v = min(*p.visible_count, p.max_visible);
+    const uint32_t tile_base = blockIdx.x * kScan2Tile;
+    if (tile_base >= v) return;
+    const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
+    uint32_t g[kScan2Items];
+#pragma unroll
+    for (int i = 0; i < kScan2Items; i++) {
+        const uint32_t r = tile_base + i * kScan2Threads + tid;
+        g[i] = r < v ? sorted[r] : 0xffffffffu;
+    }
+    uint2 q[kScan2Items];
+#pragma unroll
+    for (int i = 0; i < kScan2Items; i++)
+        q[i] = g[i] < p.max_visible ? __ldg(reinterpret_cast<const uint2*>(&p.tboxes[g[i]])) : make_uint2(1u, 0u);  // (1, 0): no tiles
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScan2Items; i++) {
+        const uint32_t r = tile_base + i * kScan2Threads + tid;
+        uint32_t x0, y0, w;
+        sum += box_tiles(q[i], p.ty_lo, p.ty_hi, x0, y0, w);
+        if (r < v) reinterpret_cast<uint2*>(p.tboxes_sorted)[r] = q[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) warp_sums[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kScan2Threads / 32; w++) t += warp_sums[w];
+        p.scan_status[blockIdx.x] = t;  // tile_sums (the look-back words of v1: same buffer, plain values here)
+    }
+}
+
+// exclusive scan of the tile sums, in place; one CTA (1465 tiles for 6 M splats; a chunk of 1024 per iteration)
+__global__ void __launch_bounds__(1024) dup_tiles_kernel(const BinParams p) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t v = min(*p.visible_count, p.max_visible);
+    const uint32_t tiles = (v + kScan2Tile - 1) / kScan2Tile;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < tiles; base += 1024) {
+        const uint32_t i = base + tid;
+        const unsigned long long x = i < tiles ? p.scan_status[i] : 0ull;
+        unsigned long long inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        unsigned long long wexcl = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 32; w++) {
+            const unsigned long long t = warp_sums[w];
+            if (w < (int)warp) wexcl += t;
+            total += t;
+        }
+        const unsigned long long carry = s_carry;
+        if (i < tiles) p.scan_status[i] = carry + wexcl + inc - x;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const unsigned long long d = s_carry;
+        if (p.needed_host) {
+            p.needed_host[0] = sat32(d);                      // duplicates this frame needed (saturated)
+            if (d > p.dup_capacity) p.needed_host[1] += 1u;   // overflow events (the host compares with the count it has seen)
+        }
+        if (d > p.dup_capacity) {
+            *p.overflow = 1u;
+            *p.dup_count = p.dup_capacity;
+        } else {
+            *p.overflow = 0u;
+            *p.dup_count = (uint32_t)d;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kScan2Threads) dup_offsets_kernel(const BinParams p) {
+    __shared__ __align__(16) uint32_t s_cnt[kScan2Tile];
+    __shared__ unsigned long long warp_sums[kScan2Threads / 32];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t v = min(*p.visible_count, p.max_visible);
+    const uint32_t tile_base = blockIdx.x * kScan2Tile;
+    if (v == 0 && blockIdx.x == 0 && tid == 0 && !p.tiles_prefixed) {  // empty frame
+        if (p.needed_host) p.needed_host[0] = 0u;
+        *p.overflow = 0u;
+        *p.dup_count = 0u;
+    }
+    if (tile_base >= v) return;
+    uint2 q[kScan2Items];
+#pragma unroll
+    for (int i = 0; i < kScan2Items; i++) {
+        const uint32_t r = tile_base + i * kScan2Threads + tid;
+        q[i] = r < v ? __ldg(reinterpret_cast<const uint2*>(p.tboxes_sorted) + r) : make_uint2(1u, 0u);
+    }
+    // my tile's base: the prefix dup_tiles_kernel left, or (few tiles: 1465 for 6 M splats, 12 KB that sit in L2) the sum of the
+    // tile sums in front of mine, read by the whole CTA while the boxes are in flight — one launch and one idle SM-array less
+    unsigned long long tile_off;
+    const uint32_t tiles = (v + kScan2Tile - 1) / kScan2Tile;
+    if (p.tiles_prefixed) {
+        tile_off = p.scan_status[blockIdx.x];
+    } else {
+        unsigned long long part = 0;
+        for (uint32_t t = tid; t < blockIdx.x; t += kScan2Threads) part += p.scan_status[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) warp_sums[warp] = part;
+        __syncthreads();
+        tile_off = 0;
+#pragma unroll
+        for (int w = 0; w < kScan2Threads / 32; w++) tile_off += warp_sums[w];
+        __syncthreads();  // warp_sums is reused by the scan below
+        if (blockIdx.x == tiles - 1 && tid == 0) {  // the last tile knows the frame's total
+            const unsigned long long d = tile_off + p.scan_status[blockIdx.x];
+            if (p.needed_host) {
+                p.needed_host[0] = sat32(d);
+                if (d > p.dup_capacity) p.needed_host[1] += 1u;
+            }
+            if (d > p.dup_capacity) {
+                *p.overflow = 1u;
+                *p.dup_count = p.dup_capacity;
+            } else {
+                *p.overflow = 0u;
+                *p.dup_count = (uint32_t)d;
+            }
+        }
+    }
+    {
+#pragma unroll
+        for (int i = 0; i < kScan2Items; i++) {
+            uint32_t x0, y0, w;
+            s_cnt[i * kScan2Threads + tid] = box_tiles(q[i], p.ty_lo, p.ty_hi, x0, y0, w);
+        }
+    }
+    __syncthreads();
+    // blocked: thread t owns splats [8 t, 8 t + 8) of the tile
+    uint32_t cnt[kScan2Items];
+    {
+        const uint4 a = reinterpret_cast<const uint4*>(s_cnt)[2 * tid], b = reinterpret_cast<const uint4*>(s_cnt)[2 * tid + 1];
+        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
+        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
+    }
+    static_assert(kScan2Items == 8, "two 128-bit vectors per thread");
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScan2Items; i++) sum += cnt[i];
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    unsigned long long wexcl = 0;
+#pragma unroll
+    for (int w = 0; w < kScan2Threads / 32; w++)
+        if (w < (int)warp) wexcl += warp_sums[w];
+    unsigned long long off = tile_off + wexcl + inc - sum;
+    const uint32_t base = tile_base + tid * kScan2Items;
+    {
+        // the splat whose run covers duplicate 4096 w is the first splat of the emit's window w
+        unsigned long long o = off;
+#pragma unroll
+        for (int i = 0; i < kScan2Items; i++) {
+            if (cnt[i]) {
+                const unsigned long long w_hi = (o + cnt[i] - 1) >> kEmitWinLog2;
+                for (unsigned long long w = (o + kEmitWin - 1) >> kEmitWinLog2; w <= w_hi && w < p.win_capacity; w++) p.win_first[w] = base + i;
+            }
+            o += cnt[i];
+        }
+    }
+    if (base + kScan2Items <= v) {
+        uint4 o0, o1;
+        o0.x = sat32(off); off += cnt[0];
+        o0.y = sat32(off); off += cnt[1];
+        o0.z = sat32(off); off += cnt[2];
+        o0.w = sat32(off); off += cnt[3];
+        o1.x = sat32(off); off += cnt[4];
+        o1.y = sat32(off); off += cnt[5];
+        o1.z = sat32(off); off += cnt[6];
+        o1.w = sat32(off); off += cnt[7];
+        reinterpret_cast<uint4*>(p.dup_offsets + base)[0] = o0;
+        reinterpret_cast<uint4*>(p.dup_offsets + base)[1] = o1;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScan2Items; i++) {
+            const uint32_t r = base + i;
+            if (r < v) p.dup_offsets[r] = sat32(off);
+            off += cnt[i];
+        }
+    }
+}
+
+// K5': OUTPUT-driven emit.  A CTA owns a window of 4096 consecutive duplicates: it finds the splats whose runs meet the window by
+// binary search in the offsets, expands them into shared memory (thread per splat; splats with more than 32 duplicates in the
+// window by a whole warp) and writes the window with 128-bit coalesced stores.  v1 walked the splats and stored every duplicate
+// with its own 4-byte store at a lane-private offset — 19 M sector transactions per frame for 77 MB, L1TEX the busiest unit at
+// 75 % — and a view with large splats serialised up to 32 such stores per lane.  Work per CTA is now constant whatever the
+// splat sizes, and the boxes arrive in depth order (scan) instead of through a second random gather.
+constexpr int kEmitUnroll = 4;
+constexpr int kEmitBig = 128;  // a window holds at most 4096 / 33 splats with more than 32 duplicates
+
+__global__ void __launch_bounds__(256) dup_emit2_kernel(const BinParams p) {
+    __shared__ __align__(16) uint32_t s_keys[kEmitWin];
+    __shared__ __align__(16) uint32_t s_vals[kEmitWin];
+    __shared__ uint32_t s_big[kEmitBig];
+    __shared__ uint32_t s_nbig;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t v = min(*p.visible_count, p.max_visible);
+    const uint32_t d = *p.dup_count;  // min(duplicates of the frame, capacity): written by the scan
+    const uint32_t* __restrict__ sorted = (p.sort_parity && *p.sort_parity) ? p.sorted_indices_alt : p.sorted_indices;
+    const uint32_t* __restrict__ offs = p.dup_offsets;
+    const uint2* __restrict__ boxes = reinterpret_cast<const uint2*>(p.tboxes_sorted);
+    for (uint32_t win = blockIdx.x; (unsigned long long)win * kEmitWin < d; win += gridDim.x) {
+        const uint32_t w0 = win * kEmitWin, w1 = min(w0 + (uint32_t)kEmitWin, d);
+        if (tid == 0) s_nbig = 0;
+        // the window's splats: from the one that covers its first duplicate to the one that covers the next window's first
+        // (both recorded by the scan; the last window runs to the end of the visible list)
+        const uint32_t r0 = __ldg(p.win_first + win);
+        const uint32_t r1 = (unsigned long long)(win + 1) * kEmitWin < d ? __ldg(p.win_first + win + 1) : v - 1u;
+        __syncthreads();
+        for (uint32_t rb = r0 + tid; rb <= r1; rb += 256 * kEmitUnroll) {
+            // kEmitUnroll splats per thread and iteration: their loads are issued together (a window of small splats is ~2600 of them)
+            uint32_t off_[kEmitUnroll], g_[kEmitUnroll];
+            uint2 q_[kEmitUnroll];
+#pragma unroll
+            for (int u = 0; u < kEmitUnroll; u++) {
+                const uint32_t r = rb + u * 256;
+                const bool ok = r <= r1;
+                off_[u] = ok ? __ldg(offs + r) : 0xffffffffu;  // (>= w1: skipped below)
+                q_[u] = ok ? __ldg(boxes + r) : make_uint2(1u, 0u);
+                g_[u] = ok ? __ldg(sorted + r) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kEmitUnroll; u++) {
+                const uint32_t off = off_[u], g = g_[u];
+                uint32_t x0, y0, w;
+                const uint32_t n = box_tiles(q_[u], p.ty_lo, p.ty_hi, x0, y0, w);
+                // (the last window runs to the end of the list: with a frame that overflowed the capacity its tail starts beyond w1)
+                const uint32_t j0 = off < w0 ? w0 - off : 0u, j1 = off < w1 ? min(n, w1 - off) : 0u;
+                if (j0 >= j1) continue;
+                if (j1 - j0 > 32u) {
+                    s_big[atomicAdd(&s_nbig, 1u)] = rb + u * 256;
+                    continue;
+                }
+                uint32_t row = 0, col = j0;
+                if (j0 >= w) {
+                    row = j0 / w;
+                    col = j0 - row * w;
+                }
+                uint32_t key = (y0 - p.ty_lo + row) * p.tiles_x + x0 + col;  // strip-relative tile id
+                uint32_t o = off + j0 - w0;
+                for (uint32_t j = j0; j < j1; j++, o++) {
+                    s_keys[o] = key;
+                    s_vals[o] = g;
+                    ++key;
+                    if (++col == w) {
+                        col = 0;
+                        key += p.tiles_x - w;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nbig = s_nbig;
+        for (uint32_t b = warp; b < nbig; b += 8) {
+            const uint32_t r = s_big[b];
+            const uint32_t off = __ldg(offs + r), g = sorted[r];
+            uint32_t x0, y0, w;
+            const uint32_t n = box_tiles(__ldg(boxes + r), p.ty_lo, p.ty_hi, x0, y0, w);
+            const uint32_t j0 = off < w0 ? w0 - off : 0u, j1 = min(n, w1 - off);
+            // j / w by multiplication: floor(j / w) == umulhi(j, ceil(2^32 / w)) whenever j * w < 2^32 (w == 1 would need 2^32)
+            const bool mul_ok = w > 1u && (unsigned long long)n * w < (1ull << 32);
+            const uint32_t inv = mul_ok ? 0xffffffffu / w + 1u : 0u;
+            for (uint32_t j = j0 + lane; j < j1; j += 32) {
+                const uint32_t qd = mul_ok ? __umulhi(j, inv) : j / w;
+                const uint32_t o = off + j - w0;
+                s_keys[o] = (y0 - p.ty_lo + qd) * p.tiles_x + (x0 + (j - qd * w));
+                s_vals[o] = g;
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = w1 - w0;
+        for (uint32_t i = tid * 4; i < cnt; i += 256 * 4) {
+            if (i + 4 <= cnt) {
+                *reinterpret_cast<uint4*>(p.dup_keys + w0 + i) = *reinterpret_cast<const uint4*>(s_keys + i);
+                *reinterpret_cast<uint4*>(p.dup_vals + w0 + i) = *reinterpret_cast<const uint4*>(s_vals + i);
+            } else {
+                for (uint32_t k = i; k < cnt; k++) {
+                    p.dup_keys[w0 + k] = s_keys[k];
+                    p.dup_vals[w0 + k] = s_vals[k];
+                }
+            }
+        }
+        __syncthreads();  // the staging buffers are reused by the CTA's next window
     }
 }
 
@@ -1021,6 +1354,10 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     bp.sort_parity = p.sort_parity;
     bp.visible_count = p.visible_count;
     bp.dup_offsets = p.buf.dup_offsets;
+    bp.tboxes_sorted = p.buf.tboxes_sorted;
+    bp.tiles_prefixed = 0;
+    bp.win_first = p.buf.win_first;
+    bp.win_capacity = p.buf.win_capacity;
     bp.dup_keys = p.buf.dup_keys;
     bp.dup_vals = p.buf.dup_vals;
     bp.dup_count = p.buf.dup_count;
@@ -1037,8 +1374,18 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
                       (p.sorted_indices_alt == nullptr || (reinterpret_cast<uintptr_t>(p.sorted_indices_alt) & 15u) == 0);
 
     const unsigned scan_grid = (unsigned)(((size_t)p.max_visible + kScanTile - 1) / kScanTile);
-    dup_scan_kernel<<<scan_grid > 0 ? scan_grid : 1, kScanThreads, 0, stream>>>(bp);
-    dup_emit_kernel<<<num_sms * 8, 256, 0, stream>>>(bp);
+    // SB_BIN=v1 keeps the round-1 scan / emit pair (A/B runs); it is also the path when there is no buffer for the sorted boxes
+    static const bool bin_v1 = [] { const char* c = std::getenv("SB_BIN"); return c && std::string(c) == "v1"; }();
+    if (bin_v1 || bp.tboxes_sorted == nullptr || bp.win_first == nullptr) {
+        dup_scan_kernel<<<scan_grid > 0 ? scan_grid : 1, kScanThreads, 0, stream>>>(bp);
+        dup_emit_kernel<<<num_sms * 8, 256, 0, stream>>>(bp);
+    } else {
+        bp.tiles_prefixed = scan_grid > 4096 ? 1u : 0u;  // beyond 16.7 M splats a CTA no longer sums the tile sums itself
+        dup_count_kernel<<<scan_grid > 0 ? scan_grid : 1, kScan2Threads, 0, stream>>>(bp);
+        if (bp.tiles_prefixed) dup_tiles_kernel<<<1, 1024, 0, stream>>>(bp);
+        dup_offsets_kernel<<<scan_grid > 0 ? scan_grid : 1, kScan2Threads, 0, stream>>>(bp);
+        dup_emit2_kernel<<<num_sms * 6, 256, 0, stream>>>(bp);
+    }
     if (p.events) cudaEventRecord(p.events[0], stream);
 
     e = launch_sort(p.buf.dup_keys, p.buf.dup_vals, p.buf.dup_count, (uint32_t)p.buf.dup_capacity, 0, bits, p.sort, num_sms, stream);
