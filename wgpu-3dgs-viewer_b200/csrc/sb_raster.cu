@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) dup_emit_kernel(const BinParams p) {
 //               boxes in depth order are coalesced, a thread's eight tile-box gathers are independent and all in flight together;
 //               block sum -> tile_sums[tile].  No ordering between CTAs, no ticket.
 //   dup_tiles   one CTA: exclusive scan of the tile sums (64-bit), the frame's duplicate total, overflow flag, host words.
-//   dup_offsets one CTA per 4096 splats: streams the sorted boxes, block scan + its tile's base -> per-splat offsets (saturated)
+//   dup_offsets one CTA per 4096 splats (blocked): streams the sorted boxes, block scan + its tile's base -> per-splat offsets (saturated)
 //               and the first splat of every 4096-duplicate emit window.
 constexpr int kEmitWinLog2 = 12;
 constexpr int kEmitWin = 1 << kEmitWinLog2;  // duplicates per emit window
@@ -358,7 +358,6 @@ __global__ void __launch_bounds__(1024) dup_tiles_kernel(const BinParams p) {
 }
 
 __global__ void __launch_bounds__(kScan2Threads) dup_offsets_kernel(const BinParams p) {
-    __shared__ __align__(16) uint32_t s_cnt[kScan2Tile];
     __shared__ unsigned long long warp_sums[kScan2Threads / 32];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t v = min(*p.visible_count, p.max_visible);
@@ -369,11 +368,27 @@ __global__ void __launch_bounds__(kScan2Threads) dup_offsets_kernel(const BinPar
         *p.dup_count = 0u;
     }
     if (tile_base >= v) return;
-    uint2 q[kScan2Items];
+    // BLOCKED: thread t owns splats [8 t, 8 t + 8) of the tile — 64 contiguous bytes of sorted boxes, four 128-bit loads (a warp
+    // covers 2 KB: every sector is used, the later loads of a thread hit the lines its first one brought)
+    const uint32_t base = tile_base + tid * kScan2Items;
+    uint32_t cnt[kScan2Items];
+    if (base + kScan2Items <= v) {
+        const uint4* bp4 = reinterpret_cast<const uint4*>(p.tboxes_sorted) + (size_t)base / 2;
+        uint4 q4[kScan2Items / 2];
 #pragma unroll
-    for (int i = 0; i < kScan2Items; i++) {
-        const uint32_t r = tile_base + i * kScan2Threads + tid;
-        q[i] = r < v ? __ldg(reinterpret_cast<const uint2*>(p.tboxes_sorted) + r) : make_uint2(1u, 0u);
+        for (int i = 0; i < kScan2Items / 2; i++) q4[i] = __ldg(bp4 + i);
+#pragma unroll
+        for (int i = 0; i < kScan2Items / 2; i++) {
+            uint32_t x0, y0, w;
+            cnt[2 * i] = box_tiles(make_uint2(q4[i].x, q4[i].y), p.ty_lo, p.ty_hi, x0, y0, w);
+            cnt[2 * i + 1] = box_tiles(make_uint2(q4[i].z, q4[i].w), p.ty_lo, p.ty_hi, x0, y0, w);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScan2Items; i++) {
+            uint32_t x0, y0, w;
+            cnt[i] = base + i < v ? box_tiles(__ldg(reinterpret_cast<const uint2*>(p.tboxes_sorted) + base + i), p.ty_lo, p.ty_hi, x0, y0, w) : 0u;
+        }
     }
     // my tile's base: the prefix dup_tiles_kernel left, or (few tiles: 1465 for 6 M splats, 12 KB that sit in L2) the sum of the
     // tile sums in front of mine, read by the whole CTA while the boxes are in flight — one launch and one idle SM-array less
@@ -407,21 +422,6 @@ __global__ void __launch_bounds__(kScan2Threads) dup_offsets_kernel(const BinPar
             }
         }
     }
-    {
-#pragma unroll
-        for (int i = 0; i < kScan2Items; i++) {
-            uint32_t x0, y0, w;
-            s_cnt[i * kScan2Threads + tid] = box_tiles(q[i], p.ty_lo, p.ty_hi, x0, y0, w);
-        }
-    }
-    __syncthreads();
-    // blocked: thread t owns splats [8 t, 8 t + 8) of the tile
-    uint32_t cnt[kScan2Items];
-    {
-        const uint4 a = reinterpret_cast<const uint4*>(s_cnt)[2 * tid], b = reinterpret_cast<const uint4*>(s_cnt)[2 * tid + 1];
-        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
-        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
-    }
     static_assert(kScan2Items == 8, "two 128-bit vectors per thread");
     unsigned long long sum = 0;
 #pragma unroll
@@ -439,7 +439,6 @@ __global__ void __launch_bounds__(kScan2Threads) dup_offsets_kernel(const BinPar
     for (int w = 0; w < kScan2Threads / 32; w++)
         if (w < (int)warp) wexcl += warp_sums[w];
     unsigned long long off = tile_off + wexcl + inc - sum;
-    const uint32_t base = tile_base + tid * kScan2Items;
     {
         // the splat whose run covers duplicate 4096 w is the first splat of the emit's window w
         unsigned long long o = off;
