@@ -35,9 +35,9 @@ SH_FMT, COV_FMT = 0, 0           # pod single/single, 224 B
 N_VIEWS = 64                     # orbit cameras (config 5a)
 METRIC = "frames_per_sec_1080p_6M_gaussians"
 REPEATS = 5                      # timed regions per measurement (the median is reported)
-KERNELS_PER_FRAME = 16           # preprocess 1, depth sort 1 + 4 (prologue, pass launches: the plan decides on the device how many do
-                                 # work; the result stays where the last pass wrote it), scan 1, emit 1, tile sort 1+1+2+1 (init,
-                                 # histogram, passes, finish), tile ranges 1, tile schedule 1, raster 1
+KERNELS_PER_FRAME = 17           # preprocess 1, depth sort 1 + 4 (prologue, pass launches: the plan decides on the device how many do
+                                 # work; the result stays where the last pass wrote it), binning 3 (dup_count, dup_offsets, dup_emit2),
+                                 # tile sort 1+1+2+1 (init, histogram, passes, finish), tile ranges 1, tile schedule 1, raster 1
 
 
 def peaks():

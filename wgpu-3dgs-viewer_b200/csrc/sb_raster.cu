@@ -2,8 +2,10 @@
 //
 // Replaces Renderer::render's instanced-quad draw + fixed-function ALPHA_BLENDING
 // (src/renderer.rs:163-195, 284-308; fragment stage src/shader/render.wesl:143-181):
-//   K4 dup_scan    depth-ordered splats -> exclusive scan of tiles-per-splat (chained scan)
-//   K5 dup_emit    (tile id, Gaussian index) duplicates, emitted in depth order
+//   K4 dup_count / dup_offsets   depth-ordered splats -> tile boxes in depth order, tile sums, then per-splat offsets (reduce-then-scan:
+//                  no look-back chain) and the first splat of every 4096-duplicate output window
+//   K5 dup_emit2   (tile id, Gaussian index) duplicates in depth order, OUTPUT-driven: a CTA expands one window into shared memory and
+//                  writes it with coalesced 128-bit stores       (SB_BIN=v1: the round-1 chained scan + per-splat emit, kept for A/B)
 //      tile sort   stable onesweep over the tile-id bits only (sb_sort.cu): because the input is
 //                  already in the reference's draw order, stability alone preserves it per tile
 //   K5b ranges     per-tile ranges of the sorted duplicates + the rasterizer's longest-list-first tile schedule
@@ -1333,10 +1335,15 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
     const uint32_t num_tiles = u.tiles_x * u.tiles_y;
 
     cudaError_t e;
-    // scan state: [counter(16B)] [status...] ; tile ranges zeroed (empty tiles -> begin=end=0)
-    const size_t scan_tiles = ((size_t)p.max_visible + kScanTile - 1) / kScanTile + 1;
-    e = cudaMemsetAsync(p.buf.scan_counter, 0, 16 + scan_tiles * sizeof(unsigned long long), stream);
-    if (e != cudaSuccess) return e;
+    // SB_BIN=v1 keeps the round-1 scan / emit pair (A/B runs); it is also the path when there is no buffer for the sorted boxes
+    static const bool bin_v1_env = [] { const char* c = std::getenv("SB_BIN"); return c && std::string(c) == "v1"; }();
+    const bool bin_v1 = bin_v1_env || p.buf.tboxes_sorted == nullptr || p.buf.win_first == nullptr;
+    // tile ranges zeroed (empty tiles -> begin=end=0); v1 scan state: [counter(16B)] [status...] (the v2 scan writes every word it reads)
+    if (bin_v1) {
+        const size_t scan_tiles = ((size_t)p.max_visible + kScanTile - 1) / kScanTile + 1;
+        e = cudaMemsetAsync(p.buf.scan_counter, 0, 16 + scan_tiles * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaMemsetAsync(p.buf.tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     // tile ids are relative to the strip's first tile row: a strip of a huge frame sorts fewer key bits (an 8K frame has 17,
@@ -1373,13 +1380,13 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
                       (p.sorted_indices_alt == nullptr || (reinterpret_cast<uintptr_t>(p.sorted_indices_alt) & 15u) == 0);
 
     const unsigned scan_grid = (unsigned)(((size_t)p.max_visible + kScanTile - 1) / kScanTile);
-    // SB_BIN=v1 keeps the round-1 scan / emit pair (A/B runs); it is also the path when there is no buffer for the sorted boxes
-    static const bool bin_v1 = [] { const char* c = std::getenv("SB_BIN"); return c && std::string(c) == "v1"; }();
-    if (bin_v1 || bp.tboxes_sorted == nullptr || bp.win_first == nullptr) {
+    if (bin_v1) {
         dup_scan_kernel<<<scan_grid > 0 ? scan_grid : 1, kScanThreads, 0, stream>>>(bp);
         dup_emit_kernel<<<num_sms * 8, 256, 0, stream>>>(bp);
     } else {
-        bp.tiles_prefixed = scan_grid > 4096 ? 1u : 0u;  // beyond 16.7 M splats a CTA no longer sums the tile sums itself
+        // beyond 16.7 M splats a CTA no longer sums the tile sums itself (SB_BIN_TILES_PREFIX=1 forces the prefix kernel: tests)
+        static const bool force_prefix = [] { const char* c = std::getenv("SB_BIN_TILES_PREFIX"); return c && std::atoi(c) != 0; }();
+        bp.tiles_prefixed = (scan_grid > 4096 || force_prefix) ? 1u : 0u;
         dup_count_kernel<<<scan_grid > 0 ? scan_grid : 1, kScan2Threads, 0, stream>>>(bp);
         if (bp.tiles_prefixed) dup_tiles_kernel<<<1, 1024, 0, stream>>>(bp);
         dup_offsets_kernel<<<scan_grid > 0 ? scan_grid : 1, kScan2Threads, 0, stream>>>(bp);
