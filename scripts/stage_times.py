@@ -20,6 +20,7 @@ ap.add_argument("--sh", type=int, default=0)
 ap.add_argument("--cov", type=int, default=0)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--strip", type=int, nargs=2, default=None, help="row0 rows: render only this strip, with strip culling (one rank of a multi-GPU frame)")
 ap.add_argument("--count", action="store_true", help="one extra instrumented frame: fragment / warp-evaluation counters")
 args = ap.parse_args()
 
@@ -36,7 +37,10 @@ for n in args.n:
     print(f"# n={n} built in {time.time() - t0:.1f}s", flush=True)
     v.update_gaussian_transform(1.0, args.mode, 3, False, 3.0)
     v.set_stage_timing(True)
-    target = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    row0, rows = args.strip if args.strip else (0, 0)
+    if args.strip:
+        v.set_strip_cull(True)
+    target = torch.zeros((rows or h, w, 4), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.Stream()
     for cam_name in args.cams:
         pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE if cam_name == "outside" else sb.scenes.CAMERA_INSIDE
@@ -47,7 +51,7 @@ for n in args.n:
         for it in range(args.iters + 3):
             with torch.cuda.stream(stream):
                 e0.record(stream)
-                v.render(target, w, h, stream=stream)
+                v.render(target, w, h, stream=stream, row0=row0, rows=rows)
                 e1.record(stream)
             stream.synchronize()
             if it < 3:
