@@ -1390,7 +1390,7 @@ cudaError_t launch_bin_and_raster(const RasterParams& p, int num_sms, cudaStream
         dup_count_kernel<<<scan_grid > 0 ? scan_grid : 1, kScan2Threads, 0, stream>>>(bp);
         if (bp.tiles_prefixed) dup_tiles_kernel<<<1, 1024, 0, stream>>>(bp);
         dup_offsets_kernel<<<scan_grid > 0 ? scan_grid : 1, kScan2Threads, 0, stream>>>(bp);
-        dup_emit2_kernel<<<num_sms * 6, 256, 0, stream>>>(bp);
+        dup_emit2_kernel<<<num_sms * 12, 256, 0, stream>>>(bp);  // two waves of six CTAs per SM: the windows of a CTA are spread over the frame
     }
     if (p.events) cudaEventRecord(p.events[0], stream);
 

@@ -1236,7 +1236,7 @@ cudaError_t launch_sort(uint32_t* keys, uint32_t* payload, const uint32_t* d_cou
     uint32_t* tickets = scratch.internal + kTicketOffset;
     uint32_t* lookback = scratch.internal + kLookbackOffset;
     sort_init_kernel<<<num_sms * 2, 256, 0, stream>>>(scratch.internal, d_count, max_count, num_passes, (uint32_t)tiles, (uint32_t)tile_size);
-    const int hist_grid = (int)min((size_t)num_sms * 2, (tiles * tile_size / 4 + 511) / 512);
+    const int hist_grid = (int)min((size_t)num_sms * 4, (tiles * tile_size / 4 + 511) / 512);
     histogram_kernel<<<hist_grid > 0 ? hist_grid : 1, 512, 0, stream>>>(keys, d_count, max_count, begin_bit, end_bit, num_passes, ghist);
 
     uint32_t* state = scratch.internal + kStateOffset;
