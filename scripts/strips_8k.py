@@ -23,6 +23,8 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--mode", default="peer", choices=["peer", "sendrecv"])
 ap.add_argument("--partition-cull", type=int, default=1, help="1: sb_strips_* (each rank preprocesses a slice of the model), 0: replicated cull")
+ap.add_argument("--tile-costs", type=float, nargs="*", default=None,
+                help="sweep of the balancer's fixed cost per tile (list entries): per-rank stage times for each")
 ap.add_argument("--check", action="store_true", help="rank 0 also renders the full frame alone and compares")
 args = ap.parse_args()
 
@@ -38,31 +40,57 @@ pods = sb.pack_gaussians(sb.scenes.synthetic_gaussians(args.n, sb.scenes.BASE_SE
 v = sb.Viewer(ctx, pods, args.n)
 pos, yaw, pitch = sb.scenes.CAMERA_OUTSIDE
 v.update_camera(pos, yaw, pitch, w, h)
-sf = sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=args.mode, balance=True, partition_cull=bool(args.partition_cull))
 stream = torch.cuda.current_stream()
 
 
-def step():
-    return sf.render()
+def measure(sf):
+    for _ in range(args.warmup):
+        full = sf.render()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        full = sf.render()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), full
 
 
-for _ in range(args.warmup):
-    full = step()
-torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(args.steps):
-    full = step()
-e1.record()
-torch.cuda.synchronize()
-ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
-if world > 1:
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if args.tile_costs:
+    # the balancer's cost model: duplicates + tile_cost per tile.  For every candidate: the frame time and every rank's own
+    # stage times (cudaEvents inside the library), so the slowest rank and what it spends its time on are visible.
+    for tc in args.tile_costs:
+        sf = sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=args.mode, balance=True, partition_cull=False, tile_cost=tc)
+        ms, _ = measure(sf)
+        v.set_stage_timing(True)
+        sf.render()
+        st = v.read_stage_times(stream)
+        v.set_stage_timing(False)
+        mine = dict(rank=rank, rows=sf.rows, sum_ms=round(sum(st.values()), 4), **{k: round(x, 4) for k, x in st.items()})
+        allr = [None] * world
+        if world > 1:
+            dist.all_gather_object(allr, mine)
+        else:
+            allr = [mine]
+        if rank == 0:
+            print(json.dumps(dict(tile_cost=tc, n_gpus=world, ms_per_frame=ms, per_rank=allr)), flush=True)
+        if world > 1:
+            dist.barrier()
+        sf.close()
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0)
+
+sf = sharding.StripFrame(ctx, v, w, h, 4, world, rank, dst=0, mode=args.mode, balance=True, partition_cull=bool(args.partition_cull))
+ms_val, full = measure(sf)
 if rank == 0:
-    out = dict(config="8K strips", gaussians=args.n, size=[w, h], n_gpus=world, ms_per_frame=float(ms.item()),
-               frames_per_s=1000.0 / float(ms.item()), strip_rows=[sharding.strip_rows(h, world, r)[1] for r in range(world)],
+    out = dict(config="8K strips", gaussians=args.n, size=[w, h], n_gpus=world, ms_per_frame=ms_val,
+               frames_per_s=1000.0 / ms_val, strip_rows=[b[1] for b in sf.bounds],
                transport=sf.mode, partitioned_cull=sf.strips is not None)
     if args.check:
         full = full.clone()

@@ -36,6 +36,11 @@ def strip_rows(height: int, world: int, rank: int) -> tuple[int, int]:
     return r0, r1 - r0
 
 
+# fixed cost of a tile (CTA start, clear, pixel stores, its share of the tile sort / ranges / schedule) in list entries; measured on
+# 8 GPUs with scripts/strips_8k.py --tile-costs (profiles/r02_multigpu.txt)
+TILE_COST = 16.0
+
+
 def balanced_strips(row_work, height: int, world: int, per_row_cost: float = 0.0) -> list[tuple[int, int]]:
     """Strip boundaries (whole tile rows, contiguous, one strip per rank) that minimise the heaviest strip's work, where a tile
     row costs row_work[y] + per_row_cost (row_work = (splat, tile) duplicates per tile row of a calibration / previous frame:
@@ -114,7 +119,7 @@ class StripFrame:
     """One frame rendered as `world` screen strips into a single buffer on rank `dst` (config 5b)."""
 
     def __init__(self, ctx, viewer, width: int, height: int, bytes_per_pixel: int, world: int, rank: int, dst: int = 0,
-                 mode: str = "peer", balance: bool = False, stream=None, partition_cull: bool = False):
+                 mode: str = "peer", balance: bool = False, stream=None, partition_cull: bool = False, tile_cost: float = TILE_COST):
         """balance: rank `dst` renders the full frame once (a calibration frame; a viewer would use its previous frame), reads the
         (splat, tile) duplicates per tile row and broadcasts strips of equal work instead of equal height."""
         import torch
@@ -140,8 +145,8 @@ class StripFrame:
                 tile_rows = (height + TILE - 1) // TILE
                 work = viewer.read_tile_row_work(tile_rows, stream)
                 del scratch
-                # a tile costs its list plus a fixed part (CTA start, clear, store): ~16 list entries per tile
-                box = [balanced_strips(work, height, world, per_row_cost=16.0 * ((width + TILE - 1) // TILE))]
+                # a tile costs its list plus a fixed part (CTA start, clear, store), expressed in list entries (TILE_COST)
+                box = [balanced_strips(work, height, world, per_row_cost=tile_cost * ((width + TILE - 1) // TILE))]
             dist.broadcast_object_list(box, src=dst)
             self.bounds = [tuple(b) for b in box[0]]
         self.balanced = bool(balance and world > 1)
