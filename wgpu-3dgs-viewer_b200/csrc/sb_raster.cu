@@ -794,7 +794,7 @@ struct DepthArgs {
 // ND ("no discard", splat mode on unorm8 targets with sd^2 >= 6.3 only): a fragment beyond the quad's alive radius has
 // alpha = a*exp(-r^2) < exp(-6.3) < kAlphaCut, so blending it is the identity exactly (sb_common.cuh) and the discard test
 // and its select can go.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH, bool ND = false>
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH, bool ND = false, bool FOLD = false>
 __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 pxy, bool inside, float sd2, float outline, PixelState& st,
                                            const DepthArgs& da) {
     const char* rp = PERM ? last - 64u * hb : last - 48u * hb;
@@ -815,7 +815,15 @@ __device__ __forceinline__ void eval_splat(const char* last, uint32_t hb, f32x2 
         const float r2 = __fmaf_rn(qx, qx, __fmul_rn(qy, qy));
         alive = r2 <= sd2;  // discard otherwise: render.wesl:145,155
         if constexpr (MODE == SB_MODE_SPLAT) {
-            const float e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
+            float e;
+            if constexpr (FOLD) {
+                // the staged axes of this build carry a factor sqrt(log2 e) (the CTA's cull folds it in, once per record and
+                // batch): r2 is already -log2 of the falloff, one multiply per evaluation less (and sd2 arrives scaled alike)
+                static_assert(!STRICT && MODE == SB_MODE_SPLAT, "the fold belongs to the fast-exp splat builds");
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-r2));
+            } else {
+                e = STRICT ? exp_neg_poly(r2) : exp_neg_fast(r2);
+            }
             alpha = __fmul_rn(q2.w, e);  // render.wesl:149
         } else {
             const float ol = r2 > outline ? 1.0f : 0.0f;  // render.wesl:159-160
@@ -930,7 +938,7 @@ __device__ __forceinline__ uint32_t block_mask(const float4* __restrict__ rec, f
 
 // SHARED: the hit masks of the batch were computed once per CTA (block_mask) and sit in shared memory; `bl` = this warp's
 // left block's bit.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false, bool ND = false, bool SHARED = false>
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool PERM, bool DEPTH = false, bool ND = false, bool SHARED = false, bool FOLD = false>
 __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs, uint32_t cnt, f32x2 pxy, float pcx, float pcy,
                                                 uint32_t lane, bool inside, float sd, float sd2, float outline, bool obb,
                                                 PixelState& st, DepthArgs da = DepthArgs{nullptr, 0, 0},
@@ -979,7 +987,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
                 uint32_t hb;  // FLO directly; `31 - __clz` is canonicalised back into a clz and costs five more integer ops
                 asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
                 todo ^= 1u << hb;
-                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH, ND>(last, hb, pxy, inside, sd2, outline, st, da);
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH, ND, FOLD>(last, hb, pxy, inside, sd2, outline, st, da);
             }
         } else {
             uint32_t todo = __brev(un);
@@ -987,7 +995,7 @@ __device__ __forceinline__ void composite_batch(const float4* __restrict__ recs,
                 uint32_t hb;
                 asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(todo));
                 todo ^= 1u << hb;
-                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH, ND>(last, hb, pxy, inside, sd2, outline, st, da);
+                eval_splat<MODE, FMT, STRICT, COUNT, PERM, DEPTH, ND, FOLD>(last, hb, pxy, inside, sd2, outline, st, da);
             }
         }
     }
@@ -1073,7 +1081,7 @@ __global__ void __launch_bounds__(256) raster_bulk_kernel(const RasterKernelPara
 // (coalesced) and fetches the 48-byte records straight from the per-Gaussian array with TMA
 // tile::gather4 (cp.async.bulk.tensor.2d ... tile::gather4 -> UTMALDG, four rows per instruction, two
 // instructions per lane and batch) into a double-buffered ring; eight consumer warps composite.
-template <int MODE, int FMT, bool STRICT, bool COUNT, bool DEPTH = false, bool ND = false>
+template <int MODE, int FMT, bool STRICT, bool COUNT, bool DEPTH = false, bool ND = false, bool FOLD = false>
 __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_constant__ RasterKernelParams p, const __grid_constant__ CUtensorMap recs_map) {
     __shared__ __align__(256) float4 stage[kG4Stages][kG4StageF4];
     __shared__ float zs[DEPTH ? kG4Stages : 1][DEPTH ? kBatchG4 : 1];  // ndc z per staged record (depth-tested passes only)
@@ -1185,8 +1193,23 @@ __global__ void __launch_bounds__(288) raster_gather4_kernel(const __grid_consta
         // CTA-level cull: thread t tests record t of the batch against the tile's sixteen blocks, once for all warps.  The
         // buffer of stage s is free: the stage was refilled only after every warp had released it (empty_bar).
         cull_mask[s][tid] = tid < cnt ? (uint16_t)block_mask(&stage[s][4u * tid], bx0, by0, p.sd, p.obb_cull != 0, p.cut_k) : (uint16_t)0;
+        if constexpr (FOLD) {
+            // fast-exp splat builds on unorm8 with sd^2 >= 6.3 (where a fragment at the discard radius no longer changes a pixel,
+            // so the rounding of r^2 at that boundary cannot show): fold sqrt(log2 e) into the staged record's inverse axes, so that
+            // the quad offset's squared length is the exponent of ex2 directly.  One thread per record and batch; the mask above
+            // was computed from the unscaled axes, and the barrier below publishes both.
+            if (tid < cnt) {
+                constexpr float kS = 1.2011224087864498f;  // sqrt(log2 e)
+                float4* r = &stage[s][4u * tid];
+                const float2 a0 = *reinterpret_cast<const float2*>(&r[0].z);  // ax bx
+                const float2 a1 = *reinterpret_cast<const float2*>(&r[1].x);  // ay by
+                *reinterpret_cast<float2*>(&r[0].z) = make_float2(a0.x * kS, a0.y * kS);
+                *reinterpret_cast<float2*>(&r[1].x) = make_float2(a1.x * kS, a1.y * kS);
+            }
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight consumer warps (the producer warp is not part of it)
-        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH, ND, true>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd, p.sd2,
+        composite_batch<MODE, FMT, STRICT, COUNT, true, DEPTH, ND, true, FOLD>(stage[s], cnt, pk2(px, py), pcx, pcy, lane, inside, p.sd,
+                                                                            FOLD ? p.sd2 * 1.44269504f : p.sd2,
                                                                      p.outline, p.obb_cull != 0, st,
                                                                      DepthArgs{DEPTH ? zs[s] : nullptr, p.depth_compare, p.depth_write},
                                                                      cull_mask[s], bl);
@@ -1301,9 +1324,17 @@ void launch_raster(const RasterKernelParams& kp, const CUtensorMap* recs_map, di
             raster_gather4_kernel<MODE, FMT, STRICT, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
         } else if (kp.no_discard) {
             if constexpr (MODE == SB_MODE_SPLAT && FMT == FMT_UNORM8 && !STRICT)
-                raster_gather4_kernel<MODE, FMT, STRICT, false, false, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
+                raster_gather4_kernel<MODE, FMT, STRICT, false, false, true, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
         } else {
-            raster_gather4_kernel<MODE, FMT, STRICT, false><<<grid, 288, 0, stream>>>(kp, *recs_map);
+            // the same arithmetic with the exact cut-off switched off (the discard test kept): frames stay bit-identical between the two
+            bool folded = false;
+            if constexpr (MODE == SB_MODE_SPLAT && FMT == FMT_UNORM8 && !STRICT) {
+                if (kp.sd2 >= 6.3f) {
+                    raster_gather4_kernel<MODE, FMT, STRICT, false, false, false, true><<<grid, 288, 0, stream>>>(kp, *recs_map);
+                    folded = true;
+                }
+            }
+            if (!folded) raster_gather4_kernel<MODE, FMT, STRICT, false><<<grid, 288, 0, stream>>>(kp, *recs_map);
         }
     } else {
         if (kp.counters) raster_bulk_kernel<MODE, FMT, STRICT, true><<<grid, 256, 0, stream>>>(kp);
