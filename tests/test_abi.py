@@ -63,6 +63,31 @@ def test_host_packer_matches_oracle(sb, ob):
             assert np.array_equal(a, b), (sh, cov)
 
 
+def test_host_packer_half_conversion_special_values(sb, ob):
+    """The packer converts to half eight at a time in hardware where the host has F16C; the oracle converts in software.  Every
+    class of value must come out the same: ties to even, the overflow threshold (65520 -> inf), denormal halves and the underflow
+    threshold (2^-25 ties to zero), signed zeros, infinities and NaNs (payload dropped), next to a dense random sweep of exponents."""
+    rng = np.random.default_rng(21)
+    specials = np.array([0.0, -0.0, 1.0, -1.0, 65504.0, 65519.99, 65520.0, 65536.0, 1e9, -1e9, np.inf, -np.inf, np.nan,
+                         2.0 ** -24, 2.0 ** -25, np.nextafter(np.float32(2.0 ** -25), np.float32(1.0)), 2.0 ** -26, 6.0e-8, 6.1e-5, 6.103515625e-05,
+                         1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20, 1.0 + 2.0 ** -11 - 2.0 ** -20, 2047.5, 2048.5,
+                         0.333333343, -0.1, 3.14159274, 1e-40, -1e-40], dtype=np.float32)
+    nanp = np.array([0x7fc12345, 0xffc00001, 0x7f800001], dtype=np.uint32).view(np.float32)  # NaNs with payloads
+    n = 4096
+    g = sb.scenes.synthetic_gaussians(n, 22)
+    sweep = (rng.standard_normal((n, 45)) * np.exp2(rng.integers(-30, 18, (n, 45)))).astype(np.float32)
+    g["sh"] = sweep
+    flat = np.concatenate([specials, nanp])
+    g["sh"].reshape(-1)[: len(flat)] = flat
+    g["sh"][100, :8] = specials[:8]          # specials inside a full vector of eight as well as in a tail
+    g["sh"][101, 37:45] = specials[8:16]
+    g["scale"][:16] = np.exp2(rng.integers(-14, 8, (16, 3))).astype(np.float32)   # covariances across the half range (cov half)
+    for sh, cov in ((1, 0), (1, 1), (0, 1), (2, 1)):
+        a = sb.pack_gaussians(g, sh, cov)
+        b = ob.pack_gaussians(g.view(ob.GAUSSIAN_DTYPE), sh, cov)
+        assert np.array_equal(a, b), (sh, cov)
+
+
 def test_camera_and_transform_pods_match_oracle(sb, ob):
     rng = np.random.default_rng(0)
     for _ in range(50):

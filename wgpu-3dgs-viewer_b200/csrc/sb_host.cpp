@@ -12,6 +12,9 @@
 #include <vector>
 
 #include <zlib.h>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/splat_b200.h"
 
@@ -38,6 +41,35 @@ uint16_t float_to_half(float f) {  // round-to-nearest-even, IEEE binary16
     const uint32_t rem = m & 0x1fffu;
     if (rem > 0x1000u || (rem == 0x1000u && (out & 1u))) out++;
     return (uint16_t)(sign | out);
+}
+
+// n floats -> n halves, the same round-to-nearest-even as float_to_half.  On x86 with F16C (every host this library has met) eight at a
+// time in hardware — the software conversion made the half-precision pod formats the slowest to pack (1.6 M Gaussians/s against 7.3 M/s
+// for single precision on eight cores); NaNs (whose payload the hardware keeps and float_to_half drops) go through the software path.
+#if defined(__x86_64__) || defined(__i386__)
+__attribute__((target("avx,f16c"))) void floats_to_halves_f16c(const float* src, uint16_t* dst, int n) {
+    int k = 0;
+    bool any_nan = false;
+    for (; k + 8 <= n; k += 8) {
+        const __m256 v = _mm256_loadu_ps(src + k);
+        any_nan = any_nan || _mm256_movemask_ps(_mm256_cmp_ps(v, v, _CMP_UNORD_Q)) != 0;
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm256_cvtps_ph(v, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+    }
+    for (; k < n; k++) dst[k] = float_to_half(src[k]);
+    if (any_nan)
+        for (k = 0; k < n; k++)
+            if (src[k] != src[k]) dst[k] = float_to_half(src[k]);
+}
+#endif
+void floats_to_halves(const float* src, uint16_t* dst, int n) {
+#if defined(__x86_64__) || defined(__i386__)
+    static const bool f16c = __builtin_cpu_supports("f16c") && __builtin_cpu_supports("avx");
+    if (f16c) {
+        floats_to_halves_f16c(src, dst, n);
+        return;
+    }
+#endif
+    for (int k = 0; k < n; k++) dst[k] = float_to_half(src[k]);
 }
 
 float half_to_float(uint16_t h) {
@@ -140,10 +172,9 @@ SbStatus sb_pack_gaussians(const SbGaussian* src, uint64_t n, int32_t sh_fmt, in
         if (sh_fmt == SB_SH_SINGLE) {
             std::memcpy(q, g.sh, 180);
         } else if (sh_fmt == SB_SH_HALF) {
-            for (int k = 0; k < 45; k++) {
-                const uint16_t h = float_to_half(g.sh[k]);
-                std::memcpy(q + 2 * k, &h, 2);
-            }
+            uint16_t h[45];
+            floats_to_halves(g.sh, h, 45);
+            std::memcpy(q, h, sizeof h);
         } else if (sh_fmt == SB_SH_NORM8) {
             float lo = g.sh[0], hi = g.sh[0];
             for (int k = 1; k < 45; k++) {
@@ -174,10 +205,9 @@ SbStatus sb_pack_gaussians(const SbGaussian* src, uint64_t n, int32_t sh_fmt, in
             if (cov_fmt == SB_COV_SINGLE) {
                 std::memcpy(c, cov, 24);
             } else {
-                for (int k = 0; k < 6; k++) {
-                    const uint16_t h = float_to_half(cov[k]);
-                    std::memcpy(c + 2 * k, &h, 2);
-                }
+                uint16_t h[6];
+                floats_to_halves(cov, h, 6);
+                std::memcpy(c, h, sizeof h);
             }
         }
     }
