@@ -123,6 +123,24 @@ def test_ply_reader_matches_oracle(sb, ob, tmp_path):
     assert len(g) == 9 and g["color"][0].tolist() == [255, 0, 0, 255]
 
 
+def test_ply_reader_block_boundaries(sb, ob, tmp_path):
+    """sb_read_ply converts the rows in 65536-row blocks on all host cores: a file that spans a full block plus a ragged one (and
+    one of exactly one block) comes out byte for byte as the oracle's row-by-row conversion."""
+    names = (["x", "y", "z", "nx", "ny", "nz"] + [f"f_dc_{i}" for i in range(3)] + [f"f_rest_{i}" for i in range(45)]
+             + ["opacity"] + [f"scale_{i}" for i in range(3)] + [f"rot_{i}" for i in range(4)])
+    rng = np.random.default_rng(33)
+    for n in (65536, 65536 + 4465):
+        props = rng.standard_normal((n, len(names))).astype("<f4")
+        props[:, names.index("opacity")] *= 4.0
+        hdr = "ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % n
+        hdr += "".join(f"property float {x}\n" for x in names) + "end_header\n"
+        path = tmp_path / f"blocks_{n}.ply"
+        path.write_bytes(hdr.encode() + props.tobytes())
+        g = sb.read_ply(str(path))
+        og = ob.gaussians_from_ply_props(props)
+        assert len(g) == n and g.tobytes() == og.tobytes()
+
+
 def test_no_context_without_gpu(sb):
     import torch
     if torch.cuda.is_available():
