@@ -428,7 +428,9 @@ SbStatus sb_read_spz(const char* path, SbGaussian** out, uint64_t* n_out) {
     if (!g) return SB_ERR_IO;
     const float pos_scale = 1.0f / (float)(1u << frac_bits);
     const float SH_C0 = 0.2820948f, kColorScale = 0.15f;
-    for (uint32_t i = 0; i < n; i++) {
+    // (the points are independent: decoded on all host cores; the inflate above is the serial part)
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
         SbGaussian& o = g[i];
         for (int c = 0; c < 3; c++) {
             const uint8_t* b = pos + (size_t)i * 9 + c * 3;
