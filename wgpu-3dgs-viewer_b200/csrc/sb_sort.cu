@@ -27,10 +27,6 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 16;
 constexpr int kSortTile = kSortThreads * kItems;  // pairs per tile
 constexpr int kMaxPasses = 4;
-#ifndef SB_MATCH_EVERY
-#define SB_MATCH_EVERY 0
-#endif
-constexpr int kMatchEvery = SB_MATCH_EVERY;  // every k-th item is ranked with MATCH.ANY (0 = never)
 
 constexpr uint32_t kLbAggregate = 1u << 30;
 constexpr uint32_t kLbPrefix = 2u << 30;
@@ -643,15 +639,6 @@ struct Sort4Smem {
     uint32_t scan_a[kV4Warps];
     uint32_t tile;
 };
-
-__device__ __forceinline__ void st_relaxed_v2(uint32_t* p, uint32_t a, uint32_t b) {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ uint2 ld_relaxed_v2(const uint32_t* p) {
-    uint2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
-}
 
 // lanes whose digit (< 2^nbits, nbits <= 9, warp-uniform) equals this lane's: one vote per significant digit bit
 __device__ __forceinline__ uint32_t match_digit9(uint32_t d, int nbits) {
